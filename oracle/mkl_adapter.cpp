@@ -1,0 +1,81 @@
+// ORACLE BUILD ONLY.  ILP64 -> LP64 adapters between the UNMODIFIED reference pcg.cpp (which is written
+// against MKL's ILP64 interface, `#define MKL_INT size_t`, /root/reference/c++/util/pcg.cpp:3) and the
+// genuine oneMKL 2024.2 LP64 sparse kernels exported by libtorch_cpu.so.  The arithmetic of SpMV and of
+// both triangular solves is MKL's own; only the five CBLAS level-1 routines are restated here because
+// libtorch_cpu.so does not export them.
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <stdexcept>
+
+// real LP64 prototypes (hand-declared; no MKL headers in this image)
+extern "C" {
+struct lp64_descr { int type, mode, diag; };
+int mkl_sparse_d_create_csr(void **A, int indexing, int rows, int cols, int *rows_start, int *rows_end,
+                            int *col_indx, double *values);
+int mkl_sparse_d_mv(int op, double alpha, void *A, lp64_descr descr, const double *x, double beta, double *y);
+int mkl_sparse_d_trsv(int op, double alpha, void *A, lp64_descr descr, const double *x, double *y);
+int mkl_sparse_destroy(void *A);
+}
+
+struct rchol_b200_ilp64_handle {
+  void *mkl = nullptr;
+  int *rs = nullptr, *re = nullptr, *ci = nullptr;
+};
+typedef rchol_b200_ilp64_handle *sparse_matrix_t;
+struct matrix_descr { int type, mode, diag; };
+
+extern "C" {
+
+int rchol_b200_mkl_create_csr(sparse_matrix_t *A, int indexing, size_t rows, size_t cols, size_t *rows_start,
+                              size_t *rows_end, size_t *col_indx, double *values) {
+  size_t nnz = rows ? rows_end[rows - 1] : 0;
+  if (rows >= (size_t)INT32_MAX || nnz >= (size_t)INT32_MAX) return 5;  // LP64 limit
+  auto *h = new rchol_b200_ilp64_handle();
+  h->rs = (int *)malloc((rows + 1) * sizeof(int));
+  h->re = (int *)malloc((rows + 1) * sizeof(int));
+  h->ci = (int *)malloc((nnz + 1) * sizeof(int));
+  for (size_t i = 0; i < rows; i++) { h->rs[i] = (int)rows_start[i]; h->re[i] = (int)rows_end[i]; }
+  for (size_t k = 0; k < nnz; k++) h->ci[k] = (int)col_indx[k];
+  int st = mkl_sparse_d_create_csr(&h->mkl, indexing, (int)rows, (int)cols, h->rs, h->re, h->ci, values);
+  *A = h;
+  return st;
+}
+int rchol_b200_mkl_mv(int op, double alpha, const sparse_matrix_t A, matrix_descr d, const double *x,
+                      double beta, double *y) {
+  lp64_descr dd{d.type, d.mode, d.diag};
+  return mkl_sparse_d_mv(op, alpha, A->mkl, dd, x, beta, y);
+}
+int rchol_b200_mkl_trsv(int op, double alpha, const sparse_matrix_t A, matrix_descr d, const double *x, double *y) {
+  lp64_descr dd{d.type, d.mode, d.diag};
+  return mkl_sparse_d_trsv(op, alpha, A->mkl, dd, x, y);
+}
+int rchol_b200_mkl_destroy(sparse_matrix_t A) {
+  int st = mkl_sparse_destroy(A->mkl);
+  free(A->rs); free(A->re); free(A->ci);
+  delete A;
+  return st;
+}
+
+void rchol_b200_cblas_dcopy(size_t n, const double *x, size_t, double *y, size_t) {
+  for (size_t i = 0; i < n; i++) y[i] = x[i];
+}
+double rchol_b200_cblas_ddot(size_t n, const double *x, size_t, const double *y, size_t) {
+  double s = 0;
+  for (size_t i = 0; i < n; i++) s += x[i] * y[i];
+  return s;
+}
+double rchol_b200_cblas_dnrm2(size_t n, const double *x, size_t) {
+  double s = 0;
+  for (size_t i = 0; i < n; i++) s += x[i] * x[i];
+  return std::sqrt(s);
+}
+void rchol_b200_cblas_dscal(size_t n, double a, double *x, size_t) {
+  for (size_t i = 0; i < n; i++) x[i] *= a;
+}
+void rchol_b200_cblas_daxpy(size_t n, double a, const double *x, size_t, double *y, size_t) {
+  for (size_t i = 0; i < n; i++) y[i] += a * x[i];
+}
+
+}  // extern "C"
