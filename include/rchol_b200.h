@@ -1,0 +1,128 @@
+/* rchol_b200 -- C ABI of the B200-native PCG solve phase for the rchol preconditioner.
+ *
+ * This is the drop-in boundary for the reference's solve-phase hot path
+ *     pcg(const SparseCSR &A, const std::vector<double> &b, double tol, int maxit,
+ *         const SparseCSR &G, std::vector<double> &x, double &relres, int &itr)
+ * (/root/reference/c++/util/pcg.hpp:13-16, implemented in c++/util/pcg.cpp:14-159 on top of Intel MKL).
+ * Plain pointers and sizes only; every matrix is passed exactly as the reference's SparseCSR holds it
+ * (c++/sparse.hpp:10-31): zero-based CSR, `uint64_t` (size_t) rowPtr[N+1] / colIdx[nnz], `double` val[nnz].
+ * Host arrays are borrowed for the duration of the call and never retained (the reference deep-copies into
+ * MKL handles, pcg.cpp:31-54); all device memory is owned by the handle and released by rcg_destroy.
+ *
+ * There is NO CPU fallback: every entry point that computes fails with RCG_ERR_CUDA when no sm_100 device
+ * is usable.  All functions return 0 (RCG_OK) on success; rcg_last_error() describes the last failure.
+ * A handle is not thread-safe; calls are synchronous (like the reference's pcg).
+ */
+#ifndef RCHOL_B200_H
+#define RCHOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rcg_handle rcg_handle;
+
+enum {
+  RCG_OK = 0,
+  RCG_ERR_CUDA = 1,        /* CUDA runtime / driver error, or no usable device          */
+  RCG_ERR_INVALID = 2,     /* bad argument (NULL pointer, size mismatch, bad partition)  */
+  RCG_ERR_STATE = 3,       /* call order: matrix or factor not set yet                   */
+  RCG_ERR_STRUCTURE = 4,   /* G is not upper triangular with a positive leading diagonal,
+                              or it violates the nested-dissection block structure       */
+  RCG_ERR_NOMEM = 5
+};
+
+/* Direction selectors of rcg_trsv, named after the two MKL calls they replace. */
+enum {
+  RCG_TRSV_FORWARD = 0,    /* y = U^{-T} rhs : mkl_sparse_d_trsv(TRANSPOSE, ...)      pcg.cpp:151 */
+  RCG_TRSV_BACKWARD = 1    /* z = U^{-1} rhs : mkl_sparse_d_trsv(NON_TRANSPOSE, ...)  pcg.cpp:155 */
+};
+
+/* Tunables (all have defaults; see DESIGN.md "SpTRSV"). */
+typedef struct rcg_options {
+  int chain_threads;       /* threads per CTA of the block-local sync-free triangular solve (0 = default) */
+  int chain_window;        /* rows of the shared-memory solution window per CTA (0 = default)             */
+  int use_graph;           /* 1 = replay one CUDA graph per PCG iteration (default), 0 = plain launches   */
+  int spmv_lanes;          /* lanes per row of the CSR SpMV (0 = choose from the row-length histogram)     */
+  int reserved[12];
+} rcg_options;
+
+/* Per-handle measurements, all device-side times from CUDA events on the handle's own stream. */
+typedef struct rcg_stats {
+  uint64_t N, nnzA, nnzG;
+  uint64_t n_blocks;               /* nested-dissection blocks (2T-1), 1 without a partition              */
+  uint64_t tree_levels;            /* log2(T)+1                                                            */
+  double upload_ms;                /* host->device copies of A, G (wall clock)                             */
+  double analysis_ms;              /* device set-up: index narrowing, transpose of G, schedules            */
+  double solve_ms;                 /* last solve: the iterations only, CUDA events                         */
+  double total_ms;                 /* last rcg_pcg: wall clock of the whole call                           */
+  double trsv_ms, spmv_ms, blas1_ms; /* last rcg_profile_iteration(): per-iteration split, CUDA events     */
+  uint64_t kernel_launches;        /* kernels launched by this handle since creation                       */
+  uint64_t launches_per_iteration; /* kernels in one PCG iteration                                         */
+  uint64_t h2d_bytes, d2h_bytes;   /* bytes copied by the last rcg_pcg call (and by set_A/set_G for h2d)   */
+  uint64_t device_bytes;           /* device memory currently owned by the handle                          */
+  double reserved[8];
+} rcg_stats;
+
+/* ---- life cycle -------------------------------------------------------------------------------------- */
+int rcg_create(rcg_handle **out, int device);                 /* device = CUDA ordinal                    */
+int rcg_create_with_options(rcg_handle **out, int device, const rcg_options *opt);
+int rcg_destroy(rcg_handle *h);
+const char *rcg_last_error(const rcg_handle *h);              /* h may be NULL: last creation error        */
+const char *rcg_version(void);
+
+/* ---- inputs (replaces pcg::create_sparse, pcg.cpp:31-54) ----------------------------------------------- */
+/* A: the (permuted) system matrix, general CSR. */
+int rcg_set_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val);
+/* G: CSR of the upper-triangular factor U as returned by rchol(...) (rchol_lap.cpp:146-149): every row sorted,
+ * diagonal first and positive.  `part` (may be NULL, npart = 0) = block boundaries of the reference's
+ * nested-dissection layout in permuted index space (rchol_parallel.cpp:64-70 `result_idx`, ground vertex
+ * dropped): npart = 2T entries, part[0] = 0, part[npart-1] = N, blocks in post-order
+ * [left subtree..., right subtree..., separator].  Without it the factor is solved as one block. */
+int rcg_set_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                   const uint64_t *part, uint64_t npart);
+
+/* ---- the kernels of the path, exposed one by one so that parity can be tested in isolation ------------- */
+int rcg_spmv(rcg_handle *h, const double *x_host, double *y_host);                 /* pcg.cpp:130-138 */
+int rcg_trsv(rcg_handle *h, int which, const double *rhs_host, double *out_host);  /* pcg.cpp:151 / :155 */
+int rcg_precond(rcg_handle *h, const double *r_host, double *z_host);              /* pcg.cpp:141-159 */
+
+/* ---- the solve (replaces pcg::iteration, pcg.cpp:57-127) ----------------------------------------------- */
+/* Zero initial guess; iterate while ||r||_2 > tol * ||b||_2 and it < maxit; relres = ||A x - b|| / ||b|| (true
+ * residual); *itr = completed iterations.  b_host and x_host are host arrays of length N. */
+int rcg_pcg(rcg_handle *h, const double *b_host, double tol, int maxit, double *x_host, double *relres, int *itr);
+
+/* Same solve with the right-hand side already resident (rcg_set_rhs) and the solution left on the device
+ * (rcg_get_solution): the timed region of the "inputs resident in HBM" benchmark. */
+int rcg_set_rhs(rcg_handle *h, const double *b_host);
+int rcg_pcg_resident(rcg_handle *h, double tol, int maxit, double *relres, int *itr);
+int rcg_get_solution(rcg_handle *h, double *x_host);
+/* Optional residual history of the last solve: ||r_k|| / ||b|| at every loop test (k = 0..itr). */
+int rcg_get_history(rcg_handle *h, double *hist, int capacity, int *count);
+
+/* One-shot form = exactly what the reference constructor does (wrap A, wrap G, iterate, destroy). */
+int rcg_pcg_oneshot(int device, uint64_t N, const uint64_t *ArowPtr, const uint64_t *AcolIdx, const double *Aval,
+                    const double *b, double tol, int maxit, const uint64_t *GrowPtr, const uint64_t *GcolIdx,
+                    const double *Gval, const uint64_t *part, uint64_t npart, double *x, double *relres, int *itr,
+                    rcg_stats *stats_or_null);
+
+/* ---- measurement ------------------------------------------------------------------------------------- */
+int rcg_get_stats(rcg_handle *h, rcg_stats *out);
+/* Runs `reps` PCG iterations' worth of kernels on the resident vectors without the convergence test and fills
+ * trsv_ms / spmv_ms / blas1_ms (averages per iteration) -- the live CUDA-event measurement bench.py reports. */
+int rcg_profile_iteration(rcg_handle *h, int reps);
+/* Times `reps` launches of a single phase with CUDA events: 0 = SpMV, 1 = forward solve, 2 = backward solve,
+ * 3 = fused vector updates.  *avg_ms receives the average duration of one phase execution. */
+int rcg_time_phase(rcg_handle *h, int phase, int reps, double *avg_ms);
+
+/* ---- diagnostics ------------------------------------------------------------------------------------- */
+/* One triangular solve with per-row tracing of the dependency-chain kernel: trace_host receives 4 uint32 per row
+ * in solve index order {finish cycle, polling-loop trips, start cycle, cta*1024+thread} (per-SM cycle counters). */
+int rcg_debug_trace(rcg_handle *h, int which, const double *rhs_host, double *out_host, uint32_t *trace_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCHOL_B200_H */

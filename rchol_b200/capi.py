@@ -1,0 +1,241 @@
+"""ctypes binding of the C ABI in ``include/rchol_b200.h`` (``rchol_b200/lib/librchol_b200.so``).
+
+This is the Python face of the drop-in boundary used by tests/ and bench.py; the C++ face is
+``rchol_b200/cxx/pcg.hpp`` (same constructor signature as /root/reference/c++/util/pcg.hpp:13-16).
+There is no fallback of any kind: if the CUDA library is missing or no B200 is visible, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librchol_b200.so")
+
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+# every symbol include/rchol_b200.h declares (tests check that the library exports all of them)
+EXPORTED = [
+    "rcg_create", "rcg_create_with_options", "rcg_destroy", "rcg_last_error", "rcg_version",
+    "rcg_set_matrix", "rcg_set_factor", "rcg_spmv", "rcg_trsv", "rcg_precond", "rcg_pcg",
+    "rcg_set_rhs", "rcg_pcg_resident", "rcg_get_solution", "rcg_get_history", "rcg_pcg_oneshot",
+    "rcg_get_stats", "rcg_profile_iteration", "rcg_time_phase", "rcg_debug_trace",
+]
+
+TRSV_FORWARD, TRSV_BACKWARD = 0, 1
+
+
+class Options(C.Structure):
+    _fields_ = [("chain_threads", C.c_int), ("chain_window", C.c_int), ("use_graph", C.c_int),
+                ("spmv_lanes", C.c_int), ("reserved", C.c_int * 12)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("N", C.c_uint64), ("nnzA", C.c_uint64), ("nnzG", C.c_uint64), ("n_blocks", C.c_uint64),
+                ("tree_levels", C.c_uint64), ("upload_ms", C.c_double), ("analysis_ms", C.c_double),
+                ("solve_ms", C.c_double), ("total_ms", C.c_double), ("trsv_ms", C.c_double),
+                ("spmv_ms", C.c_double), ("blas1_ms", C.c_double), ("kernel_launches", C.c_uint64),
+                ("launches_per_iteration", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("device_bytes", C.c_uint64), ("reserved", C.c_double * 8)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["chain_sm_mhz"] = self.reserved[0]   # SM clock seen by the last chain kernel (clock64 / globaltimer)
+        d["watchdog_row"] = int(self.reserved[1])  # 1 + row whose dependency wait timed out (0 = none)
+        return d
+
+
+class RcgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rchol_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Loads the CUDA library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()); "
+                           "rchol_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    L.rcg_create.argtypes = [C.POINTER(H), C.c_int]
+    L.rcg_create_with_options.argtypes = [C.POINTER(H), C.c_int, C.POINTER(Options)]
+    L.rcg_destroy.argtypes = [H]
+    L.rcg_last_error.restype = C.c_char_p
+    L.rcg_last_error.argtypes = [H]
+    L.rcg_version.restype = C.c_char_p
+    L.rcg_set_matrix.argtypes = [H, C.c_uint64, _u64p, _u64p, _f64p]
+    L.rcg_set_factor.argtypes = [H, C.c_uint64, _u64p, _u64p, _f64p, C.c_void_p, C.c_uint64]
+    L.rcg_spmv.argtypes = [H, _f64p, _f64p]
+    L.rcg_trsv.argtypes = [H, C.c_int, _f64p, _f64p]
+    L.rcg_precond.argtypes = [H, _f64p, _f64p]
+    L.rcg_pcg.argtypes = [H, _f64p, C.c_double, C.c_int, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.rcg_set_rhs.argtypes = [H, _f64p]
+    L.rcg_pcg_resident.argtypes = [H, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.rcg_get_solution.argtypes = [H, _f64p]
+    L.rcg_get_history.argtypes = [H, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.rcg_pcg_oneshot.argtypes = [C.c_int, C.c_uint64, _u64p, _u64p, _f64p, _f64p, C.c_double, C.c_int,
+                                  _u64p, _u64p, _f64p, C.c_void_p, C.c_uint64, _f64p,
+                                  C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(Stats)]
+    L.rcg_get_stats.argtypes = [H, C.POINTER(Stats)]
+    L.rcg_profile_iteration.argtypes = [H, C.c_int]
+    L.rcg_time_phase.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.rcg_debug_trace.argtypes = [H, C.c_int, _f64p, _f64p, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
+    for name in EXPORTED:
+        fn = getattr(L, name)
+        if name not in ("rcg_last_error", "rcg_version"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Solver:
+    """Handle-based interface: upload A and G once, then call the kernels or the PCG solve."""
+
+    def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
+                 spmv_lanes: int = 0):
+        self._L = load()
+        self._h = C.c_void_p()
+        opt = Options()
+        opt.chain_threads, opt.chain_window = int(chain_threads), int(chain_window)
+        opt.use_graph, opt.spmv_lanes = int(bool(use_graph)), int(spmv_lanes)
+        rc = self._L.rcg_create_with_options(C.byref(self._h), int(device), C.byref(opt))
+        if rc != 0:
+            raise RcgError(rc, (self._L.rcg_last_error(None) or b"").decode())
+        self.N = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RcgError(rc, (self._L.rcg_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.rcg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_matrix(self, rowPtr, colIdx, val):
+        rp = _u64(rowPtr)
+        self.N = rp.shape[0] - 1
+        self._check(self._L.rcg_set_matrix(self._h, self.N, rp, _u64(colIdx), _f64(val)))
+
+    def set_factor(self, rowPtr, colIdx, val, part: Optional[np.ndarray] = None):
+        rp = _u64(rowPtr)
+        self.N = rp.shape[0] - 1
+        if part is not None and len(part) >= 2:
+            pa = _u64(part)
+            pptr, plen = pa.ctypes.data_as(C.c_void_p), pa.shape[0]
+        else:
+            pa, pptr, plen = None, None, 0
+        self._check(self._L.rcg_set_factor(self._h, self.N, rp, _u64(colIdx), _f64(val), pptr, plen))
+
+    def spmv(self, x):
+        y = np.empty(self.N, np.float64)
+        self._check(self._L.rcg_spmv(self._h, _f64(x), y))
+        return y
+
+    def trsv(self, which: int, rhs):
+        out = np.empty(self.N, np.float64)
+        self._check(self._L.rcg_trsv(self._h, int(which), _f64(rhs), out))
+        return out
+
+    def precond(self, r):
+        z = np.empty(self.N, np.float64)
+        self._check(self._L.rcg_precond(self._h, _f64(r), z))
+        return z
+
+    def pcg(self, b, tol: float, maxit: int):
+        x = np.empty(self.N, np.float64)
+        relres, itr = C.c_double(0), C.c_int(0)
+        self._check(self._L.rcg_pcg(self._h, _f64(b), float(tol), int(maxit), x, C.byref(relres), C.byref(itr)))
+        return x, relres.value, itr.value
+
+    def set_rhs(self, b):
+        self._check(self._L.rcg_set_rhs(self._h, _f64(b)))
+
+    def pcg_resident(self, tol: float, maxit: int):
+        relres, itr = C.c_double(0), C.c_int(0)
+        self._check(self._L.rcg_pcg_resident(self._h, float(tol), int(maxit), C.byref(relres), C.byref(itr)))
+        return relres.value, itr.value
+
+    def solution(self):
+        x = np.empty(self.N, np.float64)
+        self._check(self._L.rcg_get_solution(self._h, x))
+        return x
+
+    def history(self):
+        n = C.c_int(0)
+        self._check(self._L.rcg_get_history(self._h, None, 0, C.byref(n)))
+        h = np.zeros(max(n.value, 1), np.float64)
+        self._check(self._L.rcg_get_history(self._h, h.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return h[: n.value]
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._L.rcg_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def profile_iteration(self, reps: int = 3) -> dict:
+        self._check(self._L.rcg_profile_iteration(self._h, int(reps)))
+        return self.stats()
+
+    def debug_trace(self, which: int, rhs):
+        out = np.empty(self.N, np.float64)
+        tr = np.zeros((self.N, 4), np.uint32)
+        self._check(self._L.rcg_debug_trace(self._h, int(which), _f64(rhs), out, tr))
+        return out, tr
+
+    def time_phase(self, phase: int, reps: int = 3) -> float:
+        ms = C.c_double(0)
+        self._check(self._L.rcg_time_phase(self._h, int(phase), int(reps), C.byref(ms)))
+        return ms.value
+
+
+def pcg(A, b, tol, maxit, G, part=None, device: int = 0):
+    """One-shot mirror of the reference entry point ``pcg(A, b, tol, maxit, G, x, relres, itr)``
+    (/root/reference/c++/util/pcg.hpp:13-16): returns ``(x, relres, itr, stats)``."""
+    L = load()
+    N = A[0].shape[0] - 1
+    x = np.empty(N, np.float64)
+    relres, itr = C.c_double(0), C.c_int(0)
+    st = Stats()
+    if part is not None and len(part) >= 2:
+        pa = _u64(part)
+        pptr, plen = pa.ctypes.data_as(C.c_void_p), pa.shape[0]
+    else:
+        pa, pptr, plen = None, None, 0
+    rc = L.rcg_pcg_oneshot(int(device), N, _u64(A[0]), _u64(A[1]), _f64(A[2]), _f64(b), float(tol), int(maxit),
+                           _u64(G[0]), _u64(G[1]), _f64(G[2]), pptr, plen, x, C.byref(relres), C.byref(itr),
+                           C.byref(st))
+    if rc != 0:
+        raise RcgError(rc, (L.rcg_last_error(None) or b"").decode())
+    return x, relres.value, itr.value, st.as_dict()

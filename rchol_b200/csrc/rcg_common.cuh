@@ -1,0 +1,141 @@
+// rchol_b200 -- internal declarations shared by the CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/rchol_b200.h"
+
+#define RCG_SM_COUNT_FALLBACK 148
+
+// ---------------------------------------------------------------------------------------------------------
+// Device data layout (all arrays live in HBM for the life of the handle)
+// ---------------------------------------------------------------------------------------------------------
+
+// General CSR (the system matrix A): 64-bit row pointers, 32-bit column indices, fp64 values.
+struct CsrDev {
+  int64_t *rowptr = nullptr;   // N+1
+  uint32_t *col = nullptr;     // nnz
+  double *val = nullptr;       // nnz
+  int64_t nnz = 0;
+};
+
+// A lower-triangular "solve matrix" in its own solve index space:
+//   forward  solve (U^T y = r): L = U^T, solve index = permuted row index
+//   backward solve (U z = y)  : J U J (J = index reversal), solve index = N-1-row
+// split by the nested-dissection block structure into two CSR matrices with sorted rows:
+//   loc : entries whose column lies in the row's own block (col < row) followed by the diagonal slot,
+//         which holds 1/diag -- the dependency-chain part, solved by k_tri_chain;
+//   ext : entries whose column lies in another (already solved) block -- a pure SpMV, done by k_tri_external.
+// col/val arrays are padded by 8 entries so that 16-byte-granular bulk copies never run off the end.
+struct LowerTriDev {
+  CsrDev loc;
+  CsrDev ext;
+};
+
+struct BlockDesc {             // rows [lo, hi) of one nested-dissection block, in solve index space
+  uint32_t lo, hi;
+};
+
+// One dependency group of blocks: all blocks of one tree depth.  Blocks of group g depend only on blocks of
+// groups < g (forward: leaves first; backward: root separator first).
+struct GroupHost {
+  int first = 0;               // index of the group's first block in the direction's block array
+  int count = 0;
+  uint32_t max_rows = 0;
+  int64_t ext_nnz = 0;         // external entries of the group's rows (0 => no pre-pass, chain starts from rhs)
+  int64_t loc_nnz = 0;
+  int64_t rows = 0;
+  uint32_t max_stage = 0;      // largest number of local entries in an aligned 32-row staging group
+};
+
+struct DirectionDev {          // one solve direction
+  LowerTriDev M;
+  BlockDesc *blocks = nullptr; // device, ordered by group
+  std::vector<BlockDesc> blocks_host;
+  std::vector<GroupHost> groups;
+  bool reversed = false;       // vector index = N-1-solve index
+};
+
+// Scalars of the PCG recurrences, resident on the device (pcg.cpp:82-110 keeps them on the host).
+struct PcgScalars {
+  double rz;        // r.z of the current iteration
+  double rz_prev;   // r.z of the previous iteration  (the reference recomputes prev_r.prev_cond, pcg.cpp:94)
+  double pq;        // p.q
+  double pr;        // p.r
+  double rr;        // r.r after the update (loop test of the next iteration, pcg.cpp:82)
+  double bb;        // b.b
+  int it;           // completed iterations
+  int pad;
+};
+
+struct rcg_handle {
+  int device = 0;
+  int sm_count = RCG_SM_COUNT_FALLBACK;
+  cudaStream_t stream = nullptr;
+  rcg_options opt{};
+  std::string err;
+
+  uint64_t N = 0;
+  bool haveA = false, haveG = false, haveB = false;
+  CsrDev A;
+  int spmv_lanes = 8;
+  DirectionDev fwd, bwd;
+  uint64_t nnzG = 0;
+  int n_blocks = 1, tree_levels = 1;
+
+  // work vectors (N doubles each)
+  double *b = nullptr, *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr, *y = nullptr, *z = nullptr;
+  double *io = nullptr;                 // staging vector for the single-kernel entry points
+  PcgScalars *scal = nullptr;           // device
+  double *partials = nullptr;           // reduction scratch: [0,P) slot A, [P,2P) slot B, then rz partials
+  unsigned int *counters = nullptr;     // last-block-done counters
+  int partial_cap = 0;                  // P
+  int reduce_grid = 0;                  // CTAs of the grid-stride vector kernels
+
+  uint32_t *trace = nullptr;                 // diagnostics: per-row timing trace of the chain kernel (rcg_debug_trace)
+  unsigned long long *clk_probe = nullptr;   // device {cycles, ns} written by CTA 0 of the chain kernel
+  cudaGraphExec_t iter_graph = nullptr;
+  std::vector<double> history;
+
+  rcg_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+#define RCG_CUDA(h, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" +     \
+                 std::to_string(__LINE__) + ")";                                                  \
+      return RCG_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define RCG_TRY(expr)                \
+  do {                               \
+    int _rc = (expr);                \
+    if (_rc != RCG_OK) return _rc;   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// entry points implemented in the other translation units
+// ---------------------------------------------------------------------------------------------------------
+// rcg_setup.cu
+int rcg_setup_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val);
+int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                     const uint64_t *part, uint64_t npart);
+void rcg_free_direction(DirectionDev &d);
+void rcg_free_csr(CsrDev &a);
+
+// rcg_kernels.cu  (all launches go to h->stream and bump h->stats.kernel_launches)
+int rcg_launch_spmv(rcg_handle *h, const double *x, double *y, const double *dot_r /*nullable*/, bool with_dots);
+int rcg_launch_trisolve(rcg_handle *h, DirectionDev &d, const double *rhs, double *out, const double *dotvec);
+int rcg_launch_p_update(rcg_handle *h);
+int rcg_launch_xr_update(rcg_handle *h);
+int rcg_launch_init_solve(rcg_handle *h);
+int rcg_launch_residual_norm(rcg_handle *h, double *out_host_norm2);

@@ -1,0 +1,784 @@
+// rchol_b200 -- one-off device set-up ("analysis") of the solve phase.  Replaces pcg::create_sparse
+// (/root/reference/c++/util/pcg.cpp:31-54, which deep-copies A and G into MKL handles) with:
+//   * upload of the caller's SparseCSR arrays and narrowing of the 64-bit column indices to 32 bits,
+//   * validation of G (upper triangular, diagonal first and positive: rchol_lap.cpp:358-387 `coalesce`),
+//   * L = U^T by rows (count / scan / scatter / per-row sort) for the forward solve,
+//   * J U J (index reversal) for the backward solve, so that ONE lower-triangular kernel serves both,
+//   * the nested-dissection block schedule from `part` (rchol_parallel.cpp:64-70, rchol_lap.cpp:254-261).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "rcg_common.cuh"
+
+namespace {
+
+double wall_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// exclusive scan of int64 (three small kernels; set-up only)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 1024;
+constexpr int SCAN_I = 4;
+constexpr int SCAN_TILE = SCAN_T * SCAN_I;
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t *total, int64_t *smem /*>=33*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int64_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = lane < nw ? smem[lane] : 0;
+    int64_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    smem[lane] = winc - w;          // exclusive warp offsets
+    if (lane == 31) smem[32] = winc;  // block total
+  }
+  __syncthreads();
+  int64_t res = smem[warp] + inc - v;
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void k_scan_tile_sums(const int64_t *__restrict__ in, int64_t n, int64_t *__restrict__ tile_sums) {
+  __shared__ int64_t sm[34];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_I;
+  int64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_I; i++)
+    if (base + i < n) s += in[base + i];
+  int64_t total;
+  block_exclusive_scan(s, &total, sm);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void k_scan_tile_offsets(int64_t *tile_sums, int64_t ntiles) {
+  __shared__ int64_t sm[34];
+  int64_t carry = 0;
+  for (int64_t base = 0; base < ntiles; base += blockDim.x) {
+    int64_t i = base + threadIdx.x;
+    int64_t v = i < ntiles ? tile_sums[i] : 0;
+    int64_t total;
+    int64_t ex = block_exclusive_scan(v, &total, sm);
+    if (i < ntiles) tile_sums[i] = carry + ex;
+    carry += total;
+  }
+}
+
+__global__ void k_scan_apply(int64_t *data, int64_t n, const int64_t *__restrict__ tile_offsets) {
+  __shared__ int64_t sm[34];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_I;
+  int64_t v[SCAN_I];
+  int64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_I; i++) {
+    v[i] = base + i < n ? data[base + i] : 0;
+    s += v[i];
+  }
+  int64_t total;
+  int64_t ex = block_exclusive_scan(s, &total, sm) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_I; i++) {
+    if (base + i < n) data[base + i] = ex;
+    ex += v[i];
+  }
+}
+
+int exclusive_scan_inplace(rcg_handle *h, int64_t *data, int64_t n) {
+  int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  int64_t *tile_sums = nullptr;
+  RCG_CUDA(h, cudaMalloc(&tile_sums, sizeof(int64_t) * (size_t)ntiles));
+  k_scan_tile_sums<<<(unsigned)ntiles, SCAN_T, 0, h->stream>>>(data, n, tile_sums);
+  k_scan_tile_offsets<<<1, SCAN_T, 0, h->stream>>>(tile_sums, ntiles);
+  k_scan_apply<<<(unsigned)ntiles, SCAN_T, 0, h->stream>>>(data, n, tile_sums);
+  h->stats.kernel_launches += 3;
+  RCG_CUDA(h, cudaGetLastError());
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  RCG_CUDA(h, cudaFree(tile_sums));
+  return RCG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// upload helpers
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_narrow_cols(const uint64_t *__restrict__ in, uint32_t *__restrict__ out, int64_t nnz, uint64_t N,
+                              int *err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < nnz; i += stride) {
+    uint64_t c = in[i];
+    bad |= (c >= N);
+    out[i] = (uint32_t)c;
+  }
+  if (bad) atomicExch(err, 1);
+}
+
+// rowPtr must start at 0, be non-decreasing and end at nnz
+__global__ void k_check_rowptr(const int64_t *__restrict__ rp, int64_t N, int64_t nnz, int *err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < N; i += stride) bad |= (rp[i + 1] < rp[i]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) bad |= (rp[0] != 0) || (rp[N] != nnz);
+  if (bad) atomicExch(err, 1);
+}
+
+int grid_for(const rcg_handle *h, int64_t work, int threads, int per_sm = 16) {
+  int64_t g = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)h->sm_count * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Uploads a SparseCSR (64-bit indices) and produces {int64 rowptr, u32 col, fp64 val} on the device.
+int upload_csr(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+               CsrDev &out) {
+  if (!rowPtr || (N && (!colIdx || !val))) {
+    h->err = "null matrix pointer";
+    return RCG_ERR_INVALID;
+  }
+  if (N == 0 || N >= 0xFFFFFFFFull) {
+    h->err = "matrix dimension must be in [1, 2^32-2]";
+    return RCG_ERR_INVALID;
+  }
+  const int64_t nnz = (int64_t)rowPtr[N];
+  if (nnz <= 0) {
+    h->err = "empty matrix";
+    return RCG_ERR_INVALID;
+  }
+  double t0 = wall_ms();
+  out.nnz = nnz;
+  RCG_CUDA(h, cudaMalloc(&out.rowptr, sizeof(int64_t) * (N + 1)));
+  RCG_CUDA(h, cudaMalloc(&out.col, sizeof(uint32_t) * (size_t)nnz));
+  RCG_CUDA(h, cudaMalloc(&out.val, sizeof(double) * (size_t)nnz));
+  uint64_t *col64 = nullptr;
+  int *derr = nullptr;
+  RCG_CUDA(h, cudaMalloc(&col64, sizeof(uint64_t) * (size_t)nnz));
+  RCG_CUDA(h, cudaMalloc(&derr, sizeof(int)));
+  RCG_CUDA(h, cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(out.rowptr, rowPtr, sizeof(int64_t) * (N + 1), cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(col64, colIdx, sizeof(uint64_t) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(out.val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->stats.upload_ms += wall_ms() - t0;
+  h->stats.h2d_bytes += sizeof(int64_t) * (N + 1) + (size_t)nnz * 16;
+
+  double t1 = wall_ms();
+  k_narrow_cols<<<grid_for(h, nnz, 256), 256, 0, h->stream>>>(col64, out.col, nnz, N, derr);
+  k_check_rowptr<<<grid_for(h, (int64_t)N, 256), 256, 0, h->stream>>>(out.rowptr, (int64_t)N, nnz, derr);
+  h->stats.kernel_launches += 2;
+  int herr = 0;
+  RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  RCG_CUDA(h, cudaFree(col64));
+  RCG_CUDA(h, cudaFree(derr));
+  h->stats.analysis_ms += wall_ms() - t1;
+  if (herr) {
+    h->err = "malformed CSR: column index out of range or row pointers not monotone";
+    return RCG_ERR_INVALID;
+  }
+  return RCG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// validation of G = CSR(U)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_validate_upper(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col,
+                                 const double *__restrict__ val, uint32_t N, int *err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t stride = gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < N; i += stride) {
+    int64_t s = rp[i], e = rp[i + 1];
+    if (e <= s) { bad = true; continue; }
+    bad |= (col[s] != i) || !(val[s] > 0.0);
+    uint32_t prev = i;
+    for (int64_t k = s + 1; k < e; k++) {
+      uint32_t c = col[k];
+      bad |= (c <= prev);
+      prev = c;
+    }
+  }
+  if (bad) atomicExch(err, 1);
+}
+
+// every entry (i, c) of U must have block(c) == block(i) or an ancestor of block(i):
+// ancestors of a block a are exactly the blocks whose subtree range [sub_lo[a], hi[a]) contains the row.
+__global__ void k_validate_blocks(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, uint32_t N,
+                                  const uint32_t *__restrict__ part, const uint32_t *__restrict__ sub_lo, int nb,
+                                  int *err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t stride = gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < N; i += stride) {
+    for (int64_t k = rp[i] + 1; k < rp[i + 1]; k++) {
+      uint32_t c = col[k];
+      int lo = 0, hi = nb;   // find a with part[a] <= c < part[a+1]
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (part[mid] <= c) lo = mid; else hi = mid;
+      }
+      bad |= (sub_lo[lo] > i);
+    }
+  }
+  if (bad) atomicExch(err, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// transpose  U (CSR) -> L = U^T (CSR, sorted rows)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_count_cols(const uint32_t *__restrict__ col, int64_t nnz, int64_t *__restrict__ cnt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) atomicAdd((unsigned long long *)&cnt[col[i]], 1ull);
+}
+
+// 8 lanes per U row; scatters (row, val) to the L row of every column.  Order inside an L row is arbitrary here.
+__global__ void k_scatter_transpose(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col,
+                                    const double *__restrict__ val, uint32_t N, int64_t *__restrict__ cursor,
+                                    uint32_t *__restrict__ lcol, double *__restrict__ lval) {
+  const int sub = threadIdx.x & 7;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 3;
+  for (; row < N; row += stride) {
+    const int64_t s = rp[row], e = rp[row + 1];
+    for (int64_t k = s + sub; k < e; k += 8) {
+      uint32_t c = col[k];
+      int64_t pos = (int64_t)atomicAdd((unsigned long long *)&cursor[c], 1ull);
+      lcol[pos] = (uint32_t)row;
+      lval[pos] = val[k];
+    }
+  }
+}
+
+constexpr int SORT_SMALL = 64;
+
+// thread-per-row insertion sort (rows arrive nearly sorted because U rows are scattered in ascending order);
+// longer rows are appended to `long_rows` for the block-wide bitonic sort.
+__global__ void k_sort_rows_small(const int64_t *__restrict__ rp, uint32_t *__restrict__ col, double *__restrict__ val,
+                                  uint32_t N, uint32_t *__restrict__ long_rows, unsigned int *n_long) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t stride = gridDim.x * blockDim.x;
+  for (; j < N; j += stride) {
+    const int64_t s = rp[j];
+    const int len = (int)(rp[j + 1] - s);
+    if (len > SORT_SMALL) {
+      unsigned int slot = atomicAdd(n_long, 1u);
+      long_rows[slot] = j;
+      continue;
+    }
+    for (int a = 1; a < len; a++) {
+      uint32_t kc = col[s + a];
+      double kv = val[s + a];
+      int b = a - 1;
+      while (b >= 0 && col[s + b] > kc) {
+        col[s + b + 1] = col[s + b];
+        val[s + b + 1] = val[s + b];
+        b--;
+      }
+      col[s + b + 1] = kc;
+      val[s + b + 1] = kv;
+    }
+  }
+}
+
+// CTA-per-row bitonic sort of (col, val) pairs.  Rows up to `smem_cap` entries are sorted in shared memory,
+// longer ones in place in global memory through a padded scratch area.
+__global__ void k_sort_rows_bitonic(const int64_t *__restrict__ rp, uint32_t *__restrict__ col, double *__restrict__ val,
+                                    const uint32_t *__restrict__ long_rows, int smem_cap, uint32_t *__restrict__ gkeys,
+                                    double *__restrict__ gvals, int64_t gstride) {
+  extern __shared__ unsigned char sm_raw[];
+  const uint32_t j = long_rows[blockIdx.x];
+  const int64_t s = rp[j];
+  const int len = (int)(rp[j + 1] - s);
+  int n2 = 1;
+  while (n2 < len) n2 <<= 1;
+  uint32_t *keys;
+  double *vals;
+  if (n2 <= smem_cap) {
+    vals = reinterpret_cast<double *>(sm_raw);
+    keys = reinterpret_cast<uint32_t *>(sm_raw + sizeof(double) * (size_t)smem_cap);
+  } else {
+    keys = gkeys + (int64_t)blockIdx.x * gstride;
+    vals = gvals + (int64_t)blockIdx.x * gstride;
+  }
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    keys[i] = i < len ? col[s + i] : 0xFFFFFFFFu;
+    vals[i] = i < len ? val[s + i] : 0.0;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        int ixj = i ^ jj;
+        if (ixj > i) {
+          bool up = ((i & k) == 0);
+          uint32_t a = keys[i], b = keys[ixj];
+          if ((a > b) == up) {
+            keys[i] = b; keys[ixj] = a;
+            double t = vals[i]; vals[i] = vals[ixj]; vals[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    col[s + i] = keys[i];
+    val[s + i] = vals[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// J U J : reversed copy of U (row N-1-i, column N-1-c), which is lower triangular with the diagonal last
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_reverse_entries(const uint32_t *__restrict__ col, const double *__restrict__ val, int64_t nnz,
+                                  uint32_t N, uint32_t *__restrict__ rcol, double *__restrict__ rval) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    rcol[nnz - 1 - i] = N - 1 - col[i];
+    rval[nnz - 1 - i] = val[i];
+  }
+}
+__global__ void k_reverse_rowptr(const int64_t *__restrict__ rp, int64_t nnz, uint32_t N, int64_t *__restrict__ rrp) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i <= (int64_t)N; i += stride) rrp[i] = nnz - rp[N - i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-row finishing: number of external entries, reciprocal of the diagonal
+// `bounds` = ascending block boundaries in the direction's solve index space (nb+1 entries)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_count_external(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, double *__restrict__ val,
+                                 uint32_t N, const uint32_t *__restrict__ bounds, int nb, int64_t *__restrict__ ext_cnt,
+                                 int *err) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t stride = gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; j < N; j += stride) {
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (bounds[mid] <= j) lo = mid; else hi = mid;
+    }
+    const uint32_t blo = bounds[lo];
+    const int64_t s = rp[j], e = rp[j + 1];
+    int64_t k = s;
+    while (k < e - 1 && col[k] < blo) k++;
+    ext_cnt[j] = k - s;
+    bad |= (col[e - 1] != j);
+    val[e - 1] = 1.0 / val[e - 1];
+  }
+  if (bad) atomicExch(err, 1);
+}
+
+// loc_rp = rp - ext_rp (element-wise), in place over rp
+__global__ void k_sub_rowptr(int64_t *__restrict__ rp, const int64_t *__restrict__ ext_rp, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) rp[i] -= ext_rp[i];
+}
+
+// 8 lanes per row: copy the external prefix and the local suffix of every row into the two split matrices.
+// `rp` has already been turned into the local row pointers; the combined start of row j is rp[j] + ext_rp[j].
+__global__ void k_split_rows(const int64_t *__restrict__ loc_rp, const int64_t *__restrict__ ext_rp,
+                             const uint32_t *__restrict__ col, const double *__restrict__ val, uint32_t N,
+                             const uint32_t *__restrict__ bounds, int nb,
+                             uint32_t *__restrict__ lcol, double *__restrict__ lval, uint32_t *__restrict__ ecol,
+                             double *__restrict__ eval) {
+  const int sub = threadIdx.x & 7;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 3;
+  for (; row < N; row += stride) {
+    const int64_t ls = loc_rp[row], le = loc_rp[row + 1], es = ext_rp[row], ee = ext_rp[row + 1];
+    const int64_t src = ls + es;
+    const int64_t ne = ee - es, nl = le - ls;
+    for (int64_t i = sub; i < ne; i += 8) { ecol[es + i] = col[src + i]; eval[es + i] = val[src + i]; }
+    // local part: off-diagonal values are stored as -v/diag (the diagonal slot, last, already holds 1/diag), so
+    // x_j = init_j/diag + sum v'_jc x_c and the chain kernel's last dependent operation per row is a single FMA
+    // Local columns are stored relative to the first row of the block (the chain kernel indexes its solution
+    // window with them directly).
+    const double dinv = val[src + ne + nl - 1];
+    int blo_i = 0, bhi_i = nb;
+    while (bhi_i - blo_i > 1) {
+      const int mid = (blo_i + bhi_i) >> 1;
+      if (bounds[mid] <= (uint32_t)row) blo_i = mid; else bhi_i = mid;
+    }
+    const uint32_t blo = bounds[blo_i];
+    for (int64_t i = sub; i < nl; i += 8) {
+      const double v = val[src + ne + i];
+      lcol[ls + i] = col[src + ne + i] - blo;
+      lval[ls + i] = (i == nl - 1) ? v : -(v * dinv);   // off-diagonals: negated and scaled by 1/diag
+    }
+  }
+}
+
+// per block: external / local entry counts and the largest staging group (aligned runs of 32 rows from the block start)
+__global__ void k_block_stats(const int64_t *__restrict__ loc_rp, const int64_t *__restrict__ ext_rp,
+                              const uint32_t *__restrict__ bounds, int nb, unsigned long long *__restrict__ ext_nnz,
+                              unsigned long long *__restrict__ loc_nnz, unsigned int *__restrict__ max_stage) {
+  const int b = blockIdx.x;
+  if (b >= nb) return;
+  const uint32_t lo = bounds[b], hi = bounds[b + 1];
+  unsigned int m = 0;
+  for (uint32_t j0 = lo + 32u * threadIdx.x; j0 < hi; j0 += 32u * blockDim.x) {
+    const uint32_t j1 = min(hi, j0 + 32u);
+    const int64_t e0 = loc_rp[j0] & ~3ll;
+    m = max(m, (unsigned int)(loc_rp[j1] - e0));
+  }
+  atomicMax(&max_stage[b], m);
+  if (threadIdx.x == 0) {
+    ext_nnz[b] = (unsigned long long)(ext_rp[hi] - ext_rp[lo]);
+    loc_nnz[b] = (unsigned long long)(loc_rp[hi] - loc_rp[lo]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// nested-dissection tree from `part` (post-order: [left subtree, right subtree, separator])
+// ---------------------------------------------------------------------------------------------------------
+struct TreeInfo {
+  std::vector<int> depth;        // per block
+  std::vector<uint32_t> sub_lo;  // first row of the subtree rooted at the block
+  int max_depth = 0;
+};
+
+void build_tree(const std::vector<uint32_t> &bounds, int start, int total, int depth, TreeInfo &t) {
+  // same arithmetic as /root/reference/c++/rchol_lap/rchol_lap.cpp:254-261
+  if (total == 1) {
+    t.depth[start] = depth;
+    t.sub_lo[start] = bounds[start];
+  } else {
+    int sep = start + total - 1, half = (total - 1) / 2;
+    t.depth[sep] = depth;
+    t.sub_lo[sep] = bounds[start];
+    build_tree(bounds, start, half, depth + 1, t);
+    build_tree(bounds, start + half, half, depth + 1, t);
+  }
+  t.max_depth = std::max(t.max_depth, depth);
+}
+
+int alloc_csr(rcg_handle *h, CsrDev &m, uint64_t N, int64_t nnz, bool with_rowptr) {
+  m.nnz = nnz;
+  if (with_rowptr) RCG_CUDA(h, cudaMalloc(&m.rowptr, sizeof(int64_t) * (N + 1)));
+  RCG_CUDA(h, cudaMalloc(&m.col, sizeof(uint32_t) * (size_t)(nnz + 8)));
+  RCG_CUDA(h, cudaMalloc(&m.val, sizeof(double) * (size_t)(nnz + 8)));
+  RCG_CUDA(h, cudaMemsetAsync(m.col + nnz, 0, sizeof(uint32_t) * 8, h->stream));
+  RCG_CUDA(h, cudaMemsetAsync(m.val + nnz, 0, sizeof(double) * 8, h->stream));
+  return RCG_OK;
+}
+
+// `comb` = the direction's lower-triangular matrix with sorted rows (diagonal last).  Splits it into d.M.loc /
+// d.M.ext, frees `comb`, and builds the dependency groups.
+int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::vector<uint32_t> &bounds_solve,
+                     const std::vector<int> &depth_solve, int max_depth, bool root_first) {
+  const uint32_t N = (uint32_t)h->N;
+  const int nb = (int)bounds_solve.size() - 1;
+  uint32_t *dbounds = nullptr;
+  int *derr = nullptr;
+  RCG_CUDA(h, cudaMalloc(&dbounds, sizeof(uint32_t) * (nb + 1)));
+  RCG_CUDA(h, cudaMalloc(&derr, sizeof(int)));
+  RCG_CUDA(h, cudaMemcpyAsync(dbounds, bounds_solve.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+
+  CsrDev &loc = d.M.loc, &ext = d.M.ext;
+  RCG_CUDA(h, cudaMalloc(&ext.rowptr, sizeof(int64_t) * ((size_t)N + 1)));
+  RCG_CUDA(h, cudaMemsetAsync(ext.rowptr, 0, sizeof(int64_t) * ((size_t)N + 1), h->stream));
+  k_count_external<<<grid_for(h, N, 256), 256, 0, h->stream>>>(comb.rowptr, comb.col, comb.val, N, dbounds, nb,
+                                                              ext.rowptr, derr);
+  h->stats.kernel_launches += 1;
+  int herr = 0;
+  RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  RCG_CUDA(h, cudaFree(derr));
+  if (herr) {
+    h->err = "factor row without a trailing diagonal after transposition (G is not triangular)";
+    return RCG_ERR_STRUCTURE;
+  }
+  RCG_TRY(exclusive_scan_inplace(h, ext.rowptr, (int64_t)N + 1));
+  int64_t ext_total = 0;
+  RCG_CUDA(h, cudaMemcpy(&ext_total, ext.rowptr + N, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  // comb.rowptr becomes the local row pointer array
+  k_sub_rowptr<<<grid_for(h, (int64_t)N + 1, 256), 256, 0, h->stream>>>(comb.rowptr, ext.rowptr, (int64_t)N + 1);
+  loc.rowptr = comb.rowptr;
+  comb.rowptr = nullptr;
+  RCG_TRY(alloc_csr(h, loc, N, comb.nnz - ext_total, false));
+  RCG_TRY(alloc_csr(h, ext, N, ext_total, false));
+  k_split_rows<<<grid_for(h, (int64_t)N * 8, 256), 256, 0, h->stream>>>(loc.rowptr, ext.rowptr, comb.col, comb.val, N,
+                                                                       dbounds, nb, loc.col, loc.val, ext.col, ext.val);
+  h->stats.kernel_launches += 2;
+  RCG_CUDA(h, cudaGetLastError());
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  rcg_free_csr(comb);
+
+  // per-block statistics
+  unsigned long long *dext = nullptr, *dloc = nullptr;
+  unsigned int *dstage = nullptr;
+  RCG_CUDA(h, cudaMalloc(&dext, sizeof(unsigned long long) * nb));
+  RCG_CUDA(h, cudaMalloc(&dloc, sizeof(unsigned long long) * nb));
+  RCG_CUDA(h, cudaMalloc(&dstage, sizeof(unsigned int) * nb));
+  RCG_CUDA(h, cudaMemsetAsync(dstage, 0, sizeof(unsigned int) * nb, h->stream));
+  k_block_stats<<<nb, 256, 0, h->stream>>>(loc.rowptr, ext.rowptr, dbounds, nb, dext, dloc, dstage);
+  h->stats.kernel_launches += 1;
+  std::vector<unsigned long long> hext(nb), hloc(nb);
+  std::vector<unsigned int> hstage(nb);
+  RCG_CUDA(h, cudaMemcpyAsync(hext.data(), dext, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(hloc.data(), dloc, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(hstage.data(), dstage, sizeof(unsigned int) * nb, cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(dext); cudaFree(dloc); cudaFree(dstage); cudaFree(dbounds);
+
+  // groups: forward = deepest level first, backward (reversed space) = root first
+  d.groups.clear();
+  d.blocks_host.clear();
+  for (int g = 0; g <= max_depth; g++) {
+    const int want = root_first ? g : max_depth - g;
+    GroupHost G;
+    G.first = (int)d.blocks_host.size();
+    for (int b = 0; b < nb; b++) {
+      if (depth_solve[b] != want) continue;
+      BlockDesc bd{bounds_solve[b], bounds_solve[b + 1]};
+      if (bd.hi == bd.lo) continue;   // empty separator
+      d.blocks_host.push_back(bd);
+      G.count++;
+      G.max_rows = std::max(G.max_rows, bd.hi - bd.lo);
+      G.rows += bd.hi - bd.lo;
+      G.ext_nnz += (int64_t)hext[b];
+      G.loc_nnz += (int64_t)hloc[b];
+      G.max_stage = std::max(G.max_stage, hstage[b]);
+    }
+    if (G.count > 0) d.groups.push_back(G);
+  }
+  RCG_CUDA(h, cudaMalloc(&d.blocks, sizeof(BlockDesc) * std::max<size_t>(1, d.blocks_host.size())));
+  RCG_CUDA(h, cudaMemcpyAsync(d.blocks, d.blocks_host.data(), sizeof(BlockDesc) * d.blocks_host.size(),
+                              cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RCG_OK;
+}
+
+}  // namespace
+
+void rcg_free_csr(CsrDev &a) {
+  cudaFree(a.rowptr); cudaFree(a.col); cudaFree(a.val);
+  a = CsrDev();
+}
+void rcg_free_direction(DirectionDev &d) {
+  rcg_free_csr(d.M.loc);
+  rcg_free_csr(d.M.ext);
+  cudaFree(d.blocks);
+  d = DirectionDev();
+}
+
+int rcg_setup_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val) {
+  if (h->haveA) { rcg_free_csr(h->A); h->haveA = false; }
+  if (h->haveG && N != h->N) {
+    h->err = "matrix dimension differs from the factor's";
+    return RCG_ERR_INVALID;
+  }
+  RCG_TRY(upload_csr(h, N, rowPtr, colIdx, val, h->A));
+  h->N = N;
+  h->haveA = true;
+  h->stats.N = N;
+  h->stats.nnzA = (uint64_t)h->A.nnz;
+  // lanes per row of the SpMV from the mean row length ("chosen per row-length histogram")
+  if (h->opt.spmv_lanes > 0) {
+    h->spmv_lanes = h->opt.spmv_lanes;
+  } else {
+    double mean = (double)h->A.nnz / (double)N;
+    h->spmv_lanes = mean <= 2.5 ? 2 : mean <= 5.0 ? 4 : mean <= 12.0 ? 8 : mean <= 24.0 ? 16 : 32;
+  }
+  return RCG_OK;
+}
+
+int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                     const uint64_t *part, uint64_t npart) {
+  if (h->haveG) { rcg_free_direction(h->fwd); rcg_free_direction(h->bwd); h->haveG = false; }
+  if (h->haveA && N != h->N) {
+    h->err = "factor dimension differs from the matrix's";
+    return RCG_ERR_INVALID;
+  }
+  // ---- partition -> block boundaries ---------------------------------------------------------------
+  std::vector<uint32_t> bounds;
+  if (part && npart >= 2) {
+    uint64_t nb = npart - 1;
+    if (((nb + 1) & nb) != 0 || part[0] != 0 || part[npart - 1] != N) {
+      h->err = "part must hold 2T boundaries (T a power of two) from 0 to N";
+      return RCG_ERR_INVALID;
+    }
+    for (uint64_t i = 0; i < npart; i++) {
+      if (i && part[i] < part[i - 1]) { h->err = "part is not monotone"; return RCG_ERR_INVALID; }
+      bounds.push_back((uint32_t)part[i]);
+    }
+  } else {
+    bounds = {0u, (uint32_t)N};
+  }
+  const int nb = (int)bounds.size() - 1;
+  TreeInfo tree;
+  tree.depth.assign(nb, 0);
+  tree.sub_lo.assign(nb, 0);
+  build_tree(bounds, 0, nb, 0, tree);
+
+  CsrDev U;
+  RCG_TRY(upload_csr(h, N, rowPtr, colIdx, val, U));
+  h->N = N;
+  const int64_t nnz = U.nnz;
+  const uint32_t n32 = (uint32_t)N;
+  double t0 = wall_ms();
+
+  int *derr = nullptr;
+  RCG_CUDA(h, cudaMalloc(&derr, sizeof(int)));
+  RCG_CUDA(h, cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+  k_validate_upper<<<grid_for(h, n32, 256), 256, 0, h->stream>>>(U.rowptr, U.col, U.val, n32, derr);
+  h->stats.kernel_launches += 1;
+  int herr = 0;
+  RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (herr) {
+    rcg_free_csr(U); cudaFree(derr);
+    h->err = "G must be CSR of an upper-triangular matrix with sorted rows and a positive leading diagonal";
+    return RCG_ERR_STRUCTURE;
+  }
+  if (nb > 1) {
+    uint32_t *dpart = nullptr, *dsub = nullptr;
+    RCG_CUDA(h, cudaMalloc(&dpart, sizeof(uint32_t) * (nb + 1)));
+    RCG_CUDA(h, cudaMalloc(&dsub, sizeof(uint32_t) * nb));
+    RCG_CUDA(h, cudaMemcpyAsync(dpart, bounds.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+    RCG_CUDA(h, cudaMemcpyAsync(dsub, tree.sub_lo.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, h->stream));
+    k_validate_blocks<<<grid_for(h, n32, 256), 256, 0, h->stream>>>(U.rowptr, U.col, n32, dpart, dsub, nb, derr);
+    h->stats.kernel_launches += 1;
+    RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(dpart); cudaFree(dsub);
+    if (herr) {
+      rcg_free_csr(U); cudaFree(derr);
+      h->err = "G couples a block to a non-ancestor block: `part` does not describe this factor";
+      return RCG_ERR_STRUCTURE;
+    }
+  }
+  RCG_CUDA(h, cudaFree(derr));
+
+  // ---- forward direction: L = U^T ---------------------------------------------------------------------
+  CsrDev L;
+  L.nnz = nnz;
+  RCG_CUDA(h, cudaMalloc(&L.rowptr, sizeof(int64_t) * (N + 4)));   // padded: staged in 16-byte aligned slices
+  RCG_CUDA(h, cudaMalloc(&L.col, sizeof(uint32_t) * (size_t)nnz));
+  RCG_CUDA(h, cudaMalloc(&L.val, sizeof(double) * (size_t)nnz));
+  RCG_CUDA(h, cudaMemsetAsync(L.rowptr, 0, sizeof(int64_t) * (N + 4), h->stream));
+  k_count_cols<<<grid_for(h, nnz, 256), 256, 0, h->stream>>>(U.col, nnz, L.rowptr);
+  h->stats.kernel_launches += 1;
+  RCG_TRY(exclusive_scan_inplace(h, L.rowptr, (int64_t)N + 1));
+  {
+    int64_t *cursor = nullptr;
+    RCG_CUDA(h, cudaMalloc(&cursor, sizeof(int64_t) * N));
+    RCG_CUDA(h, cudaMemcpyAsync(cursor, L.rowptr, sizeof(int64_t) * N, cudaMemcpyDeviceToDevice, h->stream));
+    k_scatter_transpose<<<grid_for(h, (int64_t)N * 8, 256), 256, 0, h->stream>>>(U.rowptr, U.col, U.val, n32, cursor,
+                                                                               L.col, L.val);
+    h->stats.kernel_launches += 1;
+    uint32_t *long_rows = nullptr;
+    unsigned int *n_long = nullptr;
+    RCG_CUDA(h, cudaMalloc(&long_rows, sizeof(uint32_t) * N));
+    RCG_CUDA(h, cudaMalloc(&n_long, sizeof(unsigned int)));
+    RCG_CUDA(h, cudaMemsetAsync(n_long, 0, sizeof(unsigned int), h->stream));
+    k_sort_rows_small<<<grid_for(h, n32, 128), 128, 0, h->stream>>>(L.rowptr, L.col, L.val, n32, long_rows, n_long);
+    h->stats.kernel_launches += 1;
+    unsigned int hn_long = 0;
+    RCG_CUDA(h, cudaMemcpyAsync(&hn_long, n_long, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (hn_long > 0) {
+      // longest row decides whether a global scratch area is needed
+      const int smem_cap = 8192;                      // entries: 8192 * 12 B = 96 KB of shared memory
+      const size_t smem_bytes = (size_t)smem_cap * 12;
+      RCG_CUDA(h, cudaFuncSetAttribute(k_sort_rows_bitonic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      // find the longest row on the host side from the row pointers of the long rows
+      std::vector<uint32_t> lr(hn_long);
+      RCG_CUDA(h, cudaMemcpy(lr.data(), long_rows, sizeof(uint32_t) * hn_long, cudaMemcpyDeviceToHost));
+      std::sort(lr.begin(), lr.end());   // deterministic processing order
+      RCG_CUDA(h, cudaMemcpy(long_rows, lr.data(), sizeof(uint32_t) * hn_long, cudaMemcpyHostToDevice));
+      int64_t maxlen = 0;
+      {
+        // read the two row pointers of every long row (a few thousand rows at most in practice)
+        std::vector<int64_t> rp2(2);
+        // cheaper: fetch the whole rowptr only when many long rows exist
+        std::vector<int64_t> all;
+        if (hn_long > 4096) {
+          all.resize(N + 1);
+          RCG_CUDA(h, cudaMemcpy(all.data(), L.rowptr, sizeof(int64_t) * (N + 1), cudaMemcpyDeviceToHost));
+          for (uint32_t r : lr) maxlen = std::max(maxlen, all[r + 1] - all[r]);
+        } else {
+          for (uint32_t r : lr) {
+            RCG_CUDA(h, cudaMemcpy(rp2.data(), L.rowptr + r, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost));
+            maxlen = std::max(maxlen, rp2[1] - rp2[0]);
+          }
+        }
+      }
+      int64_t gstride = 0;
+      uint32_t *gkeys = nullptr;
+      double *gvals = nullptr;
+      if (maxlen > smem_cap) {
+        gstride = 1;
+        while (gstride < maxlen) gstride <<= 1;
+        RCG_CUDA(h, cudaMalloc(&gkeys, sizeof(uint32_t) * (size_t)gstride * hn_long));
+        RCG_CUDA(h, cudaMalloc(&gvals, sizeof(double) * (size_t)gstride * hn_long));
+      }
+      k_sort_rows_bitonic<<<hn_long, 512, smem_bytes, h->stream>>>(L.rowptr, L.col, L.val, long_rows, smem_cap, gkeys,
+                                                                  gvals, gstride);
+      h->stats.kernel_launches += 1;
+      RCG_CUDA(h, cudaGetLastError());
+      RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+      cudaFree(gkeys); cudaFree(gvals);
+    }
+    RCG_CUDA(h, cudaFree(cursor));
+    RCG_CUDA(h, cudaFree(long_rows));
+    RCG_CUDA(h, cudaFree(n_long));
+  }
+
+  // ---- backward direction: reversed U ------------------------------------------------------------------
+  CsrDev R;
+  R.nnz = nnz;
+  RCG_CUDA(h, cudaMalloc(&R.rowptr, sizeof(int64_t) * (N + 4)));
+  RCG_CUDA(h, cudaMalloc(&R.col, sizeof(uint32_t) * (size_t)nnz));
+  RCG_CUDA(h, cudaMalloc(&R.val, sizeof(double) * (size_t)nnz));
+  k_reverse_entries<<<grid_for(h, nnz, 256), 256, 0, h->stream>>>(U.col, U.val, nnz, n32, R.col, R.val);
+  k_reverse_rowptr<<<grid_for(h, (int64_t)N + 1, 256), 256, 0, h->stream>>>(U.rowptr, nnz, n32, R.rowptr);
+  h->stats.kernel_launches += 2;
+  RCG_CUDA(h, cudaGetLastError());
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  rcg_free_csr(U);
+  h->bwd.reversed = true;
+  h->fwd.reversed = false;
+
+  // ---- schedules ---------------------------------------------------------------------------------------
+  RCG_TRY(finish_direction(h, h->fwd, L, bounds, tree.depth, tree.max_depth, /*root_first=*/false));
+  std::vector<uint32_t> rbounds(nb + 1);
+  std::vector<int> rdepth(nb);
+  for (int i = 0; i <= nb; i++) rbounds[i] = n32 - bounds[nb - i];
+  for (int b = 0; b < nb; b++) rdepth[b] = tree.depth[nb - 1 - b];
+  RCG_TRY(finish_direction(h, h->bwd, R, rbounds, rdepth, tree.max_depth, /*root_first=*/true));
+
+  h->stats.analysis_ms += wall_ms() - t0;
+  h->haveG = true;
+  h->nnzG = (uint64_t)nnz;
+  h->n_blocks = nb;
+  h->tree_levels = tree.max_depth + 1;
+  h->stats.nnzG = (uint64_t)nnz;
+  h->stats.n_blocks = (uint64_t)nb;
+  h->stats.tree_levels = (uint64_t)h->tree_levels;
+  return RCG_OK;
+}
