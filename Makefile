@@ -8,7 +8,7 @@ SRC      := rchol_b200/csrc/rcg_api.cu rchol_b200/csrc/rcg_setup.cu rchol_b200/c
 OBJ      := $(SRC:.cu=.o)
 LIB      := rchol_b200/lib/librchol_b200.so
 
-all: $(LIB)
+all: $(LIB) cxx
 
 %.o: %.cu rchol_b200/csrc/rcg_common.cuh include/rchol_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -17,5 +17,19 @@ $(LIB): $(OBJ)
 	mkdir -p rchol_b200/lib
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(OBJ) -cudart shared
 
+# C++ face of the drop-in (SparseCSR, pcg, util) and the example driver
+CXXLIB   := rchol_b200/lib/librchol_b200_cxx.so
+CXXSRC   := rchol_b200/cxx/sparse.cpp rchol_b200/cxx/pcg.cpp rchol_b200/cxx/util.cpp
+
+$(CXXLIB): $(CXXSRC) $(LIB) rchol_b200/cxx/sparse.hpp rchol_b200/cxx/pcg.hpp rchol_b200/cxx/util.hpp
+	$(HOSTCXX) -O2 -std=c++17 -fPIC -fopenmp -shared -o $@ $(CXXSRC) -Lrchol_b200/lib -lrchol_b200 -Wl,-rpath,'$$ORIGIN'
+
+cxx: $(CXXLIB)
+
+# needs baseline/_ref/librchol_producer.so (make -C baseline)
+driver: rchol_b200/cxx/ex_laplace_parallel.cpp $(CXXLIB)
+	$(HOSTCXX) -O2 -std=c++17 -o rchol_b200/lib/ex_laplace_parallel $< -Irchol_b200/cxx -Lrchol_b200/lib -lrchol_b200_cxx -lrchol_b200 \
+	    -Lbaseline/_ref -lrchol_producer -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../../baseline/_ref'
+
 clean:
-	rm -f $(OBJ) $(LIB)
+	rm -f $(OBJ) $(LIB) $(CXXLIB) rchol_b200/lib/ex_laplace_parallel

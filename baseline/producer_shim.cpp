@@ -94,6 +94,18 @@ void *refprod_factor(uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx,
   return f;
 }
 
+// Partition boundaries (part[0]=0 ... part[2T-1]=N) of the last parallel factorization, for C++ callers of the
+// reference API `rchol(A, G, P, threads)` which does not return them.  Returns the number of boundaries.
+uint64_t refprod_last_part(uint64_t *out, uint64_t capacity) {
+  uint64_t n = g_last_part_sizes.size() + 1, acc = 0;
+  if (out && capacity > 0) out[0] = 0;
+  for (uint64_t i = 0; i + 1 < n; i++) {
+    acc += g_last_part_sizes[i];
+    if (out && i + 1 < capacity) out[i + 1] = acc;
+  }
+  return n;
+}
+
 const char *refprod_error(void *h) {
   Factor *f = static_cast<Factor *>(h);
   return f->err.empty() ? nullptr : f->err.c_str();

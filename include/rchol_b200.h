@@ -46,7 +46,8 @@ typedef struct rcg_options {
   int chain_window;        /* rows of the shared-memory solution window per CTA (0 = default)             */
   int use_graph;           /* 1 = replay one CUDA graph per PCG iteration (default), 0 = plain launches   */
   int spmv_lanes;          /* lanes per row of the CSR SpMV (0 = choose from the row-length histogram)     */
-  int reserved[12];
+  int chain_generic;       /* 1 = force the non-pipelined fallback kernel of the triangular solve (testing)  */
+  int reserved[11];
 } rcg_options;
 
 /* Per-handle measurements, all device-side times from CUDA events on the handle's own stream. */

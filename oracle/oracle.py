@@ -113,8 +113,7 @@ def have_reference_pcg() -> bool:
     return os.path.exists(_REFPCG_SO)
 
 
-def reference_pcg(A, b, tol, maxit, G):
-    """The UNMODIFIED reference ``pcg`` (real MKL SpMV/SpTRSV through libtorch_cpu.so; LP64 => nnz < 2^31)."""
+def _load_ref():
     global _reflib
     if _reflib is None:
         if not have_reference_pcg():
@@ -124,12 +123,30 @@ def reference_pcg(A, b, tol, maxit, G):
         L.refpcg_run.restype = C.c_int
         L.refpcg_run.argtypes = [C.c_uint64, _u64p, _u64p, _f64p, _f64p, C.c_double, C.c_int, _u64p, _u64p, _f64p,
                                  _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.refmkl_kernels.restype = C.c_int
+        L.refmkl_kernels.argtypes = [C.c_uint64, _u64p, _u64p, _f64p, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p, _f64p]
         _reflib = L
+    return _reflib
+
+
+def reference_mkl_kernels(A, G, r):
+    """Real oneMKL SpMV and both triangular solves with the reference's descriptors: returns (A r, U^-T r, U^-1 U^-T r)."""
+    L = _load_ref()
+    N = A[0].shape[0] - 1
+    Ar, y, z = (np.zeros(N, np.float64) for _ in range(3))
+    L.refmkl_kernels(N, _c(A[0], np.uint64), _c(A[1], np.uint64), _c(A[2], np.float64), _c(G[0], np.uint64),
+                     _c(G[1], np.uint64), _c(G[2], np.float64), _c(r, np.float64), Ar, y, z)
+    return Ar, y, z
+
+
+def reference_pcg(A, b, tol, maxit, G):
+    """The UNMODIFIED reference ``pcg`` (real MKL SpMV/SpTRSV through libtorch_cpu.so; LP64 => nnz < 2^31)."""
+    _load_ref()
     N = A[0].shape[0] - 1
     x = np.zeros(N, np.float64)
     relres = C.c_double(0)
     itr = C.c_int(0)
-    _reflib.refpcg_run(N, _c(A[0], np.uint64), _c(A[1], np.uint64), _c(A[2], np.float64), _c(b, np.float64),
+    _load_ref().refpcg_run(N, _c(A[0], np.uint64), _c(A[1], np.uint64), _c(A[2], np.float64), _c(b, np.float64),
                        float(tol), int(maxit), _c(G[0], np.uint64), _c(G[1], np.uint64), _c(G[2], np.float64),
                        x, C.byref(relres), C.byref(itr))
     return dict(x=x, relres=relres.value, itr=itr.value)

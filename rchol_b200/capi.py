@@ -31,7 +31,7 @@ TRSV_FORWARD, TRSV_BACKWARD = 0, 1
 
 class Options(C.Structure):
     _fields_ = [("chain_threads", C.c_int), ("chain_window", C.c_int), ("use_graph", C.c_int),
-                ("spmv_lanes", C.c_int), ("reserved", C.c_int * 12)]
+                ("spmv_lanes", C.c_int), ("chain_generic", C.c_int), ("reserved", C.c_int * 11)]
 
 
 class Stats(C.Structure):
@@ -111,12 +111,13 @@ class Solver:
     """Handle-based interface: upload A and G once, then call the kernels or the PCG solve."""
 
     def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
-                 spmv_lanes: int = 0):
+                 spmv_lanes: int = 0, chain_generic: bool = False):
         self._L = load()
         self._h = C.c_void_p()
         opt = Options()
         opt.chain_threads, opt.chain_window = int(chain_threads), int(chain_window)
         opt.use_graph, opt.spmv_lanes = int(bool(use_graph)), int(spmv_lanes)
+        opt.chain_generic = int(bool(chain_generic))
         rc = self._L.rcg_create_with_options(C.byref(self._h), int(device), C.byref(opt))
         if rc != 0:
             raise RcgError(rc, (self._L.rcg_last_error(None) or b"").decode())

@@ -538,6 +538,9 @@ __global__ void __launch_bounds__(1024) k_tri_chain_fast(const ChainArgs P) {
         uint32_t kr = (uint32_t)(rs - e0s);           // relative index of the lane's current entry
         const uint32_t kd = (uint32_t)(re - 1 - e0s);  // relative index of the diagonal slot (holds 1/diag)
         acc *= lds_f64(sval_s + 8u * kd);
+        // NaN payloads propagate through DMUL/DFMA: canonicalise once here so that no value in the window can ever
+        // equal SENTINEL (matrix values are canonicalised at set-up)
+        if (acc != acc) acc = __longlong_as_double((long long)CANON_NAN);
         if (has_old && pend) {
           const double *sval = reinterpret_cast<const double *>(sl);
           const uint32_t *scol = reinterpret_cast<const uint32_t *>(sl + (size_t)P.cap * 8);
@@ -565,8 +568,7 @@ __global__ void __launch_bounds__(1024) k_tri_chain_fast(const ChainArgs P) {
         // One trip = one PTX block so that the predicates stay in predicate registers (through C++ every predicated
         // helper costs a P2R/ISETP pair): poll a0; if solved and an entry is pending: acc -= v0*x, advance to entry
         // kr+1 and refill the look-ahead entry; if the row is complete: publish it (window, HBM, dot).
-        // A solved value never equals SENTINEL: results of FMA/MUL are canonical NaNs on the GPU, so testing the
-        // high word is enough.
+        // A solved value never equals SENTINEL (NaNs are canonicalised on entry), so testing the high word is enough.
         for (;;) {
           asm volatile(
               "{\n\t"
@@ -825,7 +827,7 @@ int rcg_launch_trisolve(rcg_handle *h, DirectionDev &d, const double *rhs, doubl
       const int64_t want = std::max<int64_t>(2 * (int64_t)NW, 12);
       while (slots_fit(ws) < want && ws > 2048) { ws >>= 1; Cp = ws / 2; }
       int64_t S = std::min<int64_t>(slots_fit(ws), 32);
-      if (S >= (int64_t)NW + 1 || (S >= 2 && max_groups <= (int)S)) {
+      if (!h->opt.chain_generic && (S >= (int64_t)NW + 1 || (S >= 2 && max_groups <= (int)S))) {
         a.C = Cp; a.win_slots = ws; a.cap = cap_need; a.slots = (uint32_t)S;
         a.clk = h->clk_probe;
         a.trace = h->trace;

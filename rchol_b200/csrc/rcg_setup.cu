@@ -424,7 +424,8 @@ __global__ void k_split_rows(const int64_t *__restrict__ loc_rp, const int64_t *
     }
     const uint32_t blo = bounds[blo_i];
     for (int64_t i = sub; i < nl; i += 8) {
-      const double v = val[src + ne + i];
+      double v = val[src + ne + i];
+      if (v != v) v = __longlong_as_double(0x7FF8000000000000ll);   // canonical NaN: never the solve's sentinel
       lcol[ls + i] = col[src + ne + i] - blo;
       lval[ls + i] = (i == nl - 1) ? v : -(v * dinv);   // off-diagonals: negated and scaled by 1/diag
     }

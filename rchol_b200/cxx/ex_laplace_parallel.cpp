@@ -1,0 +1,51 @@
+// Example driver with the reference's command line (c++/ex_laplace_parallel.cpp:11-52): -n <grid> -t <leaves>.
+// Factorization = the reference code (host); solve = this repository's GPU path behind the reference's pcg API.
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+
+#include "pcg.hpp"
+#include "rchol_ref.hpp"
+#include "sparse.hpp"
+#include "util.hpp"
+
+int main(int argc, char *argv[]) {
+  int n = 3, threads = 2;
+  double tol = 1e-6;
+  int maxit = 200;
+  for (int i = 1; i + 1 < argc; i++) {
+    if (!strcmp(argv[i], "-n")) n = atoi(argv[i + 1]);
+    if (!strcmp(argv[i], "-t")) threads = atoi(argv[i + 1]);
+    if (!strcmp(argv[i], "-tol")) tol = atof(argv[i + 1]);
+    if (!strcmp(argv[i], "-maxit")) maxit = atoi(argv[i + 1]);
+  }
+  std::cout << std::setprecision(3);
+  SparseCSR A;
+  A = laplace_3d(n);
+  std::vector<double> b(A.size());
+  rand(b);
+
+  SparseCSR G;
+  std::vector<size_t> P;
+  rchol(A, G, P, threads);
+  std::vector<uint64_t> part64(2 * (size_t)threads);
+  const uint64_t np = refprod_last_part(part64.data(), part64.size());
+  std::vector<size_t> part(part64.begin(), part64.begin() + np);
+  std::cout << "Fill-in ratio: " << 2. * G.nnz() / A.nnz() << std::endl;
+
+  SparseCSR Aperm;
+  reorder(A, P, Aperm);
+  std::vector<double> bperm;
+  reorder(b, P, bperm);
+
+  double relres;
+  int itr;
+  std::vector<double> x;
+  pcg solver(Aperm, bperm, tol, maxit, G, part, x, relres, itr);
+  std::cout << "# CG iterations: " << itr << std::endl;
+  std::cout << "Relative residual: " << relres << std::endl;
+  std::cout << "GPU ms: upload " << solver.upload_ms << " analysis " << solver.analysis_ms << " iterations "
+            << solver.solve_ms << " total " << solver.total_ms << std::endl;
+  return 0;
+}

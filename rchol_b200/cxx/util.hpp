@@ -1,0 +1,28 @@
+// Host helpers either side of the hot path, with the reference's names and argument meaning
+// (/root/reference/c++/util/util.hpp:32-55,147-164 and util.cpp:6-57, laplace_3d.hpp:8-65).
+#ifndef UTIL_HPP
+#define UTIL_HPP
+
+#include <cstdint>
+#include <vector>
+
+#include "sparse.hpp"
+
+SparseCSR laplace_3d(int n);                                                   // 7-point Dirichlet Laplacian, n^3 rows
+void reorder(const SparseCSR &A, const std::vector<size_t> &P, SparseCSR &B);  // B = A(P,P), rows re-sorted
+void rand(std::vector<double> &x, uint64_t seed = 2024);                       // U(0,1); the reference is unseeded
+
+template <typename T>
+void reorder(std::vector<T> &x, std::vector<size_t> &p, std::vector<T> &xp) {   // xp[i] = x[p[i]]
+  xp.clear();
+  xp.reserve(p.size());
+  for (size_t i = 0; i < p.size(); i++) xp.push_back(x[p[i]]);
+}
+
+template <typename T>
+void unpermute(const std::vector<T> &xp, const std::vector<size_t> &p, std::vector<T> &x) {   // x[p[i]] = xp[i]
+  x.resize(p.size());
+  for (size_t i = 0; i < p.size(); i++) x[p[i]] = xp[i];
+}
+
+#endif

@@ -1,0 +1,224 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the C ABI (rchol_b200/capi.py ->
+rchol_b200/lib/librchol_b200.so) and is checked against golden vectors produced by the reference itself
+(tests/golden) and against the oracle (oracle/pcg_oracle.c) on seeded problems.
+
+Tolerances (BASELINE.json north_star): triangular-solve output relative error <= 1e-12 in fp64; PCG iteration count
+within +-1 of the reference; final relative residual meets the same tolerance."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, GOLDEN_CASES, load_golden, make_problem, needs_producer, relerr
+
+pytestmark = pytest.mark.gpu
+
+TRSV_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from rchol_b200 import capi as m
+    m.load()
+    return m
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as o
+    return o
+
+
+def check_solve(capi, oracle, A, b, G, part, tol=1e-8, maxit=500, **opts):
+    with capi.Solver(0, **opts) as s:
+        s.set_matrix(*A)
+        s.set_factor(*G, part)
+        assert relerr(s.spmv(b), oracle.spmv(*A, b)) < 1e-14
+        yo = oracle.trsv_forward(*G, b)
+        zo = oracle.trsv_backward(*G, yo)
+        assert relerr(s.trsv(capi.TRSV_FORWARD, b), yo) <= TRSV_TOL
+        assert relerr(s.trsv(capi.TRSV_BACKWARD, yo), zo) <= TRSV_TOL
+        assert relerr(s.precond(b), zo) <= TRSV_TOL
+        x, relres, itr = s.pcg(b, tol, maxit)
+        o = oracle.pcg(A, b, tol, maxit, G)
+        assert abs(itr - o["itr"]) <= 1, (itr, o["itr"])
+        if o["itr"] < maxit:
+            assert relres <= 2 * tol          # true residual; may exceed tol slightly (pcg.cpp:116-118)
+        if itr == o["itr"]:
+            assert relerr(x, o["x"]) < 1e-9
+            assert abs(relres - o["relres"]) <= 1e-3 * o["relres"] + 1e-15
+        st = s.stats()
+        assert st["watchdog_row"] == 0 and st["kernel_launches"] > 0
+        hist = s.history()
+        assert len(hist) == itr + 1 and abs(hist[0] - 1.0) < 1e-12
+        assert np.all(hist[:-1] > tol) and (itr == maxit or hist[-1] <= tol)
+        return itr, relres
+
+
+def test_kat_3x3(capi):
+    k = load_golden("kat3")
+    G = (k["rowPtr"], k["colIdx"], k["val"])
+    with capi.Solver(0) as s:
+        s.set_matrix(*G)
+        s.set_factor(*G)
+        np.testing.assert_allclose(s.spmv(k["b"]), [4.0, 9.0, 12.0], rtol=1e-15)
+        np.testing.assert_allclose(s.trsv(capi.TRSV_FORWARD, k["b"]), [0.5, 0.5, 0.625], rtol=1e-15)
+        np.testing.assert_allclose(s.precond(k["b"]), k["mkl_precond"], rtol=1e-15)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_goldens_from_the_reference(capi, name):
+    g = load_golden(name)
+    part = g["part"] if len(g["part"]) > 2 else None
+    with capi.Solver(0) as s:
+        s.set_matrix(*g["A"])
+        s.set_factor(*g["G"], part)
+        assert relerr(s.spmv(g["b"]), g["mkl_spmv"]) < 1e-14
+        assert relerr(s.trsv(capi.TRSV_FORWARD, g["b"]), g["mkl_fwd"]) <= TRSV_TOL
+        assert relerr(s.trsv(capi.TRSV_BACKWARD, g["mkl_fwd"]), g["mkl_precond"]) <= TRSV_TOL
+        assert relerr(s.precond(g["b"]), g["mkl_precond"]) <= TRSV_TOL
+        x, relres, itr = s.pcg(g["b"], float(g["tol"]), int(g["maxit"]))
+        assert abs(itr - int(g["ref_itr"])) <= 1
+        assert relres <= 2 * float(g["tol"])
+        if itr == int(g["ref_itr"]):
+            assert relerr(x, g["ref_x"]) < 1e-9
+    # one-shot entry point = the reference constructor's call shape
+    x, relres, itr, st = capi.pcg(g["A"], g["b"], float(g["tol"]), int(g["maxit"]), g["G"], part)
+    assert abs(itr - int(g["ref_itr"])) <= 1 and relres <= 2 * float(g["tol"])
+    assert st["h2d_bytes"] > 0 and st["total_ms"] > 0
+
+
+@needs_producer
+@pytest.mark.parametrize("kind,n,threads", [("lap3d", 2, 0), ("lap3d", 20, 0), ("lap3d", 32, 4), ("lap3d", 48, 8),
+                                             ("lap3d", 40, 64), ("aniso2d", 96, 8), ("aniso2d", 128, 1)])
+def test_seeded_problems_vs_oracle(capi, oracle, kind, n, threads):
+    A, b, G, part, f = make_problem(kind, n, threads)
+    check_solve(capi, oracle, A, b, G, part)
+
+
+@needs_producer
+@pytest.mark.parametrize("opts", [dict(chain_threads=32), dict(chain_threads=64, chain_window=64),
+                                  dict(chain_threads=512, chain_window=256), dict(chain_window=1024),
+                                  dict(chain_generic=True), dict(chain_generic=True, chain_window=128),
+                                  dict(use_graph=False), dict(spmv_lanes=4), dict(spmv_lanes=32)])
+def test_kernel_configurations(capi, oracle, opts):
+    """Small windows force many chunks and entries older than the window; chain_generic forces the fallback kernel."""
+    A, b, G, part, f = make_problem("lap3d", 24, 4)
+    check_solve(capi, oracle, A, b, G, part, **opts)
+    A, b, G, part, f = make_problem("lap3d", 18, 0)
+    check_solve(capi, oracle, A, b, G, None, **opts)
+
+
+def test_empty_separator_and_single_rows(capi, oracle):
+    # two independent 3x3 triangular blocks and an EMPTY top separator: part = [0, 3, 6, 6]
+    rp = np.array([0, 2, 4, 5, 7, 9, 10], np.uint64)
+    ci = np.array([0, 1, 1, 2, 2, 3, 5, 4, 5, 5], np.uint64)
+    v = np.array([2, -1, 3, -1, 4, 2, -0.5, 3, -1, 5.0])
+    G = (rp, ci, v)
+    b = np.arange(1.0, 7.0)
+    with capi.Solver(0) as s:
+        s.set_factor(*G, np.array([0, 3, 6, 6], np.uint64))
+        assert relerr(s.precond(b), oracle.precond(*G, b)) <= TRSV_TOL
+    # 1x1 system
+    one = (np.array([0, 1], np.uint64), np.array([0], np.uint64), np.array([4.0]))
+    g1 = (np.array([0, 1], np.uint64), np.array([0], np.uint64), np.array([2.0]))
+    x, relres, itr, st = capi.pcg(one, np.array([8.0]), 1e-12, 10, g1)
+    assert itr == 1 and abs(x[0] - 2.0) < 1e-15 and relres < 1e-15
+
+
+def test_error_reporting(capi):
+    g = load_golden("lap3d_12_t4")
+    with capi.Solver(0) as s:
+        with pytest.raises(capi.RcgError) as e:
+            s.N = g["b"].shape[0]
+            s.pcg(g["b"], 1e-8, 10)
+        assert e.value.code == 3                                  # RCG_ERR_STATE: nothing set yet
+        s.set_matrix(*g["A"])
+        with pytest.raises(capi.RcgError) as e:
+            s.set_factor(*g["G"], np.array([0, 5, 9, g["b"].shape[0]], np.uint64))   # blocks that the factor violates
+        assert e.value.code == 4                                  # RCG_ERR_STRUCTURE
+        with pytest.raises(capi.RcgError) as e:
+            s.set_factor(*g["G"], np.array([0, 5, g["b"].shape[0]], np.uint64))      # not 2T boundaries
+        assert e.value.code == 2                                  # RCG_ERR_INVALID
+        with pytest.raises(capi.RcgError) as e:
+            s.set_factor(*g["A"])                                 # A is not upper triangular
+        assert e.value.code == 4
+        bad = g["G_colIdx"].copy(); bad[3] = 10 ** 9
+        with pytest.raises(capi.RcgError) as e:
+            s.set_factor(g["G_rowPtr"], bad, g["G_val"])
+        assert e.value.code == 2
+        s.set_factor(*g["G"], g["part"])                          # still usable afterwards
+        assert s.pcg(g["b"], 1e-8, 100)[2] == int(g["ref_itr"])
+    with pytest.raises(capi.RcgError):
+        capi.Solver(99)
+
+
+def test_nan_rhs_does_not_hang(capi):
+    g = load_golden("lap3d_12_t4")
+    b = g["b"].copy(); b[7] = np.nan
+    with capi.Solver(0) as s:
+        s.set_matrix(*g["A"]); s.set_factor(*g["G"], g["part"])
+        z = s.precond(b)
+        assert np.isnan(z).any() and s.stats()["watchdog_row"] == 0
+        x, relres, itr = s.pcg(b, 1e-8, 50)
+        assert itr == 0 and np.isnan(relres)                      # `nan > tol*nan` is false: pcg.cpp:82 never enters
+        # a sentinel-valued input must not dead-lock the sync-free solve either
+        b2 = g["b"].copy(); b2.view(np.uint64)[3] = 0xFFFFFFFFFFFFFFFF
+        z = s.precond(b2)
+        assert s.stats()["watchdog_row"] == 0
+
+
+@needs_producer
+def test_properties_at_larger_size(capi):
+    """Size-independent properties on a problem the oracle is not consulted for: U^T U z = r round trip, linearity of
+    the preconditioner, and a PCG solve that meets its tolerance with the un-permuted solution solving the original
+    system."""
+    import scipy.sparse as sp
+    from rchol_b200 import problems
+    A, b, G, part, f = make_problem("lap3d", 96, 8)
+    N = f.N
+    U = sp.csr_matrix((G[2], G[1].astype(np.int64), G[0].astype(np.int64)), shape=(N, N))
+    rng = np.random.default_rng(5)
+    r1, r2 = rng.standard_normal(N), rng.standard_normal(N)
+    with capi.Solver(0) as s:
+        s.set_matrix(*A); s.set_factor(*G, part)
+        z1, z2 = s.precond(r1), s.precond(r2)
+        assert relerr(U.T @ (U @ z1), r1) < 1e-11
+        assert relerr(s.precond(2.5 * r1 - r2), 2.5 * z1 - z2) < 1e-11
+        y = s.trsv(capi.TRSV_FORWARD, r1)
+        assert relerr(U.T @ y, r1) < 1e-12 and relerr(U @ s.trsv(capi.TRSV_BACKWARD, y), y) < 1e-12
+        x, relres, itr = s.pcg(b, 1e-8, 500)
+        assert relres <= 2e-8 and 25 <= itr <= 45
+        assert s.stats()["n_blocks"] == 15 and s.stats()["tree_levels"] == 4
+    A0 = problems.laplace_3d(96)
+    A0 = sp.csr_matrix((A0[2], A0[1].astype(np.int64), A0[0].astype(np.int64)), shape=(N, N))
+    b0 = problems.random_rhs(N)
+    x0 = problems.unpermute_vector(x, f.P)
+    assert np.linalg.norm(A0 @ x0 - b0) / np.linalg.norm(b0) <= 2e-8
+
+
+@needs_producer
+def test_resident_solve_and_repeatability(capi):
+    A, b, G, part, f = make_problem("lap3d", 32, 4)
+    with capi.Solver(0) as s:
+        s.set_matrix(*A); s.set_factor(*G, part); s.set_rhs(b)
+        r1 = s.pcg_resident(1e-8, 500); x1 = s.solution()
+        r2 = s.pcg_resident(1e-8, 500); x2 = s.solution()
+        assert r1 == r2 and np.array_equal(x1, x2)                # deterministic reductions: bit-identical reruns
+        st = s.profile_iteration(2)
+        assert st["trsv_ms"] > 0 and st["spmv_ms"] > 0 and st["blas1_ms"] > 0 and st["launches_per_iteration"] >= 6
+
+
+@needs_producer
+def test_cxx_driver_runs_like_the_reference_example(capi):
+    """rchol_b200/cxx/ex_laplace_parallel (reference command line: -n, -t) = reference factorization + our pcg class."""
+    exe = os.path.join(ROOT, "rchol_b200", "lib", "ex_laplace_parallel")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built (make driver)")
+    out = subprocess.run([exe, "-n", "16", "-t", "4", "-tol", "1e-8", "-maxit", "300"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    itr = int(re.search(r"# CG iterations: (\d+)", out.stdout).group(1))
+    relres = float(re.search(r"Relative residual: ([0-9.eE+-]+)", out.stdout).group(1))
+    assert 10 <= itr <= 40 and relres <= 2e-8

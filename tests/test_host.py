@@ -1,0 +1,170 @@
+"""CPU tests of the host side: generators, permutation helpers, factor structure, and the C-ABI library
+(loads and exports every symbol the header declares -- no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, GOLDEN_CASES, load_golden, make_problem, needs_producer
+from rchol_b200 import problems
+
+
+def test_laplace_3d_closed_form_and_layout():
+    for n in (1, 2, 3, 7):
+        rp, ci, v = problems.laplace_3d(n)
+        N = n ** 3
+        assert rp.dtype == np.uint64 and ci.dtype == np.uint64 and v.dtype == np.float64
+        assert rp.shape[0] == N + 1 and int(rp[-1]) == 7 * n ** 3 - 6 * n ** 2     # laplace_3d.hpp:60-64
+        for i in range(N):
+            cols = ci[int(rp[i]):int(rp[i + 1])]
+            assert np.all(np.diff(cols.astype(np.int64)) > 0) and i in cols
+        import scipy.sparse as sp
+        A = sp.csr_matrix((v, ci.astype(np.int64), rp.astype(np.int64)), shape=(N, N))
+        assert abs(A - A.T).max() == 0 and np.all(A.diagonal() == 6.0)
+    assert int(problems.laplace_3d(3)[0][-1]) == 135
+
+
+@needs_producer
+def test_generators_match_reference():
+    from rchol_b200 import producer
+    for n in (3, 6, 11):
+        a, b = problems.laplace_3d(n), producer.ref_laplace_3d(n)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    A = problems.laplace_3d(9)
+    P = np.random.default_rng(1).permutation(9 ** 3).astype(np.uint64)
+    a, b = problems.reorder_matrix(*A, P), producer.ref_reorder(*A, P)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    x = np.arange(9 ** 3, dtype=np.float64)
+    assert np.array_equal(problems.unpermute_vector(problems.reorder_vector(x, P), P), x)
+
+
+def test_aniso_2d_is_sddm():
+    import scipy.sparse as sp
+    n = 17
+    rp, ci, v = problems.aniso_2d(n)
+    assert int(rp[-1]) == 5 * n * n - 4 * n
+    A = sp.csr_matrix((v, ci.astype(np.int64), rp.astype(np.int64)), shape=(n * n, n * n))
+    assert abs(A - A.T).max() < 1e-15
+    off = A - sp.diags(A.diagonal())
+    assert off.max() <= 0 and np.all(A.diagonal() > 0)
+    rowsum = np.asarray(A.sum(axis=1)).ravel()
+    assert np.all(rowsum > -1e-12) and rowsum[0] > 0       # boundary rows strictly dominant (ghost edges)
+    # same generator, same seed -> same matrix
+    assert all(np.array_equal(a, b) for a, b in zip(problems.aniso_2d(n), (rp, ci, v)))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_factor_structure_of_goldens(name):
+    """Invariants the GPU solve relies on: G is CSR of an upper-triangular matrix, rows sorted,
+    diagonal first and positive, and a row of block B only touches B and B's ancestor separators."""
+    g = load_golden(name)
+    rp, ci, v = (g["G_rowPtr"].astype(np.int64), g["G_colIdx"].astype(np.int64), g["G_val"])
+    N = rp.shape[0] - 1
+    part = g["part"].astype(np.int64)
+    nb = part.shape[0] - 1
+    assert part[0] == 0 and part[-1] == N and ((nb + 1) & nb) == 0
+    anc = {}
+
+    def rec(start, total, above):
+        if total == 1:
+            anc[start] = above
+        else:
+            sep, half = start + total - 1, (total - 1) // 2
+            anc[sep] = above
+            rec(start, half, above + [sep])
+            rec(start + half, half, above + [sep])
+    rec(0, nb, [])
+    blk = np.searchsorted(part, np.arange(N), side="right") - 1
+    for i in range(N):
+        cols = ci[rp[i]:rp[i + 1]]
+        assert cols[0] == i and v[rp[i]] > 0 and np.all(np.diff(cols) > 0)
+        allowed = set(anc[blk[i]] + [blk[i]])
+        assert set(blk[cols]).issubset(allowed)
+
+
+@needs_producer
+def test_producer_is_deterministic_and_validates_threads():
+    from rchol_b200 import producer
+    A = problems.laplace_3d(10)
+    f1, f2 = producer.factor(*A, threads=4, seed=7), producer.factor(*A, threads=4, seed=7)
+    assert np.array_equal(f1.colIdx, f2.colIdx) and np.array_equal(f1.val, f2.val) and np.array_equal(f1.P, f2.P)
+    assert sorted(f1.P.tolist()) == list(range(1000)) and f1.part[-1] == 1000 and len(f1.part) == 8
+    f3 = producer.factor(*A, threads=4, seed=8)
+    assert not np.array_equal(f1.val, f3.val) or not np.array_equal(f1.colIdx, f3.colIdx)
+    with pytest.raises(ValueError):
+        producer.factor(*A, threads=3)       # rchol_parallel.cpp:42-43
+
+
+def test_bytes_per_iteration_formula():
+    # BASELINE.md section 3
+    assert problems.algorithmic_bytes_per_iteration(10, 50, 30) == 12 * 50 + 4 * 11 + 2 * (12 * 30 + 4 * 11) + 136 * 10
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "rchol_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcg_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from rchol_b200 import capi
+    assert os.path.exists(capi.LIB_PATH), "run `make` / __graft_entry__.build() first"
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    declared = _header_symbols()
+    assert len(declared) >= 19
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/rchol_b200.h but not exported"
+    assert sorted(capi.EXPORTED) == declared
+    lib.rcg_version.restype = ctypes.c_char_p
+    assert b"rchol_b200" in lib.rcg_version() and b"sm_100a" in lib.rcg_version()
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """On a box without a B200 creating a solver must fail loudly (RCG_ERR_CUDA), never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    from rchol_b200 import capi
+    with pytest.raises(capi.RcgError) as e:
+        capi.Solver(0)
+    assert e.value.code == 1 and "no CPU fallback" in str(e.value)
+    g = load_golden("lap3d_8_seq")
+    with pytest.raises(capi.RcgError):
+        capi.pcg(g["A"], g["b"], 1e-8, 10, g["G"])
+
+
+def test_product_sources_never_touch_the_oracle():
+    """The CUDA library and the host mirror must not reference oracle/ (tier rule 3)."""
+    for sub in ("rchol_b200/csrc", "rchol_b200/cxx"):
+        for fn in os.listdir(os.path.join(ROOT, sub)):
+            if fn.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                assert "oracle" not in open(os.path.join(ROOT, sub, fn)).read().lower(), fn
+    for fn in ("capi.py", "problems.py", "producer.py", "__init__.py"):
+        src = open(os.path.join(ROOT, "rchol_b200", fn)).read()
+        assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_cxx_mirror_compiles_against_reference_style_driver(tmp_path):
+    """The reference's ex_laplace driver body compiles unchanged against our sparse.hpp / pcg.hpp."""
+    src = tmp_path / "drv.cpp"
+    src.write_text('''
+#include "sparse.hpp"
+#include "util.hpp"
+#include "pcg.hpp"
+int main() {
+  SparseCSR A; A = laplace_3d(3);
+  int N = A.size(); std::vector<double> b(N); rand(b);
+  SparseCSR G(A);
+  double tol = 1e-6; int maxit = 200; double relres; int itr; std::vector<double> x;
+  if (N < 0) pcg(A, b, tol, maxit, G, x, relres, itr);   // constructor-as-entry-point, like ex_laplace.cpp:42
+  return (A.nnz() == 135 && G.nnz() == 135 && G.ownMemory) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "drv"
+    lib = os.path.join(ROOT, "rchol_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-o", str(exe), str(src), "-I", os.path.join(ROOT, "rchol_b200", "cxx"),
+                           "-L", lib, "-lrchol_b200_cxx", "-lrchol_b200", f"-Wl,-rpath,{lib}"])
+    assert subprocess.call([str(exe)]) == 0
