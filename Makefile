@@ -4,13 +4,13 @@ NVCC     ?= /usr/local/cuda/bin/nvcc
 HOSTCXX  ?= /usr/bin/g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall
-SRC      := rchol_b200/csrc/rcg_api.cu rchol_b200/csrc/rcg_setup.cu rchol_b200/csrc/rcg_kernels.cu
+SRC      := rchol_b200/csrc/rcg_api.cu rchol_b200/csrc/rcg_setup.cu rchol_b200/csrc/rcg_kernels.cu rchol_b200/csrc/rcg_trisolve.cu
 OBJ      := $(SRC:.cu=.o)
 LIB      := rchol_b200/lib/librchol_b200.so
 
 all: $(LIB) cxx
 
-%.o: %.cu rchol_b200/csrc/rcg_common.cuh include/rchol_b200.h
+%.o: %.cu rchol_b200/csrc/rcg_common.cuh rchol_b200/csrc/rcg_device.cuh include/rchol_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJ)

@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on B200 hardware.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): 3D 7-point Laplacian 256^3, reference `rchol(A, G, P, threads=8)` factorization
+(computed by the UNMODIFIED reference code on the host with a fixed seed -- an input, not timed), PCG to a relative
+residual of 1e-8.  A "step" is one full PCG solve.  The metric is the algorithmic memory traffic of the PCG iterations
+divided by the time they take: bytes per iteration (SURVEY.md 8d / BASELINE.md section 3)
+    B_iter = 12 nnz(A) + 4 (N+1) + 2 [12 nnz(G) + 4 (N+1)] + 136 N
+times the iterations done, over the device time of the solve -- "GB/s per iteration vs the HBM roofline".
+`value` is measured with A, G and b resident in HBM (CUDA events around the solve); `e2e` is the same metric through the
+drop-in entry point with HOST buffers (upload of A, G, b, device set-up/analysis, solve and download of x inside the timed
+region).  The reference arm (--impl reference) times the reference's own CPU implementation of the same path on the host
+cores on a bounded sample (a fixed number of iterations per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from rchol_b200 import problems, producer  # noqa: E402
+
+TOL = 1e-8
+MAXIT = 500
+SEED = 20240
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# problem construction (inputs of the hot path; cached on local disk so that the two arms share the factor)
+# ------------------------------------------------------------------------------------------------------------
+def build_problem(n: int, threads: int):
+    cache_root = os.environ.get("RCHOL_B200_CACHE", "/tmp/rchol_b200_cache")
+    tag = os.path.join(cache_root, f"lap3d_{n}_T{threads}_s{SEED}")
+    names = ["A_rp", "A_ci", "A_v", "G_rp", "G_ci", "G_v", "part", "b", "P"]
+    if all(os.path.exists(f"{tag}.{k}.npy") for k in names):
+        t0 = time.time()
+        d = {k: np.load(f"{tag}.{k}.npy") for k in names}
+        log(f"[bench] loaded cached problem {tag} in {time.time() - t0:.1f}s")
+        return d, dict(cached=True)
+    t0 = time.time()
+    A = problems.laplace_3d(n)
+    t1 = time.time()
+    f = producer.factor(*A, threads=threads, seed=SEED)
+    t2 = time.time()
+    b = problems.random_rhs(f.N)
+    if threads > 0:
+        Ap = producer.ref_reorder(*A, f.P)
+        bp = problems.reorder_vector(b, f.P)
+    else:
+        Ap, bp = A, b
+    t3 = time.time()
+    d = dict(A_rp=Ap[0], A_ci=Ap[1], A_v=Ap[2], G_rp=f.rowPtr, G_ci=f.colIdx, G_v=f.val, part=f.part, b=bp, P=f.P)
+    log(f"[bench] generated lap3d {n}^3: gen {t1 - t0:.1f}s, reference factorization (T={threads}) {t2 - t1:.1f}s, "
+        f"reorder {t3 - t2:.1f}s, nnzG={f.nnz}")
+    try:
+        os.makedirs(cache_root, exist_ok=True)
+        for k in names:
+            np.save(f"{tag}.{k}.npy", d[k])
+    except OSError as e:  # cache is an optimisation only
+        log(f"[bench] cache not written: {e}")
+    return d, dict(cached=False, gen_s=t1 - t0, factor_s=t2 - t1, reorder_s=t3 - t2)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md): sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()          # the exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path, bounded sample
+# ------------------------------------------------------------------------------------------------------------
+def cpu_sample(d, iters: int, prefer_reference: bool):
+    """Runs `iters` PCG iterations on the host cores; returns (seconds, iterations, kind, cores, detail)."""
+    from oracle import oracle
+    A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
+    if prefer_reference and oracle.have_reference_pcg() and int(d["G_rp"][-1]) < 2 ** 31 - 1:
+        try:
+            t0 = time.time()
+            r = oracle.reference_pcg(A, d["b"], 1e-30, iters, G)      # tol unreachable: exactly `iters` iterations
+            return time.time() - t0, r["itr"], "reference", os.cpu_count(), "unmodified reference pcg.cpp + oneMKL (libtorch_cpu)"
+        except Exception as e:  # pragma: no cover
+            log(f"[bench] reference pcg unavailable ({e}); using the oracle port")
+    t0 = time.time()
+    o = oracle.pcg(A, d["b"], 1e-30, iters, G)
+    dt = time.time() - t0
+    return dt, o["itr"], "port", oracle.num_threads(), {k: float(v) for k, v in o["timings"].items()}
+
+
+def run_reference_arm(args, d, B_iter, rank, world):
+    if rank != 0:
+        return
+    iters = args.sample_iters
+    times = []
+    kind = cores = detail = None
+    for step in range(args.warmup + args.steps):
+        dt, it, kind, cores, detail = cpu_sample(d, iters, prefer_reference=True)
+        log(f"[bench/reference] step {step}: {it} iterations in {dt:.2f}s ({kind})")
+        if step >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = B_iter * iters * len(times) / total / 1e9
+    N = d["A_rp"].shape[0] - 1
+    line = dict(impl="reference", metric="pcg_gbps_per_iter", value=value, unit="GB/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / len(times), higher_is_better=True,
+                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                config=workload_config(args, d, N),
+                cpu_baseline=dict(value=value, unit="GB/s", cores=cores, kind=kind,
+                                  sample=f"{iters} PCG iterations per step (of ~33 to convergence) on the full {args.n}^3 problem"),
+                e2e=dict(value=value, unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0, detail=detail)
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, d, N):
+    return dict(workload=f"lap3d_{args.n}^3_rchol_T{args.threads}_pcg_tol1e-8", n=args.n, N=int(N),
+                nnzA=int(d["A_rp"][-1]), nnzG=int(d["G_rp"][-1]), nd_leaves=args.threads, tol=TOL, maxit=MAXIT,
+                factor_seed=SEED, l2_policy="inputs_exceed_l2 (A+G streamed per iteration >> 126 MB)")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours_single(args, d, B_iter):
+    from rchol_b200 import capi
+    A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
+    part = d["part"] if args.threads > 0 else None
+    N = A[0].shape[0] - 1
+    nnzA, nnzG = int(A[0][-1]), int(G[0][-1])
+    peak, peak_src = measured_peak_gbs()
+
+    s = capi.Solver(0)
+    t0 = time.time()
+    s.set_matrix(*A)
+    s.set_factor(*G, part)
+    s.set_rhs(d["b"])
+    setup_wall = time.time() - t0
+    st0 = s.stats()
+    log(f"[bench] upload {st0['upload_ms']:.0f} ms, analysis {st0['analysis_ms']:.0f} ms, device bytes {st0['device_bytes'] / 1e9:.2f} GB")
+
+    for w in range(args.warmup):
+        relres, itr = s.pcg_resident(TOL, MAXIT)
+        log(f"[bench] warm-up {w}: {itr} iterations, relres {relres:.3e}, {s.stats()['solve_ms']:.1f} ms")
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = s.stats()["kernel_launches"]
+    dev_ms, iters_total = 0.0, 0
+    wall0 = time.time()
+    for k in range(args.steps):
+        relres, itr = s.pcg_resident(TOL, MAXIT)
+        dev_ms += s.stats()["solve_ms"]
+        iters_total += itr
+    wall = time.time() - wall0
+    launches = s.stats()["kernel_launches"] - launches0
+    clocks = sampler.stop()
+    value = B_iter * iters_total / (dev_ms * 1e-3) / 1e9
+    x_dev = s.solution()
+
+    # ---- per-phase and per-kernel split (live CUDA events) ------------------------------------------------------
+    prof = s.profile_iteration(3)
+    # The triangular solves run as one launch triple (pre / chain / post) per tree level and window-sized segment.
+    # Dominant kernel = k_tri_chain_fast; its launches are timed one by one with CUDA events (rcg_time_group).
+    per_level = {}
+    chain_ms_total, chain_bytes_total, chain_launches = 0.0, 0, 0
+    aux_ms_total, aux_bytes_total = 0.0, 0
+    dom = None
+    for direction, dname in ((capi.TRSV_FORWARD, "fwd"), (capi.TRSV_BACKWARD, "bwd")):
+        for gi, g in enumerate(s.groups(direction)):
+            chain_ms = s.time_group(direction, gi, 0, 2)
+            pre_ms = s.time_group(direction, gi, 1, 2)
+            post_ms = s.time_group(direction, gi, 2, 2)
+            # algorithmic bytes of one launch: 12 B per entry, 4 B row pointer per row, start vector in, solution out
+            chain_bytes = 12 * g["loc_nnz"] + 4 * g["rows"] + 16 * g["rows"]
+            aux_bytes = 12 * g["ext_nnz"] + 4 * g["rows"] + 4 * 8 * g["rows"]
+            chain_ms_total += chain_ms; chain_bytes_total += chain_bytes; chain_launches += 1
+            aux_ms_total += pre_ms + post_ms; aux_bytes_total += aux_bytes
+            key = f"{dname}:{g['blocks']}blocks"
+            e = per_level.setdefault(key, dict(launches=0, rows=0, chain_ms=0.0, pre_post_ms=0.0, chain_bytes=0))
+            e["launches"] += 1; e["rows"] += g["rows"]; e["chain_ms"] += chain_ms; e["pre_post_ms"] += pre_ms + post_ms
+            e["chain_bytes"] += chain_bytes
+            if dom is None or chain_ms > dom[1]:
+                dom = (f"k_tri_chain_fast[{dname} group {gi}: {g['blocks']} blocks, {g['rows']} rows]", chain_ms, chain_bytes)
+    for e in per_level.values():
+        e["chain_gbs"] = e["chain_bytes"] / e["chain_ms"] / 1e6 if e["chain_ms"] else 0.0
+    groups = per_level
+    spmv_ms = prof["spmv_ms"]
+    ach = chain_bytes_total / chain_ms_total / 1e6
+    roofline = dict(bound="hbm", kernel="k_tri_chain_fast (all launches of one forward + one backward solve)",
+                    achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                    launches_per_solve_pair=chain_launches, bytes_per_launch=chain_bytes_total / chain_launches,
+                    ms_per_launch=chain_ms_total / chain_launches, chain_ms_per_iteration=chain_ms_total,
+                    pre_post_ms_per_iteration=aux_ms_total,
+                    pre_post_gbs=aux_bytes_total / aux_ms_total / 1e6 if aux_ms_total else 0.0,
+                    largest_launch=dict(kernel=dom[0], ms=dom[1], gbs=dom[2] / dom[1] / 1e6),
+                    note="latency-bound dependency chain of the factor (one CTA per nested-dissection block); "
+                         "see DESIGN.md 'SpTRSV' for the critical-path bound",
+                    iteration=dict(bytes=B_iter, ms=dev_ms / max(iters_total, 1), gbs=value, frac=value / peak,
+                                   trsv_ms=prof["trsv_ms"], spmv_ms=spmv_ms, blas1_ms=prof["blas1_ms"],
+                                   spmv_gbs=(12 * nnzA + 4 * N + 24 * N) / spmv_ms / 1e6 if spmv_ms else 0.0,
+                                   dag_levels=dict(fwd=prof.get("dag_levels_fwd"), bwd=prof.get("dag_levels_bwd"))),
+                    tree_levels=groups)
+    s.close()
+
+    # ---- end to end through the drop-in entry point, host buffers -------------------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_ms, e2e_iters, h2d, d2h = 0.0, 0, 0, 0
+    setup_ms = None
+    for k in range(e2e_steps):
+        t0 = time.time()
+        x, relres_e, itr_e, st = capi.pcg(A, d["b"], TOL, MAXIT, G, part)
+        e2e_ms += 1e3 * (time.time() - t0)
+        e2e_iters += itr_e
+        h2d, d2h = st["h2d_bytes"] + 8 * N, st["d2h_bytes"]
+        setup_ms = dict(upload_ms=st["upload_ms"], analysis_ms=st["analysis_ms"], solve_ms=st["solve_ms"])
+    e2e_value = B_iter * e2e_iters / (e2e_ms * 1e-3) / 1e9
+    assert np.array_equal(x, x_dev), "one-shot and resident solves differ"
+
+    # ---- CPU baseline beside it (bounded sample, rank 0) ------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        dt, it, kind, cores, detail = cpu_sample(d, args.sample_iters, prefer_reference=False)
+        cpu = dict(value=B_iter * it / dt / 1e9, unit="GB/s", cores=cores, kind=kind,
+                   sample=f"{it} PCG iterations (of {iters_total // args.steps} to convergence) on the full {args.n}^3 problem, "
+                          f"{dt:.1f} s", ms_per_iter=1e3 * dt / it, detail=detail)
+
+    line = dict(metric="pcg_gbps_per_iter", value=value, unit="GB/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f64", data="synthetic", config=workload_config(args, d, N),
+                iterations=iters_total // args.steps, relres=relres, ms_per_iter=dev_ms / max(iters_total, 1),
+                time_to_solution_ms=dict(resident=dev_ms / args.steps, end_to_end=e2e_ms / e2e_steps, parts=setup_ms),
+                wall_ms_per_step=1e3 * wall / args.steps,
+                roofline=roofline, cpu_baseline=cpu,
+                e2e=dict(value=e2e_value, unit="GB/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                         steps=e2e_steps, ms_per_step=e2e_ms / e2e_steps, host_memory="pageable (caller's SparseCSR arrays)"),
+                gpu_launches=int(launches), clocks=clocks,
+                setup=dict(upload_ms=st0["upload_ms"], analysis_ms=st0["analysis_ms"], wall_s=setup_wall))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("RCHOL_B200_BENCH_N", 256)))
+    ap.add_argument("--threads", type=int, default=8, help="leaves of the reference's nested-dissection partition")
+    ap.add_argument("--sample-iters", type=int, default=4, help="PCG iterations per CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    if args.impl == "reference" and rank != 0:
+        return 0
+    d, info = build_problem(args.n, args.threads)
+    N = d["A_rp"].shape[0] - 1
+    B_iter = problems.algorithmic_bytes_per_iteration(N, int(d["A_rp"][-1]), int(d["G_rp"][-1]))
+    if args.impl == "reference":
+        run_reference_arm(args, d, B_iter, rank, world)
+        return 0
+    if world > 1 or args.gpus > 1:
+        from rchol_b200 import multigpu
+        return multigpu.bench_main(args, d, B_iter, rank, world, workload_config(args, d, N))
+    run_ours_single(args, d, B_iter)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

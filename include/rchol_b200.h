@@ -43,7 +43,7 @@ enum {
 /* Tunables (all have defaults; see DESIGN.md "SpTRSV"). */
 typedef struct rcg_options {
   int chain_threads;       /* threads per CTA of the block-local sync-free triangular solve (0 = default) */
-  int chain_window;        /* rows of the shared-memory solution window per CTA (0 = default)             */
+  int chain_window;        /* chunk rows C of the solution window (segment = 2C rows; 0 = default 2048)    */
   int use_graph;           /* 1 = replay one CUDA graph per PCG iteration (default), 0 = plain launches   */
   int spmv_lanes;          /* lanes per row of the CSR SpMV (0 = choose from the row-length histogram)     */
   int chain_generic;       /* 1 = force the non-pipelined fallback kernel of the triangular solve (testing)  */
@@ -117,6 +117,15 @@ int rcg_profile_iteration(rcg_handle *h, int reps);
 /* Times `reps` launches of a single phase with CUDA events: 0 = SpMV, 1 = forward solve, 2 = backward solve,
  * 3 = fused vector updates.  *avg_ms receives the average duration of one phase execution. */
 int rcg_time_phase(rcg_handle *h, int phase, int reps, double *avg_ms);
+
+/* Dependency groups of a triangular solve (one per tree level; direction RCG_TRSV_FORWARD / RCG_TRSV_BACKWARD).
+ * rcg_get_group_count returns the number of groups through *count.  rcg_get_group_info fills info[0..5] =
+ * {blocks, rows, local nnz (chain kernel), external nnz (pre-pass kernel), largest block rows, largest staging group}.
+ * rcg_time_group times `reps` launches of ONE kernel of one group with CUDA events: kernel 0 = dependency-chain
+ * kernel, 1 = external (pre-pass) kernel; *avg_ms = average duration of one launch (0 if the group has no such kernel). */
+int rcg_get_group_count(rcg_handle *h, int direction, int *count);
+int rcg_get_group_info(rcg_handle *h, int direction, int group, uint64_t *info6);
+int rcg_time_group(rcg_handle *h, int direction, int group, int kernel, int reps, double *avg_ms);
 
 /* ---- diagnostics ------------------------------------------------------------------------------------- */
 /* One triangular solve with per-row tracing of the dependency-chain kernel: trace_host receives 4 uint32 per row

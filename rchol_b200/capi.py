@@ -24,6 +24,7 @@ EXPORTED = [
     "rcg_set_matrix", "rcg_set_factor", "rcg_spmv", "rcg_trsv", "rcg_precond", "rcg_pcg",
     "rcg_set_rhs", "rcg_pcg_resident", "rcg_get_solution", "rcg_get_history", "rcg_pcg_oneshot",
     "rcg_get_stats", "rcg_profile_iteration", "rcg_time_phase", "rcg_debug_trace",
+    "rcg_get_group_count", "rcg_get_group_info", "rcg_time_group",
 ]
 
 TRSV_FORWARD, TRSV_BACKWARD = 0, 1
@@ -46,6 +47,8 @@ class Stats(C.Structure):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
         d["chain_sm_mhz"] = self.reserved[0]   # SM clock seen by the last chain kernel (clock64 / globaltimer)
         d["watchdog_row"] = int(self.reserved[1])  # 1 + row whose dependency wait timed out (0 = none)
+        d["dag_levels_fwd"] = int(self.reserved[2])  # total DAG levels (sum over blocks), forward / backward solve
+        d["dag_levels_bwd"] = int(self.reserved[3])
         return d
 
 
@@ -90,6 +93,9 @@ def load():
     L.rcg_get_stats.argtypes = [H, C.POINTER(Stats)]
     L.rcg_profile_iteration.argtypes = [H, C.c_int]
     L.rcg_time_phase.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.rcg_get_group_count.argtypes = [H, C.c_int, C.POINTER(C.c_int)]
+    L.rcg_get_group_info.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    L.rcg_time_group.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.rcg_debug_trace.argtypes = [H, C.c_int, _f64p, _f64p, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
     for name in EXPORTED:
         fn = getattr(L, name)
@@ -208,6 +214,22 @@ class Solver:
     def profile_iteration(self, reps: int = 3) -> dict:
         self._check(self._L.rcg_profile_iteration(self._h, int(reps)))
         return self.stats()
+
+    def groups(self, direction: int):
+        """Dependency groups (tree levels) of one solve direction: list of dicts."""
+        n = C.c_int(0)
+        self._check(self._L.rcg_get_group_count(self._h, int(direction), C.byref(n)))
+        out = []
+        for g in range(n.value):
+            info = (C.c_uint64 * 6)()
+            self._check(self._L.rcg_get_group_info(self._h, int(direction), g, info))
+            out.append(dict(blocks=info[0], rows=info[1], loc_nnz=info[2], ext_nnz=info[3], max_rows=info[4], max_stage=info[5]))
+        return out
+
+    def time_group(self, direction: int, group: int, kernel: int, reps: int = 3) -> float:
+        ms = C.c_double(0)
+        self._check(self._L.rcg_time_group(self._h, int(direction), int(group), int(kernel), int(reps), C.byref(ms)))
+        return ms.value
 
     def debug_trace(self, which: int, rhs):
         out = np.empty(self.N, np.float64)

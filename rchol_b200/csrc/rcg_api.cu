@@ -30,7 +30,9 @@ int ensure_vectors(rcg_handle *h) {
   }
   h->reduce_grid = h->sm_count * 8;
   h->partial_cap = h->reduce_grid;
-  RCG_CUDA(h, cudaMalloc(&h->partials, sizeof(double) * (2 * (size_t)h->partial_cap + (size_t)h->n_blocks + 8)));
+  h->rz_slots = h->haveG ? rcg_post_slots(h, h->bwd, nullptr) : 0;
+  RCG_CUDA(h, cudaMalloc(&h->partials, sizeof(double) * (2 * (size_t)h->partial_cap + (size_t)h->rz_slots + 8)));
+  RCG_CUDA(h, cudaMemsetAsync(h->partials, 0, sizeof(double) * (2 * (size_t)h->partial_cap + (size_t)h->rz_slots + 8), h->stream));
   RCG_CUDA(h, cudaMalloc(&h->counters, sizeof(unsigned int) * 8));
   RCG_CUDA(h, cudaMemsetAsync(h->counters, 0, sizeof(unsigned int) * 8, h->stream));
   RCG_CUDA(h, cudaMalloc(&h->clk_probe, sizeof(unsigned long long) * 4));
@@ -386,6 +388,44 @@ int rcg_time_phase(rcg_handle *h, int phase, int reps, double *avg_ms) {
   RCG_TRY(once());   // warm-up
   RCG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < reps; i++) RCG_TRY(once());
+  RCG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  RCG_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *avg_ms = ms / reps;
+  return RCG_OK;
+}
+
+int rcg_get_group_count(rcg_handle *h, int direction, int *count) {
+  if (!h || !count) return RCG_ERR_INVALID;
+  if (!h->haveG) { h->err = "rcg_set_factor has not been called"; return RCG_ERR_STATE; }
+  *count = (int)(direction == RCG_TRSV_FORWARD ? h->fwd : h->bwd).groups.size();
+  return RCG_OK;
+}
+
+int rcg_get_group_info(rcg_handle *h, int direction, int group, uint64_t *info6) {
+  if (!h || !info6) return RCG_ERR_INVALID;
+  if (!h->haveG) { h->err = "rcg_set_factor has not been called"; return RCG_ERR_STATE; }
+  const DirectionDev &d = direction == RCG_TRSV_FORWARD ? h->fwd : h->bwd;
+  if (group < 0 || group >= (int)d.groups.size()) { h->err = "group out of range"; return RCG_ERR_INVALID; }
+  const GroupHost &g = d.groups[group];
+  info6[0] = (uint64_t)g.count; info6[1] = (uint64_t)g.rows; info6[2] = (uint64_t)g.loc_nnz;
+  info6[3] = (uint64_t)g.ext_nnz; info6[4] = g.max_rows; info6[5] = g.max_stage;
+  return RCG_OK;
+}
+
+int rcg_time_group(rcg_handle *h, int direction, int group, int kernel, int reps, double *avg_ms) {
+  RCG_TRY(require(h, false, true));
+  if (reps < 1 || !avg_ms || kernel < 0 || kernel > 2) { h->err = "bad arguments"; return RCG_ERR_INVALID; }
+  DirectionDev &d = direction == RCG_TRSV_FORWARD ? h->fwd : h->bwd;
+  if (group < 0 || group >= (int)d.groups.size()) { h->err = "group out of range"; return RCG_ERR_INVALID; }
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  *avg_ms = 0.0;
+  const double *rhs = direction == RCG_TRSV_FORWARD ? h->r : h->y;
+  double *out = direction == RCG_TRSV_FORWARD ? h->y : h->z;
+  RCG_TRY(rcg_launch_trisolve(h, d, rhs, out, nullptr, group, kernel));   // warm-up
+  RCG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < reps; i++) RCG_TRY(rcg_launch_trisolve(h, d, rhs, out, nullptr, group, kernel));
   RCG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   float ms = 0.f;

@@ -51,7 +51,10 @@ struct GroupHost {
 };
 
 struct DirectionDev {          // one solve direction
-  LowerTriDev M;
+  LowerTriDev M;               // rows in LEVEL SPACE: inside every block sorted by (DAG level, row); loc columns are
+                               // block-relative level-space positions, ext columns are vector-space indices
+  uint32_t *vecidx = nullptr;  // N: vector-space index of level-space row v (folds the backward solve's reversal)
+  double *w = nullptr;         // N+2: level-space work vector (start vector in, solution out)
   BlockDesc *blocks = nullptr; // device, ordered by group
   std::vector<BlockDesc> blocks_host;
   std::vector<GroupHost> groups;
@@ -92,6 +95,7 @@ struct rcg_handle {
   double *partials = nullptr;           // reduction scratch: [0,P) slot A, [P,2P) slot B, then rz partials
   unsigned int *counters = nullptr;     // last-block-done counters
   int partial_cap = 0;                  // P
+  int rz_slots = 0;                     // per-CTA partials of the backward solve's fused r.z
   int reduce_grid = 0;                  // CTAs of the grid-stride vector kernels
 
   uint32_t *trace = nullptr;                 // diagnostics: per-row timing trace of the chain kernel (rcg_debug_trace)
@@ -134,7 +138,12 @@ void rcg_free_csr(CsrDev &a);
 
 // rcg_kernels.cu  (all launches go to h->stream and bump h->stats.kernel_launches)
 int rcg_launch_spmv(rcg_handle *h, const double *x, double *y, const double *dot_r /*nullable*/, bool with_dots);
-int rcg_launch_trisolve(rcg_handle *h, DirectionDev &d, const double *rhs, double *out, const double *dotvec);
+// rcg_trisolve.cu
+int rcg_launch_trisolve(rcg_handle *h, DirectionDev &d, const double *rhs, double *out, const double *dotvec,
+                        int only_group = -1, int only_kernel = -1);
+int rcg_post_slots(const rcg_handle *h, const DirectionDev &d, std::vector<int> *first_slot);
+int rcg_compute_levels(rcg_handle *h, const CsrDev &loc, const BlockDesc *blocks_dev, const std::vector<GroupHost> &groups,
+                       double *w);
 int rcg_launch_p_update(rcg_handle *h);
 int rcg_launch_xr_update(rcg_handle *h);
 int rcg_launch_init_solve(rcg_handle *h);

@@ -271,7 +271,7 @@ constexpr int SORT_SMALL = 64;
 
 // thread-per-row insertion sort (rows arrive nearly sorted because U rows are scattered in ascending order);
 // longer rows are appended to `long_rows` for the block-wide bitonic sort.
-__global__ void k_sort_rows_small(const int64_t *__restrict__ rp, uint32_t *__restrict__ col, double *__restrict__ val,
+__global__ void k_sort_rows_small(const int64_t *__restrict__ rp, uint32_t *__restrict__ col, double *val,
                                   uint32_t N, uint32_t *__restrict__ long_rows, unsigned int *n_long) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t stride = gridDim.x * blockDim.x;
@@ -285,22 +285,22 @@ __global__ void k_sort_rows_small(const int64_t *__restrict__ rp, uint32_t *__re
     }
     for (int a = 1; a < len; a++) {
       uint32_t kc = col[s + a];
-      double kv = val[s + a];
+      double kv = val ? val[s + a] : 0.0;
       int b = a - 1;
       while (b >= 0 && col[s + b] > kc) {
         col[s + b + 1] = col[s + b];
-        val[s + b + 1] = val[s + b];
+        if (val) val[s + b + 1] = val[s + b];
         b--;
       }
       col[s + b + 1] = kc;
-      val[s + b + 1] = kv;
+      if (val) val[s + b + 1] = kv;
     }
   }
 }
 
 // CTA-per-row bitonic sort of (col, val) pairs.  Rows up to `smem_cap` entries are sorted in shared memory,
 // longer ones in place in global memory through a padded scratch area.
-__global__ void k_sort_rows_bitonic(const int64_t *__restrict__ rp, uint32_t *__restrict__ col, double *__restrict__ val,
+__global__ void k_sort_rows_bitonic(const int64_t *__restrict__ rp, uint32_t *__restrict__ col, double *val,
                                     const uint32_t *__restrict__ long_rows, int smem_cap, uint32_t *__restrict__ gkeys,
                                     double *__restrict__ gvals, int64_t gstride) {
   extern __shared__ unsigned char sm_raw[];
@@ -320,7 +320,7 @@ __global__ void k_sort_rows_bitonic(const int64_t *__restrict__ rp, uint32_t *__
   }
   for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     keys[i] = i < len ? col[s + i] : 0xFFFFFFFFu;
-    vals[i] = i < len ? val[s + i] : 0.0;
+    vals[i] = (i < len && val) ? val[s + i] : 0.0;
   }
   __syncthreads();
   for (int k = 2; k <= n2; k <<= 1) {
@@ -341,8 +341,65 @@ __global__ void k_sort_rows_bitonic(const int64_t *__restrict__ rp, uint32_t *__
   }
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
     col[s + i] = keys[i];
-    val[s + i] = vals[i];
+    if (val) val[s + i] = vals[i];
   }
+}
+
+// Sorts every segment [rp[i], rp[i+1]) of (key[, val]) ascending by key: thread per short segment, CTA-wide bitonic
+// sort for long ones.  Used for the rows of L = U^T, for the level segments and for the level-space rows.
+int sort_segments(rcg_handle *h, const int64_t *rp, uint32_t *key, double *val, uint32_t nseg) {
+  uint32_t *long_rows = nullptr;
+  unsigned int *n_long = nullptr;
+  RCG_CUDA(h, cudaMalloc(&long_rows, sizeof(uint32_t) * std::max<uint32_t>(nseg, 1)));
+  RCG_CUDA(h, cudaMalloc(&n_long, sizeof(unsigned int)));
+  RCG_CUDA(h, cudaMemsetAsync(n_long, 0, sizeof(unsigned int), h->stream));
+  k_sort_rows_small<<<grid_for(h, nseg, 128), 128, 0, h->stream>>>(rp, key, val, nseg, long_rows, n_long);
+  h->stats.kernel_launches += 1;
+  unsigned int hn_long = 0;
+  RCG_CUDA(h, cudaMemcpyAsync(&hn_long, n_long, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (hn_long > 0) {
+    const int smem_cap = 8192;                      // entries: 8192 * 12 B = 96 KB of shared memory
+    const size_t smem_bytes = (size_t)smem_cap * 12;
+    RCG_CUDA(h, cudaFuncSetAttribute(k_sort_rows_bitonic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    std::vector<uint32_t> lr(hn_long);
+    RCG_CUDA(h, cudaMemcpy(lr.data(), long_rows, sizeof(uint32_t) * hn_long, cudaMemcpyDeviceToHost));
+    std::sort(lr.begin(), lr.end());   // deterministic processing order
+    RCG_CUDA(h, cudaMemcpy(long_rows, lr.data(), sizeof(uint32_t) * hn_long, cudaMemcpyHostToDevice));
+    int64_t maxlen = 0;
+    {
+      std::vector<int64_t> all;
+      if (hn_long > 4096) {
+        all.resize((size_t)nseg + 1);
+        RCG_CUDA(h, cudaMemcpy(all.data(), rp, sizeof(int64_t) * ((size_t)nseg + 1), cudaMemcpyDeviceToHost));
+        for (uint32_t r : lr) maxlen = std::max(maxlen, all[r + 1] - all[r]);
+      } else {
+        int64_t rp2[2];
+        for (uint32_t r : lr) {
+          RCG_CUDA(h, cudaMemcpy(rp2, rp + r, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost));
+          maxlen = std::max(maxlen, rp2[1] - rp2[0]);
+        }
+      }
+    }
+    int64_t gstride = 0;
+    uint32_t *gkeys = nullptr;
+    double *gvals = nullptr;
+    if (maxlen > smem_cap) {
+      gstride = 1;
+      while (gstride < maxlen) gstride <<= 1;
+      // process the long segments in batches so that the padded scratch area stays bounded (<= 1 GiB)
+      RCG_CUDA(h, cudaMalloc(&gkeys, sizeof(uint32_t) * (size_t)gstride * hn_long));
+      RCG_CUDA(h, cudaMalloc(&gvals, sizeof(double) * (size_t)gstride * hn_long));
+    }
+    k_sort_rows_bitonic<<<hn_long, 512, smem_bytes, h->stream>>>(rp, key, val, long_rows, smem_cap, gkeys, gvals, gstride);
+    h->stats.kernel_launches += 1;
+    RCG_CUDA(h, cudaGetLastError());
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(gkeys); cudaFree(gvals);
+  }
+  RCG_CUDA(h, cudaFree(long_rows));
+  RCG_CUDA(h, cudaFree(n_long));
+  return RCG_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -453,6 +510,126 @@ __global__ void k_block_stats(const int64_t *__restrict__ loc_rp, const int64_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// level space: inside every block, rows are re-stored sorted by (DAG level, row index)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_of(const uint32_t *__restrict__ bounds, int nb, uint32_t j) {
+  int lo = 0, hi = nb;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (bounds[mid] <= j) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void k_levels_to_int(const double *__restrict__ lev, uint32_t N, const uint32_t *__restrict__ bounds, int nb,
+                                uint32_t *__restrict__ ilev, unsigned int *__restrict__ blkmax) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; j < N; j += stride) {
+    const double l = lev[j];
+    const uint32_t il = (l >= 0.0 && l < 4.0e9) ? (uint32_t)l : 0u;   // NaN (watchdog) -> level 0; caught by validation
+    ilev[j] = il;
+    atomicMax(&blkmax[block_of(bounds, nb, j)], il);
+  }
+}
+
+// histogram of (block, level) and, second use, stable-by-sort placement of the rows into their level segment
+__global__ void k_level_count(const uint32_t *__restrict__ ilev, uint32_t N, const uint32_t *__restrict__ bounds, int nb,
+                              const int64_t *__restrict__ lvl_off, int64_t *__restrict__ cnt) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; j < N; j += stride)
+    atomicAdd((unsigned long long *)&cnt[lvl_off[block_of(bounds, nb, j)] + ilev[j]], 1ull);
+}
+__global__ void k_level_place(const uint32_t *__restrict__ ilev, uint32_t N, const uint32_t *__restrict__ bounds, int nb,
+                              const int64_t *__restrict__ lvl_off, int64_t *__restrict__ cursor, uint32_t *__restrict__ perm) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; j < N; j += stride) {
+    const int64_t pos = (int64_t)atomicAdd((unsigned long long *)&cursor[lvl_off[block_of(bounds, nb, j)] + ilev[j]], 1ull);
+    perm[pos] = j;
+  }
+}
+__global__ void k_invert_perm(const uint32_t *__restrict__ perm, uint32_t N, uint32_t *__restrict__ inv,
+                              uint32_t *__restrict__ vecidx, int reversed) {
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; v < N; v += stride) {
+    const uint32_t j = perm[v];
+    inv[j] = v;
+    vecidx[v] = reversed ? N - 1 - j : j;
+  }
+}
+// Row lengths of the level-space matrices.  Every ND block is cut into segments of `seg` level-space rows (the
+// chain kernel's solution window covers one segment); a local entry whose column falls into an EARLIER segment of
+// the block becomes an external entry (its row is solved by an earlier launch), so that the chain kernel never has to
+// read a column older than its window.
+__global__ void k_perm_count(const int64_t *__restrict__ lrp, const uint32_t *__restrict__ lcol, const int64_t *__restrict__ erp,
+                             const uint32_t *__restrict__ perm, const uint32_t *__restrict__ inv, uint32_t N,
+                             const uint32_t *__restrict__ bounds, int nb, uint32_t seg, int64_t *__restrict__ nl_out,
+                             int64_t *__restrict__ ne_out) {
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; v < N; v += stride) {
+    const uint32_t j = perm[v];
+    const uint32_t blo = bounds[block_of(bounds, nb, j)];
+    const uint32_t segv = (v - blo) / seg;
+    const int64_t ls = lrp[j], le = lrp[j + 1];
+    int64_t same = 0;
+    for (int64_t k = ls; k < le; k++) same += ((inv[blo + lcol[k]] - blo) / seg == segv);
+    nl_out[v] = same;
+    ne_out[v] = (erp[j + 1] - erp[j]) + (le - ls - same);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { nl_out[N] = 0; ne_out[N] = 0; }
+}
+// Copy row perm[v] of the solve-space matrices to row v of the level-space ones.
+// loc columns: block-relative solve-space -> segment-relative level-space; ext columns: -> vector-space.
+__global__ void k_permute_rows(const int64_t *__restrict__ lrp, const uint32_t *__restrict__ lcol, const double *__restrict__ lval,
+                               const int64_t *__restrict__ erp, const uint32_t *__restrict__ ecol, const double *__restrict__ eval,
+                               const uint32_t *__restrict__ perm, const uint32_t *__restrict__ inv, uint32_t N,
+                               const uint32_t *__restrict__ bounds, int nb, uint32_t seg, int reversed,
+                               const int64_t *__restrict__ nlrp, uint32_t *__restrict__ nlcol, double *__restrict__ nlval,
+                               const int64_t *__restrict__ nerp, uint32_t *__restrict__ necol, double *__restrict__ neval) {
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; v < N; v += stride) {
+    const uint32_t j = perm[v];
+    const uint32_t blo = bounds[block_of(bounds, nb, j)];
+    const uint32_t segv = (v - blo) / seg;
+    const uint32_t seglo = blo + segv * seg;
+    int64_t ld = nlrp[v], ed = nerp[v];
+    for (int64_t k = erp[j]; k < erp[j + 1]; k++) {
+      const uint32_t c = ecol[k];
+      necol[ed] = reversed ? N - 1 - c : c;
+      neval[ed++] = eval[k];
+    }
+    const int64_t ls = lrp[j], le = lrp[j + 1];
+    const double dinv = lval[le - 1];   // diagonal slot = 1/diag; off-diagonals are stored as -v/diag
+    for (int64_t k = ls; k < le; k++) {
+      const uint32_t c = blo + lcol[k];   // solve-space column
+      const uint32_t vc = inv[c];
+      if ((vc - blo) / seg == segv) {
+        nlcol[ld] = vc - seglo;
+        nlval[ld++] = lval[k];
+      } else {
+        // earlier segment: un-scale (the pre kernel computes rhs - sum v x, the chain kernel applies 1/diag)
+        necol[ed] = reversed ? N - 1 - c : c;
+        neval[ed++] = -lval[k] / dinv;
+      }
+    }
+  }
+}
+// after sorting the level-space rows by column the diagonal (largest column) must be last
+__global__ void k_check_diag_last(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, uint32_t N,
+                                  const uint32_t *__restrict__ rbounds, int nrb, int *err) {
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; v < N; v += stride) bad |= (col[rp[v + 1] - 1] != v - rbounds[block_of(rbounds, nrb, v)]);
+  if (bad) atomicExch(err, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // nested-dissection tree from `part` (post-order: [left subtree, right subtree, separator])
 // ---------------------------------------------------------------------------------------------------------
 struct TreeInfo {
@@ -529,26 +706,31 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   rcg_free_csr(comb);
 
-  // per-block statistics
-  unsigned long long *dext = nullptr, *dloc = nullptr;
-  unsigned int *dstage = nullptr;
-  RCG_CUDA(h, cudaMalloc(&dext, sizeof(unsigned long long) * nb));
-  RCG_CUDA(h, cudaMalloc(&dloc, sizeof(unsigned long long) * nb));
-  RCG_CUDA(h, cudaMalloc(&dstage, sizeof(unsigned int) * nb));
-  RCG_CUDA(h, cudaMemsetAsync(dstage, 0, sizeof(unsigned int) * nb, h->stream));
-  k_block_stats<<<nb, 256, 0, h->stream>>>(loc.rowptr, ext.rowptr, dbounds, nb, dext, dloc, dstage);
-  h->stats.kernel_launches += 1;
+  // per-block statistics (external / local entry counts, largest 32-row staging group)
   std::vector<unsigned long long> hext(nb), hloc(nb);
   std::vector<unsigned int> hstage(nb);
-  RCG_CUDA(h, cudaMemcpyAsync(hext.data(), dext, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, h->stream));
-  RCG_CUDA(h, cudaMemcpyAsync(hloc.data(), dloc, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, h->stream));
-  RCG_CUDA(h, cudaMemcpyAsync(hstage.data(), dstage, sizeof(unsigned int) * nb, cudaMemcpyDeviceToHost, h->stream));
-  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
-  cudaFree(dext); cudaFree(dloc); cudaFree(dstage); cudaFree(dbounds);
+  auto block_stats = [&]() -> int {
+    unsigned long long *dext = nullptr, *dloc = nullptr;
+    unsigned int *dstage = nullptr;
+    RCG_CUDA(h, cudaMalloc(&dext, sizeof(unsigned long long) * nb));
+    RCG_CUDA(h, cudaMalloc(&dloc, sizeof(unsigned long long) * nb));
+    RCG_CUDA(h, cudaMalloc(&dstage, sizeof(unsigned int) * nb));
+    RCG_CUDA(h, cudaMemsetAsync(dstage, 0, sizeof(unsigned int) * nb, h->stream));
+    k_block_stats<<<nb, 256, 0, h->stream>>>(loc.rowptr, ext.rowptr, dbounds, nb, dext, dloc, dstage);
+    h->stats.kernel_launches += 1;
+    RCG_CUDA(h, cudaMemcpyAsync(hext.data(), dext, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaMemcpyAsync(hloc.data(), dloc, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaMemcpyAsync(hstage.data(), dstage, sizeof(unsigned int) * nb, cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(dext); cudaFree(dloc); cudaFree(dstage);
+    return RCG_OK;
+  };
+  RCG_TRY(block_stats());
 
   // groups: forward = deepest level first, backward (reversed space) = root first
   d.groups.clear();
   d.blocks_host.clear();
+  std::vector<int> bidx;   // bounds-order index of every entry of blocks_host
   for (int g = 0; g <= max_depth; g++) {
     const int want = root_first ? g : max_depth - g;
     GroupHost G;
@@ -558,6 +740,7 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
       BlockDesc bd{bounds_solve[b], bounds_solve[b + 1]};
       if (bd.hi == bd.lo) continue;   // empty separator
       d.blocks_host.push_back(bd);
+      bidx.push_back(b);
       G.count++;
       G.max_rows = std::max(G.max_rows, bd.hi - bd.lo);
       G.rows += bd.hi - bd.lo;
@@ -570,6 +753,160 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
   RCG_CUDA(h, cudaMalloc(&d.blocks, sizeof(BlockDesc) * std::max<size_t>(1, d.blocks_host.size())));
   RCG_CUDA(h, cudaMemcpyAsync(d.blocks, d.blocks_host.data(), sizeof(BlockDesc) * d.blocks_host.size(),
                               cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaMalloc(&d.w, sizeof(double) * ((size_t)N + 4)));
+  RCG_CUDA(h, cudaMemsetAsync(d.w, 0, sizeof(double) * ((size_t)N + 4), h->stream));
+  RCG_CUDA(h, cudaMalloc(&d.vecidx, sizeof(uint32_t) * (size_t)N));
+
+  // ---- level space ------------------------------------------------------------------------------------------
+  // 1. DAG level of every row inside its block: the chain kernel itself in MODE 1 (level = 1 + max over the row's
+  //    local columns), on the solve-space matrices.
+  RCG_TRY(rcg_compute_levels(h, loc, d.blocks, d.groups, d.w));
+  uint32_t *ilev = nullptr, *perm = nullptr, *inv = nullptr;
+  unsigned int *dblkmax = nullptr;
+  RCG_CUDA(h, cudaMalloc(&ilev, sizeof(uint32_t) * (size_t)N));
+  RCG_CUDA(h, cudaMalloc(&perm, sizeof(uint32_t) * (size_t)N));
+  RCG_CUDA(h, cudaMalloc(&inv, sizeof(uint32_t) * (size_t)N));
+  RCG_CUDA(h, cudaMalloc(&dblkmax, sizeof(unsigned int) * nb));
+  RCG_CUDA(h, cudaMemsetAsync(dblkmax, 0, sizeof(unsigned int) * nb, h->stream));
+  k_levels_to_int<<<grid_for(h, N, 256), 256, 0, h->stream>>>(d.w, N, dbounds, nb, ilev, dblkmax);
+  h->stats.kernel_launches += 1;
+  std::vector<unsigned int> blkmax(nb);
+  RCG_CUDA(h, cudaMemcpyAsync(blkmax.data(), dblkmax, sizeof(unsigned int) * nb, cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  // 2. counting sort by (block, level); rows of one level are then sorted by index, so the order is deterministic
+  std::vector<int64_t> lvl_off(nb + 1, 0);
+  for (int b = 0; b < nb; b++)
+    lvl_off[b + 1] = lvl_off[b] + (bounds_solve[b + 1] > bounds_solve[b] ? (int64_t)blkmax[b] + 1 : 0);
+  const int64_t nlev = lvl_off[nb];
+  int64_t *dlvl_off = nullptr, *lptr = nullptr, *cursor = nullptr;
+  RCG_CUDA(h, cudaMalloc(&dlvl_off, sizeof(int64_t) * (nb + 1)));
+  RCG_CUDA(h, cudaMalloc(&lptr, sizeof(int64_t) * ((size_t)nlev + 1)));
+  RCG_CUDA(h, cudaMalloc(&cursor, sizeof(int64_t) * ((size_t)nlev + 1)));
+  RCG_CUDA(h, cudaMemcpyAsync(dlvl_off, lvl_off.data(), sizeof(int64_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaMemsetAsync(lptr, 0, sizeof(int64_t) * ((size_t)nlev + 1), h->stream));
+  k_level_count<<<grid_for(h, N, 256), 256, 0, h->stream>>>(ilev, N, dbounds, nb, dlvl_off, lptr);
+  h->stats.kernel_launches += 1;
+  RCG_TRY(exclusive_scan_inplace(h, lptr, nlev + 1));
+  RCG_CUDA(h, cudaMemcpyAsync(cursor, lptr, sizeof(int64_t) * ((size_t)nlev + 1), cudaMemcpyDeviceToDevice, h->stream));
+  k_level_place<<<grid_for(h, N, 256), 256, 0, h->stream>>>(ilev, N, dbounds, nb, dlvl_off, cursor, perm);
+  h->stats.kernel_launches += 1;
+  RCG_TRY(sort_segments(h, lptr, perm, nullptr, (uint32_t)nlev));
+  k_invert_perm<<<grid_for(h, N, 256), 256, 0, h->stream>>>(perm, N, inv, d.vecidx, d.reversed ? 1 : 0);
+  h->stats.kernel_launches += 1;
+  h->stats.reserved[root_first ? 3 : 2] = (double)nlev;   // total DAG levels of the direction (sum over blocks)
+  cudaFree(dlvl_off); cudaFree(lptr); cudaFree(cursor); cudaFree(ilev); cudaFree(dblkmax);
+  // 3. level-space matrices, with every block cut into window-sized segments
+  uint32_t seg = 1;
+  {
+    const uint32_t cw = h->opt.chain_window > 0 ? (uint32_t)h->opt.chain_window : 2048u;
+    while ((seg << 1) <= cw && (seg << 1) != 0) seg <<= 1;
+    seg = std::max(64u, seg * 2u);   // one segment = the chain kernel's window (current + previous chunk)
+  }
+  CsrDev nloc, next;
+  RCG_CUDA(h, cudaMalloc(&nloc.rowptr, sizeof(int64_t) * ((size_t)N + 4)));
+  RCG_CUDA(h, cudaMalloc(&next.rowptr, sizeof(int64_t) * ((size_t)N + 4)));
+  RCG_CUDA(h, cudaMemsetAsync(nloc.rowptr, 0, sizeof(int64_t) * ((size_t)N + 4), h->stream));
+  RCG_CUDA(h, cudaMemsetAsync(next.rowptr, 0, sizeof(int64_t) * ((size_t)N + 4), h->stream));
+  k_perm_count<<<grid_for(h, N, 256), 256, 0, h->stream>>>(loc.rowptr, loc.col, ext.rowptr, perm, inv, N, dbounds, nb, seg,
+                                                          nloc.rowptr, next.rowptr);
+  h->stats.kernel_launches += 1;
+  RCG_TRY(exclusive_scan_inplace(h, nloc.rowptr, (int64_t)N + 1));
+  RCG_TRY(exclusive_scan_inplace(h, next.rowptr, (int64_t)N + 1));
+  int64_t nl_total = 0, ne_total = 0;
+  RCG_CUDA(h, cudaMemcpy(&nl_total, nloc.rowptr + N, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  RCG_CUDA(h, cudaMemcpy(&ne_total, next.rowptr + N, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  RCG_TRY(alloc_csr(h, nloc, N, nl_total, false));
+  RCG_TRY(alloc_csr(h, next, N, ne_total, false));
+  k_permute_rows<<<grid_for(h, N, 256), 256, 0, h->stream>>>(loc.rowptr, loc.col, loc.val, ext.rowptr, ext.col, ext.val, perm,
+                                                            inv, N, dbounds, nb, seg, d.reversed ? 1 : 0, nloc.rowptr,
+                                                            nloc.col, nloc.val, next.rowptr, next.col, next.val);
+  h->stats.kernel_launches += 1;
+  RCG_CUDA(h, cudaGetLastError());
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  rcg_free_csr(loc);
+  rcg_free_csr(ext);
+  cudaFree(perm); cudaFree(inv);
+  loc = nloc;
+  ext = next;
+  RCG_TRY(sort_segments(h, loc.rowptr, loc.col, loc.val, N));
+
+  // 4. refined blocks (one per segment) and dependency groups: tree level by tree level, segment by segment
+  std::vector<uint32_t> rbounds;      // ascending boundaries of the refined blocks (level space)
+  std::vector<int> r_parent, r_segidx;
+  for (int b = 0; b < nb; b++) {
+    const uint32_t lo = bounds_solve[b], hi = bounds_solve[b + 1];
+    int k = 0;
+    for (uint32_t s0 = lo; s0 < hi; s0 += seg, k++) {
+      rbounds.push_back(s0);
+      r_parent.push_back(b);
+      r_segidx.push_back(k);
+    }
+  }
+  rbounds.push_back(N);
+  const int nrb = (int)rbounds.size() - 1;
+  cudaFree(dbounds);
+  RCG_CUDA(h, cudaMalloc(&dbounds, sizeof(uint32_t) * (nrb + 1)));
+  RCG_CUDA(h, cudaMemcpyAsync(dbounds, rbounds.data(), sizeof(uint32_t) * (nrb + 1), cudaMemcpyHostToDevice, h->stream));
+  {
+    int *derr2 = nullptr, herr2 = 0;
+    RCG_CUDA(h, cudaMalloc(&derr2, sizeof(int)));
+    RCG_CUDA(h, cudaMemsetAsync(derr2, 0, sizeof(int), h->stream));
+    k_check_diag_last<<<grid_for(h, N, 256), 256, 0, h->stream>>>(loc.rowptr, loc.col, N, dbounds, nrb, derr2);
+    h->stats.kernel_launches += 1;
+    RCG_CUDA(h, cudaMemcpyAsync(&herr2, derr2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(derr2);
+    if (herr2) {
+      h->err = "internal error: level ordering is not a topological order of the factor's dependency graph";
+      return RCG_ERR_STRUCTURE;
+    }
+  }
+  std::vector<unsigned long long> rext(nrb), rloc(nrb);
+  std::vector<unsigned int> rstage(nrb);
+  {
+    unsigned long long *dext = nullptr, *dloc = nullptr;
+    unsigned int *dstage = nullptr;
+    RCG_CUDA(h, cudaMalloc(&dext, sizeof(unsigned long long) * nrb));
+    RCG_CUDA(h, cudaMalloc(&dloc, sizeof(unsigned long long) * nrb));
+    RCG_CUDA(h, cudaMalloc(&dstage, sizeof(unsigned int) * nrb));
+    RCG_CUDA(h, cudaMemsetAsync(dstage, 0, sizeof(unsigned int) * nrb, h->stream));
+    k_block_stats<<<nrb, 256, 0, h->stream>>>(loc.rowptr, ext.rowptr, dbounds, nrb, dext, dloc, dstage);
+    h->stats.kernel_launches += 1;
+    RCG_CUDA(h, cudaMemcpyAsync(rext.data(), dext, sizeof(unsigned long long) * nrb, cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaMemcpyAsync(rloc.data(), dloc, sizeof(unsigned long long) * nrb, cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaMemcpyAsync(rstage.data(), dstage, sizeof(unsigned int) * nrb, cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(dext); cudaFree(dloc); cudaFree(dstage);
+  }
+  std::vector<GroupHost> tree_groups;
+  tree_groups.swap(d.groups);
+  d.blocks_host.clear();
+  for (int g = 0; g <= max_depth; g++) {
+    const int want = root_first ? g : max_depth - g;
+    for (int k = 0;; k++) {        // segment index
+      GroupHost G;
+      G.first = (int)d.blocks_host.size();
+      for (int rb = 0; rb < nrb; rb++) {
+        if (r_segidx[rb] != k || depth_solve[r_parent[rb]] != want) continue;
+        BlockDesc bd{rbounds[rb], rbounds[rb + 1]};
+        d.blocks_host.push_back(bd);
+        G.count++;
+        G.max_rows = std::max(G.max_rows, bd.hi - bd.lo);
+        G.rows += bd.hi - bd.lo;
+        G.ext_nnz += (int64_t)rext[rb];
+        G.loc_nnz += (int64_t)rloc[rb];
+        G.max_stage = std::max(G.max_stage, rstage[rb]);
+      }
+      if (G.count == 0) break;
+      d.groups.push_back(G);
+    }
+  }
+  cudaFree(d.blocks);
+  d.blocks = nullptr;
+  RCG_CUDA(h, cudaMalloc(&d.blocks, sizeof(BlockDesc) * std::max<size_t>(1, d.blocks_host.size())));
+  RCG_CUDA(h, cudaMemcpyAsync(d.blocks, d.blocks_host.data(), sizeof(BlockDesc) * d.blocks_host.size(),
+                              cudaMemcpyHostToDevice, h->stream));
+  cudaFree(dbounds);
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   return RCG_OK;
 }
@@ -584,6 +921,8 @@ void rcg_free_direction(DirectionDev &d) {
   rcg_free_csr(d.M.loc);
   rcg_free_csr(d.M.ext);
   cudaFree(d.blocks);
+  cudaFree(d.vecidx);
+  cudaFree(d.w);
   d = DirectionDev();
 }
 
@@ -692,62 +1031,8 @@ int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const ui
     k_scatter_transpose<<<grid_for(h, (int64_t)N * 8, 256), 256, 0, h->stream>>>(U.rowptr, U.col, U.val, n32, cursor,
                                                                                L.col, L.val);
     h->stats.kernel_launches += 1;
-    uint32_t *long_rows = nullptr;
-    unsigned int *n_long = nullptr;
-    RCG_CUDA(h, cudaMalloc(&long_rows, sizeof(uint32_t) * N));
-    RCG_CUDA(h, cudaMalloc(&n_long, sizeof(unsigned int)));
-    RCG_CUDA(h, cudaMemsetAsync(n_long, 0, sizeof(unsigned int), h->stream));
-    k_sort_rows_small<<<grid_for(h, n32, 128), 128, 0, h->stream>>>(L.rowptr, L.col, L.val, n32, long_rows, n_long);
-    h->stats.kernel_launches += 1;
-    unsigned int hn_long = 0;
-    RCG_CUDA(h, cudaMemcpyAsync(&hn_long, n_long, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (hn_long > 0) {
-      // longest row decides whether a global scratch area is needed
-      const int smem_cap = 8192;                      // entries: 8192 * 12 B = 96 KB of shared memory
-      const size_t smem_bytes = (size_t)smem_cap * 12;
-      RCG_CUDA(h, cudaFuncSetAttribute(k_sort_rows_bitonic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      // find the longest row on the host side from the row pointers of the long rows
-      std::vector<uint32_t> lr(hn_long);
-      RCG_CUDA(h, cudaMemcpy(lr.data(), long_rows, sizeof(uint32_t) * hn_long, cudaMemcpyDeviceToHost));
-      std::sort(lr.begin(), lr.end());   // deterministic processing order
-      RCG_CUDA(h, cudaMemcpy(long_rows, lr.data(), sizeof(uint32_t) * hn_long, cudaMemcpyHostToDevice));
-      int64_t maxlen = 0;
-      {
-        // read the two row pointers of every long row (a few thousand rows at most in practice)
-        std::vector<int64_t> rp2(2);
-        // cheaper: fetch the whole rowptr only when many long rows exist
-        std::vector<int64_t> all;
-        if (hn_long > 4096) {
-          all.resize(N + 1);
-          RCG_CUDA(h, cudaMemcpy(all.data(), L.rowptr, sizeof(int64_t) * (N + 1), cudaMemcpyDeviceToHost));
-          for (uint32_t r : lr) maxlen = std::max(maxlen, all[r + 1] - all[r]);
-        } else {
-          for (uint32_t r : lr) {
-            RCG_CUDA(h, cudaMemcpy(rp2.data(), L.rowptr + r, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost));
-            maxlen = std::max(maxlen, rp2[1] - rp2[0]);
-          }
-        }
-      }
-      int64_t gstride = 0;
-      uint32_t *gkeys = nullptr;
-      double *gvals = nullptr;
-      if (maxlen > smem_cap) {
-        gstride = 1;
-        while (gstride < maxlen) gstride <<= 1;
-        RCG_CUDA(h, cudaMalloc(&gkeys, sizeof(uint32_t) * (size_t)gstride * hn_long));
-        RCG_CUDA(h, cudaMalloc(&gvals, sizeof(double) * (size_t)gstride * hn_long));
-      }
-      k_sort_rows_bitonic<<<hn_long, 512, smem_bytes, h->stream>>>(L.rowptr, L.col, L.val, long_rows, smem_cap, gkeys,
-                                                                  gvals, gstride);
-      h->stats.kernel_launches += 1;
-      RCG_CUDA(h, cudaGetLastError());
-      RCG_CUDA(h, cudaStreamSynchronize(h->stream));
-      cudaFree(gkeys); cudaFree(gvals);
-    }
+    RCG_TRY(sort_segments(h, L.rowptr, L.col, L.val, n32));
     RCG_CUDA(h, cudaFree(cursor));
-    RCG_CUDA(h, cudaFree(long_rows));
-    RCG_CUDA(h, cudaFree(n_long));
   }
 
   // ---- backward direction: reversed U ------------------------------------------------------------------
