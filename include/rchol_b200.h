@@ -47,7 +47,8 @@ typedef struct rcg_options {
   int use_graph;           /* 1 = replay one CUDA graph per PCG iteration (default), 0 = plain launches   */
   int spmv_lanes;          /* lanes per row of the CSR SpMV (0 = choose from the row-length histogram)     */
   int chain_generic;       /* 1 = force the non-pipelined fallback kernel of the triangular solve (testing)  */
-  int reserved[11];
+  int chain_mode;          /* 0/1 = sync-free polling kernel (default), 2 = role-specialised kernel (experimental) */
+  int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2) */
 } rcg_options;
 
 /* Per-handle measurements, all device-side times from CUDA events on the handle's own stream. */

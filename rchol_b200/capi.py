@@ -32,7 +32,7 @@ TRSV_FORWARD, TRSV_BACKWARD = 0, 1
 
 class Options(C.Structure):
     _fields_ = [("chain_threads", C.c_int), ("chain_window", C.c_int), ("use_graph", C.c_int),
-                ("spmv_lanes", C.c_int), ("chain_generic", C.c_int), ("reserved", C.c_int * 11)]
+                ("spmv_lanes", C.c_int), ("chain_generic", C.c_int), ("chain_mode", C.c_int), ("reserved", C.c_int * 10)]
 
 
 class Stats(C.Structure):
@@ -49,6 +49,7 @@ class Stats(C.Structure):
         d["watchdog_row"] = int(self.reserved[1])  # 1 + row whose dependency wait timed out (0 = none)
         d["dag_levels_fwd"] = int(self.reserved[2])  # total DAG levels (sum over blocks), forward / backward solve
         d["dag_levels_bwd"] = int(self.reserved[3])
+        d["crit_cycles"] = dict(wait=self.reserved[4], prologue=self.reserved[5], batches=self.reserved[6], n_batch=self.reserved[7])
         return d
 
 
@@ -117,13 +118,17 @@ class Solver:
     """Handle-based interface: upload A and G once, then call the kernels or the PCG solve."""
 
     def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
-                 spmv_lanes: int = 0, chain_generic: bool = False):
+                 spmv_lanes: int = 0, chain_generic: bool = False, chain_mode: int = 0, backoff_ns: int = 0, dbg: int = 0, producers: int = 0):
         self._L = load()
         self._h = C.c_void_p()
         opt = Options()
         opt.chain_threads, opt.chain_window = int(chain_threads), int(chain_window)
         opt.use_graph, opt.spmv_lanes = int(bool(use_graph)), int(spmv_lanes)
         opt.chain_generic = int(bool(chain_generic))
+        opt.chain_mode = int(chain_mode)
+        opt.reserved[0] = int(backoff_ns)
+        opt.reserved[1] = int(dbg)
+        opt.reserved[2] = int(producers)
         rc = self._L.rcg_create_with_options(C.byref(self._h), int(device), C.byref(opt))
         if rc != 0:
             raise RcgError(rc, (self._L.rcg_last_error(None) or b"").decode())

@@ -35,8 +35,8 @@ int ensure_vectors(rcg_handle *h) {
   RCG_CUDA(h, cudaMemsetAsync(h->partials, 0, sizeof(double) * (2 * (size_t)h->partial_cap + (size_t)h->rz_slots + 8), h->stream));
   RCG_CUDA(h, cudaMalloc(&h->counters, sizeof(unsigned int) * 8));
   RCG_CUDA(h, cudaMemsetAsync(h->counters, 0, sizeof(unsigned int) * 8, h->stream));
-  RCG_CUDA(h, cudaMalloc(&h->clk_probe, sizeof(unsigned long long) * 4));
-  RCG_CUDA(h, cudaMemsetAsync(h->clk_probe, 0, sizeof(unsigned long long) * 4, h->stream));
+  RCG_CUDA(h, cudaMalloc(&h->clk_probe, sizeof(unsigned long long) * 8));
+  RCG_CUDA(h, cudaMemsetAsync(h->clk_probe, 0, sizeof(unsigned long long) * 8, h->stream));
   RCG_CUDA(h, cudaMalloc(&h->scal, sizeof(PcgScalars)));
   RCG_CUDA(h, cudaMemsetAsync(h->scal, 0, sizeof(PcgScalars), h->stream));
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -364,10 +364,13 @@ int rcg_get_stats(rcg_handle *h, rcg_stats *out) {
   if (h->b) dev += sizeof(double) * h->N * 8;
   out->device_bytes = dev;
   if (h->clk_probe) {
-    unsigned long long ck[4] = {0, 0, 0, 0};
+    unsigned long long ck[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (cudaMemcpy(ck, h->clk_probe, sizeof(ck), cudaMemcpyDeviceToHost) == cudaSuccess && ck[1] > 0)
       out->reserved[0] = (double)ck[0] / (double)ck[1] * 1000.0;   // SM MHz seen by the last chain kernel
     out->reserved[1] = (double)ck[2];                              // 1 + row of a dependency-wait time-out (0 = none)
+    for (int i = 0; i < 4; i++) out->reserved[4 + i] = (double)ck[3 + i];   // diagnostics of the critical warp (cycles)
+    h->dbg_nbatch = (double)ck[7];
+    out->kernel_launches = out->kernel_launches;
   }
   return RCG_OK;
 }

@@ -34,8 +34,10 @@ struct LowerTriDev {
   CsrDev ext;
 };
 
-struct BlockDesc {             // rows [lo, hi) of one nested-dissection block, in solve index space
+struct BlockDesc {             // rows [lo, hi) of one block (a window-sized segment of a nested-dissection block)
   uint32_t lo, hi;
+  uint32_t grp0;               // index of the block's first 32-row group in DirectionDev::grp_mask
+  uint32_t pad;
 };
 
 // One dependency group of blocks: all blocks of one tree depth.  Blocks of group g depend only on blocks of
@@ -55,6 +57,7 @@ struct DirectionDev {          // one solve direction
                                // block-relative level-space positions, ext columns are vector-space indices
   uint32_t *vecidx = nullptr;  // N: vector-space index of level-space row v (folds the backward solve's reversal)
   double *w = nullptr;         // N+2: level-space work vector (start vector in, solution out)
+  uint32_t *grp_mask = nullptr; // per 32-row group of a block: bit l set <=> row l of the group starts a new DAG level
   BlockDesc *blocks = nullptr; // device, ordered by group
   std::vector<BlockDesc> blocks_host;
   std::vector<GroupHost> groups;
@@ -103,6 +106,7 @@ struct rcg_handle {
   cudaGraphExec_t iter_graph = nullptr;
   std::vector<double> history;
 
+  double dbg_nbatch = 0;
   rcg_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };

@@ -619,6 +619,51 @@ __global__ void k_permute_rows(const int64_t *__restrict__ lrp, const uint32_t *
     }
   }
 }
+__global__ void k_gather_u32(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t n,
+                             uint32_t *__restrict__ dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = src[idx[i]];
+}
+// one thread per 32-row group: bit l of the mask is set when row l of the group starts a new DAG level
+// (bit 0 always: a batch of the critical warp never crosses a group boundary)
+__global__ void k_group_masks(const uint32_t *__restrict__ lvl, const uint32_t *__restrict__ rbounds, int nrb,
+                              const uint32_t *__restrict__ grp0, uint32_t ngrp, uint32_t *__restrict__ mask) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; g < ngrp; g += stride) {
+    int lo = 0, hi = nrb;                      // refined block of the group: largest rb with grp0[rb] <= g
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (grp0[mid] <= g) lo = mid; else hi = mid;
+    }
+    const uint32_t j0 = rbounds[lo] + 32u * (g - grp0[lo]);
+    const uint32_t nr = min(32u, rbounds[lo + 1] - j0);
+    uint32_t m = 1u;
+    for (uint32_t l = 1; l < nr; l++)
+      if (lvl[j0 + l] != lvl[j0 + l - 1]) m |= (1u << l);
+    mask[g] = m;
+  }
+}
+// Number of trailing off-diagonal entries of every level-space row whose column lies within the last `K` DAG
+// levels (at most RCG_NEAR_MAX): these "near" entries are applied by the critical warp of k_tri_chain_lv, everything
+// older by the helper warps.  The count is packed into bits 28..31 of the diagonal slot's column entry.
+__global__ void k_pack_near(const int64_t *__restrict__ rp, uint32_t *__restrict__ col, const uint32_t *__restrict__ lvl,
+                            uint32_t N, const uint32_t *__restrict__ rbounds, int nrb, uint32_t K, uint32_t nmax) {
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; v < N; v += stride) {
+    const uint32_t lo = rbounds[block_of(rbounds, nrb, v)];
+    const uint32_t lv = lvl[v];
+    const int64_t s = rp[v], d = rp[v + 1] - 1;
+    uint32_t nn = 0;
+    for (int64_t k = d - 1; k >= s && nn < nmax; k--) {
+      if (lvl[lo + col[k]] + K < lv) break;
+      nn++;
+    }
+    col[d] = (col[d] & 0x0FFFFFFFu) | (nn << 28);
+  }
+}
 // after sorting the level-space rows by column the diagonal (largest column) must be last
 __global__ void k_check_diag_last(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, uint32_t N,
                                   const uint32_t *__restrict__ rbounds, int nrb, int *err) {
@@ -794,7 +839,7 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
   k_invert_perm<<<grid_for(h, N, 256), 256, 0, h->stream>>>(perm, N, inv, d.vecidx, d.reversed ? 1 : 0);
   h->stats.kernel_launches += 1;
   h->stats.reserved[root_first ? 3 : 2] = (double)nlev;   // total DAG levels of the direction (sum over blocks)
-  cudaFree(dlvl_off); cudaFree(lptr); cudaFree(cursor); cudaFree(ilev); cudaFree(dblkmax);
+  cudaFree(dlvl_off); cudaFree(lptr); cudaFree(cursor); cudaFree(dblkmax);
   // 3. level-space matrices, with every block cut into window-sized segments
   uint32_t seg = 1;
   {
@@ -823,9 +868,15 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
   h->stats.kernel_launches += 1;
   RCG_CUDA(h, cudaGetLastError());
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  // level of every level-space row (for the group masks below)
+  uint32_t *lvl_ls = nullptr;
+  RCG_CUDA(h, cudaMalloc(&lvl_ls, sizeof(uint32_t) * (size_t)N));
+  k_gather_u32<<<grid_for(h, N, 256), 256, 0, h->stream>>>(ilev, perm, N, lvl_ls);
+  h->stats.kernel_launches += 1;
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   rcg_free_csr(loc);
   rcg_free_csr(ext);
-  cudaFree(perm); cudaFree(inv);
+  cudaFree(perm); cudaFree(inv); cudaFree(ilev);
   loc = nloc;
   ext = next;
   RCG_TRY(sort_segments(h, loc.rowptr, loc.col, loc.val, N));
@@ -878,6 +929,22 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
     RCG_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaFree(dext); cudaFree(dloc); cudaFree(dstage);
   }
+  // 32-row groups of the refined blocks and their level-start masks (critical-warp batching in k_tri_chain_lv)
+  std::vector<uint32_t> r_grp0(nrb);
+  uint32_t ngrp_total = 0;
+  for (int rb = 0; rb < nrb; rb++) { r_grp0[rb] = ngrp_total; ngrp_total += (rbounds[rb + 1] - rbounds[rb] + 31) / 32; }
+  {
+    uint32_t *dgrp0 = nullptr;
+    RCG_CUDA(h, cudaMalloc(&dgrp0, sizeof(uint32_t) * std::max(1, nrb)));
+    RCG_CUDA(h, cudaMemcpyAsync(dgrp0, r_grp0.data(), sizeof(uint32_t) * nrb, cudaMemcpyHostToDevice, h->stream));
+    RCG_CUDA(h, cudaMalloc(&d.grp_mask, sizeof(uint32_t) * std::max<uint32_t>(1, ngrp_total)));
+    k_group_masks<<<grid_for(h, ngrp_total, 256), 256, 0, h->stream>>>(lvl_ls, dbounds, nrb, dgrp0, ngrp_total, d.grp_mask);
+    k_pack_near<<<grid_for(h, N, 256), 256, 0, h->stream>>>(loc.rowptr, loc.col, lvl_ls, N, dbounds, nrb, 12u, 6u);
+    h->stats.kernel_launches += 2;
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(dgrp0);
+    cudaFree(lvl_ls);
+  }
   std::vector<GroupHost> tree_groups;
   tree_groups.swap(d.groups);
   d.blocks_host.clear();
@@ -888,7 +955,7 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
       G.first = (int)d.blocks_host.size();
       for (int rb = 0; rb < nrb; rb++) {
         if (r_segidx[rb] != k || depth_solve[r_parent[rb]] != want) continue;
-        BlockDesc bd{rbounds[rb], rbounds[rb + 1]};
+        BlockDesc bd{rbounds[rb], rbounds[rb + 1], r_grp0[rb], 0u};
         d.blocks_host.push_back(bd);
         G.count++;
         G.max_rows = std::max(G.max_rows, bd.hi - bd.lo);
@@ -923,6 +990,7 @@ void rcg_free_direction(DirectionDev &d) {
   cudaFree(d.blocks);
   cudaFree(d.vecidx);
   cudaFree(d.w);
+  cudaFree(d.grp_mask);
   d = DirectionDev();
 }
 

@@ -41,8 +41,8 @@ if __name__ == "__main__":
     if which == "small":
         run(16, 0, [(128, 0)])
         run(32, 4, [(256, 0)])
-        run(64, 8, [(256, 8192), (256, 4096), (128, 2048)])
+        run(64, 8, [(0, 0), (256, 4096), (128, 1024)])
         run(64, 0, [(256, 8192)])
-        run(128, 8, [(256, 8192), (256, 4096), (512, 4096), (128, 2048)], do_pcg_oracle=False)
+        run(128, 8, [(0, 0), (256, 2048), (512, 4096), (128, 1024)], do_pcg_oracle=False)
     elif which == "big":
         run(256, 8, [(256, 4096), (512, 4096), (512, 2048), (768, 4096)], do_pcg_oracle=False)

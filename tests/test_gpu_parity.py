@@ -102,7 +102,9 @@ def test_seeded_problems_vs_oracle(capi, oracle, kind, n, threads):
 @pytest.mark.parametrize("opts", [dict(chain_threads=32), dict(chain_threads=64, chain_window=64),
                                   dict(chain_threads=512, chain_window=256), dict(chain_window=1024),
                                   dict(chain_generic=True), dict(chain_generic=True, chain_window=128),
-                                  dict(use_graph=False), dict(spmv_lanes=4), dict(spmv_lanes=32)])
+                                  dict(use_graph=False), dict(spmv_lanes=4), dict(spmv_lanes=32),
+                                  dict(chain_mode=2), dict(chain_mode=2, chain_threads=256, chain_window=512),
+                                  dict(producers=1), dict(producers=4, chain_threads=128)])
 def test_kernel_configurations(capi, oracle, opts):
     """Small windows force many chunks and entries older than the window; chain_generic forces the fallback kernel."""
     A, b, G, part, f = make_problem("lap3d", 24, 4)
