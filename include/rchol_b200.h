@@ -86,6 +86,26 @@ int rcg_set_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint
 int rcg_set_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                    const uint64_t *part, uint64_t npart);
 
+/* General form of rcg_set_factor: `nblocks` consecutive blocks with boundaries bounds[0..nblocks] (bounds[0] = 0,
+ * bounds[nblocks] = N) and a tree depth per block; a row of a block may only couple to its own block and to blocks of
+ * SMALLER depth.  Used by the multi-GPU layout below. */
+int rcg_set_factor_blocks(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                          const uint64_t *bounds, const int32_t *depth, uint64_t nblocks);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ----------------------------------------
+ * Rank r of 2^g owns the depth-g subtree r of the reference's nested-dissection tree (rchol_parallel.cpp:62-70) and
+ * a replica of the 2^g - 1 separators above it.  The LOCAL index space of a rank is
+ *     [ rows of the own subtree (n_sub of them, in their global order) | rows of the top separators (global order) ]
+ * and the caller passes the local matrices in that index space: A_local = rows (subtree + top) x columns (subtree +
+ * top) of A, with the [top, top] block present on rank 0 only (the top rows of A p are summed over the ranks);
+ * G_local = the same rows and columns of U, via rcg_set_factor_blocks.  Vectors are local ([subtree | top], the top
+ * part identical on every rank).  rcg_nccl_unique_id produces the 128-byte NCCL id on one rank (the caller
+ * broadcasts it); rcg_dist_init must be called before the matrices are set; `top_depth` = g.  Afterwards rcg_spmv,
+ * rcg_trsv, rcg_precond and rcg_pcg* work on the distributed problem (all ranks must call them together). */
+int rcg_nccl_unique_id(void *out128);
+int rcg_dist_init(rcg_handle *h, int nranks, int rank, const void *unique_id128, uint64_t n_sub, int top_depth);
+int rcg_dist_finalize(rcg_handle *h);
+
 /* ---- the kernels of the path, exposed one by one so that parity can be tested in isolation ------------- */
 int rcg_spmv(rcg_handle *h, const double *x_host, double *y_host);                 /* pcg.cpp:130-138 */
 int rcg_trsv(rcg_handle *h, int which, const double *rhs_host, double *out_host);  /* pcg.cpp:151 / :155 */

@@ -25,6 +25,7 @@ EXPORTED = [
     "rcg_set_rhs", "rcg_pcg_resident", "rcg_get_solution", "rcg_get_history", "rcg_pcg_oneshot",
     "rcg_get_stats", "rcg_profile_iteration", "rcg_time_phase", "rcg_debug_trace",
     "rcg_get_group_count", "rcg_get_group_info", "rcg_time_group",
+    "rcg_set_factor_blocks", "rcg_nccl_unique_id", "rcg_dist_init", "rcg_dist_finalize",
 ]
 
 TRSV_FORWARD, TRSV_BACKWARD = 0, 1
@@ -97,6 +98,10 @@ def load():
     L.rcg_get_group_count.argtypes = [H, C.c_int, C.POINTER(C.c_int)]
     L.rcg_get_group_info.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.rcg_time_group.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.rcg_set_factor_blocks.argtypes = [H, C.c_uint64, _u64p, _u64p, _f64p, _u64p, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), C.c_uint64]
+    L.rcg_nccl_unique_id.argtypes = [C.c_void_p]
+    L.rcg_dist_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
+    L.rcg_dist_finalize.argtypes = [H]
     L.rcg_debug_trace.argtypes = [H, C.c_int, _f64p, _f64p, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
     for name in EXPORTED:
         fn = getattr(L, name)
@@ -169,6 +174,16 @@ class Solver:
         else:
             pa, pptr, plen = None, None, 0
         self._check(self._L.rcg_set_factor(self._h, self.N, rp, _u64(colIdx), _f64(val), pptr, plen))
+
+    def set_factor_blocks(self, rowPtr, colIdx, val, bounds, depth):
+        rp = _u64(rowPtr)
+        self.N = rp.shape[0] - 1
+        d = np.ascontiguousarray(depth, dtype=np.int32)
+        self._check(self._L.rcg_set_factor_blocks(self._h, self.N, rp, _u64(colIdx), _f64(val), _u64(bounds), d, d.shape[0]))
+
+    def dist_init(self, nranks: int, rank: int, unique_id: bytes, n_sub: int, top_depth: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self._L.rcg_dist_init(self._h, int(nranks), int(rank), buf, int(n_sub), int(top_depth)))
 
     def spmv(self, x):
         y = np.empty(self.N, np.float64)
@@ -246,6 +261,14 @@ class Solver:
         ms = C.c_double(0)
         self._check(self._L.rcg_time_phase(self._h, int(phase), int(reps), C.byref(ms)))
         return ms.value
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = load().rcg_nccl_unique_id(buf)
+    if rc != 0:
+        raise RcgError(rc, "ncclGetUniqueId failed")
+    return buf.raw
 
 
 def pcg(A, b, tol, maxit, G, part=None, device: int = 0):

@@ -29,6 +29,11 @@ int ensure_vectors(rcg_handle *h) {
     RCG_CUDA(h, cudaMemsetAsync(*v, 0, bytes, h->stream));
   }
   h->reduce_grid = h->sm_count * 8;
+  if (h->dist.on) {
+    if (h->dist.n_sub > h->N) { h->err = "n_sub exceeds the local dimension"; return RCG_ERR_INVALID; }
+    h->dist.dot_limit = h->dist.rank == 0 ? (uint32_t)h->N : h->dist.n_sub;
+    if (!h->dist.sbuf) RCG_CUDA(h, cudaMalloc(&h->dist.sbuf, sizeof(double) * (h->N - h->dist.n_sub + 2)));
+  }
   h->partial_cap = h->reduce_grid;
   h->rz_slots = h->haveG ? rcg_post_slots(h, h->bwd, nullptr) : 0;
   RCG_CUDA(h, cudaMalloc(&h->partials, sizeof(double) * (2 * (size_t)h->partial_cap + (size_t)h->rz_slots + 8)));
@@ -51,6 +56,7 @@ void free_vectors(rcg_handle *h) {
   cudaFree(h->scal); h->scal = nullptr;
   cudaFree(h->clk_probe); h->clk_probe = nullptr;
   if (h->iter_graph) { cudaGraphExecDestroy(h->iter_graph); h->iter_graph = nullptr; }
+  if (h->dist.sbuf) { cudaFree(h->dist.sbuf); h->dist.sbuf = nullptr; }
   h->haveB = false;
 }
 
@@ -68,7 +74,13 @@ int enqueue_iteration(rcg_handle *h) {
   RCG_TRY(rcg_launch_trisolve(h, h->fwd, h->r, h->y, nullptr));        // y = U^{-T} r          :151
   RCG_TRY(rcg_launch_trisolve(h, h->bwd, h->y, h->z, h->r));           // z = U^{-1} y, r.z     :155, :93
   RCG_TRY(rcg_launch_p_update(h));                                      // p = z + beta p        :89-96
-  RCG_TRY(rcg_launch_spmv(h, h->p, h->q, h->r, true));                  // q = A p, p.q, p.r     :100-102
+  if (h->dist.on) {   // multi-GPU: the top-separator rows of q are summed over the ranks before the dot products
+    RCG_TRY(rcg_launch_spmv(h, h->p, h->q, nullptr, false));
+    if (h->N > h->dist.n_sub) RCG_TRY(rcg_allreduce_sum(h, h->q + h->dist.n_sub, h->N - h->dist.n_sub));
+    RCG_TRY(rcg_launch_dots_pq_pr(h));
+  } else {
+    RCG_TRY(rcg_launch_spmv(h, h->p, h->q, h->r, true));                // q = A p, p.q, p.r     :100-102
+  }
   RCG_TRY(rcg_launch_xr_update(h));                                     // x, r, r.r, it++       :103-110
   return RCG_OK;
 }
@@ -197,6 +209,7 @@ int rcg_destroy(rcg_handle *h) {
   if (!h) return RCG_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  rcg_dist_finalize(h);
   free_vectors(h);
   if (h->haveA) rcg_free_csr(h->A);
   if (h->haveG) { rcg_free_direction(h->fwd); rcg_free_direction(h->bwd); }
@@ -222,6 +235,14 @@ int rcg_set_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint
   return rcg_setup_factor(h, N, rowPtr, colIdx, val, part, npart);
 }
 
+int rcg_set_factor_blocks(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                          const uint64_t *bounds, const int32_t *depth, uint64_t nblocks) {
+  if (!h) return RCG_ERR_INVALID;
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  free_vectors(h);
+  return rcg_setup_factor_blocks(h, N, rowPtr, colIdx, val, bounds, depth, nblocks);
+}
+
 int rcg_spmv(rcg_handle *h, const double *x_host, double *y_host) {
   RCG_TRY(require(h, true, false));
   if (!x_host || !y_host) { h->err = "null vector"; return RCG_ERR_INVALID; }
@@ -229,6 +250,7 @@ int rcg_spmv(rcg_handle *h, const double *x_host, double *y_host) {
   const size_t bytes = sizeof(double) * h->N;
   RCG_CUDA(h, cudaMemcpyAsync(h->io, x_host, bytes, cudaMemcpyHostToDevice, h->stream));
   RCG_TRY(rcg_launch_spmv(h, h->io, h->q, nullptr, false));
+  if (h->dist.on && h->N > h->dist.n_sub) RCG_TRY(rcg_allreduce_sum(h, h->q + h->dist.n_sub, h->N - h->dist.n_sub));
   RCG_CUDA(h, cudaMemcpyAsync(y_host, h->q, bytes, cudaMemcpyDeviceToHost, h->stream));
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   return RCG_OK;

@@ -43,6 +43,7 @@ struct BlockDesc {             // rows [lo, hi) of one block (a window-sized seg
 // One dependency group of blocks: all blocks of one tree depth.  Blocks of group g depend only on blocks of
 // groups < g (forward: leaves first; backward: root separator first).
 struct GroupHost {
+  int depth = 0;               // tree depth of the group's blocks (0 = root separator)
   int first = 0;               // index of the group's first block in the direction's block array
   int count = 0;
   uint32_t max_rows = 0;
@@ -76,8 +77,21 @@ struct PcgScalars {
   int pad;
 };
 
+// Multi-GPU layout (one process per GPU): the local index space of a rank is [rows of its own depth-g subtree |
+// rows of the replicated top separators]; NCCL sums the three things that cross subtree boundaries.
+struct DistState {
+  bool on = false;
+  int rank = 0, nranks = 1;
+  uint32_t n_sub = 0;          // local rows [0, n_sub) = own subtree, [n_sub, N) = replicated top separators
+  int top_depth = 0;           // groups with depth < top_depth are the replicated top separators
+  void *comm = nullptr;        // ncclComm_t
+  double *sbuf = nullptr;      // N - n_sub doubles: subtree -> top-separator coupling of the forward solve
+  uint32_t dot_limit = 0;      // rows counted in dot products on this rank (top rows count on rank 0 only)
+};
+
 struct rcg_handle {
   int device = 0;
+  DistState dist;
   int sm_count = RCG_SM_COUNT_FALLBACK;
   cudaStream_t stream = nullptr;
   rcg_options opt{};
@@ -137,6 +151,8 @@ struct rcg_handle {
 int rcg_setup_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val);
 int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                      const uint64_t *part, uint64_t npart);
+int rcg_setup_factor_blocks(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                            const uint64_t *bounds, const int32_t *depth, uint64_t nblocks);
 void rcg_free_direction(DirectionDev &d);
 void rcg_free_csr(CsrDev &a);
 
@@ -151,4 +167,9 @@ int rcg_compute_levels(rcg_handle *h, const CsrDev &loc, const BlockDesc *blocks
 int rcg_launch_p_update(rcg_handle *h);
 int rcg_launch_xr_update(rcg_handle *h);
 int rcg_launch_init_solve(rcg_handle *h);
+int rcg_launch_sum_rz(rcg_handle *h);
+int rcg_launch_dots_pq_pr(rcg_handle *h);
+// rcg_dist.cu
+int rcg_allreduce_sum(rcg_handle *h, double *dev_ptr, size_t count);
+extern "C" int rcg_dist_finalize(rcg_handle *h);
 int rcg_launch_residual_norm(rcg_handle *h, double *out_host_norm2);

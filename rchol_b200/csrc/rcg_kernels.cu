@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(256) k_spmv(const int64_t *__restrict__ rowptr
 // r = b, x = 0, p = 0 ; bb = rr = b.b ; it = 0        (pcg.cpp:67-81; x0 = 0 is assumed by the reference)
 __global__ void __launch_bounds__(256) k_init_solve(const double *__restrict__ b, double *__restrict__ x,
                                                     double *__restrict__ r, double *__restrict__ p, uint32_t N,
-                                                    double *partials, int pstride, unsigned int *counter,
-                                                    PcgScalars *scal) {
+                                                    uint32_t dot_limit, double *partials, int pstride,
+                                                    unsigned int *counter, PcgScalars *scal) {
   __shared__ double sm[32];
   double s = 0.0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_init_solve(const double *__restrict__ b
     r[i] = bi;
     x[i] = 0.0;
     p[i] = 0.0;
-    s = fma(bi, bi, s);
+    if (i < dot_limit) s = fma(bi, bi, s);
   }
   double v[1] = {s};
   double *const out[1] = {&scal->bb};
@@ -80,29 +80,47 @@ __global__ void __launch_bounds__(256) k_init_solve(const double *__restrict__ b
   }
 }
 
-// rz = sum of the backward solve's per-block partials; beta = rz / rz_prev (0 in the first iteration, where the
-// reference copies z into p, pcg.cpp:87-90); p = z + beta p.
-__global__ void __launch_bounds__(256) k_p_update(const double *__restrict__ z, double *__restrict__ p, uint32_t N,
-                                                  const double *__restrict__ rz_partials, int n_partials,
-                                                  PcgScalars *scal) {
+// rz = sum of the backward solve's per-CTA partials (k_tri_post), in index order
+__global__ void __launch_bounds__(256) k_sum_rz(const double *__restrict__ rz_partials, int n_partials, PcgScalars *scal) {
   __shared__ double sm[32];
   const double rz = sum_partials(rz_partials, n_partials, sm);
+  if (threadIdx.x == 0) scal->rz = rz;
+}
+
+// beta = rz / rz_prev (0 in the first iteration, where the reference copies z into p, pcg.cpp:87-90); p = z + beta p.
+__global__ void __launch_bounds__(256) k_p_update(const double *__restrict__ z, double *__restrict__ p, uint32_t N,
+                                                  const PcgScalars *__restrict__ scal) {
   const int it = scal->it;
-  const double beta = it == 0 ? 0.0 : rz / scal->rz_prev;
+  const double beta = it == 0 ? 0.0 : scal->rz / scal->rz_prev;
   if (it == 0) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) p[i] = z[i];
   } else {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
       p[i] = fma(beta, p[i], z[i]);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) scal->rz = rz;
+}
+
+// p.q and p.r over the first `limit` rows (multi-GPU: after q's top rows have been all-reduced)
+__global__ void __launch_bounds__(256) k_dots_pq_pr(const double *__restrict__ p, const double *__restrict__ q,
+                                                    const double *__restrict__ r, uint32_t limit, double *partials,
+                                                    int pstride, unsigned int *counter, PcgScalars *scal) {
+  __shared__ double sm[32];
+  double pq = 0.0, pr = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < limit; i += gridDim.x * blockDim.x) {
+    const double pi = p[i];
+    pq = fma(pi, q[i], pq);
+    pr = fma(pi, r[i], pr);
+  }
+  double v[2] = {pq, pr};
+  double *const out[2] = {&scal->pq, &scal->pr};
+  publish_and_finalize<2>(v, partials, pstride, counter, out, sm);
 }
 
 // alpha = (p.r)/(p.q) ; x += alpha p ; r -= alpha q ; rr = r.r ; it++ ; rz_prev = rz      (pcg.cpp:101-110)
 __global__ void __launch_bounds__(256) k_xr_update(const double *__restrict__ p, const double *__restrict__ q,
                                                    double *__restrict__ x, double *__restrict__ r, uint32_t N,
-                                                   double *partials, int pstride, unsigned int *counter,
-                                                   PcgScalars *scal) {
+                                                   uint32_t dot_limit, double *partials, int pstride,
+                                                   unsigned int *counter, PcgScalars *scal) {
   __shared__ double sm[32];
   const double alpha = scal->pr / scal->pq;
   double s = 0.0;
@@ -111,7 +129,7 @@ __global__ void __launch_bounds__(256) k_xr_update(const double *__restrict__ p,
     x[i] = fma(alpha, pi, x[i]);
     const double ri = fma(-alpha, q[i], r[i]);
     r[i] = ri;
-    s = fma(ri, ri, s);
+    if (i < dot_limit) s = fma(ri, ri, s);
   }
   double v[1] = {s};
   double *const out[1] = {&scal->rr};
@@ -129,7 +147,7 @@ __global__ void k_advance(PcgScalars *scal) {
 
 // q = A x was computed; s = sum (q - b)^2     (true residual, pcg.cpp:116-118)
 __global__ void __launch_bounds__(256) k_residual_norm(const double *__restrict__ q, const double *__restrict__ b,
-                                                       uint32_t N, double *partials, int pstride,
+                                                       uint32_t N /* rows counted */, double *partials, int pstride,
                                                        unsigned int *counter, double *out_norm2) {
   __shared__ double sm[32];
   double s = 0.0;
@@ -169,27 +187,49 @@ int rcg_launch_spmv(rcg_handle *h, const double *x, double *y, const double *dot
 }
 
 int rcg_launch_init_solve(rcg_handle *h) {
-  k_init_solve<<<h->reduce_grid, 256, 0, h->stream>>>(h->b, h->x, h->r, h->p, (uint32_t)h->N, h->partials,
+  const uint32_t lim = h->dist.on ? h->dist.dot_limit : (uint32_t)h->N;
+  k_init_solve<<<h->reduce_grid, 256, 0, h->stream>>>(h->b, h->x, h->r, h->p, (uint32_t)h->N, lim, h->partials,
                                                      h->partial_cap, h->counters + 1, h->scal);
   h->stats.kernel_launches += 1;
   RCG_CUDA(h, cudaGetLastError());
+  if (h->dist.on) RCG_TRY(rcg_allreduce_sum(h, &h->scal->bb, 1));
+  return RCG_OK;
+}
+
+int rcg_launch_sum_rz(rcg_handle *h) {
+  const double *rz_part = h->partials + 2 * (size_t)h->partial_cap;
+  k_sum_rz<<<1, 256, 0, h->stream>>>(rz_part, h->rz_slots, h->scal);
+  h->stats.kernel_launches += 1;
+  RCG_CUDA(h, cudaGetLastError());
+  if (h->dist.on) RCG_TRY(rcg_allreduce_sum(h, &h->scal->rz, 1));
   return RCG_OK;
 }
 
 int rcg_launch_p_update(rcg_handle *h) {
-  const double *rz_part = h->partials + 2 * (size_t)h->partial_cap;
-  k_p_update<<<h->reduce_grid, 256, 0, h->stream>>>(h->z, h->p, (uint32_t)h->N, rz_part, h->rz_slots,
-                                                   h->scal);
+  RCG_TRY(rcg_launch_sum_rz(h));
+  k_p_update<<<h->reduce_grid, 256, 0, h->stream>>>(h->z, h->p, (uint32_t)h->N, h->scal);
   h->stats.kernel_launches += 1;
   RCG_CUDA(h, cudaGetLastError());
   return RCG_OK;
 }
 
+int rcg_launch_dots_pq_pr(rcg_handle *h) {
+  k_dots_pq_pr<<<h->reduce_grid, 256, 0, h->stream>>>(h->p, h->q, h->r, h->dist.dot_limit, h->partials, h->partial_cap,
+                                                     h->counters + 4, h->scal);
+  h->stats.kernel_launches += 1;
+  RCG_CUDA(h, cudaGetLastError());
+  return rcg_allreduce_sum(h, &h->scal->pq, 2);   // pq and pr are adjacent
+}
+
 int rcg_launch_xr_update(rcg_handle *h) {
-  k_xr_update<<<h->reduce_grid, 256, 0, h->stream>>>(h->p, h->q, h->x, h->r, (uint32_t)h->N, h->partials, h->partial_cap,
-                                                    h->counters + 2, h->scal);
+  const uint32_t lim = h->dist.on ? h->dist.dot_limit : (uint32_t)h->N;
+  k_xr_update<<<h->reduce_grid, 256, 0, h->stream>>>(h->p, h->q, h->x, h->r, (uint32_t)h->N, lim, h->partials,
+                                                    h->partial_cap, h->counters + 2, h->scal);
+  h->stats.kernel_launches += 1;
+  RCG_CUDA(h, cudaGetLastError());
+  if (h->dist.on) RCG_TRY(rcg_allreduce_sum(h, &h->scal->rr, 1));
   k_advance<<<1, 1, 0, h->stream>>>(h->scal);
-  h->stats.kernel_launches += 2;
+  h->stats.kernel_launches += 1;
   RCG_CUDA(h, cudaGetLastError());
   return RCG_OK;
 }
@@ -197,10 +237,13 @@ int rcg_launch_xr_update(rcg_handle *h) {
 int rcg_launch_residual_norm(rcg_handle *h, double *out_host_norm2) {
   // q = A x ; ||q - b||^2 -> scal->pq is reused as the output slot
   RCG_TRY(rcg_launch_spmv(h, h->x, h->q, nullptr, false));
-  k_residual_norm<<<h->reduce_grid, 256, 0, h->stream>>>(h->q, h->b, (uint32_t)h->N, h->partials, h->partial_cap,
+  if (h->dist.on && h->N > h->dist.n_sub) RCG_TRY(rcg_allreduce_sum(h, h->q + h->dist.n_sub, h->N - h->dist.n_sub));
+  const uint32_t lim = h->dist.on ? h->dist.dot_limit : (uint32_t)h->N;
+  k_residual_norm<<<h->reduce_grid, 256, 0, h->stream>>>(h->q, h->b, lim, h->partials, h->partial_cap,
                                                         h->counters + 3, &h->scal->pq);
   h->stats.kernel_launches += 1;
   RCG_CUDA(h, cudaGetLastError());
+  if (h->dist.on) RCG_TRY(rcg_allreduce_sum(h, &h->scal->pq, 1));
   RCG_CUDA(h, cudaMemcpyAsync(out_host_norm2, &h->scal->pq, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   return RCG_OK;

@@ -240,6 +240,26 @@ __global__ void k_validate_blocks(const int64_t *__restrict__ rp, const uint32_t
   if (bad) atomicExch(err, 1);
 }
 
+// general block lists: an entry (i, c) of U with block(c) != block(i) needs depth(block(c)) < depth(block(i))
+__global__ void k_validate_depths(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, uint32_t N,
+                                  const uint32_t *__restrict__ part, const uint32_t *__restrict__ depth, int nb, int *err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t stride = gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < N; i += stride) {
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (part[mid] <= i) lo = mid; else hi = mid; }
+    const int bi = lo;
+    for (int64_t k = rp[i] + 1; k < rp[i + 1]; k++) {
+      const uint32_t c = col[k];
+      lo = 0; hi = nb;
+      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (part[mid] <= c) lo = mid; else hi = mid; }
+      bad |= (lo != bi) && !(depth[lo] < depth[bi]);
+    }
+  }
+  if (bad) atomicExch(err, 1);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // transpose  U (CSR) -> L = U^T (CSR, sorted rows)
 // ---------------------------------------------------------------------------------------------------------
@@ -952,6 +972,7 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
     const int want = root_first ? g : max_depth - g;
     for (int k = 0;; k++) {        // segment index
       GroupHost G;
+      G.depth = want;
       G.first = (int)d.blocks_host.size();
       for (int rb = 0; rb < nrb; rb++) {
         if (r_segidx[rb] != k || depth_solve[r_parent[rb]] != want) continue;
@@ -1015,9 +1036,11 @@ int rcg_setup_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const ui
   return RCG_OK;
 }
 
+static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                             const std::vector<uint32_t> &bounds, const TreeInfo &tree, bool strict_tree);
+
 int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                      const uint64_t *part, uint64_t npart) {
-  if (h->haveG) { rcg_free_direction(h->fwd); rcg_free_direction(h->bwd); h->haveG = false; }
   if (h->haveA && N != h->N) {
     h->err = "factor dimension differs from the matrix's";
     return RCG_ERR_INVALID;
@@ -1042,7 +1065,41 @@ int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const ui
   tree.depth.assign(nb, 0);
   tree.sub_lo.assign(nb, 0);
   build_tree(bounds, 0, nb, 0, tree);
+  return setup_factor_impl(h, N, rowPtr, colIdx, val, bounds, tree, true);
+}
 
+// General form: `nblocks` consecutive blocks with boundaries bounds[0..nblocks] and a depth per block; a row of a block
+// may only couple to its own block and to blocks of SMALLER depth (solved later in the forward solve, earlier in the
+// backward solve).  Used by the multi-GPU layout, whose local index space is [own subtree | replicated top separators].
+int rcg_setup_factor_blocks(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                            const uint64_t *bounds64, const int32_t *depth, uint64_t nblocks) {
+  if (h->haveA && N != h->N) {
+    h->err = "factor dimension differs from the matrix's";
+    return RCG_ERR_INVALID;
+  }
+  if (!bounds64 || !depth || nblocks == 0 || bounds64[0] != 0 || bounds64[nblocks] != N) {
+    h->err = "blocks must cover [0, N)";
+    return RCG_ERR_INVALID;
+  }
+  std::vector<uint32_t> bounds;
+  TreeInfo tree;
+  for (uint64_t i = 0; i <= nblocks; i++) {
+    if (i && bounds64[i] < bounds64[i - 1]) { h->err = "block boundaries are not monotone"; return RCG_ERR_INVALID; }
+    bounds.push_back((uint32_t)bounds64[i]);
+  }
+  for (uint64_t i = 0; i < nblocks; i++) {
+    if (depth[i] < 0 || depth[i] > 62) { h->err = "block depth out of range"; return RCG_ERR_INVALID; }
+    tree.depth.push_back(depth[i]);
+    tree.sub_lo.push_back(0);
+    tree.max_depth = std::max(tree.max_depth, (int)depth[i]);
+  }
+  return setup_factor_impl(h, N, rowPtr, colIdx, val, bounds, tree, false);
+}
+
+static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                             const std::vector<uint32_t> &bounds, const TreeInfo &tree, bool strict_tree) {
+  if (h->haveG) { rcg_free_direction(h->fwd); rcg_free_direction(h->bwd); h->haveG = false; }
+  const int nb = (int)bounds.size() - 1;
   CsrDev U;
   RCG_TRY(upload_csr(h, N, rowPtr, colIdx, val, U));
   h->N = N;
@@ -1069,6 +1126,11 @@ int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const ui
     RCG_CUDA(h, cudaMalloc(&dsub, sizeof(uint32_t) * nb));
     RCG_CUDA(h, cudaMemcpyAsync(dpart, bounds.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
     RCG_CUDA(h, cudaMemcpyAsync(dsub, tree.sub_lo.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, h->stream));
+    if (!strict_tree) {   // depth-based rule: reuse the sub_lo slot for the depths
+      std::vector<uint32_t> dep(tree.depth.begin(), tree.depth.end());
+      RCG_CUDA(h, cudaMemcpyAsync(dsub, dep.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, h->stream));
+      k_validate_depths<<<grid_for(h, n32, 256), 256, 0, h->stream>>>(U.rowptr, U.col, n32, dpart, dsub, nb, derr);
+    } else
     k_validate_blocks<<<grid_for(h, n32, 256), 256, 0, h->stream>>>(U.rowptr, U.col, n32, dpart, dsub, nb, derr);
     h->stats.kernel_launches += 1;
     RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

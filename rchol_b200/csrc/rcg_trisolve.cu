@@ -24,7 +24,10 @@ template <int LPR>
 __global__ void __launch_bounds__(256) k_tri_pre(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
                                                  const double *__restrict__ val, const BlockDesc *__restrict__ blocks,
                                                  const uint32_t *__restrict__ vecidx, const double *__restrict__ rhs,
-                                                 const double *out, double *__restrict__ w) {
+                                                 const double *out, double *__restrict__ w, uint32_t col_min,
+                                                 const double *__restrict__ corr) {
+  // col_min / corr (multi-GPU, top separators only): external entries with column < col_min (the rank's own subtree)
+  // are left out here -- their sum over ALL ranks arrives in corr[], indexed like the vectors minus col_min.
   const BlockDesc b = blocks[blockIdx.y];
   const int sub = threadIdx.x % LPR;
   const uint32_t rows_per_cta = blockDim.x / LPR;
@@ -33,18 +36,46 @@ __global__ void __launch_bounds__(256) k_tri_pre(const int64_t *__restrict__ row
     double acc = 0.0;
     if (LPR > 1 && v < b.hi) {
       const int64_t e = rowptr[v + 1];
-      for (int64_t k = rowptr[v] + sub; k < e; k += LPR) acc = fma(val[k], out[col[k]], acc);
+      for (int64_t k = rowptr[v] + sub; k < e; k += LPR) {
+        const uint32_t c = col[k];
+        if (c >= col_min) acc = fma(val[k], out[c], acc);
+      }
     }
 #pragma unroll
     for (int o = LPR >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (v < b.hi && sub == 0) w[v] = rhs[vecidx[v]] - acc;
+    if (v < b.hi && sub == 0) {
+      const uint32_t i = vecidx[v];
+      w[v] = (corr ? rhs[i] - corr[i - col_min] : rhs[i]) - acc;
+    }
+  }
+}
+
+// multi-GPU forward solve: contribution of the rank's own subtree to the right-hand side of the top separators,
+// sbuf[i - n_sub] = sum over external entries with column < n_sub of M[v,c] out[c]   (then summed over ranks by NCCL)
+__global__ void __launch_bounds__(256) k_tri_couple(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+                                                    const double *__restrict__ val, const BlockDesc *__restrict__ blocks,
+                                                    const uint32_t *__restrict__ vecidx, const double *__restrict__ out,
+                                                    double *__restrict__ sbuf, uint32_t n_sub) {
+  const BlockDesc b = blocks[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const uint32_t wpc = blockDim.x >> 5;
+  for (uint32_t v = b.lo + blockIdx.x * wpc + (threadIdx.x >> 5); v < b.hi; v += gridDim.x * wpc) {
+    double acc = 0.0;
+    const int64_t e = rowptr[v + 1];
+    for (int64_t k = rowptr[v] + lane; k < e; k += 32) {
+      const uint32_t c = col[k];
+      if (c < n_sub) acc = fma(val[k], out[c], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sbuf[vecidx[v] - n_sub] = acc;
   }
 }
 
 // post: scatter the solved block back to vector space; optional fused dot product (r.z of the PCG recurrence)
 __global__ void __launch_bounds__(256) k_tri_post(const BlockDesc *__restrict__ blocks, const uint32_t *__restrict__ vecidx,
                                                   const double *__restrict__ w, double *__restrict__ out,
-                                                  const double *__restrict__ dotvec, double *dot_partials) {
+                                                  const double *__restrict__ dotvec, double *dot_partials,
+                                                  uint32_t dot_limit) {
   __shared__ double red[32];
   const BlockDesc b = blocks[blockIdx.y];
   double dot = 0.0;
@@ -52,7 +83,7 @@ __global__ void __launch_bounds__(256) k_tri_post(const BlockDesc *__restrict__ 
     const uint32_t i = vecidx[v];
     const double x = w[v];
     out[i] = x;
-    if (dotvec) dot = fma(x, dotvec[i], dot);
+    if (dotvec && i < dot_limit) dot = fma(x, dotvec[i], dot);
   }
   if (dot_partials) {
     const double t = block_sum(dot, red);
@@ -873,21 +904,41 @@ int rcg_launch_trisolve(rcg_handle *h, DirectionDev &d, const double *rhs, doubl
   double *rz_part = h->partials + 2 * (size_t)h->partial_cap;
   std::vector<int> first_slot;
   rcg_post_slots(h, d, &first_slot);
+  const bool dist_fwd = h->dist.on && !d.reversed && h->N > h->dist.n_sub;
+  const uint32_t dot_limit = h->dist.on ? h->dist.dot_limit : 0xFFFFFFFFu;
+  bool coupled = false;
   int gi = -1;
   for (const GroupHost &g : d.groups) {
     ++gi;
     if (only_group >= 0 && gi != only_group) continue;
     const BlockDesc *blocks = d.blocks + g.first;
+    const bool top = dist_fwd && g.depth < h->dist.top_depth;
+    if (top && !coupled) {
+      // Multi-GPU forward solve, before the first top separator: every rank adds up what its own subtree contributes
+      // to the right-hand sides of ALL top-separator rows, and NCCL sums that over the ranks (SURVEY 8e "reduce").
+      for (const GroupHost &t : d.groups) {
+        if (t.depth >= h->dist.top_depth) continue;
+        dim3 grid(aux_grid_x(h, t, 8), (unsigned)t.count);
+        k_tri_couple<<<grid, 256, 0, h->stream>>>(d.M.ext.rowptr, d.M.ext.col, d.M.ext.val, d.blocks + t.first, d.vecidx, out,
+                                                 h->dist.sbuf, h->dist.n_sub);
+        h->stats.kernel_launches += 1;
+      }
+      RCG_CUDA(h, cudaGetLastError());
+      RCG_TRY(rcg_allreduce_sum(h, h->dist.sbuf, h->N - h->dist.n_sub));
+      coupled = true;
+    }
     // ---- pre --------------------------------------------------------------------------------------------
     if (only_kernel < 0 || only_kernel == 1) {
       const CsrDev &E = d.M.ext;
       const double mean = g.rows ? (double)g.ext_nnz / (double)g.rows : 0.0;
       const int lpr = g.ext_nnz == 0 ? 1 : mean <= 6.0 ? 4 : mean <= 24.0 ? 8 : 32;
       dim3 grid(aux_grid_x(h, g, 256 / lpr), (unsigned)g.count);
-      if (lpr == 1) k_tri_pre<1><<<grid, 256, 0, h->stream>>>(E.rowptr, E.col, E.val, blocks, d.vecidx, rhs, out, d.w);
-      else if (lpr == 4) k_tri_pre<4><<<grid, 256, 0, h->stream>>>(E.rowptr, E.col, E.val, blocks, d.vecidx, rhs, out, d.w);
-      else if (lpr == 8) k_tri_pre<8><<<grid, 256, 0, h->stream>>>(E.rowptr, E.col, E.val, blocks, d.vecidx, rhs, out, d.w);
-      else k_tri_pre<32><<<grid, 256, 0, h->stream>>>(E.rowptr, E.col, E.val, blocks, d.vecidx, rhs, out, d.w);
+      const uint32_t cmin = top ? h->dist.n_sub : 0u;
+      const double *corr = top ? h->dist.sbuf : nullptr;
+      if (lpr == 1) k_tri_pre<1><<<grid, 256, 0, h->stream>>>(E.rowptr, E.col, E.val, blocks, d.vecidx, rhs, out, d.w, cmin, corr);
+      else if (lpr == 4) k_tri_pre<4><<<grid, 256, 0, h->stream>>>(E.rowptr, E.col, E.val, blocks, d.vecidx, rhs, out, d.w, cmin, corr);
+      else if (lpr == 8) k_tri_pre<8><<<grid, 256, 0, h->stream>>>(E.rowptr, E.col, E.val, blocks, d.vecidx, rhs, out, d.w, cmin, corr);
+      else k_tri_pre<32><<<grid, 256, 0, h->stream>>>(E.rowptr, E.col, E.val, blocks, d.vecidx, rhs, out, d.w, cmin, corr);
       h->stats.kernel_launches += 1;
     }
     // ---- chain ------------------------------------------------------------------------------------------
@@ -895,7 +946,8 @@ int rcg_launch_trisolve(rcg_handle *h, DirectionDev &d, const double *rhs, doubl
     // ---- post -------------------------------------------------------------------------------------------
     if (only_kernel < 0 || only_kernel == 2) {
       dim3 grid(aux_grid_x(h, g, 256), (unsigned)g.count);
-      k_tri_post<<<grid, 256, 0, h->stream>>>(blocks, d.vecidx, d.w, out, dotvec, dotvec ? rz_part + first_slot[gi] : nullptr);
+      k_tri_post<<<grid, 256, 0, h->stream>>>(blocks, d.vecidx, d.w, out, dotvec, dotvec ? rz_part + first_slot[gi] : nullptr,
+                                             dot_limit);
       h->stats.kernel_launches += 1;
     }
   }
