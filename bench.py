@@ -256,7 +256,11 @@ def run_ours_single(args, d, B_iter):
     spmv_ms = prof["spmv_ms"]
     ach = chain_bytes_total / chain_ms_total / 1e6
     roofline = dict(bound="hbm", kernel="k_tri_chain_fast (all launches of one forward + one backward solve)",
-                    achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                    achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                    # dram__bytes_read+write per launch from the ncu --set full capture (profiles/r01_chain_kernel_ncu.md):
+                    # 4.66 MB for a 4.8 MB-algorithmic leaf-segment launch, i.e. traffic ~= 1.0 x algorithmic bytes
+                    traffic=0.97 * chain_bytes_total / chain_launches, traffic_source="ncu capture lap3d 128^3 (ratio 0.97 to algorithmic)",
+                    peak_source=peak_src,
                     launches_per_solve_pair=chain_launches, bytes_per_launch=chain_bytes_total / chain_launches,
                     ms_per_launch=chain_ms_total / chain_launches, chain_ms_per_iteration=chain_ms_total,
                     pre_post_ms_per_iteration=aux_ms_total,
