@@ -43,12 +43,15 @@ enum {
 /* Tunables (all have defaults; see DESIGN.md "SpTRSV"). */
 typedef struct rcg_options {
   int chain_threads;       /* threads per CTA of the block-local sync-free triangular solve (0 = default) */
-  int chain_window;        /* chunk rows C of the solution window (segment = 2C rows; 0 = default 2048)    */
+  int chain_window;        /* blocked solve: rows of the solution window (32*Dfar, default 4096); level-space kernels:
+                              chunk rows C of the window (segment = 2C rows; 0 = default 2048)                */
   int use_graph;           /* 1 = replay one CUDA graph per PCG iteration (default), 0 = plain launches   */
   int spmv_lanes;          /* lanes per row of the CSR SpMV (0 = choose from the row-length histogram)     */
   int chain_generic;       /* 1 = force the non-pipelined fallback kernel of the triangular solve (testing)  */
-  int chain_mode;          /* 0/1 = sync-free polling kernel (default), 2 = role-specialised kernel (experimental) */
-  int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2) */
+  int chain_mode;          /* 0/3 = blocked-inverse chain (default), 1 = level-space sync-free polling kernel,
+                              2 = level-space role-specialised kernel (experimental)                                 */
+  int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2),
+                              [3] blocked solve: recent chunk distance Kr (default 2), [6] 1 = plain (non-cooperative) launch */
 } rcg_options;
 
 /* Per-handle measurements, all device-side times from CUDA events on the handle's own stream. */
@@ -152,6 +155,14 @@ int rcg_time_group(rcg_handle *h, int direction, int group, int kernel, int reps
 /* One triangular solve with per-row tracing of the dependency-chain kernel: trace_host receives 4 uint32 per row
  * in solve index order {finish cycle, polling-loop trips, start cycle, cta*1024+thread} (per-SM cycle counters). */
 int rcg_debug_trace(rcg_handle *h, int which, const double *rhs_host, double *out_host, uint32_t *trace_host);
+
+/* Layout of the blocked triangular solve (DESIGN.md "SpTRSV"), for the layout tests: info[0..11] = {active, chunks,
+ * far tiles, blocks, bytes of blob A, bytes of blob B, far entries, Kr, E, Dfar, N, levels}; rcg_debug_blocked_copy copies
+ * one device array to the host: 0 offA, 1 offB, 2 blobA, 3 blobB, 4 far rowptr, 5 far col, 6 far val, 7 tile_need,
+ * 8 blocks (8 x uint32 each: lo, hi, chunk0, tile0, gidx, pad), 9 per-level plan (10 x uint64 each). */
+int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16);
+int rcg_debug_counters(rcg_handle *h, uint64_t *out16);   /* raw cycle counters of the last chain kernel (rcg_options.reserved[1] bit 0) */
+int rcg_debug_blocked_copy(rcg_handle *h, int direction, int what, void *dst, uint64_t bytes);
 
 #ifdef __cplusplus
 }

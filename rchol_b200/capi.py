@@ -26,6 +26,7 @@ EXPORTED = [
     "rcg_get_stats", "rcg_profile_iteration", "rcg_time_phase", "rcg_debug_trace",
     "rcg_get_group_count", "rcg_get_group_info", "rcg_time_group",
     "rcg_set_factor_blocks", "rcg_nccl_unique_id", "rcg_dist_init", "rcg_dist_finalize",
+    "rcg_debug_blocked_info", "rcg_debug_blocked_copy", "rcg_debug_counters",
 ]
 
 TRSV_FORWARD, TRSV_BACKWARD = 0, 1
@@ -103,6 +104,9 @@ def load():
     L.rcg_dist_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
     L.rcg_dist_finalize.argtypes = [H]
     L.rcg_debug_trace.argtypes = [H, C.c_int, _f64p, _f64p, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
+    L.rcg_debug_blocked_info.argtypes = [H, C.c_int, C.POINTER(C.c_uint64)]
+    L.rcg_debug_blocked_copy.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+    L.rcg_debug_counters.argtypes = [H, C.POINTER(C.c_uint64)]
     for name in EXPORTED:
         fn = getattr(L, name)
         if name not in ("rcg_last_error", "rcg_version"):
@@ -123,7 +127,8 @@ class Solver:
     """Handle-based interface: upload A and G once, then call the kernels or the PCG solve."""
 
     def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
-                 spmv_lanes: int = 0, chain_generic: bool = False, chain_mode: int = 0, backoff_ns: int = 0, dbg: int = 0, producers: int = 0):
+                 spmv_lanes: int = 0, chain_generic: bool = False, chain_mode: int = 0, backoff_ns: int = 0, dbg: int = 0, producers: int = 0,
+                 recent: int = 0, plain_launch: bool = False):
         self._L = load()
         self._h = C.c_void_p()
         opt = Options()
@@ -134,6 +139,8 @@ class Solver:
         opt.reserved[0] = int(backoff_ns)
         opt.reserved[1] = int(dbg)
         opt.reserved[2] = int(producers)
+        opt.reserved[3] = int(recent)
+        opt.reserved[6] = int(bool(plain_launch))
         rc = self._L.rcg_create_with_options(C.byref(self._h), int(device), C.byref(opt))
         if rc != 0:
             raise RcgError(rc, (self._L.rcg_last_error(None) or b"").decode())
@@ -256,6 +263,37 @@ class Solver:
         tr = np.zeros((self.N, 4), np.uint32)
         self._check(self._L.rcg_debug_trace(self._h, int(which), _f64(rhs), out, tr))
         return out, tr
+
+    def counters(self):
+        out = (C.c_uint64 * 16)()
+        self._check(self._L.rcg_debug_counters(self._h, out))
+        return [int(v) for v in out]
+
+    def blocked_layout(self, direction: int) -> dict:
+        """Raw copy of the blocked triangular-solve layout of one direction (tests/blocked_emulator.py interprets it)."""
+        info = (C.c_uint64 * 16)()
+        self._check(self._L.rcg_debug_blocked_info(self._h, int(direction), info))
+        keys = ["active", "nchunks", "ntiles", "nblocks", "bytesA", "bytesB", "far_nnz", "Kr", "E", "Dfar", "N", "nlevels"]
+        out = {k: int(info[i]) for i, k in enumerate(keys)}
+        if not out["active"]:
+            return out
+
+        def grab(what, dtype, count):
+            a = np.zeros(max(int(count), 1), dtype=dtype)
+            self._check(self._L.rcg_debug_blocked_copy(self._h, int(direction), what, a.ctypes.data_as(C.c_void_p), a.nbytes))
+            return a[: int(count)]
+
+        out["offA"] = grab(0, np.int64, out["nchunks"] + 1)
+        out["offB"] = grab(1, np.int64, out["nchunks"] + 1)
+        out["blobA"] = grab(2, np.uint8, out["bytesA"])
+        out["blobB"] = grab(3, np.uint8, out["bytesB"])
+        out["far_rp"] = grab(4, np.int64, out["N"] + 1)
+        out["far_col"] = grab(5, np.uint32, out["far_nnz"])
+        out["far_val"] = grab(6, np.float64, out["far_nnz"])
+        out["tile_need"] = grab(7, np.uint32, out["ntiles"])
+        out["blocks"] = grab(8, np.uint32, out["nblocks"] * 8).reshape(-1, 8)
+        out["levels"] = grab(9, np.uint64, out["nlevels"] * 10).reshape(-1, 10)
+        return out
 
     def time_phase(self, phase: int, reps: int = 3) -> float:
         ms = C.c_double(0)

@@ -40,8 +40,12 @@ int ensure_vectors(rcg_handle *h) {
   RCG_CUDA(h, cudaMemsetAsync(h->partials, 0, sizeof(double) * (2 * (size_t)h->partial_cap + (size_t)h->rz_slots + 8), h->stream));
   RCG_CUDA(h, cudaMalloc(&h->counters, sizeof(unsigned int) * 8));
   RCG_CUDA(h, cudaMemsetAsync(h->counters, 0, sizeof(unsigned int) * 8, h->stream));
-  RCG_CUDA(h, cudaMalloc(&h->clk_probe, sizeof(unsigned long long) * 8));
-  RCG_CUDA(h, cudaMemsetAsync(h->clk_probe, 0, sizeof(unsigned long long) * 8, h->stream));
+  RCG_CUDA(h, cudaMalloc(&h->clk_probe, sizeof(unsigned long long) * 16));
+  RCG_CUDA(h, cudaMemsetAsync(h->clk_probe, 0, sizeof(unsigned long long) * 16, h->stream));
+  if (!h->abort_flag) {
+    RCG_CUDA(h, cudaMalloc(&h->abort_flag, sizeof(unsigned int) * 4));
+    RCG_CUDA(h, cudaMemsetAsync(h->abort_flag, 0, sizeof(unsigned int) * 4, h->stream));
+  }
   RCG_CUDA(h, cudaMalloc(&h->scal, sizeof(PcgScalars)));
   RCG_CUDA(h, cudaMemsetAsync(h->scal, 0, sizeof(PcgScalars), h->stream));
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -55,6 +59,7 @@ void free_vectors(rcg_handle *h) {
   cudaFree(h->counters); h->counters = nullptr;
   cudaFree(h->scal); h->scal = nullptr;
   cudaFree(h->clk_probe); h->clk_probe = nullptr;
+  cudaFree(h->abort_flag); h->abort_flag = nullptr;
   if (h->iter_graph) { cudaGraphExecDestroy(h->iter_graph); h->iter_graph = nullptr; }
   if (h->dist.sbuf) { cudaFree(h->dist.sbuf); h->dist.sbuf = nullptr; }
   h->haveB = false;
@@ -149,6 +154,7 @@ int solve_resident(rcg_handle *h, double tol, int maxit, double *relres, int *it
   RCG_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->stats.solve_ms = ms;
   h->stats.d2h_bytes = d2h;
+  RCG_TRY(rcg_check_abort(h));
   if (relres) *relres = std::sqrt(res2) / nb;
   if (itr) *itr = it;
   return RCG_OK;
@@ -266,7 +272,7 @@ int rcg_trsv(rcg_handle *h, int which, const double *rhs_host, double *out_host)
   RCG_TRY(rcg_launch_trisolve(h, which == RCG_TRSV_FORWARD ? h->fwd : h->bwd, h->io, h->y, nullptr));
   RCG_CUDA(h, cudaMemcpyAsync(out_host, h->y, bytes, cudaMemcpyDeviceToHost, h->stream));
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
-  return RCG_OK;
+  return rcg_check_abort(h);
 }
 
 // Diagnostics: runs one triangular solve with per-row tracing; trace_host receives 4 uint32 per row (solve index
@@ -299,7 +305,7 @@ int rcg_precond(rcg_handle *h, const double *r_host, double *z_host) {
   RCG_TRY(rcg_launch_trisolve(h, h->bwd, h->y, h->z, nullptr));
   RCG_CUDA(h, cudaMemcpyAsync(z_host, h->z, bytes, cudaMemcpyDeviceToHost, h->stream));
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
-  return RCG_OK;
+  return rcg_check_abort(h);
 }
 
 int rcg_set_rhs(rcg_handle *h, const double *b_host) {
@@ -456,6 +462,69 @@ int rcg_time_group(rcg_handle *h, int direction, int group, int kernel, int reps
   float ms = 0.f;
   RCG_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   *avg_ms = ms / reps;
+  return RCG_OK;
+}
+
+// Raw diagnostic counters of the last chain kernel (16 x uint64; meaning depends on the kernel, see rcg_blocked.cu).
+int rcg_debug_counters(rcg_handle *h, uint64_t *out16) {
+  if (!h || !out16) return RCG_ERR_INVALID;
+  memset(out16, 0, sizeof(uint64_t) * 16);
+  if (!h->clk_probe) return RCG_OK;
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  RCG_CUDA(h, cudaMemcpy(out16, h->clk_probe, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
+  return RCG_OK;
+}
+
+// Diagnostics of the blocked solve layout (tests): sizes, then raw copies of the device arrays.
+int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16) {
+  if (!h || !info16) return RCG_ERR_INVALID;
+  if (!h->haveG) { h->err = "rcg_set_factor has not been called"; return RCG_ERR_STATE; }
+  const BlockedDev &B = (direction == RCG_TRSV_FORWARD ? h->fwd : h->bwd).bc;
+  memset(info16, 0, sizeof(uint64_t) * 16);
+  info16[0] = B.on ? 1 : 0;
+  info16[1] = B.nchunks; info16[2] = B.ntiles; info16[3] = B.nblocks;
+  info16[4] = (uint64_t)B.bytesA; info16[5] = (uint64_t)B.bytesB; info16[6] = (uint64_t)B.far.nnz;
+  info16[7] = B.Kr; info16[8] = B.E; info16[9] = B.Dfar; info16[10] = h->N;
+  info16[11] = B.levels.size();
+  return RCG_OK;
+}
+
+int rcg_debug_blocked_copy(rcg_handle *h, int direction, int what, void *dst, uint64_t bytes) {
+  if (!h || !dst) return RCG_ERR_INVALID;
+  if (!h->haveG) { h->err = "rcg_set_factor has not been called"; return RCG_ERR_STATE; }
+  const DirectionDev &d = direction == RCG_TRSV_FORWARD ? h->fwd : h->bwd;
+  const BlockedDev &B = d.bc;
+  if (!B.on) { h->err = "blocked layout is not active"; return RCG_ERR_STATE; }
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  const void *src = nullptr;
+  uint64_t have = 0;
+  switch (what) {
+    case 0: src = B.offA; have = sizeof(int64_t) * ((uint64_t)B.nchunks + 1); break;
+    case 1: src = B.offB; have = sizeof(int64_t) * ((uint64_t)B.nchunks + 1); break;
+    case 2: src = B.blobA; have = (uint64_t)B.bytesA; break;
+    case 3: src = B.blobB; have = (uint64_t)B.bytesB; break;
+    case 4: src = B.far.rowptr; have = sizeof(int64_t) * (h->N + 1); break;
+    case 5: src = B.far.col; have = sizeof(uint32_t) * (uint64_t)B.far.nnz; break;
+    case 6: src = B.far.val; have = sizeof(double) * (uint64_t)B.far.nnz; break;
+    case 7: src = B.tile_need; have = sizeof(uint32_t) * (uint64_t)B.ntiles; break;
+    case 8: src = B.blocks; have = sizeof(BcBlock) * (uint64_t)B.nblocks; break;
+    case 9: {   // per level: {depth, first, count, capA, capB, SA, SB, groups, helpers, smem}
+      std::vector<uint64_t> v;
+      for (size_t i = 0; i < B.levels.size(); i++) {
+        const GroupHost &G = d.groups[i];
+        const BcLevel &L = B.levels[i];
+        const uint64_t row[10] = {(uint64_t)G.depth, (uint64_t)G.first, (uint64_t)G.count, L.capA, L.capB, L.SA, L.SB, L.groups, L.helpers, (uint64_t)L.smem};
+        v.insert(v.end(), row, row + 10);
+      }
+      if (bytes < v.size() * 8) { h->err = "buffer too small"; return RCG_ERR_INVALID; }
+      memcpy(dst, v.data(), v.size() * 8);
+      return RCG_OK;
+    }
+    default: h->err = "bad selector"; return RCG_ERR_INVALID;
+  }
+  if (bytes < have) { h->err = "buffer too small"; return RCG_ERR_INVALID; }
+  if (have) RCG_CUDA(h, cudaMemcpy(dst, src, have, cudaMemcpyDeviceToHost));
   return RCG_OK;
 }
 

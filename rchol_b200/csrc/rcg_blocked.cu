@@ -1,0 +1,1138 @@
+// rchol_b200 -- blocked-inverse sparse triangular solve with the rchol factor (sm_100a): the default replacement of
+// the two mkl_sparse_d_trsv calls of /root/reference/c++/util/pcg.cpp:141-159.
+//
+// Why: the reference keeps the natural order inside the nested-dissection leaves (find_separator.cpp:116-118), so the
+// dependency DAG of a leaf is ~0.2 x rows deep (5 rows per level): a row-by-row (or level-by-level) substitution is a
+// chain of ~450 000 dependent hops per leaf at 256^3 / T=8.  Here the rows of a block are cut into chunks of 32 and
+// the 32x32 lower-triangular diagonal block of every chunk is inverted densely at set-up, so the chain advances one
+// CHUNK per hop (x_k = Winv_k * t_k, one shared-memory mat-vec by one warp), 6-7x fewer and not much longer hops.
+//
+// One launch per tree level.  CTA roles inside the launch (grid = groups x (1 + helpers) <= SM count, co-resident):
+//   chain CTA (one per group, walks the blocks assigned to the group one after the other)
+//     warp 0        critical warp : per chunk  t = t' - recent entries ; x = Winv t ; window <- x ; prog++
+//                                   ALONE on its scheduler: warps 4, 8, 12 only take part in the CTA barriers (a polling
+//                                   warp on the same scheduler costs the critical warp its issue slots)
+//     warps 5-7, 9-11, 13-15  near helpers : chunk k -> helper k % 9, run ahead of the critical warp:
+//                                   t' = start - early entries (jagged diagonals) - late entries (ELL)
+//     warp 1 / 2    TMA producers : stream blob A (Winv + recent) / blob B (early + late) into two staging rings
+//     warp 3        publisher     : copies solved chunks window -> out[] (vector space), fused dot product, and publishes
+//                                   the block's progress counter with release semantics
+//   far CTAs (`helpers` per group): start[j] = rhs[j] - sum over far entries (other blocks, or >= Dfar chunks back in
+//                                   the own block); tile by tile (8 chunks), each tile as soon as the chain's published
+//                                   progress covers the tile's newest far column; tile flag released to the chain CTA.
+// Every spin wait is bounded (clock64 time-out -> abort flag, all waits of all CTAs then fall through): corrupt input
+// or a scheduling accident cannot hang the GPU; the host turns the flag into an error.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "rcg_device.cuh"
+
+namespace {
+
+constexpr int BC_THREADS = 512;           // 16 warps: critical (alone on its scheduler), 2 producers, publisher, 9 near helpers
+constexpr uint32_t BC_NH = 9;
+constexpr uint32_t BC_TR = 32;            // ring of t' vectors between helpers and the critical warp
+constexpr uint32_t BC_TILE = 8;           // chunks per far tile
+constexpr uint32_t BC_WBYTES = 1024 * 8;  // Winv, full 32x32 (zeros above the diagonal): [column pair p][row] double2
+constexpr uint32_t BC_RBATCH = 3072;      // one batch of 8 recent slots: [4 pairs][32 rows] double2 values, then
+                                          // [2 halves][32 rows] uint4 byte offsets into the window
+constexpr uint32_t BC_AHDR = 16, BC_BHDR = 80;
+constexpr long long BC_TIMEOUT_CYCLES = 3000000000ll;   // ~1.5 s at 1.965 GHz
+constexpr int BC_SMEM_MAX = 232448 - 1024;
+
+__host__ __device__ __forceinline__ uint32_t r16(uint32_t v) { return (v + 15u) & ~15u; }
+// A lone warp is bound by instruction issue: Winv is stored in full so that the mat-vec is 16 LDS.128 without
+// predicates (ptxas turns predicated shared loads into divergent branches), conflict-free, immediate offsets only.
+// byte offset of the double2 {Winv[row][2p], Winv[row][2p+1]} inside the W part of blob A
+__host__ __device__ __forceinline__ uint32_t w_pair_off(uint32_t p, uint32_t row) { return 512u * p + 16u * row; }
+__host__ __device__ __forceinline__ uint32_t rec_batches(uint32_t nslots) { return nslots <= 8u ? 1u : (nslots + 7u) / 8u; }
+
+// ---------------------------------------------------------------------------------------------------------
+// memory-model primitives
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_cta_s(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_s(uint32_t saddr, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile_u32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .u16 h;\n\tld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lds_u16_if(uint32_t &v, uint32_t saddr, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\t.reg .u16 h;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u16 h, 0;\n\t@q ld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}"
+               : "=r"(v)
+               : "r"(saddr), "r"((uint32_t)p)
+               : "memory");
+}
+__device__ __forceinline__ void sts_f64(uint32_t saddr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(saddr), "d"(v) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {   // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+
+// Bounded waiting.  guard_poll() is called after every failed poll; it returns true when the wait must be abandoned
+// (this CTA or another one timed out).  Results are then garbage and the host reports RCG_ERR_CUDA.
+struct Guard {
+  uint32_t abort_s;          // shared-space address of the CTA's abort word
+  unsigned int *abort_g;     // device-wide abort word
+  uint32_t n;
+  long long t0;
+};
+__device__ __forceinline__ bool guard_poll(Guard &G, uint32_t code) {
+  ++G.n;
+  if ((G.n & 7u) == 1u && lds_volatile_u32(G.abort_s) != 0u) return true;   // (first failed poll, then every 8th)
+  if ((G.n & 63u) == 0u) {
+    if (__ldcg(G.abort_g) != 0u) { sts_volatile_u32(G.abort_s, 1u); return true; }
+    const long long now = clock64();
+    if (G.n == 64u) G.t0 = now;
+    else if (now - G.t0 > BC_TIMEOUT_CYCLES) {
+      atomicCAS(G.abort_g, 0u, code);
+      sts_volatile_u32(G.abort_s, 1u);
+      return true;
+    }
+  }
+  return false;
+}
+#define BC_WAIT(cond, code, sleep_ns)                    \
+  do {                                                   \
+    G.n = 0;                                             \
+    while (!(cond)) {                                    \
+      if (guard_poll(G, (code))) break;                  \
+      if ((sleep_ns) > 0) __nanosleep(sleep_ns);         \
+    }                                                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// set-up kernels
+// ---------------------------------------------------------------------------------------------------------
+struct BcGeom {               // blocks in ascending solve order (device arrays of nb+1 entries)
+  const uint32_t *bounds, *chunk0, *tile0;
+  int nb;
+  uint32_t Kr, E, Dfar, wmask;
+};
+
+__device__ __forceinline__ int find_le(const uint32_t *__restrict__ a, int n, uint32_t v) {   // largest i < n with a[i] <= v
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// Row j (sorted by column, diagonal last) splits into contiguous runs:
+//   [s, p_far) far | [p_far, p_early) early | [p_early, p_late) late | [p_late, p_rec) recent | [p_rec, p_diag) own chunk | p_diag
+struct RowSplit { int64_t s, p_far, p_early, p_late, p_rec, p_diag; };
+
+__device__ __forceinline__ RowSplit split_row(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, uint32_t j,
+                                              uint32_t blo, uint32_t k, const BcGeom &g) {
+  RowSplit r;
+  r.s = rp[j];
+  r.p_diag = rp[j + 1] - 1;
+  const int ik = (int)k;
+  const uint32_t c_far = blo + 32u * (uint32_t)max(0, ik + 1 - (int)g.Dfar);
+  const uint32_t c_early = blo + 32u * (uint32_t)max(0, ik - (int)g.E);
+  const uint32_t c_late = blo + 32u * (uint32_t)max(0, ik - (int)g.Kr);
+  const uint32_t c_rec = blo + 32u * k;
+  int64_t p = r.s;
+  while (p < r.p_diag && col[p] < c_far) p++;
+  r.p_far = p;
+  while (p < r.p_diag && col[p] < c_early) p++;
+  r.p_early = p;
+  while (p < r.p_diag && col[p] < c_late) p++;
+  r.p_late = p;
+  while (p < r.p_diag && col[p] < c_rec) p++;
+  r.p_rec = p;
+  return r;
+}
+
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t warp_add_u32(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// warp per chunk: blob sizes, far row lengths, far-tile requirements
+__global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, BcGeom g,
+                                                  uint32_t nchunks, int64_t *__restrict__ sizeA, int64_t *__restrict__ sizeB,
+                                                  int64_t *__restrict__ far_cnt, uint32_t *__restrict__ tile_need, int *err) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t wpc = blockDim.x >> 5;
+  for (uint32_t gc = blockIdx.x * wpc + (threadIdx.x >> 5); gc < nchunks; gc += gridDim.x * wpc) {
+    const int b = find_le(g.chunk0, g.nb, gc);
+    const uint32_t k = gc - g.chunk0[b], blo = g.bounds[b], bhi = g.bounds[b + 1];
+    const uint32_t j = blo + 32u * k + lane;
+    uint32_t n_rec = 0, n_late = 0, n_early = 0, need = 0;
+    if (j < bhi) {
+      const RowSplit r = split_row(rp, col, j, blo, k, g);
+      if (col[r.p_diag] != j) atomicExch(err, 1);
+      far_cnt[j] = r.p_far - r.s;
+      n_early = (uint32_t)(r.p_early - r.p_far);
+      n_late = (uint32_t)(r.p_late - r.p_early);
+      n_rec = (uint32_t)(r.p_rec - r.p_late);
+      if (r.p_far > r.s) {
+        const uint32_t c = col[r.p_far - 1];
+        if (c >= blo) need = ((c - blo) >> 5) + 1u;
+      }
+    }
+    const uint32_t nslots = warp_max_u32(n_rec), nl = warp_max_u32(n_late);
+    const uint32_t ne_max = warp_max_u32(n_early), ne_tot = warp_add_u32(n_early);
+    need = warp_max_u32(need);
+    if (lane == 0) {
+      sizeA[gc] = (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
+      sizeB[gc] = (int64_t)(BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot) + 320u * nl);
+      if (need) atomicMax(&tile_need[g.tile0[b] + k / BC_TILE], need);
+    }
+  }
+}
+
+// warp per chunk: writes blob A (Winv, recent ELL), blob B (early jagged diagonals, late ELL) and the far CSR rows
+__global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col,
+                                                 const double *__restrict__ val, BcGeom g, uint32_t nchunks, uint32_t N,
+                                                 int reversed, const int64_t *__restrict__ offA, const int64_t *__restrict__ offB,
+                                                 unsigned char *__restrict__ blobA, unsigned char *__restrict__ blobB,
+                                                 const int64_t *__restrict__ far_rp, uint32_t *__restrict__ far_col,
+                                                 double *__restrict__ far_val) {
+  __shared__ double Wm_all[4][32][33];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double(*Wm)[33] = Wm_all[wib];
+  const uint32_t wpc = blockDim.x >> 5;
+  for (uint32_t gc = blockIdx.x * wpc + wib; gc < nchunks; gc += gridDim.x * wpc) {
+    const int b = find_le(g.chunk0, g.nb, gc);
+    const uint32_t k = gc - g.chunk0[b], blo = g.bounds[b], bhi = g.bounds[b + 1];
+    const uint32_t j = blo + 32u * k + lane;
+    const bool valid = j < bhi;
+    const uint32_t nr = min(32u, bhi - (blo + 32u * k));
+    RowSplit r;
+    r.s = r.p_far = r.p_early = r.p_late = r.p_rec = r.p_diag = 0;
+    if (valid) r = split_row(rp, col, j, blo, k, g);
+    const uint32_t n_early = (uint32_t)(r.p_early - r.p_far), n_late = (uint32_t)(r.p_late - r.p_early);
+    const uint32_t n_rec = (uint32_t)(r.p_rec - r.p_late), n_diag = (uint32_t)(r.p_diag - r.p_rec);
+    const uint32_t nslots = warp_max_u32(n_rec), nl = warp_max_u32(n_late);
+    const uint32_t ne_max = warp_max_u32(n_early), ne_tot = warp_add_u32(n_early);
+    unsigned char *A = blobA + offA[gc];
+    unsigned char *B = blobB + offB[gc];
+
+    // ---- far rows (vector-space columns, raw values) ---------------------------------------------------
+    if (valid) {
+      int64_t o = far_rp[j];
+      for (int64_t p = r.s; p < r.p_far; p++, o++) {
+        const uint32_t c = col[p];
+        far_col[o] = reversed ? N - 1u - c : c;
+        far_val[o] = val[p];
+      }
+    }
+    // ---- Winv: row i of the inverse of the chunk's diagonal block, all columns in parallel ----------------
+    const double dii_mine = valid ? val[r.p_diag] : 1.0;
+    for (uint32_t i = 0; i < 32u; i++) {
+      const uint32_t ni = __shfl_sync(0xffffffffu, n_diag, (int)i);
+      const long long p0 = __shfl_sync(0xffffffffu, (long long)r.p_rec, (int)i);
+      const double dii = __shfl_sync(0xffffffffu, dii_mine, (int)i);
+      double s = lane == i ? 1.0 : 0.0;
+      if (i < nr) {
+        for (uint32_t e = 0; e < ni; e++) {
+          const uint32_t m = col[p0 + e] - blo - 32u * k;   // < i
+          s = fma(-val[p0 + e], Wm[m][lane], s);
+        }
+        s = s / dii;
+      }
+      Wm[i][lane] = s;
+      __syncwarp();
+    }
+    {
+      unsigned char *Wp = A + BC_AHDR;
+      for (uint32_t pp = 0; pp < 16u; pp++) {
+        double *dst = reinterpret_cast<double *>(Wp + w_pair_off(pp, lane));
+        dst[0] = Wm[lane][2u * pp];
+        dst[1] = Wm[lane][2u * pp + 1u];
+      }
+      if (lane == 0) {
+        uint32_t *hd = reinterpret_cast<uint32_t *>(A);
+        hd[0] = rec_batches(nslots); hd[1] = nr; hd[2] = nslots; hd[3] = 0;
+      }
+    }
+    __syncwarp();
+    // ---- recent entries: batches of 8 slots; values [4 pairs][32 rows] double2, window byte offsets
+    //      [2 halves][32 rows] uint4.  Padding: value 0, offset of the slot behind the window that always holds 0.0
+    {
+      const uint32_t nbt = rec_batches(nslots);
+      for (uint32_t bt = 0; bt < nbt; bt++) {
+        unsigned char *R = A + BC_AHDR + BC_WBYTES + (size_t)BC_RBATCH * bt;
+        for (uint32_t u = 0; u < 8u; u++) {
+          const uint32_t sidx = 8u * bt + u;
+          const bool have = sidx < n_rec;
+          reinterpret_cast<double *>(R + 512u * (u >> 1) + 16u * lane)[u & 1u] = have ? val[r.p_late + sidx] : 0.0;
+          reinterpret_cast<uint32_t *>(R + 2048u + 512u * (u >> 2) + 16u * lane)[u & 3u] =
+              8u * (have ? ((col[r.p_late + sidx] - blo) & g.wmask) : (g.wmask + 1u));
+        }
+      }
+    }
+    // ---- blob B ----------------------------------------------------------------------------------------
+    {
+      uint32_t rank = 0;
+      for (uint32_t l = 0; l < 32u; l++) {
+        const uint32_t o = __shfl_sync(0xffffffffu, n_early, (int)l);
+        rank += (o > n_early || (o == n_early && l < lane)) ? 1u : 0u;
+      }
+      if (lane == 0) {
+        uint32_t *hd = reinterpret_cast<uint32_t *>(B);
+        hd[0] = ne_max; hd[1] = ne_tot; hd[2] = nl; hd[3] = 0;
+      }
+      B[16u + rank] = (unsigned char)lane;   // perm: sorted position -> row
+      B[48u + lane] = (unsigned char)rank;   // rank: row -> sorted position
+      unsigned char *cnt = B + BC_BHDR;
+      double *ev = reinterpret_cast<double *>(B + BC_BHDR + r16(ne_max));
+      uint16_t *ec = reinterpret_cast<uint16_t *>(B + BC_BHDR + r16(ne_max) + r16(8u * ne_tot));
+      uint32_t base = 0;
+      for (uint32_t s = 0; s < ne_max; s++) {
+        const uint32_t cs = (uint32_t)__popc(__ballot_sync(0xffffffffu, n_early > s));
+        if (lane == 0) cnt[s] = (unsigned char)cs;
+        if (s < n_early) {
+          ev[base + rank] = val[r.p_far + s];
+          ec[base + rank] = (uint16_t)((col[r.p_far + s] - blo) & g.wmask);
+        }
+        base += cs;
+      }
+      double *lv = reinterpret_cast<double *>(B + BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot));
+      uint16_t *lc = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(lv) + 256u * nl);
+      for (uint32_t s = 0; s < nl; s++) {
+        const bool have = s < n_late;
+        lv[s * 32u + lane] = have ? val[r.p_early + s] : 0.0;
+        lc[s * 32u + lane] = have ? (uint16_t)((col[r.p_early + s] - blo) & g.wmask) : (uint16_t)(g.wmask + 1u);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void k_gather_i64(const int64_t *__restrict__ src, const uint32_t *__restrict__ idx, int n, int64_t *__restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the solve kernel
+// ---------------------------------------------------------------------------------------------------------
+struct BcArgs {
+  const BcBlock *blocks;       // blocks of this level
+  uint32_t nblocks, ngroups, helpers;
+  const int64_t *offA, *offB;
+  const unsigned char *blobA, *blobB;
+  const int64_t *far_rp;
+  const uint32_t *far_col;
+  const double *far_val;
+  const uint32_t *tile_need;
+  uint32_t *tileflag, *gprog;
+  double *w;
+  const double *rhs;
+  double *out;
+  const double *dotvec;        // nullable
+  double *dot_partials;        // nullable: one slot per block (gidx)
+  uint32_t dot_limit;
+  uint32_t N;
+  int reversed;
+  uint32_t Kr, E, Dfar, W;     // W = 32*Dfar window rows (power of two)
+  uint32_t SA, SB, capA, capB;
+  uint32_t col_min;            // multi-GPU top separators: far columns below col_min are left out ...
+  const double *corr;          // ... their sum over all ranks arrives here (indexed by vector index - col_min)
+  unsigned int *abort_g;
+  unsigned long long *clk;     // nullable diagnostics
+  uint32_t dbg;                // bit 0: cycle profile of the critical warp and of near helper 0 (CTA 0) into clk[3..12]
+};
+
+__global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t per = 1u + P.helpers;
+  const uint32_t grp = blockIdx.x / per, role = blockIdx.x % per;
+
+  // shared-memory carve-up (chain CTAs; far CTAs only use the control words)
+  double *win = reinterpret_cast<double *>(smem);
+  double *tprime = win + P.W + 16;   // win[W] holds 0.0: the slot padding entries point at
+  double *scratch = tprime + BC_TR * 32u;
+  unsigned char *ringA = reinterpret_cast<unsigned char *>(scratch + 32);
+  unsigned char *ringB = ringA + (size_t)P.SA * P.capA;
+  uint64_t *fullA = reinterpret_cast<uint64_t *>(ringB + (size_t)P.SB * P.capB);
+  uint64_t *emptyA = fullA + P.SA;
+  uint64_t *fullB = emptyA + P.SA;
+  uint64_t *emptyB = fullB + P.SB;
+  unsigned long long *ptrB = reinterpret_cast<unsigned long long *>(emptyB + P.SB);
+  uint32_t *seqB = reinterpret_cast<uint32_t *>(ptrB + P.SB);   // running chunk index whose blob the slot holds
+  uint32_t *tready = seqB + P.SB;
+  uint32_t *ctl = tready + BC_TR;   // [0] prog: solved chunks of the current block, [1] published chunks, [2] abort
+
+  if (threadIdx.x < P.SA) { mbar_init(fullA + threadIdx.x, 1); mbar_init(emptyA + threadIdx.x, 1); }
+  if (threadIdx.x < P.SB) { mbar_init(fullB + threadIdx.x, 1); mbar_init(emptyB + threadIdx.x, 1); seqB[threadIdx.x] = 0xFFFFFFFFu; }
+  if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = 0; ctl[2] = 0; }
+  if (threadIdx.x < 16) win[P.W + threadIdx.x] = 0.0;
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  Guard G;
+  G.abort_s = smem_u32(ctl + 2);
+  G.abort_g = P.abort_g;
+  G.n = 0;
+  G.t0 = 0;
+  const uint32_t prog_s = smem_u32(ctl), pub_s = smem_u32(ctl + 1);
+
+  if (role > 0) {
+    // =========================== far CTA: start vector of the chain, tile by tile ===========================
+    const uint32_t hid = role - 1u;
+    const uint32_t sub = lane & 7u;
+    for (uint32_t bi = grp; bi < P.nblocks; bi += P.ngroups) {
+      const BcBlock b = P.blocks[bi];
+      const uint32_t nch = (b.hi - b.lo + 31u) >> 5, ntile = (nch + BC_TILE - 1u) / BC_TILE;
+      for (uint32_t t = hid; t < ntile; t += P.helpers) {
+        const uint32_t need = P.tile_need[b.tile0 + t];
+        if (need > 0u && threadIdx.x == 0) BC_WAIT(ld_acquire_gpu(P.gprog + b.gidx) >= need, 0x100u, 200);
+        __syncthreads();
+        const uint32_t r0 = b.lo + t * (32u * BC_TILE), r1 = min(b.hi, r0 + 32u * BC_TILE);
+        for (uint32_t base = r0 + warp * 4u; base < r1; base += (BC_THREADS / 32) * 4u) {
+          const uint32_t j = base + (lane >> 3);
+          const bool valid = j < r1;
+          double acc = 0.0;
+          if (valid) {
+            const int64_t e1 = P.far_rp[j + 1];
+            for (int64_t e = P.far_rp[j] + sub; e < e1; e += 8) {
+              const uint32_t c = P.far_col[e];
+              if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
+            }
+          }
+          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          if (valid && sub == 0u) {
+            const uint32_t i = P.reversed ? P.N - 1u - j : j;
+            double s = P.rhs[i];
+            if (P.corr) s -= P.corr[i - P.col_min];
+            __stcg(P.w + j, s - acc);
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          __threadfence();
+          st_release_gpu(P.tileflag + b.tile0 + t, 1u);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================= chain CTA ============================================================
+  const uint32_t wmask = P.W - 1u;
+  const uint32_t win_s = smem_u32(win), tp_s = smem_u32(tprime), sc_s = smem_u32(scratch), trdy_s = smem_u32(tready);
+  uint32_t ia0 = 0;   // chunks of the blocks this CTA has finished: running index of the staging rings
+  long long pc[7] = {0, 0, 0, 0, 0, 0, 0};   // profiling (dbg bit 0), critical warp of CTA 0: cycles waiting for blob A / for t' /
+                                          // recent entries / chunks / mat-vec / store + release
+  long long ph[5] = {0, 0, 0, 0, 0};   // near helper 0 of CTA 0: tile flag + start vector, blob B, early, wait for prog, late
+  long long clk0 = 0;
+  if (P.clk && blockIdx.x == 0 && threadIdx.x == 0) clk0 = clock64();
+
+  for (uint32_t bi = grp; bi < P.nblocks; bi += P.ngroups) {
+    const BcBlock b = P.blocks[bi];
+    const uint32_t nch = (b.hi - b.lo + 31u) >> 5;
+    if (threadIdx.x < BC_TR) tready[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) { ctl[0] = 0u; ctl[1] = 0u; }
+    __syncthreads();
+
+    if (warp == 0) {
+      // ------------------------------ critical warp ------------------------------------------------------
+      // Measured (scripts/ubench/mv.cu): a lone warp pays ~240 cycles for the 32x32 mat-vec and ~500 for the whole
+      // chunk when nothing else gets in its way; every exposed shared-memory round trip adds 50-100.  So the loop is
+      // software-pipelined: the loads of chunk k+1 that do not depend on the chain (half of Winv, the first batch of
+      // recent entries) are issued right after the mat-vec FMAs of chunk k, and their latency hides behind the
+      // reduction, the window store, the release and the poll of the next t'.
+      const bool prof = (P.dbg & 1u) != 0u && blockIdx.x == 0;
+      constexpr uint32_t WPRE = 6;   // column pairs of Winv held in registers ahead of time
+      uint32_t slot = ia0 % P.SA, par = (ia0 / P.SA) & 1u;
+      double w[2 * WPRE];
+      uint32_t o0, o1, o2, o3, o4, o5, o6, o7, nbt;
+      double v0, v1, v2, v3, v4, v5, v6, v7;
+      uint32_t w_s, r_s;
+#define BC_PRELOAD()                                                                                                      \
+      do {                                                                                                                \
+        const uint32_t a_s_ = smem_u32(ringA + (size_t)slot * P.capA);                                                    \
+        w_s = a_s_ + BC_AHDR + 16u * lane;                                                                                \
+        r_s = w_s + BC_WBYTES;                                                                                            \
+        _Pragma("unroll") for (uint32_t pp = 0; pp < WPRE; pp++)                                                          \
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w[2 * pp]), "=d"(w[2 * pp + 1]) : "r"(w_s + 512u * pp) : "memory"); \
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(r_s + 2048u) : "memory"); \
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o4), "=r"(o5), "=r"(o6), "=r"(o7) : "r"(r_s + 2560u) : "memory"); \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(r_s) : "memory");                      \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(r_s + 512u) : "memory");               \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v4), "=d"(v5) : "r"(r_s + 1024u) : "memory");              \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v6), "=d"(v7) : "r"(r_s + 1536u) : "memory");              \
+        nbt = lds_u32(a_s_);                                                                                              \
+      } while (0)
+      if (nch > 0) {
+        BC_WAIT(mbar_try(fullA + slot, par), 0x200u, 0);
+        BC_PRELOAD();
+      }
+      for (uint32_t k = 0; k < nch; k++) {
+        const uint32_t ts = k & (BC_TR - 1u);
+        long long c1 = 0;
+        if (prof) c1 = clock64();
+        // t' and its ready flag are read together; the value is only used when the flag (read first) was set
+        uint32_t rdy = ld_acquire_cta_s(trdy_s + 4u * ts);
+        double t = lds_f64(tp_s + 8u * (ts * 32u + lane));
+        if (rdy != k + 1u) {
+          BC_WAIT(ld_acquire_cta_s(trdy_s + 4u * ts) == k + 1u, 0x300u, 0);
+          t = lds_f64(tp_s + 8u * (ts * 32u + lane));
+          if (prof) pc[6] += 1;
+        }
+        long long c2 = 0;
+        if (prof) c2 = clock64();
+        double t1, t2, t3;
+        {
+          const double x0 = lds_f64(win_s + o0), x1 = lds_f64(win_s + o1), x2 = lds_f64(win_s + o2), x3 = lds_f64(win_s + o3);
+          const double x4 = lds_f64(win_s + o4), x5 = lds_f64(win_s + o5), x6 = lds_f64(win_s + o6), x7 = lds_f64(win_s + o7);
+          t = fma(-v0, x0, t);
+          t1 = -v1 * x1;
+          t2 = -v2 * x2;
+          t3 = -v3 * x3;
+          t = fma(-v4, x4, t);
+          t1 = fma(-v5, x5, t1);
+          t2 = fma(-v6, x6, t2);
+          t3 = fma(-v7, x7, t3);
+        }
+        for (uint32_t bt = 1; bt < nbt; bt++) {   // more than 8 recent slots
+          const uint32_t q_s = r_s + BC_RBATCH * bt;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(q_s + 2048u) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o4), "=r"(o5), "=r"(o6), "=r"(o7) : "r"(q_s + 2560u) : "memory");
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(q_s) : "memory");
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(q_s + 512u) : "memory");
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v4), "=d"(v5) : "r"(q_s + 1024u) : "memory");
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v6), "=d"(v7) : "r"(q_s + 1536u) : "memory");
+          const double x0 = lds_f64(win_s + o0), x1 = lds_f64(win_s + o1), x2 = lds_f64(win_s + o2), x3 = lds_f64(win_s + o3);
+          const double x4 = lds_f64(win_s + o4), x5 = lds_f64(win_s + o5), x6 = lds_f64(win_s + o6), x7 = lds_f64(win_s + o7);
+          t = fma(-v0, x0, t);
+          t1 = fma(-v1, x1, t1);
+          t2 = fma(-v2, x2, t2);
+          t3 = fma(-v3, x3, t3);
+          t = fma(-v4, x4, t);
+          t1 = fma(-v5, x5, t1);
+          t2 = fma(-v6, x6, t2);
+          t3 = fma(-v7, x7, t3);
+        }
+        t = (t + t1) + (t2 + t3);
+        sts_f64(sc_s + 8u * lane, t);
+        __syncwarp();
+        long long c3 = 0;
+        if (prof) c3 = clock64();
+        // staging slot of the next chunk: test its barrier now (non-blocking), the answer is needed a mat-vec later
+        uint32_t nslot = slot + 1u, npar = par;
+        if (nslot == P.SA) { nslot = 0; npar ^= 1u; }
+        const bool more = k + 1u < nch;
+        bool a_ready = more && mbar_test(fullA + nslot, npar);
+        double a0, a1, a2, a3;
+        {
+          double x0, x1, y0, y1;
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(sc_s) : "memory");
+          a0 = w[0] * x0;
+          a1 = w[1] * x1;
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(sc_s + 16u) : "memory");
+          a2 = w[2] * x0;
+          a3 = w[3] * x1;
+#pragma unroll
+          for (uint32_t pp = 2; pp < WPRE; pp += 2u) {
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(sc_s + 16u * pp) : "memory");
+            a0 = fma(w[2 * pp], x0, a0);
+            a1 = fma(w[2 * pp + 1], x1, a1);
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(sc_s + 16u * pp + 16u) : "memory");
+            a2 = fma(w[2 * pp + 2], x0, a2);
+            a3 = fma(w[2 * pp + 3], x1, a3);
+          }
+#pragma unroll
+          for (uint32_t pp = WPRE; pp < 16u; pp += 2u) {
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(y0), "=d"(y1) : "r"(w_s + 512u * pp) : "memory");
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(sc_s + 16u * pp) : "memory");
+            a0 = fma(y0, x0, a0);
+            a1 = fma(y1, x1, a1);
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(y0), "=d"(y1) : "r"(w_s + 512u * pp + 512u) : "memory");
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(sc_s + 16u * pp + 16u) : "memory");
+            a2 = fma(y0, x0, a2);
+            a3 = fma(y1, x1, a3);
+          }
+        }
+        long long c4 = 0;
+        if (prof) c4 = clock64();
+        // next chunk's chain-independent loads (same registers: the mat-vec above has issued its last use of them)
+        const uint32_t oslot = slot;
+        if (more) {
+          slot = nslot;
+          par = npar;
+          if (!a_ready) {
+            long long c0 = 0;
+            if (prof) c0 = clock64();
+            BC_WAIT(mbar_try(fullA + slot, par), 0x200u, 0);
+            if (prof) pc[0] += clock64() - c0;
+          }
+          BC_PRELOAD();
+        }
+        const double x = (a0 + a1) + (a2 + a3);
+        sts_f64(win_s + 8u * ((32u * k + lane) & wmask), x);
+        __syncwarp();
+        if (lane == 0) {
+          st_release_cta_s(prog_s, k + 1u);
+          mbar_arrive(emptyA + oslot);
+        }
+        if (prof) { pc[1] += c2 - c1; pc[2] += c3 - c2; pc[3] += 1; pc[4] += c4 - c3; pc[5] += clock64() - c4; }
+      }
+#undef BC_PRELOAD
+    } else if ((warp & 3u) != 0u && warp > 3u) {
+      // ------------------------------ near helpers -------------------------------------------------------
+      const uint32_t hidx = ((warp >> 2) - 1u) * 3u + (warp & 3u) - 1u;   // warps 5,6,7, 9,10,11, 13,14,15
+      const bool hprof = (P.dbg & 1u) != 0u && blockIdx.x == 0 && warp == 5;
+      uint32_t tiles_known = 0;
+      for (uint32_t k = hidx; k < nch; k += BC_NH) {
+        const uint32_t i = ia0 + k, slot = i % P.SB;
+        const uint32_t tile = k / BC_TILE;
+        long long h0 = 0;
+        if (hprof) h0 = clock64();
+        if (tile >= tiles_known) {
+          if (lane == 0) BC_WAIT(ld_acquire_gpu(P.tileflag + b.tile0 + tile) != 0u, 0x400u, 100);
+          __syncwarp();
+          tiles_known = tile + 1u;
+        }
+        const uint32_t j = b.lo + 32u * k + lane;
+        const double t0 = j < b.hi ? __ldcg(P.w + j) : 0.0;
+        long long h1 = 0;
+        if (hprof) h1 = clock64();
+        // The slot's sequence word is tested BEFORE the barrier's parity: helpers take chunks out of order, so with fewer
+        // slots than helpers a helper can be two uses ahead of its slot, where the parity test alone is already true.
+        BC_WAIT(lds_volatile_u32(smem_u32(seqB + slot)) == i && mbar_try(fullB + slot, (i / P.SB) & 1u), 0x500u, 200);
+        const unsigned char *bp = reinterpret_cast<const unsigned char *>(ptrB[slot]);
+        const uint32_t *hd = reinterpret_cast<const uint32_t *>(bp);
+        const bool skip = (P.dbg & 6u) != 0u;   // timing experiments only (results are wrong)
+        const uint32_t ne_max = skip ? 0u : hd[0], ne_tot = skip ? 0u : hd[1], nl = skip ? 0u : hd[2];
+        const uint32_t perm = bp[16u + lane], rank = bp[48u + lane];
+        const unsigned char *cnt = bp + BC_BHDR;
+        const double *ev = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max));
+        const uint16_t *ec = reinterpret_cast<const uint16_t *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot));
+        const double *lv = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot));
+        const uint16_t *lc = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(lv) + 256u * nl);
+        // early entries: columns in chunks <= k-E-1.  Four jagged diagonals per trip (their counts are one aligned
+        // 32-bit load; the padding of the count array is zero), loads independent, two FMA chains.
+        const uint32_t need1 = k > P.E ? k - P.E : 0u;
+        long long h2 = 0;
+        if (hprof) h2 = clock64();
+        BC_WAIT(ld_acquire_cta_s(prog_s) >= need1, 0x600u, 200);
+        double ts = __shfl_sync(0xffffffffu, t0, (int)perm), ts1 = 0.0;
+        uint32_t base = 0;
+        for (uint32_t s = 0; s < ne_max; s += 4u) {
+          const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cnt + s);
+          const uint32_t n0 = c4 & 255u, n1 = (c4 >> 8) & 255u, n2 = (c4 >> 16) & 255u, n3 = c4 >> 24;
+          const uint32_t b1 = base + n0, b2 = b1 + n1, b3 = b2 + n2;
+          double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+          if (lane < n0) { v0 = ev[base + lane]; x0 = win[ec[base + lane]]; }
+          if (lane < n1) { v1 = ev[b1 + lane]; x1 = win[ec[b1 + lane]]; }
+          if (lane < n2) { v2 = ev[b2 + lane]; x2 = win[ec[b2 + lane]]; }
+          if (lane < n3) { v3 = ev[b3 + lane]; x3 = win[ec[b3 + lane]]; }
+          ts = fma(-v0, x0, ts);
+          ts1 = fma(-v1, x1, ts1);
+          ts = fma(-v2, x2, ts);
+          ts1 = fma(-v3, x3, ts1);
+          base = b3 + n3;
+        }
+        ts += ts1;
+        double t = __shfl_sync(0xffffffffu, ts, (int)rank);
+        // late entries: columns in chunks k-E .. k-Kr-1.  Values and window slots of the first LB slots are loaded
+        // before the wait; the t' slot and the window slot of chunk k must be free as well.
+        constexpr uint32_t LB = 16;
+        uint32_t lcr[LB];
+        double lvr[LB];
+#pragma unroll
+        for (uint32_t u = 0; u < LB; u++) {
+          lcr[u] = 0;
+          lvr[u] = 0.0;
+          if (u < nl) { lcr[u] = lc[u * 32u + lane]; lvr[u] = lv[u * 32u + lane]; }
+        }
+        uint32_t need2 = k > P.Kr ? k - P.Kr : 0u;
+        if (k + 1u > BC_TR) need2 = max(need2, k + 1u - BC_TR);
+        long long h3 = 0;
+        if (hprof) h3 = clock64();
+        // (polling costs shared-memory issue slots the critical warp needs: sleep while the chain is two or more
+        //  chunks away, spin only for the last one)
+        {
+          uint32_t pnow = 0;
+          G.n = 0;
+          while ((pnow = ld_acquire_cta_s(prog_s)) < need2) {
+            if (guard_poll(G, 0x700u)) break;
+            if (need2 - pnow > 1u) __nanosleep(300);
+          }
+        }
+        if (k >= P.Dfar) BC_WAIT(ld_acquire_cta_s(pub_s) >= k - P.Dfar + 1u, 0x800u, 100);
+        long long h4 = 0;
+        if (hprof) h4 = clock64();
+        {
+          double xv[LB], q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+          for (uint32_t u = 0; u < LB; u++) {
+            xv[u] = 0.0;
+            lds_f64_if(xv[u], win_s + 8u * lcr[u], u < nl);
+          }
+#pragma unroll
+          for (uint32_t u = 0; u < LB; u += 4u) {
+            t = fma(-lvr[u], xv[u], t);
+            q1 = fma(-lvr[u + 1u], xv[u + 1u], q1);
+            q2 = fma(-lvr[u + 2u], xv[u + 2u], q2);
+            q3 = fma(-lvr[u + 3u], xv[u + 3u], q3);
+          }
+          for (uint32_t s = LB; s < nl; s++) q1 = fma(-lv[s * 32u + lane], win[lc[s * 32u + lane]], q1);
+          t = (t + q1) + (q2 + q3);
+        }
+        const uint32_t tsl = k & (BC_TR - 1u);
+        sts_f64(tp_s + 8u * (tsl * 32u + lane), t);
+        __syncwarp();
+        if (lane == 0) {
+          st_release_cta_s(trdy_s + 4u * tsl, k + 1u);
+          mbar_arrive(emptyB + slot);
+        }
+        if (hprof) { ph[0] += h1 - h0; ph[1] += h2 - h1; ph[2] += h3 - h2; ph[3] += h4 - h3; ph[4] += clock64() - h4; }
+      }
+    } else if (warp == 1) {
+      // ------------------------------ TMA producer, ring A -----------------------------------------------
+      for (uint32_t base = 0; base < nch; base += 32u) {
+        const uint32_t gl = b.chunk0 + min(base + lane, nch - 1u);
+        const int64_t O0 = P.offA[gl], O1 = P.offA[gl + 1];
+        for (uint32_t l = 0; l < 32u && base + l < nch; l++) {
+          const uint32_t i = ia0 + base + l, slot = i % P.SA, use = i / P.SA;
+          const int64_t e0 = __shfl_sync(0xffffffffu, O0, (int)l), e1 = __shfl_sync(0xffffffffu, O1, (int)l);
+          if (use > 0u) BC_WAIT(mbar_try(emptyA + slot, (use - 1u) & 1u), 0x900u, 20);
+          if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(e1 - e0);
+            mbar_expect_tx(fullA + slot, bytes);
+            bulk_g2s(ringA + (size_t)slot * P.capA, P.blobA + e0, bytes, fullA + slot);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp == 2) {
+      // ------------------------------ TMA producer, ring B -----------------------------------------------
+      for (uint32_t base = 0; base < nch; base += 32u) {
+        const uint32_t gl = b.chunk0 + min(base + lane, nch - 1u);
+        const int64_t O0 = P.offB[gl], O1 = P.offB[gl + 1];
+        for (uint32_t l = 0; l < 32u && base + l < nch; l++) {
+          const uint32_t i = ia0 + base + l, slot = i % P.SB, use = i / P.SB;
+          const int64_t e0 = __shfl_sync(0xffffffffu, O0, (int)l), e1 = __shfl_sync(0xffffffffu, O1, (int)l);
+          if (use > 0u) BC_WAIT(mbar_try(emptyB + slot, (use - 1u) & 1u), 0xA00u, 20);
+          if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(e1 - e0);
+            if (e1 - e0 <= (int64_t)P.capB && !(P.dbg & 4u)) {
+              unsigned char *dst = ringB + (size_t)slot * P.capB;
+              ptrB[slot] = (unsigned long long)dst;
+              sts_volatile_u32(smem_u32(seqB + slot), i);
+              mbar_expect_tx(fullB + slot, bytes);
+              bulk_g2s(dst, P.blobB + e0, bytes, fullB + slot);
+            } else {   // does not fit a staging slot: the helper reads it from HBM
+              ptrB[slot] = (unsigned long long)(P.blobB + e0);
+              sts_volatile_u32(smem_u32(seqB + slot), i);
+              mbar_arrive(fullB + slot);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp == 3) {
+      // ------------------------------ publisher ----------------------------------------------------------
+      uint32_t done = 0;
+      double dot = 0.0;
+      while (done < nch) {
+        uint32_t p = done;
+        BC_WAIT((p = ld_acquire_cta_s(prog_s)) > done, 0xB00u, 400);
+        if (p <= done) break;   // aborted
+        for (uint32_t k = done; k < p; k += 4u) {
+          double x[4], dv[4];
+          uint32_t idx[4];
+          bool ok[4];
+#pragma unroll
+          for (uint32_t u = 0; u < 4u; u++) {
+            const uint32_t j = b.lo + 32u * (k + u) + lane;
+            ok[u] = (k + u < p) && j < b.hi;
+            idx[u] = P.reversed ? P.N - 1u - j : j;
+            x[u] = lds_f64(win_s + 8u * ((32u * (k + u) + lane) & wmask));
+            dv[u] = (ok[u] && P.dotvec && idx[u] < P.dot_limit) ? P.dotvec[idx[u]] : 0.0;
+          }
+#pragma unroll
+          for (uint32_t u = 0; u < 4u; u++) {
+            if (ok[u]) {
+              P.out[idx[u]] = x[u];
+              dot = fma(x[u], dv[u], dot);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          st_release_gpu(P.gprog + b.gidx, p);
+          st_release_cta_s(pub_s, p);
+        }
+        done = p;
+      }
+      dot = warp_sum(dot);
+      if (lane == 0 && P.dot_partials) P.dot_partials[b.gidx] = dot;
+    }
+    __syncthreads();
+    ia0 += nch;
+  }
+  if (P.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    P.clk[0] = (unsigned long long)(clock64() - clk0);
+    if (P.dbg & 1u) {
+      for (int q = 0; q < 4; q++) P.clk[3 + q] = (unsigned long long)pc[q];
+      P.clk[13] = (unsigned long long)pc[4];
+      P.clk[14] = (unsigned long long)pc[5];
+      P.clk[15] = (unsigned long long)pc[6];   // failed polls of t'
+    }
+  }
+  if (P.clk && (P.dbg & 1u) && blockIdx.x == 0 && threadIdx.x == 160)
+    for (int q = 0; q < 5; q++) P.clk[8 + q] = (unsigned long long)ph[q];
+}
+
+// multi-GPU forward solve: contribution of the rank's own subtree to the right-hand sides of the top separators,
+// sbuf[i - n_sub] = sum over far entries with column < n_sub of L[j,c] out[c]   (then summed over the ranks by NCCL)
+__global__ void __launch_bounds__(256) k_bc_couple(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col,
+                                                   const double *__restrict__ val, const BcBlock *__restrict__ blocks,
+                                                   const double *__restrict__ out, double *__restrict__ sbuf, uint32_t n_sub) {
+  const BcBlock b = blocks[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const uint32_t wpc = blockDim.x >> 5;
+  for (uint32_t v = b.lo + blockIdx.x * wpc + (threadIdx.x >> 5); v < b.hi; v += gridDim.x * wpc) {
+    double acc = 0.0;
+    const int64_t e = rp[v + 1];
+    for (int64_t k = rp[v] + lane; k < e; k += 32) {
+      const uint32_t c = col[k];
+      if (c < n_sub) acc = fma(val[k], out[c], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sbuf[v - n_sub] = acc;   // forward direction: vector index == solve index
+  }
+}
+
+uint32_t floor_pow2_u32(uint32_t v) {
+  uint32_t p = 1;
+  while ((p << 1) <= v && (p << 1) != 0) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+bool rcg_use_blocked(const rcg_handle *h) {
+  return !h->opt.chain_generic && (h->opt.chain_mode == 0 || h->opt.chain_mode == 3);
+}
+
+void rcg_free_blocked(BlockedDev &b) {
+  cudaFree(b.offA); cudaFree(b.offB); cudaFree(b.blobA); cudaFree(b.blobB);
+  rcg_free_csr(b.far);
+  cudaFree(b.tile_need); cudaFree(b.flags); cudaFree(b.w); cudaFree(b.blocks);
+  b = BlockedDev();
+}
+
+// `comb`: the direction's lower-triangular matrix in its solve index space, rows sorted by column, diagonal last, raw
+// values.  Builds the blocked layout and frees `comb`.  bounds/depth describe the blocks in ascending solve order.
+int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::vector<uint32_t> &bounds,
+                      const std::vector<int> &depth, int max_depth, bool root_first) {
+  BlockedDev &B = d.bc;
+  const uint32_t N = (uint32_t)h->N;
+  const int nb = (int)bounds.size() - 1;
+  // ---- thresholds ------------------------------------------------------------------------------------
+  B.Kr = h->opt.reserved[3] > 0 ? (uint32_t)std::min(h->opt.reserved[3], 4) : 2u;
+  B.E = 16u;
+  uint32_t win_rows = h->opt.chain_window > 0 ? (uint32_t)h->opt.chain_window : 4096u;
+  B.Dfar = std::min(512u, std::max(32u, floor_pow2_u32(std::max(32u, win_rows) / 32u)));
+  // ---- chunk / tile numbering ------------------------------------------------------------------------
+  std::vector<uint32_t> chunk0(nb + 1, 0), tile0(nb + 1, 0);
+  for (int b = 0; b < nb; b++) {
+    const uint32_t nch = (bounds[b + 1] - bounds[b] + 31u) / 32u;
+    chunk0[b + 1] = chunk0[b] + nch;
+    tile0[b + 1] = tile0[b] + (nch + BC_TILE - 1u) / BC_TILE;
+  }
+  B.nchunks = chunk0[nb];
+  B.ntiles = tile0[nb];
+  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0
+  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 3 * (nb + 1)));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom, bounds.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom + (nb + 1), chunk0.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom + 2 * (nb + 1), tile0.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+  BcGeom g;
+  g.bounds = dgeom; g.chunk0 = dgeom + (nb + 1); g.tile0 = dgeom + 2 * (nb + 1);
+  g.nb = nb; g.Kr = B.Kr; g.E = B.E; g.Dfar = B.Dfar; g.wmask = 32u * B.Dfar - 1u;
+
+  // ---- sizes ---------------------------------------------------------------------------------------------
+  int *derr = nullptr;
+  RCG_CUDA(h, cudaMalloc(&derr, sizeof(int)));
+  RCG_CUDA(h, cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+  RCG_CUDA(h, cudaMalloc(&B.offA, sizeof(int64_t) * ((size_t)B.nchunks + 1)));
+  RCG_CUDA(h, cudaMalloc(&B.offB, sizeof(int64_t) * ((size_t)B.nchunks + 1)));
+  RCG_CUDA(h, cudaMalloc(&B.far.rowptr, sizeof(int64_t) * ((size_t)N + 1)));
+  RCG_CUDA(h, cudaMalloc(&B.tile_need, sizeof(uint32_t) * std::max(1u, B.ntiles)));
+  RCG_CUDA(h, cudaMemsetAsync(B.offA, 0, sizeof(int64_t) * ((size_t)B.nchunks + 1), h->stream));
+  RCG_CUDA(h, cudaMemsetAsync(B.offB, 0, sizeof(int64_t) * ((size_t)B.nchunks + 1), h->stream));
+  RCG_CUDA(h, cudaMemsetAsync(B.far.rowptr, 0, sizeof(int64_t) * ((size_t)N + 1), h->stream));
+  RCG_CUDA(h, cudaMemsetAsync(B.tile_need, 0, sizeof(uint32_t) * std::max(1u, B.ntiles), h->stream));
+  const int cgrid = (int)std::min<int64_t>(((int64_t)B.nchunks + 7) / 8, (int64_t)h->sm_count * 16);
+  k_bc_count<<<std::max(1, cgrid), 256, 0, h->stream>>>(comb.rowptr, comb.col, g, B.nchunks, B.offA, B.offB, B.far.rowptr,
+                                                       B.tile_need, derr);
+  h->stats.kernel_launches += 1;
+  int herr = 0;
+  RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  RCG_CUDA(h, cudaFree(derr));
+  if (herr) {
+    cudaFree(dgeom);
+    h->err = "factor row without a trailing diagonal after transposition (G is not triangular)";
+    return RCG_ERR_STRUCTURE;
+  }
+  RCG_TRY(rcg_exclusive_scan(h, B.offA, (int64_t)B.nchunks + 1));
+  RCG_TRY(rcg_exclusive_scan(h, B.offB, (int64_t)B.nchunks + 1));
+  RCG_TRY(rcg_exclusive_scan(h, B.far.rowptr, (int64_t)N + 1));
+  int64_t far_total = 0;
+  RCG_CUDA(h, cudaMemcpy(&B.bytesA, B.offA + B.nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  RCG_CUDA(h, cudaMemcpy(&B.bytesB, B.offB + B.nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  RCG_CUDA(h, cudaMemcpy(&far_total, B.far.rowptr + N, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  B.far.nnz = far_total;
+  RCG_CUDA(h, cudaMalloc(&B.blobA, (size_t)B.bytesA + 256));
+  RCG_CUDA(h, cudaMalloc(&B.blobB, (size_t)B.bytesB + 256));
+  RCG_CUDA(h, cudaMemsetAsync(B.blobA, 0, (size_t)B.bytesA + 256, h->stream));
+  RCG_CUDA(h, cudaMemsetAsync(B.blobB, 0, (size_t)B.bytesB + 256, h->stream));
+  RCG_CUDA(h, cudaMalloc(&B.far.col, sizeof(uint32_t) * (size_t)(far_total + 8)));
+  RCG_CUDA(h, cudaMalloc(&B.far.val, sizeof(double) * (size_t)(far_total + 8)));
+  const int fgrid = (int)std::min<int64_t>(((int64_t)B.nchunks + 3) / 4, (int64_t)h->sm_count * 16);
+  k_bc_fill<<<std::max(1, fgrid), 128, 0, h->stream>>>(comb.rowptr, comb.col, comb.val, g, B.nchunks, N, d.reversed ? 1 : 0,
+                                                      B.offA, B.offB, B.blobA, B.blobB, B.far.rowptr, B.far.col, B.far.val);
+  h->stats.kernel_launches += 1;
+  RCG_CUDA(h, cudaGetLastError());
+
+  // ---- levels (dependency groups) and their blocks -----------------------------------------------------------
+  d.groups.clear();
+  B.blocks_host.clear();
+  std::vector<int> src_block;
+  for (int gl = 0; gl <= max_depth; gl++) {
+    const int want = root_first ? gl : max_depth - gl;
+    GroupHost G;
+    G.depth = want;
+    G.first = (int)B.blocks_host.size();
+    for (int b = 0; b < nb; b++) {
+      if (depth[b] != want || bounds[b + 1] == bounds[b]) continue;
+      BcBlock bd;
+      memset(&bd, 0, sizeof(bd));
+      bd.lo = bounds[b]; bd.hi = bounds[b + 1]; bd.chunk0 = chunk0[b]; bd.tile0 = tile0[b];
+      bd.gidx = (uint32_t)B.blocks_host.size();
+      B.blocks_host.push_back(bd);
+      src_block.push_back(b);
+      G.count++;
+      G.max_rows = std::max(G.max_rows, bd.hi - bd.lo);
+      G.rows += bd.hi - bd.lo;
+    }
+    if (G.count > 0) d.groups.push_back(G);
+  }
+  B.nblocks = (uint32_t)B.blocks_host.size();
+  RCG_CUDA(h, cudaMalloc(&B.blocks, sizeof(BcBlock) * std::max<size_t>(1, B.blocks_host.size())));
+  RCG_CUDA(h, cudaMemcpyAsync(B.blocks, B.blocks_host.data(), sizeof(BcBlock) * B.blocks_host.size(), cudaMemcpyHostToDevice,
+                              h->stream));
+  RCG_CUDA(h, cudaMalloc(&B.flags, sizeof(uint32_t) * ((size_t)B.ntiles + B.nblocks + 4)));
+  RCG_CUDA(h, cudaMemsetAsync(B.flags, 0, sizeof(uint32_t) * ((size_t)B.ntiles + B.nblocks + 4), h->stream));
+  RCG_CUDA(h, cudaMalloc(&B.w, sizeof(double) * ((size_t)N + 4)));
+  RCG_CUDA(h, cudaMemsetAsync(B.w, 0, sizeof(double) * ((size_t)N + 4), h->stream));
+
+  // ---- per-level staging plan from the blob sizes ------------------------------------------------------------
+  std::vector<int64_t> hA((size_t)B.nchunks + 1), hB((size_t)B.nchunks + 1);
+  RCG_CUDA(h, cudaMemcpyAsync(hA.data(), B.offA, sizeof(int64_t) * hA.size(), cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(hB.data(), B.offB, sizeof(int64_t) * hB.size(), cudaMemcpyDeviceToHost, h->stream));
+  // far entries per block (bench statistics)
+  std::vector<int64_t> far_ends(2 * (size_t)B.nblocks);
+  {
+    std::vector<uint32_t> idx;
+    for (const BcBlock &bd : B.blocks_host) { idx.push_back(bd.lo); idx.push_back(bd.hi); }
+    uint32_t *didx = nullptr;
+    int64_t *dout = nullptr;
+    RCG_CUDA(h, cudaMalloc(&didx, sizeof(uint32_t) * std::max<size_t>(1, idx.size())));
+    RCG_CUDA(h, cudaMalloc(&dout, sizeof(int64_t) * std::max<size_t>(1, idx.size())));
+    RCG_CUDA(h, cudaMemcpyAsync(didx, idx.data(), sizeof(uint32_t) * idx.size(), cudaMemcpyHostToDevice, h->stream));
+    k_gather_i64<<<((int)idx.size() + 255) / 256, 256, 0, h->stream>>>(B.far.rowptr, didx, (int)idx.size(), dout);
+    RCG_CUDA(h, cudaMemcpyAsync(far_ends.data(), dout, sizeof(int64_t) * idx.size(), cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(didx); cudaFree(dout);
+  }
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  B.levels.clear();
+  const uint32_t W = 32u * B.Dfar;
+  for (GroupHost &G : d.groups) {
+    int64_t maxA = 0, maxB = 0, sumB = 0, nchl = 0;
+    for (int bi = G.first; bi < G.first + G.count; bi++) {
+      const BcBlock &bd = B.blocks_host[bi];
+      const uint32_t nch = (bd.hi - bd.lo + 31u) / 32u;
+      for (uint32_t c = bd.chunk0; c < bd.chunk0 + nch; c++) {
+        maxA = std::max(maxA, hA[c + 1] - hA[c]);
+        maxB = std::max(maxB, hB[c + 1] - hB[c]);
+        sumB += hB[c + 1] - hB[c];
+      }
+      nchl += nch;
+      G.ext_nnz += far_ends[2 * (size_t)bi + 1] - far_ends[2 * (size_t)bi];
+      G.loc_nnz += (hA[bd.chunk0 + nch] - hA[bd.chunk0]) + (hB[bd.chunk0 + nch] - hB[bd.chunk0]);   // bytes of the chain part
+    }
+    G.max_stage = (uint32_t)maxA;
+    BcLevel L;
+    const int64_t meanB = nchl ? sumB / nchl : 0;
+    L.capA = (uint32_t)((maxA + 127) & ~127ll);
+    int64_t capB = std::min<int64_t>(maxB, std::max<int64_t>(3 * meanB, 6144));
+    capB = std::min<int64_t>(capB, 24576);
+    L.capB = (uint32_t)((capB + 127) & ~127ll);
+    const int64_t fixed = (int64_t)W * 8 + 128 + BC_TR * 32 * 8 + 256 + BC_TR * 4 + 64 + 1024;
+    int64_t avail = (int64_t)BC_SMEM_MAX - fixed;
+    // ring A feeds one consumer (latency cover), ring B feeds BC_NH helpers that hold their slot while they work
+    int64_t SA = std::max<int64_t>(3, std::min<int64_t>(10, (avail * 4 / 10) / L.capA));
+    int64_t SB = std::max<int64_t>(3, std::min<int64_t>(2 * BC_NH + 4, (avail - SA * L.capA) / (L.capB + 24)));
+    while (SA > 3 && SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) SA--;
+    while (SB > 3 && SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) SB--;
+    if (SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) {
+      cudaFree(dgeom);
+      h->err = "blocked solve: staging slots do not fit shared memory (window too large for this factor)";
+      return RCG_ERR_INVALID;
+    }
+    L.SA = (uint32_t)SA; L.SB = (uint32_t)SB;
+    L.smem = (size_t)(fixed - 1024 + SA * L.capA + SB * L.capB + (2 * SA + 2 * SB) * 8 + SB * 12);
+    const uint32_t sms = (uint32_t)h->sm_count;
+    L.groups = std::max(1u, std::min<uint32_t>((uint32_t)G.count, sms / 2u));
+    L.helpers = std::max(1u, sms / L.groups - 1u);
+    B.levels.push_back(L);
+  }
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(dgeom);
+  rcg_free_csr(comb);
+  if (!h->abort_flag) {
+    RCG_CUDA(h, cudaMalloc(&h->abort_flag, sizeof(unsigned int) * 4));
+    RCG_CUDA(h, cudaMemset(h->abort_flag, 0, sizeof(unsigned int) * 4));
+  }
+  B.on = true;
+  return RCG_OK;
+}
+
+int rcg_check_abort(rcg_handle *h) {
+  if (!h->abort_flag) return RCG_OK;
+  unsigned int f = 0;
+  RCG_CUDA(h, cudaMemcpyAsync(&f, h->abort_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (f) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "blocked triangular solve: a dependency wait timed out (code 0x%x); results are invalid", f);
+    h->err = buf;
+    cudaMemsetAsync(h->abort_flag, 0, sizeof(unsigned int), h->stream);
+    return RCG_ERR_CUDA;
+  }
+  return RCG_OK;
+}
+
+int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double *out, const double *dotvec, int only_group,
+                       int only_kernel) {
+  BlockedDev &B = d.bc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
+    attr_set = true;
+  }
+  if (only_kernel > 0) return RCG_OK;   // the level kernel is the only kernel of a group
+  RCG_CUDA(h, cudaMemsetAsync(B.flags, 0, sizeof(uint32_t) * ((size_t)B.ntiles + B.nblocks), h->stream));
+  double *rz_part = h->partials + 2 * (size_t)h->partial_cap;
+  const bool dist_fwd = h->dist.on && !d.reversed && h->N > h->dist.n_sub;
+  const uint32_t dot_limit = h->dist.on ? h->dist.dot_limit : 0xFFFFFFFFu;
+  bool coupled = false;
+  for (size_t gi = 0; gi < d.groups.size(); gi++) {
+    if (only_group >= 0 && (int)gi != only_group) continue;
+    const GroupHost &G = d.groups[gi];
+    const BcLevel &L = B.levels[gi];
+    const bool top = dist_fwd && G.depth < h->dist.top_depth;
+    if (top && !coupled) {
+      for (const GroupHost &t : d.groups) {
+        if (t.depth >= h->dist.top_depth) continue;
+        const uint32_t gx = std::max(1u, std::min<uint32_t>((t.max_rows + 7u) / 8u, (uint32_t)h->sm_count * 8u / (uint32_t)t.count));
+        dim3 grid(gx, (unsigned)t.count);
+        k_bc_couple<<<grid, 256, 0, h->stream>>>(B.far.rowptr, B.far.col, B.far.val, B.blocks + t.first, out, h->dist.sbuf,
+                                                h->dist.n_sub);
+        h->stats.kernel_launches += 1;
+      }
+      RCG_CUDA(h, cudaGetLastError());
+      RCG_TRY(rcg_allreduce_sum(h, h->dist.sbuf, h->N - h->dist.n_sub));
+      coupled = true;
+    }
+    BcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.blocks = B.blocks + G.first;
+    a.nblocks = (uint32_t)G.count; a.ngroups = L.groups; a.helpers = L.helpers;
+    a.offA = B.offA; a.offB = B.offB; a.blobA = B.blobA; a.blobB = B.blobB;
+    a.far_rp = B.far.rowptr; a.far_col = B.far.col; a.far_val = B.far.val;
+    a.tile_need = B.tile_need;
+    a.tileflag = B.flags; a.gprog = B.flags + B.ntiles;
+    a.w = B.w; a.rhs = rhs; a.out = out;
+    a.dotvec = dotvec; a.dot_partials = dotvec ? rz_part : nullptr; a.dot_limit = dot_limit;
+    a.N = (uint32_t)h->N; a.reversed = d.reversed ? 1 : 0;
+    a.Kr = B.Kr; a.E = B.E; a.Dfar = B.Dfar; a.W = 32u * B.Dfar;
+    a.SA = L.SA; a.SB = L.SB; a.capA = L.capA; a.capB = L.capB;
+    a.col_min = top ? h->dist.n_sub : 0u;
+    a.corr = top ? h->dist.sbuf : nullptr;
+    a.abort_g = h->abort_flag;
+    a.clk = h->clk_probe;
+    a.dbg = (uint32_t)h->opt.reserved[1];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.groups * (1u + L.helpers));
+    cfg.blockDim = dim3(BC_THREADS);
+    cfg.dynamicSmemBytes = L.smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = h->opt.reserved[6] ? 0 : 1;   // reserved[6] = 1: plain launch (the grid never exceeds the SM count)
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_bc_solve, a);
+    if (e != cudaSuccess && cfg.numAttrs == 1) {
+      // co-residency is what the cooperative attribute guarantees; a context that cannot give it (or cannot capture it)
+      // still runs the launch correctly when the GPU is otherwise idle, because the grid never exceeds the SM count
+      cudaGetLastError();
+      cfg.numAttrs = 0;
+      e = cudaLaunchKernelEx(&cfg, k_bc_solve, a);
+    }
+    RCG_CUDA(h, e);
+    h->stats.kernel_launches += 1;
+  }
+  RCG_CUDA(h, cudaGetLastError());
+  return RCG_OK;
+}

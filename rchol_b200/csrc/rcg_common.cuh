@@ -53,6 +53,52 @@ struct GroupHost {
   uint32_t max_stage = 0;      // largest number of local entries in an aligned 32-row staging group
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Blocked-inverse chain layout (the default triangular solve, rcg_blocked.cu).  Inside every nested-dissection block
+// the rows keep their solve order and are cut into CHUNKS of 32 consecutive rows.  For chunk k of a block:
+//     x_k = Winv_k ( rhs_k - sum over all entries outside the chunk's diagonal block  L[j,c] x_c )
+// where Winv_k is the dense inverse of the chunk's 32x32 lower-triangular diagonal block (computed once at set-up;
+// exact-arithmetic equivalent of the row-by-row substitution).  The dependency chain of a block is then one step per
+// CHUNK instead of one step per DAG level.  Entries outside the diagonal block are classified by their chunk distance
+// d = chunk(row) - chunk(col) inside the block:
+//     1 <= d <= Kr     "recent"  applied by the critical warp of the block's chain CTA        (blob A, ELL)
+//     Kr < d <= E      "late"    applied by a helper warp of the chain CTA, low latency       (blob B, ELL)
+//     E  < d <  Dfar   "early"   applied by the same helper warp ahead of time                (blob B, jagged diagonals)
+//     d >= Dfar, and entries of other (already solved) blocks: "far" -- a row-gather SpMV done by OTHER CTAs of the
+//                      same launch, which hand the start vector to the chain CTA through HBM/L2 with release/acquire flags.
+// ---------------------------------------------------------------------------------------------------------
+struct BcBlock {               // one nested-dissection block (device copy; ordered by tree level)
+  uint32_t lo, hi;             // rows [lo, hi) in the direction's solve index space
+  uint32_t chunk0;             // global index of the block's first chunk
+  uint32_t tile0;              // global index of the block's first far tile (8 chunks)
+  uint32_t gidx;               // index of the block in the direction: progress counter, dot-partial slot
+  uint32_t pad[3];
+};
+
+struct BcLevel {               // per tree level: shared-memory plan of the launch
+  uint32_t capA = 0, capB = 0; // staging slot sizes in bytes
+  uint32_t SA = 0, SB = 0;     // staging slots
+  uint32_t groups = 0;         // chain CTAs of the launch
+  uint32_t helpers = 0;        // far CTAs per chain CTA
+  size_t smem = 0;
+};
+
+struct BlockedDev {
+  bool on = false;
+  uint32_t Kr = 2, E = 16, Dfar = 128;   // chunk-distance thresholds (see above); window = 32*Dfar rows
+  uint32_t nchunks = 0, ntiles = 0, nblocks = 0;
+  int64_t *offA = nullptr, *offB = nullptr;          // nchunks+1 byte offsets into the blobs
+  unsigned char *blobA = nullptr, *blobB = nullptr;
+  int64_t bytesA = 0, bytesB = 0;
+  CsrDev far;                                        // rows in solve space, columns in vector space, raw values
+  uint32_t *tile_need = nullptr;                     // per far tile: chunks of the own block that must be published first
+  uint32_t *flags = nullptr;                         // [0, ntiles) tile-ready flags, [ntiles, ntiles+nblocks) block progress
+  double *w = nullptr;                               // N+2: start vector of the chain (rhs - far part), solve space
+  BcBlock *blocks = nullptr;                         // device, ordered like DirectionDev::groups
+  std::vector<BcBlock> blocks_host;
+  std::vector<BcLevel> levels;                       // parallel to DirectionDev::groups
+};
+
 struct DirectionDev {          // one solve direction
   LowerTriDev M;               // rows in LEVEL SPACE: inside every block sorted by (DAG level, row); loc columns are
                                // block-relative level-space positions, ext columns are vector-space indices
@@ -63,6 +109,7 @@ struct DirectionDev {          // one solve direction
   std::vector<BlockDesc> blocks_host;
   std::vector<GroupHost> groups;
   bool reversed = false;       // vector index = N-1-solve index
+  BlockedDev bc;               // blocked-inverse chain layout (default); M / vecidx / w / grp_mask are then unused
 };
 
 // Scalars of the PCG recurrences, resident on the device (pcg.cpp:82-110 keeps them on the host).
@@ -117,6 +164,7 @@ struct rcg_handle {
 
   uint32_t *trace = nullptr;                 // diagnostics: per-row timing trace of the chain kernel (rcg_debug_trace)
   unsigned long long *clk_probe = nullptr;   // device {cycles, ns} written by CTA 0 of the chain kernel
+  unsigned int *abort_flag = nullptr;        // device: non-zero when a dependency wait of the blocked solve timed out
   cudaGraphExec_t iter_graph = nullptr;
   std::vector<double> history;
 
@@ -155,6 +203,16 @@ int rcg_setup_factor_blocks(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, c
                             const uint64_t *bounds, const int32_t *depth, uint64_t nblocks);
 void rcg_free_direction(DirectionDev &d);
 void rcg_free_csr(CsrDev &a);
+
+int rcg_exclusive_scan(rcg_handle *h, int64_t *data, int64_t n);
+// rcg_blocked.cu
+bool rcg_use_blocked(const rcg_handle *h);
+int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::vector<uint32_t> &bounds,
+                      const std::vector<int> &depth, int max_depth, bool root_first);
+int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double *out, const double *dotvec,
+                       int only_group, int only_kernel);
+void rcg_free_blocked(BlockedDev &b);
+int rcg_check_abort(rcg_handle *h);
 
 // rcg_kernels.cu  (all launches go to h->stream and bump h->stats.kernel_launches)
 int rcg_launch_spmv(rcg_handle *h, const double *x, double *y, const double *dot_r /*nullable*/, bool with_dots);

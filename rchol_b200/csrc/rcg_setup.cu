@@ -734,6 +734,7 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
                      const std::vector<int> &depth_solve, int max_depth, bool root_first) {
   const uint32_t N = (uint32_t)h->N;
   const int nb = (int)bounds_solve.size() - 1;
+  if (rcg_use_blocked(h)) return rcg_build_blocked(h, d, comb, bounds_solve, depth_solve, max_depth, root_first);
   uint32_t *dbounds = nullptr;
   int *derr = nullptr;
   RCG_CUDA(h, cudaMalloc(&dbounds, sizeof(uint32_t) * (nb + 1)));
@@ -1001,6 +1002,8 @@ int finish_direction(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::ve
 
 }  // namespace
 
+int rcg_exclusive_scan(rcg_handle *h, int64_t *data, int64_t n) { return exclusive_scan_inplace(h, data, n); }
+
 void rcg_free_csr(CsrDev &a) {
   cudaFree(a.rowptr); cudaFree(a.col); cudaFree(a.val);
   a = CsrDev();
@@ -1012,6 +1015,7 @@ void rcg_free_direction(DirectionDev &d) {
   cudaFree(d.vecidx);
   cudaFree(d.w);
   cudaFree(d.grp_mask);
+  rcg_free_blocked(d.bc);
   d = DirectionDev();
 }
 

@@ -887,6 +887,7 @@ uint32_t aux_grid_x(const rcg_handle *h, const GroupHost &g, uint32_t rows_per_c
 
 // number of dot-partial slots a direction's post kernels write (one per CTA), and each group's first slot
 int rcg_post_slots(const rcg_handle *h, const DirectionDev &d, std::vector<int> *first_slot) {
+  if (d.bc.on) return (int)d.bc.nblocks;   // blocked solve: one partial per block, written by the block's publisher warp
   int total = 0;
   if (first_slot) first_slot->clear();
   for (const GroupHost &g : d.groups) {
@@ -901,6 +902,7 @@ int rcg_post_slots(const rcg_handle *h, const DirectionDev &d, std::vector<int> 
 // only_group / only_kernel (measurement): run a single group and a single kernel of it (0 chain, 1 pre, 2 post).
 int rcg_launch_trisolve(rcg_handle *h, DirectionDev &d, const double *rhs, double *out, const double *dotvec,
                         int only_group, int only_kernel) {
+  if (d.bc.on) return rcg_launch_blocked(h, d, rhs, out, dotvec, only_group, only_kernel);
   double *rz_part = h->partials + 2 * (size_t)h->partial_cap;
   std::vector<int> first_slot;
   rcg_post_slots(h, d, &first_slot);

@@ -1,0 +1,108 @@
+"""Host interpreter of the blocked triangular-solve layout (TEST INFRASTRUCTURE, never on the product path).
+
+``solve_from_layout`` replays, chunk by chunk and with the same shared-memory window ring, what k_bc_solve
+(rchol_b200/csrc/rcg_blocked.cu) does with the arrays that the set-up kernels built on the device.  It separates
+"the set-up produced a wrong layout" from "the solve kernel mis-reads a right layout" in one GPU run.
+"""
+import numpy as np
+
+AHDR, BHDR, WBYTES, RBATCH = 16, 80, 1024 * 8, 3072
+
+
+def r16(v):
+    return (v + 15) & ~15
+
+
+def w_pair_off(p, row):
+    """Byte offset of {Winv[row][2p], Winv[row][2p+1]} in the W part of blob A (rcg_blocked.cu)."""
+    return 512 * p + 16 * row
+
+
+def rec_batches(nslots):
+    return 1 if nslots <= 8 else (nslots + 7) // 8
+
+
+def unpack_winv(raw):
+    """1024 doubles [column pair][row] double2 -> dense 32x32."""
+    return raw.reshape(16, 32, 2).transpose(1, 0, 2).reshape(32, 32).copy()
+
+
+def unpack_recent(raw_bytes, nbt):
+    """Batches of 8 recent slots -> (values [8*nbt, 32], window slots [8*nbt, 32])."""
+    rv = np.zeros((8 * nbt, 32))
+    rc = np.zeros((8 * nbt, 32), np.int64)
+    for bt in range(nbt):
+        R = raw_bytes[RBATCH * bt: RBATCH * (bt + 1)]
+        vals = R[:2048].view(np.float64).reshape(4, 32, 2)      # [pair][row][2]
+        offs = R[2048:].view(np.uint32).reshape(2, 32, 4)        # [half][row][4] byte offsets into the window
+        for u in range(8):
+            rv[8 * bt + u] = vals[u >> 1, :, u & 1]
+            rc[8 * bt + u] = offs[u >> 2, :, u & 3] // 8
+    return rv, rc
+
+
+def solve_from_layout(lay, rhs, reversed_):
+    N, Dfar = lay["N"], lay["Dfar"]
+    wrows = 32 * Dfar
+    wmask = wrows - 1
+    out = np.zeros(N)
+    A, B = lay["blobA"], lay["blobB"]
+    far_rp, far_col, far_val = lay["far_rp"], lay["far_col"].astype(np.int64), lay["far_val"]
+    stats = dict(chunks=0, rec_slots=0, late_slots=0, early_max=0, early_tot=0)
+    for lo, hi, chunk0, tile0, gidx, *_ in lay["blocks"].astype(np.int64):
+        nch = (hi - lo + 31) // 32
+        win = np.full(wrows + 1, np.nan)
+        win[wrows] = 0.0   # the slot padding entries point at
+        for k in range(nch):
+            g = chunk0 + k
+            j = lo + 32 * k + np.arange(32)
+            valid = j < hi
+            t0 = np.zeros(32)
+            for l in np.nonzero(valid)[0]:
+                jj = j[l]
+                i = N - 1 - jj if reversed_ else jj
+                s, e = far_rp[jj], far_rp[jj + 1]
+                t0[l] = rhs[i] - np.dot(far_val[s:e], out[far_col[s:e]])
+            need = lay["tile_need"][tile0 + k // 8]
+            assert need <= 8 * (k // 8), "far tile would wait for a chunk of its own tile"
+            # ---- blob B: early (jagged diagonals) + late (ELL) --------------------------------------------
+            b = B[lay["offB"][g]: lay["offB"][g + 1]]
+            ne_max, ne_tot, nl = (int(v) for v in b[:12].view(np.uint32))
+            perm, rank = b[16:48].astype(np.int64), b[48:80].astype(np.int64)
+            assert sorted(perm) == list(range(32)) and np.array_equal(perm[rank], np.arange(32))
+            cnt = b[BHDR: BHDR + ne_max].astype(np.int64)
+            o = BHDR + r16(ne_max)
+            ev = b[o: o + 8 * ne_tot].view(np.float64)
+            o += r16(8 * ne_tot)
+            ec = b[o: o + 2 * ne_tot].view(np.uint16).astype(np.int64)
+            o += r16(2 * ne_tot)
+            lv = b[o: o + 256 * nl].view(np.float64).reshape(nl, 32)
+            lc = b[o + 256 * nl: o + 320 * nl].view(np.uint16).astype(np.int64).reshape(nl, 32)
+            assert o + 320 * nl == len(b) and cnt.sum() == ne_tot
+            ts = t0[perm]
+            base = 0
+            for s in range(ne_max):
+                cs = cnt[s]
+                ts[:cs] -= ev[base: base + cs] * win[ec[base: base + cs]]
+                base += cs
+            t = ts[rank]
+            for s in range(nl):
+                t -= lv[s] * win[lc[s]]
+            # ---- blob A: Winv + recent (ELL) ------------------------------------------------------------
+            a = A[lay["offA"][g]: lay["offA"][g + 1]]
+            nbt, nr, nslots = (int(v) for v in a[:12].view(np.uint32))
+            assert nr == int(valid.sum()) and nbt == rec_batches(nslots) and len(a) == AHDR + WBYTES + RBATCH * nbt
+            W = unpack_winv(a[AHDR: AHDR + WBYTES].view(np.float64))
+            rv, rc = unpack_recent(a[AHDR + WBYTES:], nbt)
+            for s in range(8 * nbt):
+                t -= rv[s] * win[rc[s]]
+            x = W @ t
+            win[(32 * k + np.arange(32)) & wmask] = x
+            jv = j[valid]
+            out[(N - 1 - jv) if reversed_ else jv] = x[valid]
+            stats["chunks"] += 1
+            stats["rec_slots"] += nslots
+            stats["late_slots"] += nl
+            stats["early_max"] += ne_max
+            stats["early_tot"] += ne_tot
+    return out, stats

@@ -1,0 +1,197 @@
+"""Python restatement of the blocked triangular-solve layout built by k_bc_count / k_bc_fill
+(rchol_b200/csrc/rcg_blocked.cu).  TEST INFRASTRUCTURE: used to check the device-built layout field by field and, with
+tests/blocked_emulator.py, to exercise the algorithm on the CPU (-m "not gpu")."""
+import numpy as np
+import scipy.sparse as sp
+
+from blocked_emulator import AHDR, BHDR, WBYTES, RBATCH, r16, w_pair_off, rec_batches
+
+
+def tree_depths(nb):
+    """Depth of every block of the reference's post-order layout (rchol_lap.cpp:254-261)."""
+    depth = np.zeros(nb, np.int64)
+
+    def rec(start, total, d):
+        if total == 1:
+            depth[start] = d
+        else:
+            depth[start + total - 1] = d
+            h = (total - 1) // 2
+            rec(start, h, d + 1)
+            rec(start + h, h, d + 1)
+    rec(0, nb, 0)
+    return depth
+
+
+def direction_matrix(G, part, backward):
+    """Lower-triangular solve matrix of a direction in its solve index space + block bounds / depths."""
+    rp, ci, v = (np.asarray(a) for a in G)
+    N = len(rp) - 1
+    U = sp.csr_matrix((v, ci.astype(np.int64), rp.astype(np.int64)), shape=(N, N))
+    bounds = np.array([0, N], np.int64) if part is None or len(part) < 2 else np.asarray(part, np.int64)
+    nb = len(bounds) - 1
+    depth = tree_depths(nb)
+    if not backward:
+        L = U.T.tocsr()
+    else:
+        J = np.arange(N)[::-1]
+        L = U[J][:, J].tocsr()
+        bounds = N - bounds[::-1]
+        depth = depth[::-1]
+    L.sort_indices()
+    return L, bounds, depth
+
+
+def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, reversed_=False):
+    N = L.shape[0]
+    rp, col, val = L.indptr.astype(np.int64), L.indices.astype(np.int64), L.data
+    nb = len(bounds) - 1
+    wmask = 32 * Dfar - 1
+    chunk0 = np.zeros(nb + 1, np.int64)
+    tile0 = np.zeros(nb + 1, np.int64)
+    for b in range(nb):
+        nch = (bounds[b + 1] - bounds[b] + 31) // 32
+        chunk0[b + 1] = chunk0[b] + nch
+        tile0[b + 1] = tile0[b] + (nch + 7) // 8
+    nchunks, ntiles = int(chunk0[nb]), int(tile0[nb])
+    blobsA, blobsB = [None] * nchunks, [None] * nchunks
+    tile_need = np.zeros(ntiles, np.uint32)
+    far_rows = [None] * N
+    for b in range(nb):
+        blo, bhi = int(bounds[b]), int(bounds[b + 1])
+        for k in range((bhi - blo + 31) // 32):
+            g = int(chunk0[b]) + k
+            rows = [j for j in range(blo + 32 * k, min(bhi, blo + 32 * k + 32))]
+            nr = len(rows)
+            c_far = blo + 32 * max(0, k + 1 - Dfar)
+            c_early = blo + 32 * max(0, k - E)
+            c_late = blo + 32 * max(0, k - Kr)
+            c_rec = blo + 32 * k
+            parts = []
+            D = np.zeros((32, 32))
+            for l, j in enumerate(rows):
+                s, e = rp[j], rp[j + 1]
+                assert col[e - 1] == j
+                cj, vj = col[s:e - 1], val[s:e - 1]
+                m_far = cj < c_far
+                m_early = (cj >= c_far) & (cj < c_early)
+                m_late = (cj >= c_early) & (cj < c_late)
+                m_rec = (cj >= c_late) & (cj < c_rec)
+                m_diag = cj >= c_rec
+                parts.append((cj[m_early], vj[m_early], cj[m_late], vj[m_late], cj[m_rec], vj[m_rec]))
+                D[l, cj[m_diag] - c_rec] = vj[m_diag]
+                D[l, l] = val[e - 1]
+                fc = cj[m_far]
+                far_rows[j] = ((N - 1 - fc) if reversed_ else fc, vj[m_far])
+                loc = fc[fc >= blo]
+                if len(loc):
+                    t = int(tile0[b]) + k // 8
+                    tile_need[t] = max(tile_need[t], (int(loc[-1]) - blo) // 32 + 1)
+            for l in range(nr, 32):
+                D[l, l] = 1.0
+                parts.append((np.zeros(0, np.int64), np.zeros(0), np.zeros(0, np.int64), np.zeros(0), np.zeros(0, np.int64), np.zeros(0)))
+            W = np.zeros((32, 32))
+            for i in range(32):
+                e_i = np.zeros(32)
+                e_i[i] = 1.0
+                W[i] = (e_i - D[i, :i] @ W[:i]) / D[i, i]
+            n_early = np.array([len(p[0]) for p in parts])
+            n_late = np.array([len(p[2]) for p in parts])
+            n_rec = np.array([len(p[4]) for p in parts])
+            nslots, nl, ne_max, ne_tot = int(n_rec.max()), int(n_late.max()), int(n_early.max()), int(n_early.sum())
+            # blob A
+            nbt = rec_batches(nslots)
+            a = np.zeros(AHDR + WBYTES + RBATCH * nbt, np.uint8)
+            a[:12].view(np.uint32)[:] = [nbt, nr, nslots]
+            wp = a[AHDR:AHDR + WBYTES].view(np.float64)
+            for pp in range(16):
+                for row in range(32):
+                    o = w_pair_off(pp, row) // 8
+                    wp[o] = W[row, 2 * pp]
+                    wp[o + 1] = W[row, 2 * pp + 1]
+            for bt in range(nbt):
+                R = a[AHDR + WBYTES + RBATCH * bt: AHDR + WBYTES + RBATCH * (bt + 1)]
+                vals = R[:2048].view(np.float64).reshape(4, 32, 2)
+                offs = R[2048:].view(np.uint32).reshape(2, 32, 4)
+                offs[:] = 8 * (wmask + 1)
+                for l, p in enumerate(parts):
+                    for u in range(8):
+                        sidx = 8 * bt + u
+                        if sidx < len(p[4]):
+                            vals[u >> 1, l, u & 1] = p[5][sidx]
+                            offs[u >> 2, l, u & 3] = 8 * ((p[4][sidx] - blo) & wmask)
+            blobsA[g] = a
+            # blob B
+            order = sorted(range(32), key=lambda l: (-n_early[l], l))
+            rank = np.zeros(32, np.int64)
+            rank[order] = np.arange(32)
+            bb = np.zeros(BHDR + r16(ne_max) + r16(8 * ne_tot) + r16(2 * ne_tot) + 320 * nl, np.uint8)
+            bb[:12].view(np.uint32)[:] = [ne_max, ne_tot, nl]
+            bb[16:48] = order
+            bb[48:80] = rank
+            o = BHDR + r16(ne_max)
+            ev = bb[o: o + 8 * ne_tot].view(np.float64)
+            o += r16(8 * ne_tot)
+            ec = bb[o: o + 2 * ne_tot].view(np.uint16)
+            o += r16(2 * ne_tot)
+            lv = bb[o: o + 256 * nl].view(np.float64).reshape(nl, 32)
+            lc = bb[o + 256 * nl:].view(np.uint16).reshape(nl, 32)
+            base = 0
+            for s in range(ne_max):
+                cs = int((n_early > s).sum())
+                bb[BHDR + s] = cs
+                for l in range(32):
+                    if n_early[l] > s:
+                        ev[base + rank[l]] = parts[l][1][s]
+                        ec[base + rank[l]] = (parts[l][0][s] - blo) & wmask
+                base += cs
+            lc[:] = wmask + 1
+            for l, p in enumerate(parts):
+                lv[:len(p[2]), l] = p[3]
+                lc[:len(p[2]), l] = (p[2] - blo) & wmask
+            blobsB[g] = bb
+    offA = np.concatenate([[0], np.cumsum([len(a) for a in blobsA])]).astype(np.int64)
+    offB = np.concatenate([[0], np.cumsum([len(a) for a in blobsB])]).astype(np.int64)
+    far_rp = np.concatenate([[0], np.cumsum([len(r[0]) for r in far_rows])]).astype(np.int64)
+    blocks = []
+    max_depth = int(depth.max()) if nb else 0
+    for gl in range(max_depth + 1):
+        want = gl if root_first else max_depth - gl
+        for b in range(nb):
+            if depth[b] == want and bounds[b + 1] > bounds[b]:
+                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), 0, 0, 0])
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
+    return dict(active=1, nchunks=nchunks, ntiles=ntiles, nblocks=len(blocks), N=N, Kr=Kr, E=E, Dfar=Dfar,
+                offA=offA, offB=offB, blobA=cat(blobsA, np.uint8), blobB=cat(blobsB, np.uint8), far_rp=far_rp,
+                far_col=cat([r[0] for r in far_rows], np.uint32), far_val=cat([r[1] for r in far_rows], np.float64),
+                tile_need=tile_need, blocks=np.array(blocks, np.uint32).reshape(-1, 8))
+
+
+def compare_layouts(dev, ref, val_tol=1e-12):
+    """Device-built layout against the Python restatement: integers exact, values to val_tol (relative to max)."""
+    for k in ("nchunks", "ntiles", "nblocks", "N", "Kr", "E", "Dfar"):
+        assert dev[k] == ref[k], k
+    for k in ("offA", "offB", "far_rp", "far_col", "tile_need", "blocks"):
+        assert np.array_equal(dev[k], ref[k]), k
+    np.testing.assert_allclose(dev["far_val"], ref["far_val"], rtol=0, atol=0)
+    for name, off in (("blobA", "offA"), ("blobB", "offB")):
+        da, ra = dev[name], ref[name]
+        assert len(da) == len(ra), name
+    # blob A: header + values + column slots
+    for g in range(ref["nchunks"]):
+        a, r = dev["blobA"][ref["offA"][g]: ref["offA"][g + 1]], ref["blobA"][ref["offA"][g]: ref["offA"][g + 1]]
+        assert np.array_equal(a[:12], r[:12]), ("A header", g)
+        nslots = int(r[:12].view(np.uint32)[2])
+        wd, wr = a[AHDR:AHDR + WBYTES].view(np.float64), r[AHDR:AHDR + WBYTES].view(np.float64)
+        assert np.abs(wd - wr).max() <= val_tol * max(1.0, np.abs(wr).max()), ("Winv", g)
+        assert np.array_equal(a[AHDR + WBYTES:], r[AHDR + WBYTES:]), ("recent", g, nslots)
+        b, rb = dev["blobB"][ref["offB"][g]: ref["offB"][g + 1]], ref["blobB"][ref["offB"][g]: ref["offB"][g + 1]]
+        assert np.array_equal(b[:12], rb[:12]) and np.array_equal(b[16:80], rb[16:80]), ("B header", g)
+        ne_max, ne_tot, nl = (int(v) for v in rb[:12].view(np.uint32))
+        assert np.array_equal(b[BHDR:BHDR + ne_max], rb[BHDR:BHDR + ne_max]), ("cnt", g)
+        o = BHDR + r16(ne_max)
+        assert np.array_equal(b[o:o + 8 * ne_tot], rb[o:o + 8 * ne_tot]), ("early val", g)
+        o += r16(8 * ne_tot)
+        assert np.array_equal(b[o:o + 2 * ne_tot], rb[o:o + 2 * ne_tot]), ("early col", g)
+        o += r16(2 * ne_tot)
+        assert np.array_equal(b[o:], rb[o:]), ("late", g)
