@@ -228,51 +228,52 @@ def run_ours_single(args, d, B_iter):
 
     # ---- per-phase and per-kernel split (live CUDA events) ------------------------------------------------------
     prof = s.profile_iteration(3)
-    # The triangular solves run as one launch triple (pre / chain / post) per tree level and window-sized segment.
-    # Dominant kernel = k_tri_chain_fast; its launches are timed one by one with CUDA events (rcg_time_group).
+    # The triangular solves run as ONE launch per tree level and direction (k_bc_solve, rcg_blocked.cu): the dominant
+    # kernel.  Every launch is timed with CUDA events on the library's stream (rcg_time_group).
+    # Algorithmic bytes of a launch: 12 B per factor entry of the level's rows, 4 B row pointer per row,
+    # right-hand side in and solution out (16 B per row).
     per_level = {}
-    chain_ms_total, chain_bytes_total, chain_launches = 0.0, 0, 0
-    aux_ms_total, aux_bytes_total = 0.0, 0
+    chain_ms_total, chain_bytes_total, chain_launches, blob_bytes_total, far_nnz_total = 0.0, 0, 0, 0, 0
     dom = None
     for direction, dname in ((capi.TRSV_FORWARD, "fwd"), (capi.TRSV_BACKWARD, "bwd")):
         for gi, g in enumerate(s.groups(direction)):
-            chain_ms = s.time_group(direction, gi, 0, 2)
-            pre_ms = s.time_group(direction, gi, 1, 2)
-            post_ms = s.time_group(direction, gi, 2, 2)
-            # algorithmic bytes of one launch: 12 B per entry, 4 B row pointer per row, start vector in, solution out
-            chain_bytes = 12 * g["loc_nnz"] + 4 * g["rows"] + 16 * g["rows"]
-            aux_bytes = 12 * g["ext_nnz"] + 4 * g["rows"] + 4 * 8 * g["rows"]
-            chain_ms_total += chain_ms; chain_bytes_total += chain_bytes; chain_launches += 1
-            aux_ms_total += pre_ms + post_ms; aux_bytes_total += aux_bytes
-            key = f"{dname}:{g['blocks']}blocks"
-            e = per_level.setdefault(key, dict(launches=0, rows=0, chain_ms=0.0, pre_post_ms=0.0, chain_bytes=0))
-            e["launches"] += 1; e["rows"] += g["rows"]; e["chain_ms"] += chain_ms; e["pre_post_ms"] += pre_ms + post_ms
-            e["chain_bytes"] += chain_bytes
-            if dom is None or chain_ms > dom[1]:
-                dom = (f"k_tri_chain_fast[{dname} group {gi}: {g['blocks']} blocks, {g['rows']} rows]", chain_ms, chain_bytes)
-    for e in per_level.values():
-        e["chain_gbs"] = e["chain_bytes"] / e["chain_ms"] / 1e6 if e["chain_ms"] else 0.0
-    groups = per_level
+            ms = s.time_group(direction, gi, 0, 3)
+            nnz_level = g["loc_nnz"] + g["ext_nnz"]
+            lbytes = 12 * nnz_level + 4 * g["rows"] + 16 * g["rows"]
+            chain_ms_total += ms; chain_bytes_total += lbytes; chain_launches += 1
+            blob_bytes_total += g["max_stage"]; far_nnz_total += g["ext_nnz"]
+            per_level[f"{dname}:level{gi}:{g['blocks']}blocks"] = dict(
+                rows=g["rows"], entries_chain_ctas=g["loc_nnz"], entries_far_ctas=g["ext_nnz"], chain_blob_bytes=g["max_stage"],
+                ms=ms, algorithmic_bytes=lbytes, gbs=lbytes / ms / 1e6 if ms else 0.0,
+                chunks_per_block_per_us=g["rows"] / 32 / max(g["blocks"], 1) / ms / 1e3 if ms else 0.0)
+            if dom is None or ms > dom[1]:
+                dom = (f"k_bc_solve[{dname} level {gi}: {g['blocks']} blocks, {g['rows']} rows]", ms, lbytes)
     spmv_ms = prof["spmv_ms"]
     ach = chain_bytes_total / chain_ms_total / 1e6
-    roofline = dict(bound="hbm", kernel="k_tri_chain_fast (all launches of one forward + one backward solve)",
+    # bytes the launches actually stream: chain blobs (dense inverses included) + 12 B per far entry + vectors
+    moved = blob_bytes_total + 12 * far_nnz_total + 2 * (4 + 24) * N
+    traffic_ratio = None
+    try:
+        traffic_ratio = float(json.load(open(os.path.join(ROOT, "profiles", "r01_bc_traffic.json")))["dram_bytes_over_algorithmic"])
+    except Exception:
+        pass
+    roofline = dict(bound="hbm", kernel="k_bc_solve (one launch per tree level: all launches of one forward + one backward solve)",
                     achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
-                    # dram__bytes_read+write per launch from the ncu --set full capture (profiles/r01_chain_kernel_ncu.md):
-                    # 4.66 MB for a 4.8 MB-algorithmic leaf-segment launch, i.e. traffic ~= 1.0 x algorithmic bytes
-                    traffic=0.97 * chain_bytes_total / chain_launches, traffic_source="ncu capture lap3d 128^3 (ratio 0.97 to algorithmic)",
+                    # dram__bytes_read+write of the dominant launch from the ncu --set full capture, scaled per launch
+                    traffic=(traffic_ratio * chain_bytes_total / chain_launches) if traffic_ratio else None,
+                    traffic_source="ncu --set full capture of the leaf-level launch, lap3d 128^3 (profiles/r01_bc_traffic.json)",
                     peak_source=peak_src,
                     launches_per_solve_pair=chain_launches, bytes_per_launch=chain_bytes_total / chain_launches,
-                    ms_per_launch=chain_ms_total / chain_launches, chain_ms_per_iteration=chain_ms_total,
-                    pre_post_ms_per_iteration=aux_ms_total,
-                    pre_post_gbs=aux_bytes_total / aux_ms_total / 1e6 if aux_ms_total else 0.0,
+                    ms_per_launch=chain_ms_total / chain_launches, trsv_kernel_ms_per_iteration=chain_ms_total,
+                    streamed_bytes_per_iteration=moved, streamed_gbs=moved / chain_ms_total / 1e6,
                     largest_launch=dict(kernel=dom[0], ms=dom[1], gbs=dom[2] / dom[1] / 1e6),
-                    note="latency-bound dependency chain of the factor (one CTA per nested-dissection block); "
-                         "see DESIGN.md 'SpTRSV' for the critical-path bound",
+                    note="dependency chain of the factor, one chain CTA per nested-dissection block: with T=8 leaves only 8 "
+                         "SMs carry the chain, so the kernel is bound by the per-chunk latency of the chain (DESIGN.md "
+                         "'SpTRSV'), not by HBM",
                     iteration=dict(bytes=B_iter, ms=dev_ms / max(iters_total, 1), gbs=value, frac=value / peak,
                                    trsv_ms=prof["trsv_ms"], spmv_ms=spmv_ms, blas1_ms=prof["blas1_ms"],
-                                   spmv_gbs=(12 * nnzA + 4 * N + 24 * N) / spmv_ms / 1e6 if spmv_ms else 0.0,
-                                   dag_levels=dict(fwd=prof.get("dag_levels_fwd"), bwd=prof.get("dag_levels_bwd"))),
-                    tree_levels=groups)
+                                   spmv_gbs=(12 * nnzA + 4 * N + 24 * N) / spmv_ms / 1e6 if spmv_ms else 0.0),
+                    tree_levels=per_level)
     s.close()
 
     # ---- end to end through the drop-in entry point, host buffers -------------------------------------------------

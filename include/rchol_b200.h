@@ -51,7 +51,8 @@ typedef struct rcg_options {
   int chain_mode;          /* 0/3 = blocked-inverse chain (default), 1 = level-space sync-free polling kernel,
                               2 = level-space role-specialised kernel (experimental)                                 */
   int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2),
-                              [3] blocked solve: recent chunk distance Kr (default 2), [6] 1 = plain (non-cooperative) launch */
+                              [3] blocked solve: recent chunk distance Kr (default 2), [4] window rows of the separator blocks
+                              (default 1024), [6] 1 = plain (non-cooperative) launch */
 } rcg_options;
 
 /* Per-handle measurements, all device-side times from CUDA events on the handle's own stream. */
@@ -144,9 +145,11 @@ int rcg_time_phase(rcg_handle *h, int phase, int reps, double *avg_ms);
 
 /* Dependency groups of a triangular solve (one per tree level; direction RCG_TRSV_FORWARD / RCG_TRSV_BACKWARD).
  * rcg_get_group_count returns the number of groups through *count.  rcg_get_group_info fills info[0..5] =
- * {blocks, rows, local nnz (chain kernel), external nnz (pre-pass kernel), largest block rows, largest staging group}.
- * rcg_time_group times `reps` launches of ONE kernel of one group with CUDA events: kernel 0 = dependency-chain
- * kernel, 1 = external (pre-pass) kernel; *avg_ms = average duration of one launch (0 if the group has no such kernel). */
+ * {blocks, rows, entries handled by the chain CTAs, entries handled as a row-gather SpMV (far CTAs / pre-pass kernel),
+ * largest block rows, blocked solve: bytes of the level's chain blobs (level-space kernels: largest staging group)}.
+ * rcg_time_group times `reps` launches of ONE kernel of one group with CUDA events: kernel 0 = the level's solve kernel
+ * (blocked solve: k_bc_solve, the only kernel of a level), 1 / 2 = pre-pass / scatter kernels of the level-space path;
+ * *avg_ms = average duration of one launch (0 if the group has no such kernel). */
 int rcg_get_group_count(rcg_handle *h, int direction, int *count);
 int rcg_get_group_info(rcg_handle *h, int direction, int group, uint64_t *info6);
 int rcg_time_group(rcg_handle *h, int direction, int group, int kernel, int reps, double *avg_ms);

@@ -441,7 +441,7 @@ int rcg_get_group_info(rcg_handle *h, int direction, int group, uint64_t *info6)
   if (group < 0 || group >= (int)d.groups.size()) { h->err = "group out of range"; return RCG_ERR_INVALID; }
   const GroupHost &g = d.groups[group];
   info6[0] = (uint64_t)g.count; info6[1] = (uint64_t)g.rows; info6[2] = (uint64_t)g.loc_nnz;
-  info6[3] = (uint64_t)g.ext_nnz; info6[4] = g.max_rows; info6[5] = g.max_stage;
+  info6[3] = (uint64_t)g.ext_nnz; info6[4] = g.max_rows; info6[5] = d.bc.on ? (uint64_t)g.blob_bytes : g.max_stage;
   return RCG_OK;
 }
 
@@ -487,6 +487,7 @@ int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16) {
   info16[4] = (uint64_t)B.bytesA; info16[5] = (uint64_t)B.bytesB; info16[6] = (uint64_t)B.far.nnz;
   info16[7] = B.Kr; info16[8] = B.E; info16[9] = B.Dfar; info16[10] = h->N;
   info16[11] = B.levels.size();
+  info16[12] = B.Dfar_sep;
   return RCG_OK;
 }
 

@@ -149,9 +149,9 @@ __device__ __forceinline__ bool guard_poll(Guard &G, uint32_t code) {
 // set-up kernels
 // ---------------------------------------------------------------------------------------------------------
 struct BcGeom {               // blocks in ascending solve order (device arrays of nb+1 entries)
-  const uint32_t *bounds, *chunk0, *tile0;
+  const uint32_t *bounds, *chunk0, *tile0, *dfar;   // dfar: per block (leaves keep a large window, separators a small one)
   int nb;
-  uint32_t Kr, E, Dfar, wmask;
+  uint32_t Kr, E;
 };
 
 __device__ __forceinline__ int find_le(const uint32_t *__restrict__ a, int n, uint32_t v) {   // largest i < n with a[i] <= v
@@ -168,12 +168,12 @@ __device__ __forceinline__ int find_le(const uint32_t *__restrict__ a, int n, ui
 struct RowSplit { int64_t s, p_far, p_early, p_late, p_rec, p_diag; };
 
 __device__ __forceinline__ RowSplit split_row(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, uint32_t j,
-                                              uint32_t blo, uint32_t k, const BcGeom &g) {
+                                              uint32_t blo, uint32_t k, const BcGeom &g, uint32_t Dfar) {
   RowSplit r;
   r.s = rp[j];
   r.p_diag = rp[j + 1] - 1;
   const int ik = (int)k;
-  const uint32_t c_far = blo + 32u * (uint32_t)max(0, ik + 1 - (int)g.Dfar);
+  const uint32_t c_far = blo + 32u * (uint32_t)max(0, ik + 1 - (int)Dfar);
   const uint32_t c_early = blo + 32u * (uint32_t)max(0, ik - (int)g.E);
   const uint32_t c_late = blo + 32u * (uint32_t)max(0, ik - (int)g.Kr);
   const uint32_t c_rec = blo + 32u * k;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     const uint32_t j = blo + 32u * k + lane;
     uint32_t n_rec = 0, n_late = 0, n_early = 0, need = 0;
     if (j < bhi) {
-      const RowSplit r = split_row(rp, col, j, blo, k, g);
+      const RowSplit r = split_row(rp, col, j, blo, k, g, g.dfar[b]);
       if (col[r.p_diag] != j) atomicExch(err, 1);
       far_cnt[j] = r.p_far - r.s;
       n_early = (uint32_t)(r.p_early - r.p_far);
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
                                                  int reversed, const int64_t *__restrict__ offA, const int64_t *__restrict__ offB,
                                                  unsigned char *__restrict__ blobA, unsigned char *__restrict__ blobB,
                                                  const int64_t *__restrict__ far_rp, uint32_t *__restrict__ far_col,
-                                                 double *__restrict__ far_val) {
+                                                 double *__restrict__ far_val, uint32_t *__restrict__ far_split) {
   __shared__ double Wm_all[4][32][33];
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double(*Wm)[33] = Wm_all[wib];
@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
     const uint32_t nr = min(32u, bhi - (blo + 32u * k));
     RowSplit r;
     r.s = r.p_far = r.p_early = r.p_late = r.p_rec = r.p_diag = 0;
-    if (valid) r = split_row(rp, col, j, blo, k, g);
+    const uint32_t wmask = 32u * g.dfar[b] - 1u;
+    if (valid) r = split_row(rp, col, j, blo, k, g, g.dfar[b]);
     const uint32_t n_early = (uint32_t)(r.p_early - r.p_far), n_late = (uint32_t)(r.p_late - r.p_early);
     const uint32_t n_rec = (uint32_t)(r.p_rec - r.p_late), n_diag = (uint32_t)(r.p_diag - r.p_rec);
     const uint32_t nslots = warp_max_u32(n_rec), nl = warp_max_u32(n_late);
@@ -256,11 +257,14 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
     // ---- far rows (vector-space columns, raw values) ---------------------------------------------------
     if (valid) {
       int64_t o = far_rp[j];
+      uint32_t n_other = 0;   // leading entries whose column belongs to another block (sorted rows: they come first)
       for (int64_t p = r.s; p < r.p_far; p++, o++) {
         const uint32_t c = col[p];
+        n_other += c < blo ? 1u : 0u;
         far_col[o] = reversed ? N - 1u - c : c;
         far_val[o] = val[p];
       }
+      far_split[j] = n_other;
     }
     // ---- Winv: row i of the inverse of the chunk's diagonal block, all columns in parallel ----------------
     const double dii_mine = valid ? val[r.p_diag] : 1.0;
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
           const bool have = sidx < n_rec;
           reinterpret_cast<double *>(R + 512u * (u >> 1) + 16u * lane)[u & 1u] = have ? val[r.p_late + sidx] : 0.0;
           reinterpret_cast<uint32_t *>(R + 2048u + 512u * (u >> 2) + 16u * lane)[u & 3u] =
-              8u * (have ? ((col[r.p_late + sidx] - blo) & g.wmask) : (g.wmask + 1u));
+              8u * (have ? ((col[r.p_late + sidx] - blo) & wmask) : (wmask + 1u));
         }
       }
     }
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
         if (lane == 0) cnt[s] = (unsigned char)cs;
         if (s < n_early) {
           ev[base + rank] = val[r.p_far + s];
-          ec[base + rank] = (uint16_t)((col[r.p_far + s] - blo) & g.wmask);
+          ec[base + rank] = (uint16_t)((col[r.p_far + s] - blo) & wmask);
         }
         base += cs;
       }
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
       for (uint32_t s = 0; s < nl; s++) {
         const bool have = s < n_late;
         lv[s * 32u + lane] = have ? val[r.p_early + s] : 0.0;
-        lc[s * 32u + lane] = have ? (uint16_t)((col[r.p_early + s] - blo) & g.wmask) : (uint16_t)(g.wmask + 1u);
+        lc[s * 32u + lane] = have ? (uint16_t)((col[r.p_early + s] - blo) & wmask) : (uint16_t)(wmask + 1u);
       }
     }
     __syncwarp();
@@ -362,6 +366,7 @@ struct BcArgs {
   const uint32_t *far_col;
   const double *far_val;
   const uint32_t *tile_need;
+  const uint32_t *far_split;   // per row: leading far entries whose column belongs to another block
   uint32_t *tileflag, *gprog;
   double *w;
   const double *rhs;
@@ -373,6 +378,7 @@ struct BcArgs {
   int reversed;
   uint32_t Kr, E, Dfar, W;     // W = 32*Dfar window rows (power of two)
   uint32_t SA, SB, capA, capB;
+  uint32_t far_lpr;            // lanes per far row: 8 or 32
   uint32_t col_min;            // multi-GPU top separators: far columns below col_min are left out ...
   const double *corr;          // ... their sum over all ranks arrives here (indexed by vector index - col_min)
   unsigned int *abort_g;
@@ -417,41 +423,76 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
 
   if (role > 0) {
     // =========================== far CTA: start vector of the chain, tile by tile ===========================
+    // Pass 1 (never waits): entries whose column belongs to another, already solved block -- the bulk of a separator's
+    // far part.  Tiles without far entries inside the own block are complete after it and are released at once.
+    // Pass 2: entries >= Dfar chunks back in the own block, tile by tile as the chain's published progress allows.
     const uint32_t hid = role - 1u;
-    const uint32_t sub = lane & 7u;
+    const uint32_t lpr = P.far_lpr, rpw = 32u / lpr;   // lanes per row (8, or 32 for the long rows of separators), rows per warp
+    const uint32_t sub = lane & (lpr - 1u);
     for (uint32_t bi = grp; bi < P.nblocks; bi += P.ngroups) {
       const BcBlock b = P.blocks[bi];
       const uint32_t nch = (b.hi - b.lo + 31u) >> 5, ntile = (nch + BC_TILE - 1u) / BC_TILE;
-      for (uint32_t t = hid; t < ntile; t += P.helpers) {
-        const uint32_t need = P.tile_need[b.tile0 + t];
-        if (need > 0u && threadIdx.x == 0) BC_WAIT(ld_acquire_gpu(P.gprog + b.gidx) >= need, 0x100u, 200);
-        __syncthreads();
-        const uint32_t r0 = b.lo + t * (32u * BC_TILE), r1 = min(b.hi, r0 + 32u * BC_TILE);
-        for (uint32_t base = r0 + warp * 4u; base < r1; base += (BC_THREADS / 32) * 4u) {
-          const uint32_t j = base + (lane >> 3);
-          const bool valid = j < r1;
-          double acc = 0.0;
-          if (valid) {
-            const int64_t e1 = P.far_rp[j + 1];
-            for (int64_t e = P.far_rp[j] + sub; e < e1; e += 8) {
-              const uint32_t c = P.far_col[e];
-              if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
+      // own tiles t_i = hid + i*helpers; pass 1 of tile i runs after pass 0 of tile i + LA: the other-block work of the
+      // next tiles is done before this CTA waits for the chain
+      constexpr uint32_t LA = 2;
+      const uint32_t nown = hid < ntile ? (ntile - hid + P.helpers - 1u) / P.helpers : 0u;
+      for (uint32_t it = 0; it < nown + LA; it++) {
+        for (uint32_t pass = 0; pass < 2u; pass++) {
+          if (pass == 0u ? it >= nown : it < LA) continue;
+          const uint32_t t = hid + (pass == 0u ? it : it - LA) * P.helpers;
+          const uint32_t need = P.tile_need[b.tile0 + t];
+          if (pass == 1u) {
+            if (need == 0u) continue;
+            if (threadIdx.x == 0) BC_WAIT(ld_acquire_gpu(P.gprog + b.gidx) >= need, 0x100u, 200);
+            __syncthreads();
+          }
+          const uint32_t r0 = b.lo + t * (32u * BC_TILE), r1 = min(b.hi, r0 + 32u * BC_TILE);
+          for (uint32_t base = r0 + warp * rpw; base < r1; base += (BC_THREADS / 32) * rpw) {
+            const uint32_t j = base + lane / lpr;
+            const bool valid = j < r1;
+            double acc = 0.0;
+            if (valid) {
+              const int64_t es = P.far_rp[j] + P.far_split[j];   // [rp, es) other blocks, [es, rp1) own block
+              const int64_t e0 = pass == 0u ? P.far_rp[j] : es, e1 = pass == 0u ? es : P.far_rp[j + 1];
+              double acc1 = 0.0;
+              int64_t e = e0 + sub;
+              for (; e + lpr < e1; e += 2u * lpr) {
+                const uint32_t c = P.far_col[e], c2 = P.far_col[e + lpr];
+                if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
+                if (c2 >= P.col_min) acc1 = fma(P.far_val[e + lpr], __ldcg(P.out + c2), acc1);
+              }
+              if (e < e1) {
+                const uint32_t c = P.far_col[e];
+                if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
+              }
+              acc += acc1;
+            }
+            if (lpr == 32u) {
+              acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+              acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (valid && sub == 0u) {
+              double s;
+              if (pass == 0u) {
+                const uint32_t i = P.reversed ? P.N - 1u - j : j;
+                s = P.rhs[i];
+                if (P.corr) s -= P.corr[i - P.col_min];
+              } else {
+                s = __ldcg(P.w + j);   // written by this very thread in pass 0
+              }
+              __stcg(P.w + j, s - acc);
             }
           }
-          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-          if (valid && sub == 0u) {
-            const uint32_t i = P.reversed ? P.N - 1u - j : j;
-            double s = P.rhs[i];
-            if (P.corr) s -= P.corr[i - P.col_min];
-            __stcg(P.w + j, s - acc);
+          if (pass == 1u || need == 0u) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+              __threadfence();
+              st_release_gpu(P.tileflag + b.tile0 + t, 1u);
+            }
           }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          __threadfence();
-          st_release_gpu(P.tileflag + b.tile0 + t, 1u);
         }
       }
     }
@@ -718,7 +759,25 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
             q2 = fma(-lvr[u + 2u], xv[u + 2u], q2);
             q3 = fma(-lvr[u + 3u], xv[u + 3u], q3);
           }
-          for (uint32_t s = LB; s < nl; s++) q1 = fma(-lv[s * 32u + lane], win[lc[s * 32u + lane]], q1);
+          for (uint32_t s0 = LB; s0 < nl; s0 += 8u) {   // long late rows (separator blocks): batches of 8, loads first
+            uint32_t cc[8];
+            double vv[8], xx[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u++) {
+              const bool have = s0 + u < nl;
+              cc[u] = have ? lc[(s0 + u) * 32u + lane] : P.W;
+              vv[u] = have ? lv[(s0 + u) * 32u + lane] : 0.0;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u++) xx[u] = win[cc[u]];
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u += 4u) {
+              t = fma(-vv[u], xx[u], t);
+              q1 = fma(-vv[u + 1u], xx[u + 1u], q1);
+              q2 = fma(-vv[u + 2u], xx[u + 2u], q2);
+              q3 = fma(-vv[u + 3u], xx[u + 3u], q3);
+            }
+          }
           t = (t + q1) + (q2 + q3);
         }
         const uint32_t tsl = k & (BC_TR - 1u);
@@ -863,7 +922,7 @@ bool rcg_use_blocked(const rcg_handle *h) {
 void rcg_free_blocked(BlockedDev &b) {
   cudaFree(b.offA); cudaFree(b.offB); cudaFree(b.blobA); cudaFree(b.blobB);
   rcg_free_csr(b.far);
-  cudaFree(b.tile_need); cudaFree(b.flags); cudaFree(b.w); cudaFree(b.blocks);
+  cudaFree(b.tile_need); cudaFree(b.flags); cudaFree(b.w); cudaFree(b.blocks); cudaFree(b.far_split);
   b = BlockedDev();
 }
 
@@ -879,8 +938,13 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   B.E = 16u;
   uint32_t win_rows = h->opt.chain_window > 0 ? (uint32_t)h->opt.chain_window : 4096u;
   B.Dfar = std::min(512u, std::max(32u, floor_pow2_u32(std::max(32u, win_rows) / 32u)));
+  // Separator blocks are small, dense and have every far CTA of the launch to themselves: a short window sends most of
+  // their entries to the far CTAs and keeps their chain blobs small enough for many staging slots.
+  const uint32_t sep_rows = h->opt.reserved[4] > 0 ? (uint32_t)h->opt.reserved[4] : 1024u;
+  B.Dfar_sep = std::min(B.Dfar, std::max(32u, floor_pow2_u32(std::max(32u, sep_rows) / 32u)));
   // ---- chunk / tile numbering ------------------------------------------------------------------------
-  std::vector<uint32_t> chunk0(nb + 1, 0), tile0(nb + 1, 0);
+  std::vector<uint32_t> chunk0(nb + 1, 0), tile0(nb + 1, 0), dfar(nb + 1, B.Dfar);
+  for (int b = 0; b < nb; b++) dfar[b] = (depth[b] == max_depth) ? B.Dfar : B.Dfar_sep;
   for (int b = 0; b < nb; b++) {
     const uint32_t nch = (bounds[b + 1] - bounds[b] + 31u) / 32u;
     chunk0[b + 1] = chunk0[b] + nch;
@@ -888,14 +952,16 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   }
   B.nchunks = chunk0[nb];
   B.ntiles = tile0[nb];
-  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0
-  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 3 * (nb + 1)));
+  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0 | dfar
+  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 4 * (nb + 1)));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom + 3 * (nb + 1), dfar.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom, bounds.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + (nb + 1), chunk0.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 2 * (nb + 1), tile0.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   BcGeom g;
   g.bounds = dgeom; g.chunk0 = dgeom + (nb + 1); g.tile0 = dgeom + 2 * (nb + 1);
-  g.nb = nb; g.Kr = B.Kr; g.E = B.E; g.Dfar = B.Dfar; g.wmask = 32u * B.Dfar - 1u;
+  g.dfar = dgeom + 3 * (nb + 1);
+  g.nb = nb; g.Kr = B.Kr; g.E = B.E;
 
   // ---- sizes ---------------------------------------------------------------------------------------------
   int *derr = nullptr;
@@ -934,11 +1000,13 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   RCG_CUDA(h, cudaMalloc(&B.blobB, (size_t)B.bytesB + 256));
   RCG_CUDA(h, cudaMemsetAsync(B.blobA, 0, (size_t)B.bytesA + 256, h->stream));
   RCG_CUDA(h, cudaMemsetAsync(B.blobB, 0, (size_t)B.bytesB + 256, h->stream));
+  RCG_CUDA(h, cudaMalloc(&B.far_split, sizeof(uint32_t) * ((size_t)N + 1)));
+  RCG_CUDA(h, cudaMemsetAsync(B.far_split, 0, sizeof(uint32_t) * ((size_t)N + 1), h->stream));
   RCG_CUDA(h, cudaMalloc(&B.far.col, sizeof(uint32_t) * (size_t)(far_total + 8)));
   RCG_CUDA(h, cudaMalloc(&B.far.val, sizeof(double) * (size_t)(far_total + 8)));
   const int fgrid = (int)std::min<int64_t>(((int64_t)B.nchunks + 3) / 4, (int64_t)h->sm_count * 16);
   k_bc_fill<<<std::max(1, fgrid), 128, 0, h->stream>>>(comb.rowptr, comb.col, comb.val, g, B.nchunks, N, d.reversed ? 1 : 0,
-                                                      B.offA, B.offB, B.blobA, B.blobB, B.far.rowptr, B.far.col, B.far.val);
+                                                      B.offA, B.offB, B.blobA, B.blobB, B.far.rowptr, B.far.col, B.far.val, B.far_split);
   h->stats.kernel_launches += 1;
   RCG_CUDA(h, cudaGetLastError());
 
@@ -957,6 +1025,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       memset(&bd, 0, sizeof(bd));
       bd.lo = bounds[b]; bd.hi = bounds[b + 1]; bd.chunk0 = chunk0[b]; bd.tile0 = tile0[b];
       bd.gidx = (uint32_t)B.blocks_host.size();
+      bd.pad[0] = dfar[b];
       B.blocks_host.push_back(bd);
       src_block.push_back(b);
       G.count++;
@@ -979,7 +1048,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   RCG_CUDA(h, cudaMemcpyAsync(hA.data(), B.offA, sizeof(int64_t) * hA.size(), cudaMemcpyDeviceToHost, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(hB.data(), B.offB, sizeof(int64_t) * hB.size(), cudaMemcpyDeviceToHost, h->stream));
   // far entries per block (bench statistics)
-  std::vector<int64_t> far_ends(2 * (size_t)B.nblocks);
+  std::vector<int64_t> far_ends(2 * (size_t)B.nblocks), row_ends(2 * (size_t)B.nblocks);
   {
     std::vector<uint32_t> idx;
     for (const BcBlock &bd : B.blocks_host) { idx.push_back(bd.lo); idx.push_back(bd.hi); }
@@ -991,12 +1060,15 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     k_gather_i64<<<((int)idx.size() + 255) / 256, 256, 0, h->stream>>>(B.far.rowptr, didx, (int)idx.size(), dout);
     RCG_CUDA(h, cudaMemcpyAsync(far_ends.data(), dout, sizeof(int64_t) * idx.size(), cudaMemcpyDeviceToHost, h->stream));
     RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    k_gather_i64<<<((int)idx.size() + 255) / 256, 256, 0, h->stream>>>(comb.rowptr, didx, (int)idx.size(), dout);
+    RCG_CUDA(h, cudaMemcpyAsync(row_ends.data(), dout, sizeof(int64_t) * idx.size(), cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaFree(didx); cudaFree(dout);
   }
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   B.levels.clear();
-  const uint32_t W = 32u * B.Dfar;
   for (GroupHost &G : d.groups) {
+    const uint32_t W = 32u * B.blocks_host[G.first].pad[0];
     int64_t maxA = 0, maxB = 0, sumB = 0, nchl = 0;
     for (int bi = G.first; bi < G.first + G.count; bi++) {
       const BcBlock &bd = B.blocks_host[bi];
@@ -1007,8 +1079,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
         sumB += hB[c + 1] - hB[c];
       }
       nchl += nch;
-      G.ext_nnz += far_ends[2 * (size_t)bi + 1] - far_ends[2 * (size_t)bi];
-      G.loc_nnz += (hA[bd.chunk0 + nch] - hA[bd.chunk0]) + (hB[bd.chunk0 + nch] - hB[bd.chunk0]);   // bytes of the chain part
+      const int64_t far_n = far_ends[2 * (size_t)bi + 1] - far_ends[2 * (size_t)bi];
+      G.ext_nnz += far_n;                                                                   // entries done by the far CTAs
+      G.loc_nnz += (row_ends[2 * (size_t)bi + 1] - row_ends[2 * (size_t)bi]) - far_n;       // entries done by the chain CTA
+      G.blob_bytes += (hA[bd.chunk0 + nch] - hA[bd.chunk0]) + (hB[bd.chunk0 + nch] - hB[bd.chunk0]);
     }
     G.max_stage = (uint32_t)maxA;
     BcLevel L;
@@ -1032,6 +1106,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     L.SA = (uint32_t)SA; L.SB = (uint32_t)SB;
     L.smem = (size_t)(fixed - 1024 + SA * L.capA + SB * L.capB + (2 * SA + 2 * SB) * 8 + SB * 12);
     const uint32_t sms = (uint32_t)h->sm_count;
+    L.Dfar = B.blocks_host[G.first].pad[0];
     L.groups = std::max(1u, std::min<uint32_t>((uint32_t)G.count, sms / 2u));
     L.helpers = std::max(1u, sms / L.groups - 1u);
     B.levels.push_back(L);
@@ -1101,12 +1176,14 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     a.offA = B.offA; a.offB = B.offB; a.blobA = B.blobA; a.blobB = B.blobB;
     a.far_rp = B.far.rowptr; a.far_col = B.far.col; a.far_val = B.far.val;
     a.tile_need = B.tile_need;
+    a.far_split = B.far_split;
     a.tileflag = B.flags; a.gprog = B.flags + B.ntiles;
     a.w = B.w; a.rhs = rhs; a.out = out;
     a.dotvec = dotvec; a.dot_partials = dotvec ? rz_part : nullptr; a.dot_limit = dot_limit;
     a.N = (uint32_t)h->N; a.reversed = d.reversed ? 1 : 0;
-    a.Kr = B.Kr; a.E = B.E; a.Dfar = B.Dfar; a.W = 32u * B.Dfar;
+    a.Kr = B.Kr; a.E = B.E; a.Dfar = L.Dfar; a.W = 32u * L.Dfar;
     a.SA = L.SA; a.SB = L.SB; a.capA = L.capA; a.capB = L.capB;
+    a.far_lpr = (G.rows > 0 && G.ext_nnz / G.rows > 64) ? 32u : 8u;
     a.col_min = top ? h->dist.n_sub : 0u;
     a.corr = top ? h->dist.sbuf : nullptr;
     a.abort_g = h->abort_flag;

@@ -51,6 +51,7 @@ struct GroupHost {
   int64_t loc_nnz = 0;
   int64_t rows = 0;
   uint32_t max_stage = 0;      // largest number of local entries in an aligned 32-row staging group
+  int64_t blob_bytes = 0;      // blocked solve: bytes of the level's chain blobs (Winv + recent + late + early entries)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -72,7 +73,7 @@ struct BcBlock {               // one nested-dissection block (device copy; orde
   uint32_t chunk0;             // global index of the block's first chunk
   uint32_t tile0;              // global index of the block's first far tile (8 chunks)
   uint32_t gidx;               // index of the block in the direction: progress counter, dot-partial slot
-  uint32_t pad[3];
+  uint32_t pad[3];             // pad[0] = window of the block in chunks (Dfar)
 };
 
 struct BcLevel {               // per tree level: shared-memory plan of the launch
@@ -80,17 +81,20 @@ struct BcLevel {               // per tree level: shared-memory plan of the laun
   uint32_t SA = 0, SB = 0;     // staging slots
   uint32_t groups = 0;         // chain CTAs of the launch
   uint32_t helpers = 0;        // far CTAs per chain CTA
+  uint32_t Dfar = 0;           // window of the level's blocks in chunks
   size_t smem = 0;
 };
 
 struct BlockedDev {
   bool on = false;
-  uint32_t Kr = 2, E = 16, Dfar = 128;   // chunk-distance thresholds (see above); window = 32*Dfar rows
+  uint32_t Kr = 2, E = 16, Dfar = 128;   // chunk-distance thresholds (see above); window = 32*Dfar rows (leaf blocks)
+  uint32_t Dfar_sep = 32;                // window of the separator blocks
   uint32_t nchunks = 0, ntiles = 0, nblocks = 0;
   int64_t *offA = nullptr, *offB = nullptr;          // nchunks+1 byte offsets into the blobs
   unsigned char *blobA = nullptr, *blobB = nullptr;
   int64_t bytesA = 0, bytesB = 0;
   CsrDev far;                                        // rows in solve space, columns in vector space, raw values
+  uint32_t *far_split = nullptr;                     // per row: leading far entries that belong to other blocks
   uint32_t *tile_need = nullptr;                     // per far tile: chunks of the own block that must be published first
   uint32_t *flags = nullptr;                         // [0, ntiles) tile-ready flags, [ntiles, ntiles+nblocks) block progress
   double *w = nullptr;                               // N+2: start vector of the chain (rhs - far part), solve space

@@ -27,10 +27,11 @@ for cfg in cfgs:
     win, rec = cfg[0], cfg[1] if len(cfg) > 1 else 0
     mode = cfg[2] if len(cfg) > 2 else 0
     dbg = cfg[3] if len(cfg) > 3 else 0
-    s = capi.Solver(0, chain_window=win, recent=rec, chain_mode=mode, dbg=dbg)
+    sepw = cfg[4] if len(cfg) > 4 else 0
+    s = capi.Solver(0, chain_window=win, recent=rec, chain_mode=mode, dbg=dbg, sep_window=sepw)
     t = time.time(); s.set_matrix(*A); s.set_factor(*G, part); t_set = time.time() - t
     st = s.stats()
-    print(f"--- window={win} recent={rec} mode={mode}: set-up wall {t_set:.2f}s upload {st['upload_ms']:.0f} analysis {st['analysis_ms']:.0f} ms", flush=True)
+    print(f"--- window={win} recent={rec} mode={mode} sep_window={sepw}: set-up wall {t_set:.2f}s upload {st['upload_ms']:.0f} analysis {st['analysis_ms']:.0f} ms", flush=True)
     if check:
         y = s.trsv(capi.TRSV_FORWARD, b); z = s.trsv(capi.TRSV_BACKWARD, yo); zz = s.precond(b)
         print(f"    fwd relerr {relerr(y, yo):.2e} bwd {relerr(z, zo):.2e} precond {relerr(zz, zo):.2e}", flush=True)

@@ -42,15 +42,15 @@ def unpack_recent(raw_bytes, nbt):
 
 
 def solve_from_layout(lay, rhs, reversed_):
-    N, Dfar = lay["N"], lay["Dfar"]
-    wrows = 32 * Dfar
-    wmask = wrows - 1
+    N = lay["N"]
     out = np.zeros(N)
     A, B = lay["blobA"], lay["blobB"]
     far_rp, far_col, far_val = lay["far_rp"], lay["far_col"].astype(np.int64), lay["far_val"]
     stats = dict(chunks=0, rec_slots=0, late_slots=0, early_max=0, early_tot=0)
-    for lo, hi, chunk0, tile0, gidx, *_ in lay["blocks"].astype(np.int64):
+    for lo, hi, chunk0, tile0, gidx, dfar, *_ in lay["blocks"].astype(np.int64):
         nch = (hi - lo + 31) // 32
+        wrows = 32 * dfar          # window of this block (leaves: Dfar, separators: Dfar_sep)
+        wmask = wrows - 1
         win = np.full(wrows + 1, np.nan)
         win[wrows] = 0.0   # the slot padding entries point at
         for k in range(nch):

@@ -42,11 +42,14 @@ def direction_matrix(G, part, backward):
     return L, bounds, depth
 
 
-def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, reversed_=False):
+def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False):
     N = L.shape[0]
     rp, col, val = L.indptr.astype(np.int64), L.indices.astype(np.int64), L.data
     nb = len(bounds) - 1
-    wmask = 32 * Dfar - 1
+    max_depth = int(np.max(depth)) if nb else 0
+    Dfar_sep = min(Dfar, Dfar_sep)
+    dfar_of = [Dfar if depth[b] == max_depth else Dfar_sep for b in range(nb)]
+    Dfar_leaf = Dfar
     chunk0 = np.zeros(nb + 1, np.int64)
     tile0 = np.zeros(nb + 1, np.int64)
     for b in range(nb):
@@ -59,6 +62,8 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, reversed_=F
     far_rows = [None] * N
     for b in range(nb):
         blo, bhi = int(bounds[b]), int(bounds[b + 1])
+        Dfar = dfar_of[b]
+        wmask = 32 * Dfar - 1
         for k in range((bhi - blo + 31) // 32):
             g = int(chunk0[b]) + k
             rows = [j for j in range(blo + 32 * k, min(bhi, blo + 32 * k + 32))]
@@ -154,14 +159,13 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, reversed_=F
     offB = np.concatenate([[0], np.cumsum([len(a) for a in blobsB])]).astype(np.int64)
     far_rp = np.concatenate([[0], np.cumsum([len(r[0]) for r in far_rows])]).astype(np.int64)
     blocks = []
-    max_depth = int(depth.max()) if nb else 0
     for gl in range(max_depth + 1):
         want = gl if root_first else max_depth - gl
         for b in range(nb):
             if depth[b] == want and bounds[b + 1] > bounds[b]:
-                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), 0, 0, 0])
+                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], 0, 0])
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
-    return dict(active=1, nchunks=nchunks, ntiles=ntiles, nblocks=len(blocks), N=N, Kr=Kr, E=E, Dfar=Dfar,
+    return dict(active=1, nchunks=nchunks, ntiles=ntiles, nblocks=len(blocks), N=N, Kr=Kr, E=E, Dfar=Dfar_leaf, Dfar_sep=Dfar_sep,
                 offA=offA, offB=offB, blobA=cat(blobsA, np.uint8), blobB=cat(blobsB, np.uint8), far_rp=far_rp,
                 far_col=cat([r[0] for r in far_rows], np.uint32), far_val=cat([r[1] for r in far_rows], np.float64),
                 tile_need=tile_need, blocks=np.array(blocks, np.uint32).reshape(-1, 8))
@@ -169,7 +173,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, reversed_=F
 
 def compare_layouts(dev, ref, val_tol=1e-12):
     """Device-built layout against the Python restatement: integers exact, values to val_tol (relative to max)."""
-    for k in ("nchunks", "ntiles", "nblocks", "N", "Kr", "E", "Dfar"):
+    for k in ("nchunks", "ntiles", "nblocks", "N", "Kr", "E", "Dfar", "Dfar_sep"):
         assert dev[k] == ref[k], k
     for k in ("offA", "offB", "far_rp", "far_col", "tile_need", "blocks"):
         assert np.array_equal(dev[k], ref[k]), k

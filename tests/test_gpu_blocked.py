@@ -42,7 +42,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
         s.set_factor(*G, part)
         lay_f, lay_b = s.blocked_layout(capi.TRSV_FORWARD), s.blocked_layout(capi.TRSV_BACKWARD)
         assert lay_f["active"] and lay_b["active"]
-        kw = dict(Kr=lay_f["Kr"], E=lay_f["E"], Dfar=lay_f["Dfar"])
+        kw = dict(Kr=lay_f["Kr"], E=lay_f["E"], Dfar=lay_f["Dfar"], Dfar_sep=lay_f["Dfar_sep"])
         L, bounds, depth = direction_matrix(G, part, False)
         compare_layouts(lay_f, build_layout(L, bounds, depth, False, **kw))
         L, bounds, depth = direction_matrix(G, part, True)
@@ -58,7 +58,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
 @needs_producer
 @pytest.mark.parametrize("opts", [dict(), dict(recent=1), dict(recent=3), dict(chain_window=1024), dict(chain_window=2048, recent=1),
                                   dict(chain_window=8192), dict(plain_launch=True), dict(use_graph=False, chain_window=1024),
-                                  dict(chain_mode=1), dict(chain_mode=3)])
+                                  dict(chain_mode=1), dict(chain_mode=3), dict(sep_window=4096), dict(chain_window=2048, sep_window=2048)])
 @pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 33, 2), ("aniso2d", 160, 4), ("lap3d", 40, 0)])
 def test_blocked_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
