@@ -31,7 +31,8 @@
 namespace {
 
 constexpr int BC_THREADS = 512;           // 16 warps: critical (alone on its scheduler), 2 producers, publisher, 9 near helpers
-constexpr uint32_t BC_NH = 9;
+constexpr uint32_t BC_NH = 9;            // near helpers of the single-critical-warp variant (the split variant has 8)
+constexpr uint32_t BC_SCR = 576;          // scratch doubles: [0,32) t vector(s), [32, 32+4*128) partial sums of the split chain
 constexpr uint32_t BC_TR = 32;            // ring of t' vectors between helpers and the critical warp
 constexpr uint32_t BC_TILE = 8;           // chunks per far tile
 constexpr uint32_t BC_WBYTES = 1024 * 8;  // Winv, full 32x32 (zeros above the diagonal): [column pair p][row] double2
@@ -88,6 +89,18 @@ __device__ __forceinline__ void lds_u16_if(uint32_t &v, uint32_t saddr, bool p) 
 }
 __device__ __forceinline__ void sts_f64(uint32_t saddr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(saddr), "d"(v) : "memory");
+}
+// arrive that cannot issue before the registers a and b (results of shared-memory loads) have arrived
+__device__ __forceinline__ void mbar_arrive_after(uint64_t *bar, uint32_t a, double b) {
+  asm volatile(
+      "{\n\t.reg .b32 lo, hi, z;\n\t"
+      "mov.b64 {lo, hi}, %2;\n\t"
+      "or.b32 z, lo, %1;\n\t"
+      "and.b32 z, z, 0;\n\t"
+      "add.u32 z, z, %0;\n\t"
+      "mbarrier.arrive.shared::cta.b64 _, [z];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(a), "d"(b)
+      : "memory");
 }
 __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
@@ -386,7 +399,14 @@ struct BcArgs {
   uint32_t dbg;                // bit 0: cycle profile of the critical warp and of near helper 0 (CTA 0) into clk[3..12]
 };
 
+// CW = 1: one critical warp (first version, kept selectable: chain_mode 3).  CW = 4: the chain's per-chunk work is split
+// over four warps, one per scheduler (see "split chain" below) -- a lone warp is bound by instruction issue.
+// PROF: cycle counters of the critical warp(s) and of near helper 0 (dbg bit 0); a separate instantiation so that the
+// production chain loop stays straight-line code (a lone warp pays a fetch bubble for every taken branch).
+template <int CW, bool PROF>
 __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
+  constexpr uint32_t W_PRODA = CW == 1 ? 1u : 5u, W_PRODB = CW == 1 ? 2u : 6u, W_PUB = CW == 1 ? 3u : 7u;
+  constexpr uint32_t NH = CW == 1 ? BC_NH : 8u;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t per = 1u + P.helpers;
@@ -396,7 +416,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
   double *win = reinterpret_cast<double *>(smem);
   double *tprime = win + P.W + 16;   // win[W] holds 0.0: the slot padding entries point at
   double *scratch = tprime + BC_TR * 32u;
-  unsigned char *ringA = reinterpret_cast<unsigned char *>(scratch + 32);
+  unsigned char *ringA = reinterpret_cast<unsigned char *>(scratch + BC_SCR);
   unsigned char *ringB = ringA + (size_t)P.SA * P.capA;
   uint64_t *fullA = reinterpret_cast<uint64_t *>(ringB + (size_t)P.SB * P.capB);
   uint64_t *emptyA = fullA + P.SA;
@@ -407,7 +427,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
   uint32_t *tready = seqB + P.SB;
   uint32_t *ctl = tready + BC_TR;   // [0] prog: solved chunks of the current block, [1] published chunks, [2] abort
 
-  if (threadIdx.x < P.SA) { mbar_init(fullA + threadIdx.x, 1); mbar_init(emptyA + threadIdx.x, 1); }
+  if (threadIdx.x < P.SA) { mbar_init(fullA + threadIdx.x, 1); mbar_init(emptyA + threadIdx.x, CW); }
+  if (threadIdx.x < BC_SCR) scratch[threadIdx.x] = 0.0;
   if (threadIdx.x < P.SB) { mbar_init(fullB + threadIdx.x, 1); mbar_init(emptyB + threadIdx.x, 1); seqB[threadIdx.x] = 0xFFFFFFFFu; }
   if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = 0; ctl[2] = 0; }
   if (threadIdx.x < 16) win[P.W + threadIdx.x] = 0.0;
@@ -503,7 +524,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
   const uint32_t wmask = P.W - 1u;
   const uint32_t win_s = smem_u32(win), tp_s = smem_u32(tprime), sc_s = smem_u32(scratch), trdy_s = smem_u32(tready);
   uint32_t ia0 = 0;   // chunks of the blocks this CTA has finished: running index of the staging rings
-  long long pc[7] = {0, 0, 0, 0, 0, 0, 0};   // profiling (dbg bit 0), critical warp of CTA 0: cycles waiting for blob A / for t' /
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // profiling (dbg bit 0), critical warp of CTA 0: cycles waiting for blob A / for t' /
                                           // recent entries / chunks / mat-vec / store + release
   long long ph[5] = {0, 0, 0, 0, 0};   // near helper 0 of CTA 0: tile flag + start vector, blob B, early, wait for prog, late
   long long clk0 = 0;
@@ -516,14 +537,14 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
     if (threadIdx.x == 0) { ctl[0] = 0u; ctl[1] = 0u; }
     __syncthreads();
 
-    if (warp == 0) {
+    if (CW == 1 && warp == 0) {
       // ------------------------------ critical warp ------------------------------------------------------
       // Measured (scripts/ubench/mv.cu): a lone warp pays ~240 cycles for the 32x32 mat-vec and ~500 for the whole
       // chunk when nothing else gets in its way; every exposed shared-memory round trip adds 50-100.  So the loop is
       // software-pipelined: the loads of chunk k+1 that do not depend on the chain (half of Winv, the first batch of
       // recent entries) are issued right after the mat-vec FMAs of chunk k, and their latency hides behind the
       // reduction, the window store, the release and the poll of the next t'.
-      const bool prof = (P.dbg & 1u) != 0u && blockIdx.x == 0;
+      const bool prof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0;
       constexpr uint32_t WPRE = 6;   // column pairs of Winv held in registers ahead of time
       uint32_t slot = ia0 % P.SA, par = (ia0 / P.SA) & 1u;
       double w[2 * WPRE];
@@ -660,23 +681,194 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
         if (prof) { pc[1] += c2 - c1; pc[2] += c3 - c2; pc[3] += 1; pc[4] += c4 - c3; pc[5] += clock64() - c4; }
       }
 #undef BC_PRELOAD
-    } else if ((warp & 3u) != 0u && warp > 3u) {
+    } else if (CW == 4 && warp < 4u) {
+      // ------------------------------ split chain: four critical warps ------------------------------------
+      // Warp cw (one per scheduler) owns rows 8cw..8cw+7 of the chunk for the recent entries (four lanes per row, two of
+      // the eight slots each) and columns 8cw..8cw+7 of Winv for the mat-vec (lane = row of the result):
+      //   gather x of the two previous chunks  ->  t[row] = t' - recent  (4-lane shuffle reduction)
+      //   -> t[8cw..8cw+7] broadcast through 64 bytes of shared memory -> 8 DFMA with the warp's slice of Winv
+      //   -> partial[k & 3][cw][lane]  -> named barrier (4 critical warps + scribe)
+      // x_k is never materialised by the critical warps: a gather of x_k[c] reads the four partial sums and adds them in
+      // the same order as the scribe does when it writes the window.  Four partial buffers indexed by the chunk number
+      // mod 4 (two bits of the window offset the set-up stored with the entry): chunk k reads the buffers of k-1 and k-2
+      // while a faster warp may already write that of k+1; one barrier per chunk.
+      // Measured (ncu source page, profiles/): a lone warp pays ~4 cycles per dependent instruction, a fetch bubble per
+      // taken branch and 30-130 cycles per shared-memory round trip, so the loop is straight-line code, every wait is a
+      // compact bounded spin, and the loads of chunk k+1 that do not depend on the chain (Winv slice, recent values and
+      // offsets, t' and its flag, the staging barrier's phase) are issued before the barrier of chunk k.
+      const bool prof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0 && warp == 0u;
+      const uint32_t cw = warp, rowg = 8u * cw + (lane >> 2), sub = lane & 3u;
+      const uint32_t part_s = sc_s + 256u, tb_s = sc_s + 64u * cw;
+      const uint32_t pw_s = part_s + 256u * cw + 8u * lane;   // this lane's slot in buffer 0
+      const uint32_t rec_off = 512u * sub + 16u * rowg, off_off = 2048u + 512u * (sub >> 1) + 16u * rowg + 8u * (sub & 1u);
+      const uint32_t fullA_s = smem_u32(fullA), emptyA_s = smem_u32(emptyA), ringA_s = smem_u32(ringA);
+      uint32_t slot = ia0 % P.SA, par = (ia0 / P.SA) & 1u;
+      double wa[8];
+      double rv0 = 0.0, rv1 = 0.0, tpv = 0.0;
+      uint32_t ro0 = 0u, ro1 = 0u, nbt = 1u, a_s = 0u, tpf = 0u, a_ok = 0u;
+      uint32_t spins = 0;
+      // bounded spin without the guard's bookkeeping (the time-out is counted in polls: ~0.5 s)
+#define BC4_SPIN(cond_, code_)                                                                                            \
+      while (__builtin_expect(!(cond_), 0)) {                                                                             \
+        if (++spins > (1u << 24)) { atomicCAS(P.abort_g, 0u, (code_)); sts_volatile_u32(G.abort_s, 1u); break; }          \
+      }
+#define BC4_MBAR_TEST(ok_, bar_s_, par_)                                                                                  \
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" \
+                   : "=r"(ok_) : "r"(bar_s_), "r"(par_) : "memory")
+      // recent values / offsets / batch count of the chunk staged in `slot`
+#define BC4_LOAD_REC()                                                                                                    \
+      do {                                                                                                                \
+        a_s = ringA_s + slot * P.capA;                                                                                    \
+        const uint32_t r_s_ = a_s + BC_AHDR + BC_WBYTES;                                                                  \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rv0), "=d"(rv1) : "r"(r_s_ + rec_off) : "memory");         \
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ro0), "=r"(ro1) : "r"(r_s_ + off_off) : "memory");         \
+        nbt = lds_u32(a_s);                                                                                               \
+      } while (0)
+#define BC4_LOAD_W(w_)                                                                                                    \
+      do {                                                                                                                \
+        const uint32_t w_s_ = a_s + BC_AHDR + 2048u * cw + 16u * lane;                                                    \
+        _Pragma("unroll") for (uint32_t pp = 0; pp < 4u; pp++)                                                            \
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w_[2 * pp]), "=d"(w_[2 * pp + 1]) : "r"(w_s_ + 512u * pp) : "memory"); \
+      } while (0)
+      // flag of t' of chunk k_, not waited for: it is tested at the top of the next chunk, and the value is loaded there
+      // through an address that depends on the flag (so neither the compiler nor ptxas can hoist it above the flag)
+#define BC4_LOAD_TP(k_)                                                                                                   \
+      do {                                                                                                                \
+        tpf = lds_volatile_u32(trdy_s + 4u * ((k_) & (BC_TR - 1u)));                                                      \
+      } while (0)
+      // gather x[c] of one of the two previous chunks from the partial sums (buffer = chunk number mod 4)
+#define BC4_GATHER(x_, ro_)                                                                                               \
+      do {                                                                                                                \
+        const uint32_t g_ = part_s + (((ro_) & 0x300u) << 2) + ((ro_) & 0xF8u);                                           \
+        const double p0_ = lds_f64(g_), p1_ = lds_f64(g_ + 256u), p2_ = lds_f64(g_ + 512u), p3_ = lds_f64(g_ + 768u);     \
+        x_ = (p0_ + p1_) + (p2_ + p3_);                                                                                   \
+      } while (0)
+#define BC4_CHUNK(MORE_)                                                                                                  \
+      do {                                                                                                                \
+        constexpr bool more_ = MORE_;                                                                                     \
+        long long c1_ = 0;                                                                                                \
+        if (prof) c1_ = clock64();                                                                                        \
+        /* staging slot of the next chunk: phase test now, answer needed after the mat-vec */                             \
+        const uint32_t oslot_ = slot;                                                                                     \
+        if (more_) { if (++slot == P.SA) { slot = 0; par ^= 1u; } BC4_MBAR_TEST(a_ok, fullA_s + 8u * slot, par); }         \
+        double acc_;                                                                                                      \
+        {                                                                                                                 \
+          double x0_, x1_;                                                                                                \
+          BC4_GATHER(x0_, ro0);                                                                                           \
+          BC4_GATHER(x1_, ro1);                                                                                           \
+          BC4_LOAD_W(wa);   /* behind the gathers in the shared-memory queue, needed a reduction later */                 \
+          acc_ = -rv0 * x0_;                                                                                              \
+          acc_ = fma(-rv1, x1_, acc_);                                                                                    \
+        }                                                                                                                 \
+        if (__builtin_expect(nbt > 1u, 0))                                                                                \
+        _Pragma("unroll 1") for (uint32_t bt_ = 1; bt_ < nbt; bt_++) { /* more than 8 recent slots */                     \
+          const uint32_t q_s_ = a_s + BC_AHDR + BC_WBYTES + BC_RBATCH * bt_;                                              \
+          double v0_, v1_, x0_, x1_;                                                                                      \
+          uint32_t o0_, o1_;                                                                                              \
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0_), "=d"(v1_) : "r"(q_s_ + rec_off) : "memory");       \
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o0_), "=r"(o1_) : "r"(q_s_ + off_off) : "memory");       \
+          BC4_GATHER(x0_, o0_);                                                                                           \
+          BC4_GATHER(x1_, o1_);                                                                                           \
+          acc_ = fma(-v0_, x0_, acc_);                                                                                    \
+          acc_ = fma(-v1_, x1_, acc_);                                                                                    \
+        }                                                                                                                 \
+        if (__builtin_expect(tpf != k + 1u, 0)) {                                                                         \
+          BC4_SPIN((tpf = ld_acquire_cta_s(trdy_s + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);                         \
+          if (prof) pc[6] += 1;                                                                                           \
+        }                                                                                                                 \
+        tpv = lds_f64(tp_s + 8u * ((k & (BC_TR - 1u)) * 32u + rowg) + ((tpf ^ (k + 1u)) & 0x7u) * 8u);                    \
+        acc_ += sub == 0u ? tpv : 0.0;                                                                                    \
+        long long c2_ = 0;                                                                                                \
+        if (prof) { c2_ = clock64() + (acc_ == 1.25e-300 ? 1 : 0); pc[1] += c2_ - c1_; }                                  \
+        acc_ += __shfl_xor_sync(0xffffffffu, acc_, 1);                                                                    \
+        acc_ += __shfl_xor_sync(0xffffffffu, acc_, 2);                                                                    \
+        long long c3_ = 0;                                                                                                \
+        if (prof) { c3_ = clock64() + (acc_ == 1.25e-300 ? 1 : 0); pc[2] += c3_ - c2_; }                                  \
+        if (sub == 0u) sts_f64(tb_s + 2u * lane, acc_);                                                                   \
+        __syncwarp();                                                                                                     \
+        double t0_, t1_, t2_, t3_, t4_, t5_, t6_, t7_;                                                                    \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t0_), "=d"(t1_) : "r"(tb_s) : "memory");                   \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t2_), "=d"(t3_) : "r"(tb_s + 16u) : "memory");             \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t4_), "=d"(t5_) : "r"(tb_s + 32u) : "memory");             \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t6_), "=d"(t7_) : "r"(tb_s + 48u) : "memory");             \
+        long long c4_ = 0;                                                                                                \
+        if (prof) { c4_ = clock64(); pc[4] += c4_ - c3_; }                                                                \
+        double a0_ = wa[0] * t0_, a1_ = wa[1] * t1_;                                                                      \
+        a0_ = fma(wa[2], t2_, a0_);                                                                                       \
+        a1_ = fma(wa[3], t3_, a1_);                                                                                       \
+        a0_ = fma(wa[4], t4_, a0_);                                                                                       \
+        a1_ = fma(wa[5], t5_, a1_);                                                                                       \
+        a0_ = fma(wa[6], t6_, a0_);                                                                                       \
+        a1_ = fma(wa[7], t7_, a1_);                                                                                       \
+        const double a_ = a0_ + a1_;                                                                                      \
+        sts_f64(pw_s + ((k & 3u) << 10), a_);                                                                             \
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(emptyA_s + 8u * oslot_) : "memory"); \
+        /* chain-independent loads of the next chunk: in flight across the barrier */                                     \
+        if (more_) {                                                                                                      \
+          BC4_LOAD_TP(k + 1u);                                                                                            \
+          if (__builtin_expect(a_ok == 0u, 0)) {                                                                          \
+            long long c0_ = 0;                                                                                            \
+            if (prof) c0_ = clock64();                                                                                    \
+            BC4_SPIN(mbar_try(fullA + slot, par), 0x200u);                                                                \
+            if (prof) pc[0] += clock64() - c0_;                                                                           \
+          }                                                                                                               \
+          BC4_LOAD_REC();                                                                                                 \
+        }                                                                                                                 \
+        long long c5_ = 0;                                                                                                \
+        if (prof) { c5_ = clock64() + (a_ == 1.25e-300 ? 1 : 0); pc[5] += c5_ - c4_; }                                    \
+        asm volatile("bar.sync 1, 160;" ::: "memory");                                                                    \
+        if (prof) { pc[7] += clock64() - c5_; pc[3] += 1; }                                                               \
+      } while (0)
+      if (nch > 0) {
+        BC4_SPIN(mbar_try(fullA + slot, par), 0x200u);
+        BC4_LOAD_REC();
+        BC4_LOAD_TP(0u);
+      }
+      uint32_t k = 0;
+      for (; k + 1u < nch; k++) BC4_CHUNK(true);
+      if (k < nch) BC4_CHUNK(false);
+#undef BC4_CHUNK
+#undef BC4_GATHER
+#undef BC4_LOAD_TP
+#undef BC4_LOAD_W
+#undef BC4_LOAD_REC
+#undef BC4_MBAR_TEST
+#undef BC4_SPIN
+    } else if (CW == 4 && warp == 4u) {
+      // ------------------------------ scribe: window <- x, progress counter -------------------------------
+      const uint32_t pr_s = sc_s + 256u + 8u * lane;
+      for (uint32_t k = 0; k < nch; k++) {
+        asm volatile("bar.sync 1, 160;" ::: "memory");
+        const uint32_t q_s = pr_s + ((k & 3u) << 10);
+        const double p0 = lds_f64(q_s), p1 = lds_f64(q_s + 256u), p2 = lds_f64(q_s + 512u), p3 = lds_f64(q_s + 768u);
+        sts_f64(win_s + 8u * ((32u * k + lane) & wmask), (p0 + p1) + (p2 + p3));
+        __syncwarp();
+        if (lane == 0) st_release_cta_s(prog_s, k + 1u);
+      }
+    } else if (CW == 1 ? ((warp & 3u) != 0u && warp > 3u) : warp >= 8u) {
       // ------------------------------ near helpers -------------------------------------------------------
-      const uint32_t hidx = ((warp >> 2) - 1u) * 3u + (warp & 3u) - 1u;   // warps 5,6,7, 9,10,11, 13,14,15
-      const bool hprof = (P.dbg & 1u) != 0u && blockIdx.x == 0 && warp == 5;
+      // CW = 1: warps 5,6,7, 9,10,11, 13,14,15 ; CW = 4: warps 8..15
+      const uint32_t hidx = CW == 1 ? ((warp >> 2) - 1u) * 3u + (warp & 3u) - 1u : warp - 8u;
+      const bool hprof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0 && hidx == 0u;
+      // The start vector of a chunk (written by the far CTAs, tile flag + L2 round trips) is fetched one own chunk ahead:
+      // the flag of the next own chunk's tile is read at the top of the iteration (the value comes back while the helper
+      // works), tested before the helper starts to wait for the chain, and the start vector is loaded there.
       uint32_t tiles_known = 0;
-      for (uint32_t k = hidx; k < nch; k += BC_NH) {
+      double t0n = 0.0;
+      if (hidx < nch) {
+        BC_WAIT(ld_acquire_gpu(P.tileflag + b.tile0 + hidx / BC_TILE) != 0u, 0x400u, 100);
+        tiles_known = hidx / BC_TILE + 1u;
+        const uint32_t j = b.lo + 32u * hidx + lane;
+        t0n = j < b.hi ? __ldcg(P.w + j) : 0.0;
+      }
+      for (uint32_t k = hidx; k < nch; k += NH) {
         const uint32_t i = ia0 + k, slot = i % P.SB;
-        const uint32_t tile = k / BC_TILE;
         long long h0 = 0;
         if (hprof) h0 = clock64();
-        if (tile >= tiles_known) {
-          if (lane == 0) BC_WAIT(ld_acquire_gpu(P.tileflag + b.tile0 + tile) != 0u, 0x400u, 100);
-          __syncwarp();
-          tiles_known = tile + 1u;
-        }
-        const uint32_t j = b.lo + 32u * k + lane;
-        const double t0 = j < b.hi ? __ldcg(P.w + j) : 0.0;
+        const double t0 = t0n;
+        const uint32_t kn = k + NH, tilen = kn / BC_TILE;
+        uint32_t fln = 1u;
+        if (kn < nch && tilen >= tiles_known) fln = ld_acquire_gpu(P.tileflag + b.tile0 + tilen);
         long long h1 = 0;
         if (hprof) h1 = clock64();
         // The slot's sequence word is tested BEFORE the barrier's parity: helpers take chunks out of order, so with fewer
@@ -697,7 +889,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
         const uint32_t need1 = k > P.E ? k - P.E : 0u;
         long long h2 = 0;
         if (hprof) h2 = clock64();
-        BC_WAIT(ld_acquire_cta_s(prog_s) >= need1, 0x600u, 200);
+        if (!(P.dbg & 32u)) BC_WAIT(ld_acquire_cta_s(prog_s) >= need1, 0x600u, 200);
         double ts = __shfl_sync(0xffffffffu, t0, (int)perm), ts1 = 0.0;
         uint32_t base = 0;
         for (uint32_t s = 0; s < ne_max; s += 4u) {
@@ -728,7 +920,17 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
           lvr[u] = 0.0;
           if (u < nl) { lcr[u] = lc[u * 32u + lane]; lvr[u] = lv[u * 32u + lane]; }
         }
+        // the staging slot is free once the late entries are in registers (the arrive depends on the last of them)
+        const bool slot_done = nl <= LB;
+        if (slot_done && lane == 0) mbar_arrive_after(emptyB + slot, lcr[LB - 1u], lvr[LB - 1u]);
+        if (kn < nch) {
+          if (fln == 0u) BC_WAIT(ld_acquire_gpu(P.tileflag + b.tile0 + tilen) != 0u, 0x400u, 100);
+          tiles_known = tilen + 1u;
+          const uint32_t jn = b.lo + 32u * kn + lane;
+          t0n = jn < b.hi ? __ldcg(P.w + jn) : 0.0;
+        }
         uint32_t need2 = k > P.Kr ? k - P.Kr : 0u;
+        if (P.dbg & 32u) need2 = 0u;   // timing experiment only: free-running chain (results are wrong)
         if (k + 1u > BC_TR) need2 = max(need2, k + 1u - BC_TR);
         long long h3 = 0;
         if (hprof) h3 = clock64();
@@ -739,10 +941,10 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
           G.n = 0;
           while ((pnow = ld_acquire_cta_s(prog_s)) < need2) {
             if (guard_poll(G, 0x700u)) break;
-            if (need2 - pnow > 1u) __nanosleep(300);
+            if (need2 - pnow > 1u || (P.dbg & 16u)) __nanosleep(300);
           }
         }
-        if (k >= P.Dfar) BC_WAIT(ld_acquire_cta_s(pub_s) >= k - P.Dfar + 1u, 0x800u, 100);
+        if (k >= P.Dfar && !(P.dbg & 32u)) BC_WAIT(ld_acquire_cta_s(pub_s) >= k - P.Dfar + 1u, 0x800u, 100);
         long long h4 = 0;
         if (hprof) h4 = clock64();
         {
@@ -785,11 +987,11 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
         __syncwarp();
         if (lane == 0) {
           st_release_cta_s(trdy_s + 4u * tsl, k + 1u);
-          mbar_arrive(emptyB + slot);
+          if (!slot_done) mbar_arrive(emptyB + slot);
         }
         if (hprof) { ph[0] += h1 - h0; ph[1] += h2 - h1; ph[2] += h3 - h2; ph[3] += h4 - h3; ph[4] += clock64() - h4; }
       }
-    } else if (warp == 1) {
+    } else if (warp == W_PRODA) {
       // ------------------------------ TMA producer, ring A -----------------------------------------------
       for (uint32_t base = 0; base < nch; base += 32u) {
         const uint32_t gl = b.chunk0 + min(base + lane, nch - 1u);
@@ -806,7 +1008,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
           __syncwarp();
         }
       }
-    } else if (warp == 2) {
+    } else if (warp == W_PRODB) {
       // ------------------------------ TMA producer, ring B -----------------------------------------------
       for (uint32_t base = 0; base < nch; base += 32u) {
         const uint32_t gl = b.chunk0 + min(base + lane, nch - 1u);
@@ -832,7 +1034,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
           __syncwarp();
         }
       }
-    } else if (warp == 3) {
+    } else if (warp == W_PUB) {
       // ------------------------------ publisher ----------------------------------------------------------
       uint32_t done = 0;
       double dot = 0.0;
@@ -880,10 +1082,11 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
       for (int q = 0; q < 4; q++) P.clk[3 + q] = (unsigned long long)pc[q];
       P.clk[13] = (unsigned long long)pc[4];
       P.clk[14] = (unsigned long long)pc[5];
+      P.clk[7] = (unsigned long long)pc[7];    // split chain: cycles in the per-chunk barrier
       P.clk[15] = (unsigned long long)pc[6];   // failed polls of t'
     }
   }
-  if (P.clk && (P.dbg & 1u) && blockIdx.x == 0 && threadIdx.x == 160)
+  if (P.clk && (P.dbg & 1u) && blockIdx.x == 0 && threadIdx.x == (CW == 1 ? 160u : 256u))
     for (int q = 0; q < 5; q++) P.clk[8 + q] = (unsigned long long)ph[q];
 }
 
@@ -934,7 +1137,8 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   const uint32_t N = (uint32_t)h->N;
   const int nb = (int)bounds.size() - 1;
   // ---- thresholds ------------------------------------------------------------------------------------
-  B.Kr = h->opt.reserved[3] > 0 ? (uint32_t)std::min(h->opt.reserved[3], 4) : 2u;
+  // (the split chain keeps the solution of two chunks in its partial-sum buffers: recent distance at most 2)
+  B.Kr = h->opt.reserved[3] > 0 ? (uint32_t)std::min(h->opt.reserved[3], h->opt.chain_mode == 3 ? 4 : 2) : 2u;
   B.E = 16u;
   uint32_t win_rows = h->opt.chain_window > 0 ? (uint32_t)h->opt.chain_window : 4096u;
   B.Dfar = std::min(512u, std::max(32u, floor_pow2_u32(std::max(32u, win_rows) / 32u)));
@@ -1091,7 +1295,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     int64_t capB = std::min<int64_t>(maxB, std::max<int64_t>(3 * meanB, 6144));
     capB = std::min<int64_t>(capB, 24576);
     L.capB = (uint32_t)((capB + 127) & ~127ll);
-    const int64_t fixed = (int64_t)W * 8 + 128 + BC_TR * 32 * 8 + 256 + BC_TR * 4 + 64 + 1024;
+    const int64_t fixed = (int64_t)W * 8 + 128 + BC_TR * 32 * 8 + BC_SCR * 8 + BC_TR * 4 + 64 + 1024;
     int64_t avail = (int64_t)BC_SMEM_MAX - fixed;
     // ring A feeds one consumer (latency cover), ring B feeds BC_NH helpers that hold their slot while they work
     int64_t SA = std::max<int64_t>(3, std::min<int64_t>(10, (avail * 4 / 10) / L.capA));
@@ -1142,7 +1346,10 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
   BlockedDev &B = d.bc;
   static bool attr_set = false;
   if (!attr_set) {
-    RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
+    RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
+    RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
+    RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
+    RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
     attr_set = true;
   }
   if (only_kernel > 0) return RCG_OK;   // the level kernel is the only kernel of a group
@@ -1199,13 +1406,16 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     at[0].val.cooperative = 1;
     cfg.attrs = at;
     cfg.numAttrs = h->opt.reserved[6] ? 0 : 1;   // reserved[6] = 1: plain launch (the grid never exceeds the SM count)
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_bc_solve, a);
+    const bool split = h->opt.chain_mode != 3;   // default: four critical warps
+    void (*kern)(const BcArgs) = (a.dbg & 1u) ? (split ? k_bc_solve<4, true> : k_bc_solve<1, true>)
+                                              : (split ? k_bc_solve<4, false> : k_bc_solve<1, false>);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
     if (e != cudaSuccess && cfg.numAttrs == 1) {
       // co-residency is what the cooperative attribute guarantees; a context that cannot give it (or cannot capture it)
       // still runs the launch correctly when the GPU is otherwise idle, because the grid never exceeds the SM count
       cudaGetLastError();
       cfg.numAttrs = 0;
-      e = cudaLaunchKernelEx(&cfg, k_bc_solve, a);
+      e = cudaLaunchKernelEx(&cfg, kern, a);
     }
     RCG_CUDA(h, e);
     h->stats.kernel_launches += 1;

@@ -50,7 +50,7 @@ for cfg in cfgs:
             if dbg:
                 c = s.counters()
                 nchk = max(c[6], 1)
-                print(f"        CTA0 total {c[0]} cyc; critical per chunk {c[0]/nchk:.0f}: blockedA {c[3]/nchk:.0f} t' {c[4]/nchk:.0f} recent {c[5]/nchk:.0f} matvec {c[13]/nchk:.0f} preload+store {c[14]/nchk:.0f} late-t' {c[15]/nchk:.3f} (chunks {c[6]});"
+                print(f"        CTA0 total {c[0]} cyc; critical per chunk {c[0]/nchk:.0f}: blockedA {c[3]/nchk:.0f} t' {c[4]/nchk:.0f} recent {c[5]/nchk:.0f} matvec {c[13]/nchk:.0f} preload+store {c[14]/nchk:.0f} late-t' {c[15]/nchk:.3f} barrier {c[7]/nchk:.0f} (chunks {c[6]});"
                       f" helper0 per own chunk: start {c[8]*9/nchk:.0f} blobB {c[9]*9/nchk:.0f} early {c[10]*9/nchk:.0f} waitprog {c[11]*9/nchk:.0f} late {c[12]*9/nchk:.0f}", flush=True)
     info = (capi.C.c_uint64 * 16)()
     s._L.rcg_debug_blocked_info(s._h, 0, info)
