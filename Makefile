@@ -3,7 +3,7 @@
 NVCC     ?= /usr/local/cuda/bin/nvcc
 HOSTCXX  ?= /usr/bin/g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall
+NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-fopenmp
 SRC      := rchol_b200/csrc/rcg_api.cu rchol_b200/csrc/rcg_setup.cu rchol_b200/csrc/rcg_kernels.cu rchol_b200/csrc/rcg_trisolve.cu rchol_b200/csrc/rcg_blocked.cu rchol_b200/csrc/rcg_dist.cu
 OBJ      := $(SRC:.cu=.o)
 LIB      := rchol_b200/lib/librchol_b200.so
@@ -15,7 +15,7 @@ all: $(LIB) cxx
 
 $(LIB): $(OBJ)
 	mkdir -p rchol_b200/lib
-	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(OBJ) -cudart shared -ldl
+	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(OBJ) -cudart shared -ldl -lgomp
 
 # C++ face of the drop-in (SparseCSR, pcg, util) and the example driver
 CXXLIB   := rchol_b200/lib/librchol_b200_cxx.so

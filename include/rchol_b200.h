@@ -52,7 +52,8 @@ typedef struct rcg_options {
                               2 = level-space role-specialised kernel (experimental)                                 */
   int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2),
                               [3] blocked solve: recent chunk distance Kr (default 2), [4] window rows of the separator blocks
-                              (default 1024), [6] 1 = plain (non-cooperative) launch */
+                              (default 1024), [5] blocked solve: distance E (chunks) that separates the "early" from the "late" entries
+                              (default 16), [6] 1 = plain (non-cooperative) launch */
 } rcg_options;
 
 /* Per-handle measurements, all device-side times from CUDA events on the handle's own stream. */

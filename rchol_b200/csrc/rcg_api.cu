@@ -219,6 +219,10 @@ int rcg_destroy(rcg_handle *h) {
   free_vectors(h);
   if (h->haveA) rcg_free_csr(h->A);
   if (h->haveG) { rcg_free_direction(h->fwd); rcg_free_direction(h->bwd); }
+  for (int i = 0; i < 2; i++) {
+    if (h->stage_buf[i]) cudaFreeHost(h->stage_buf[i]);
+    if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+  }
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);

@@ -36,8 +36,10 @@ constexpr uint32_t BC_SCR = 576;          // scratch doubles: [0,32) t vector(s)
 constexpr uint32_t BC_TR = 32;            // ring of t' vectors between helpers and the critical warp
 constexpr uint32_t BC_TILE = 8;           // chunks per far tile
 constexpr uint32_t BC_WBYTES = 1024 * 8;  // Winv, full 32x32 (zeros above the diagonal): [column pair p][row] double2
-constexpr uint32_t BC_RBATCH = 3072;      // one batch of 8 recent slots: [4 pairs][32 rows] double2 values, then
-                                          // [2 halves][32 rows] uint4 byte offsets into the window
+constexpr uint32_t BC_RBATCH = 3072;      // one batch of 8 recent slots: [32 rows][4 pairs] double2 values, then
+                                          // [32 rows][2 halves] uint4 byte offsets into the window (row-major: the
+                                          // split chain reads 8 rows x 64 B = 512 contiguous bytes per warp, no bank
+                                          // conflicts; measured 16 -> 4 wavefronts per load, profiles/r01_bc_solve_ncu.md)
 constexpr uint32_t BC_AHDR = 16, BC_BHDR = 80;
 constexpr long long BC_TIMEOUT_CYCLES = 3000000000ll;   // ~1.5 s at 1.965 GHz
 constexpr int BC_SMEM_MAX = 232448 - 1024;
@@ -309,8 +311,8 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
       }
     }
     __syncwarp();
-    // ---- recent entries: batches of 8 slots; values [4 pairs][32 rows] double2, window byte offsets
-    //      [2 halves][32 rows] uint4.  Padding: value 0, offset of the slot behind the window that always holds 0.0
+    // ---- recent entries: batches of 8 slots; values [32 rows][4 pairs] double2, window byte offsets
+    //      [32 rows][2 halves] uint4.  Padding: value 0, offset of the slot behind the window that always holds 0.0
     {
       const uint32_t nbt = rec_batches(nslots);
       for (uint32_t bt = 0; bt < nbt; bt++) {
@@ -318,8 +320,8 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
         for (uint32_t u = 0; u < 8u; u++) {
           const uint32_t sidx = 8u * bt + u;
           const bool have = sidx < n_rec;
-          reinterpret_cast<double *>(R + 512u * (u >> 1) + 16u * lane)[u & 1u] = have ? val[r.p_late + sidx] : 0.0;
-          reinterpret_cast<uint32_t *>(R + 2048u + 512u * (u >> 2) + 16u * lane)[u & 3u] =
+          reinterpret_cast<double *>(R + 64u * lane + 16u * (u >> 1))[u & 1u] = have ? val[r.p_late + sidx] : 0.0;
+          reinterpret_cast<uint32_t *>(R + 2048u + 32u * lane + 16u * (u >> 2))[u & 3u] =
               8u * (have ? ((col[r.p_late + sidx] - blo) & wmask) : (wmask + 1u));
         }
       }
@@ -555,15 +557,15 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
       do {                                                                                                                \
         const uint32_t a_s_ = smem_u32(ringA + (size_t)slot * P.capA);                                                    \
         w_s = a_s_ + BC_AHDR + 16u * lane;                                                                                \
-        r_s = w_s + BC_WBYTES;                                                                                            \
+        r_s = a_s_ + BC_AHDR + BC_WBYTES + 64u * lane; /* row-major recent batch: 64 B of values per row */                                                                                           \
         _Pragma("unroll") for (uint32_t pp = 0; pp < WPRE; pp++)                                                          \
           asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w[2 * pp]), "=d"(w[2 * pp + 1]) : "r"(w_s + 512u * pp) : "memory"); \
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(r_s + 2048u) : "memory"); \
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o4), "=r"(o5), "=r"(o6), "=r"(o7) : "r"(r_s + 2560u) : "memory"); \
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(r_s + 2048u - 32u * lane) : "memory"); \
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o4), "=r"(o5), "=r"(o6), "=r"(o7) : "r"(r_s + 2048u - 32u * lane + 16u) : "memory"); \
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(r_s) : "memory");                      \
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(r_s + 512u) : "memory");               \
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v4), "=d"(v5) : "r"(r_s + 1024u) : "memory");              \
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v6), "=d"(v7) : "r"(r_s + 1536u) : "memory");              \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(r_s + 16u) : "memory");               \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v4), "=d"(v5) : "r"(r_s + 32u) : "memory");              \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v6), "=d"(v7) : "r"(r_s + 48u) : "memory");              \
         nbt = lds_u32(a_s_);                                                                                              \
       } while (0)
       if (nch > 0) {
@@ -599,12 +601,12 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
         }
         for (uint32_t bt = 1; bt < nbt; bt++) {   // more than 8 recent slots
           const uint32_t q_s = r_s + BC_RBATCH * bt;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(q_s + 2048u) : "memory");
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o4), "=r"(o5), "=r"(o6), "=r"(o7) : "r"(q_s + 2560u) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(q_s + 2048u - 32u * lane) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o4), "=r"(o5), "=r"(o6), "=r"(o7) : "r"(q_s + 2048u - 32u * lane + 16u) : "memory");
           asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(q_s) : "memory");
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(q_s + 512u) : "memory");
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v4), "=d"(v5) : "r"(q_s + 1024u) : "memory");
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v6), "=d"(v7) : "r"(q_s + 1536u) : "memory");
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(q_s + 16u) : "memory");
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v4), "=d"(v5) : "r"(q_s + 32u) : "memory");
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v6), "=d"(v7) : "r"(q_s + 48u) : "memory");
           const double x0 = lds_f64(win_s + o0), x1 = lds_f64(win_s + o1), x2 = lds_f64(win_s + o2), x3 = lds_f64(win_s + o3);
           const double x4 = lds_f64(win_s + o4), x5 = lds_f64(win_s + o5), x6 = lds_f64(win_s + o6), x7 = lds_f64(win_s + o7);
           t = fma(-v0, x0, t);
@@ -689,9 +691,10 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
       //   -> t[8cw..8cw+7] broadcast through 64 bytes of shared memory -> 8 DFMA with the warp's slice of Winv
       //   -> partial[k & 3][cw][lane]  -> named barrier (4 critical warps + scribe)
       // x_k is never materialised by the critical warps: a gather of x_k[c] reads the four partial sums and adds them in
-      // the same order as the scribe does when it writes the window.  Four partial buffers indexed by the chunk number
-      // mod 4 (two bits of the window offset the set-up stored with the entry): chunk k reads the buffers of k-1 and k-2
-      // while a faster warp may already write that of k+1; one barrier per chunk.
+      // the same order as the scribe does when it writes the window.  Four partial buffers per warp indexed by the chunk
+      // number mod 4, laid out [warp][chunk mod 4][row] so that the low 10 bits of the window byte offset the set-up
+      // stored with the entry ARE the offset inside a warp's partials (one LOP3 per gather: the lone warp is issue-bound);
+      // chunk k reads the buffers of k-1 and k-2 while a faster warp may already write that of k+1; one barrier per chunk.
       // Measured (ncu source page, profiles/): a lone warp pays ~4 cycles per dependent instruction, a fetch bubble per
       // taken branch and 30-130 cycles per shared-memory round trip, so the loop is straight-line code, every wait is a
       // compact bounded spin, and the loads of chunk k+1 that do not depend on the chain (Winv slice, recent values and
@@ -699,8 +702,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
       const bool prof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0 && warp == 0u;
       const uint32_t cw = warp, rowg = 8u * cw + (lane >> 2), sub = lane & 3u;
       const uint32_t part_s = sc_s + 256u, tb_s = sc_s + 64u * cw;
-      const uint32_t pw_s = part_s + 256u * cw + 8u * lane;   // this lane's slot in buffer 0
-      const uint32_t rec_off = 512u * sub + 16u * rowg, off_off = 2048u + 512u * (sub >> 1) + 16u * rowg + 8u * (sub & 1u);
+      const uint32_t pw_s = part_s + 1024u * cw + 8u * lane;   // this lane's slot in buffer 0 of this warp's partial sums
+      const uint32_t rec_off = 64u * rowg + 16u * sub, off_off = 2048u + 32u * rowg + 8u * sub;
       const uint32_t fullA_s = smem_u32(fullA), emptyA_s = smem_u32(emptyA), ringA_s = smem_u32(ringA);
       uint32_t slot = ia0 % P.SA, par = (ia0 / P.SA) & 1u;
       double wa[8];
@@ -737,46 +740,49 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
         tpf = lds_volatile_u32(trdy_s + 4u * ((k_) & (BC_TR - 1u)));                                                      \
       } while (0)
       // gather x[c] of one of the two previous chunks from the partial sums (buffer = chunk number mod 4)
-#define BC4_GATHER(x_, ro_)                                                                                               \
+      // The chain's per-chunk latency is the sum of what a lone, issue-bound warp does between two barriers (ncu source
+      // page, profiles/r01_bc_solve_ncu.md), so the order of the statements below is the schedule: every shared-memory
+      // load is issued as early as its address allows (gathers, Winv slice, t'), the staging-ring bookkeeping sits where
+      // the warp waits for the t broadcast anyway, and nothing but two LOP3 separates the barrier from the first gather.
+#define BC4_GATHER_LD(p_, ro_)                                                                                            \
       do {                                                                                                                \
-        const uint32_t g_ = part_s + (((ro_) & 0x300u) << 2) + ((ro_) & 0xF8u);                                           \
-        const double p0_ = lds_f64(g_), p1_ = lds_f64(g_ + 256u), p2_ = lds_f64(g_ + 512u), p3_ = lds_f64(g_ + 768u);     \
-        x_ = (p0_ + p1_) + (p2_ + p3_);                                                                                   \
+        const uint32_t g_ = part_s + ((ro_) & 0x3F8u);   /* [warp][chunk mod 4][row]: the window offset's low bits */    \
+        p_[0] = lds_f64(g_); p_[1] = lds_f64(g_ + 1024u); p_[2] = lds_f64(g_ + 2048u); p_[3] = lds_f64(g_ + 3072u);       \
       } while (0)
 #define BC4_CHUNK(MORE_)                                                                                                  \
       do {                                                                                                                \
         constexpr bool more_ = MORE_;                                                                                     \
         long long c1_ = 0;                                                                                                \
         if (prof) c1_ = clock64();                                                                                        \
-        /* staging slot of the next chunk: phase test now, answer needed after the mat-vec */                             \
-        const uint32_t oslot_ = slot;                                                                                     \
-        if (more_) { if (++slot == P.SA) { slot = 0; par ^= 1u; } BC4_MBAR_TEST(a_ok, fullA_s + 8u * slot, par); }         \
+        double pa_[4], pb_[4];                                                                                            \
+        BC4_GATHER_LD(pa_, ro0);                                                                                          \
+        BC4_GATHER_LD(pb_, ro1);                                                                                          \
+        BC4_LOAD_W(wa);   /* behind the gathers in the shared-memory queue, needed a reduction later */                   \
+        if (__builtin_expect(tpf != k + 1u, 0)) {                                                                         \
+          BC4_SPIN((tpf = ld_acquire_cta_s(trdy_s + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);                         \
+          if (prof) pc[6] += 1;                                                                                           \
+        }                                                                                                                 \
+        /* t' through an address that depends on the flag; in flight while the gathers are summed */                      \
+        tpv = lds_f64(tp_s + 8u * ((k & (BC_TR - 1u)) * 32u + rowg) + ((tpf ^ (k + 1u)) & 0x7u) * 8u);                    \
         double acc_;                                                                                                      \
         {                                                                                                                 \
-          double x0_, x1_;                                                                                                \
-          BC4_GATHER(x0_, ro0);                                                                                           \
-          BC4_GATHER(x1_, ro1);                                                                                           \
-          BC4_LOAD_W(wa);   /* behind the gathers in the shared-memory queue, needed a reduction later */                 \
+          const double x0_ = (pa_[0] + pa_[1]) + (pa_[2] + pa_[3]);                                                       \
+          const double x1_ = (pb_[0] + pb_[1]) + (pb_[2] + pb_[3]);                                                       \
           acc_ = -rv0 * x0_;                                                                                              \
           acc_ = fma(-rv1, x1_, acc_);                                                                                    \
         }                                                                                                                 \
         if (__builtin_expect(nbt > 1u, 0))                                                                                \
         _Pragma("unroll 1") for (uint32_t bt_ = 1; bt_ < nbt; bt_++) { /* more than 8 recent slots */                     \
           const uint32_t q_s_ = a_s + BC_AHDR + BC_WBYTES + BC_RBATCH * bt_;                                              \
-          double v0_, v1_, x0_, x1_;                                                                                      \
+          double v0_, v1_;                                                                                                \
           uint32_t o0_, o1_;                                                                                              \
           asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0_), "=d"(v1_) : "r"(q_s_ + rec_off) : "memory");       \
           asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o0_), "=r"(o1_) : "r"(q_s_ + off_off) : "memory");       \
-          BC4_GATHER(x0_, o0_);                                                                                           \
-          BC4_GATHER(x1_, o1_);                                                                                           \
-          acc_ = fma(-v0_, x0_, acc_);                                                                                    \
-          acc_ = fma(-v1_, x1_, acc_);                                                                                    \
+          BC4_GATHER_LD(pa_, o0_);                                                                                        \
+          BC4_GATHER_LD(pb_, o1_);                                                                                        \
+          acc_ = fma(-v0_, (pa_[0] + pa_[1]) + (pa_[2] + pa_[3]), acc_);                                                  \
+          acc_ = fma(-v1_, (pb_[0] + pb_[1]) + (pb_[2] + pb_[3]), acc_);                                                  \
         }                                                                                                                 \
-        if (__builtin_expect(tpf != k + 1u, 0)) {                                                                         \
-          BC4_SPIN((tpf = ld_acquire_cta_s(trdy_s + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);                         \
-          if (prof) pc[6] += 1;                                                                                           \
-        }                                                                                                                 \
-        tpv = lds_f64(tp_s + 8u * ((k & (BC_TR - 1u)) * 32u + rowg) + ((tpf ^ (k + 1u)) & 0x7u) * 8u);                    \
         acc_ += sub == 0u ? tpv : 0.0;                                                                                    \
         long long c2_ = 0;                                                                                                \
         if (prof) { c2_ = clock64() + (acc_ == 1.25e-300 ? 1 : 0); pc[1] += c2_ - c1_; }                                  \
@@ -791,6 +797,9 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t2_), "=d"(t3_) : "r"(tb_s + 16u) : "memory");             \
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t4_), "=d"(t5_) : "r"(tb_s + 32u) : "memory");             \
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t6_), "=d"(t7_) : "r"(tb_s + 48u) : "memory");             \
+        /* staging slot of the next chunk: ring bookkeeping and phase test while the t broadcast is in flight */          \
+        const uint32_t oslot_ = slot;                                                                                     \
+        if (more_) { if (++slot == P.SA) { slot = 0; par ^= 1u; } BC4_MBAR_TEST(a_ok, fullA_s + 8u * slot, par); }         \
         long long c4_ = 0;                                                                                                \
         if (prof) { c4_ = clock64(); pc[4] += c4_ - c3_; }                                                                \
         double a0_ = wa[0] * t0_, a1_ = wa[1] * t1_;                                                                      \
@@ -801,7 +810,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
         a0_ = fma(wa[6], t6_, a0_);                                                                                       \
         a1_ = fma(wa[7], t7_, a1_);                                                                                       \
         const double a_ = a0_ + a1_;                                                                                      \
-        sts_f64(pw_s + ((k & 3u) << 10), a_);                                                                             \
+        sts_f64(pw_s + ((k & 3u) << 8), a_);                                                                              \
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(emptyA_s + 8u * oslot_) : "memory"); \
         /* chain-independent loads of the next chunk: in flight across the barrier */                                     \
         if (more_) {                                                                                                      \
@@ -828,7 +837,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
       for (; k + 1u < nch; k++) BC4_CHUNK(true);
       if (k < nch) BC4_CHUNK(false);
 #undef BC4_CHUNK
-#undef BC4_GATHER
+#undef BC4_GATHER_LD
 #undef BC4_LOAD_TP
 #undef BC4_LOAD_W
 #undef BC4_LOAD_REC
@@ -839,8 +848,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
       const uint32_t pr_s = sc_s + 256u + 8u * lane;
       for (uint32_t k = 0; k < nch; k++) {
         asm volatile("bar.sync 1, 160;" ::: "memory");
-        const uint32_t q_s = pr_s + ((k & 3u) << 10);
-        const double p0 = lds_f64(q_s), p1 = lds_f64(q_s + 256u), p2 = lds_f64(q_s + 512u), p3 = lds_f64(q_s + 768u);
+        const uint32_t q_s = pr_s + ((k & 3u) << 8);
+        const double p0 = lds_f64(q_s), p1 = lds_f64(q_s + 1024u), p2 = lds_f64(q_s + 2048u), p3 = lds_f64(q_s + 3072u);
         sts_f64(win_s + 8u * ((32u * k + lane) & wmask), (p0 + p1) + (p2 + p3));
         __syncwarp();
         if (lane == 0) st_release_cta_s(prog_s, k + 1u);
@@ -1139,7 +1148,9 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   // ---- thresholds ------------------------------------------------------------------------------------
   // (the split chain keeps the solution of two chunks in its partial-sum buffers: recent distance at most 2)
   B.Kr = h->opt.reserved[3] > 0 ? (uint32_t)std::min(h->opt.reserved[3], h->opt.chain_mode == 3 ? 4 : 2) : 2u;
-  B.E = 16u;
+  // chunks k-E .. k-Kr-1 are the "late" class (gathered by the near helper AFTER the chain reached chunk k-Kr);
+  // older chunks inside the window are "early" (gathered before).  reserved[5] overrides (tuning experiments).
+  B.E = h->opt.reserved[5] > 0 ? (uint32_t)std::min(16, std::max<int>(h->opt.reserved[5], (int)B.Kr + 1)) : 16u;
   uint32_t win_rows = h->opt.chain_window > 0 ? (uint32_t)h->opt.chain_window : 4096u;
   B.Dfar = std::min(512u, std::max(32u, floor_pow2_u32(std::max(32u, win_rows) / 32u)));
   // Separator blocks are small, dense and have every far CTA of the launch to themselves: a short window sends most of

@@ -175,6 +175,10 @@ struct rcg_handle {
   double dbg_nbatch = 0;
   rcg_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // two pinned staging buffers of the host->device upload (rcg_setup.cu), allocated at the first upload
+  void *stage_buf[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 // ---------------------------------------------------------------------------------------------------------

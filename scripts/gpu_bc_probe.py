@@ -13,14 +13,23 @@ def relerr(a, b):
 
 n, T = int(sys.argv[1]), int(sys.argv[2])
 cfgs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[3:]] or [(0, 0)]
-t = time.time(); A = problems.laplace_3d(n); f = producer.factor(*A, threads=T)
-print(f"=== lap3d n={n} T={T} factor {time.time()-t:.1f}s nnzG {f.nnz}", flush=True)
-G = (f.rowPtr, f.colIdx, f.val)
-b = problems.random_rhs(f.N)
-if T > 0:
-    A = producer.ref_reorder(*A, f.P); b = problems.reorder_vector(b, f.P)
-part = f.part if T > 0 else None
-check = f.N <= 3_000_000
+if os.environ.get("RCHOL_PROBE_CACHE"):      # share the problem (and its factorization) with bench.py's on-disk cache
+    import bench
+    d, _ = bench.build_problem(n, T)
+    A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"]); b = d["b"]
+    part = d["part"] if T > 0 else None
+    N = A[0].shape[0] - 1
+    print(f"=== lap3d n={n} T={T} (bench cache) nnzG {int(G[0][-1])}", flush=True)
+else:
+    t = time.time(); A = problems.laplace_3d(n); f = producer.factor(*A, threads=T)
+    print(f"=== lap3d n={n} T={T} factor {time.time()-t:.1f}s nnzG {f.nnz}", flush=True)
+    G = (f.rowPtr, f.colIdx, f.val)
+    b = problems.random_rhs(f.N)
+    if T > 0:
+        A = producer.ref_reorder(*A, f.P); b = problems.reorder_vector(b, f.P)
+    part = f.part if T > 0 else None
+    N = f.N
+check = N <= 3_000_000
 if check:
     t = time.time(); yo = oracle.trsv_forward(*G, b); zo = oracle.trsv_backward(*G, yo); print(f"oracle trsv {time.time()-t:.1f}s", flush=True)
 for cfg in cfgs:
@@ -28,10 +37,11 @@ for cfg in cfgs:
     mode = cfg[2] if len(cfg) > 2 else 0
     dbg = cfg[3] if len(cfg) > 3 else 0
     sepw = cfg[4] if len(cfg) > 4 else 0
-    s = capi.Solver(0, chain_window=win, recent=rec, chain_mode=mode, dbg=dbg, sep_window=sepw)
+    early = cfg[5] if len(cfg) > 5 else 0
+    s = capi.Solver(0, chain_window=win, recent=rec, chain_mode=mode, dbg=dbg, sep_window=sepw, early=early)
     t = time.time(); s.set_matrix(*A); s.set_factor(*G, part); t_set = time.time() - t
     st = s.stats()
-    print(f"--- window={win} recent={rec} mode={mode} sep_window={sepw}: set-up wall {t_set:.2f}s upload {st['upload_ms']:.0f} analysis {st['analysis_ms']:.0f} ms", flush=True)
+    print(f"--- window={win} recent={rec} mode={mode} sep_window={sepw} early={early} dbg={dbg}: set-up wall {t_set:.2f}s upload {st['upload_ms']:.0f} analysis {st['analysis_ms']:.0f} ms", flush=True)
     if check:
         y = s.trsv(capi.TRSV_FORWARD, b); z = s.trsv(capi.TRSV_BACKWARD, yo); zz = s.precond(b)
         print(f"    fwd relerr {relerr(y, yo):.2e} bwd {relerr(z, zo):.2e} precond {relerr(zz, zo):.2e}", flush=True)

@@ -33,11 +33,11 @@ def unpack_recent(raw_bytes, nbt):
     rc = np.zeros((8 * nbt, 32), np.int64)
     for bt in range(nbt):
         R = raw_bytes[RBATCH * bt: RBATCH * (bt + 1)]
-        vals = R[:2048].view(np.float64).reshape(4, 32, 2)      # [pair][row][2]
-        offs = R[2048:].view(np.uint32).reshape(2, 32, 4)        # [half][row][4] byte offsets into the window
+        vals = R[:2048].view(np.float64).reshape(32, 4, 2)      # [row][pair][2]
+        offs = R[2048:].view(np.uint32).reshape(32, 2, 4)        # [row][half][4] byte offsets into the window
         for u in range(8):
-            rv[8 * bt + u] = vals[u >> 1, :, u & 1]
-            rc[8 * bt + u] = offs[u >> 2, :, u & 3] // 8
+            rv[8 * bt + u] = vals[:, u >> 1, u & 1]
+            rc[8 * bt + u] = offs[:, u >> 2, u & 3] // 8
     return rv, rc
 
 

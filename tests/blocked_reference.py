@@ -116,15 +116,15 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
                     wp[o + 1] = W[row, 2 * pp + 1]
             for bt in range(nbt):
                 R = a[AHDR + WBYTES + RBATCH * bt: AHDR + WBYTES + RBATCH * (bt + 1)]
-                vals = R[:2048].view(np.float64).reshape(4, 32, 2)
-                offs = R[2048:].view(np.uint32).reshape(2, 32, 4)
+                vals = R[:2048].view(np.float64).reshape(32, 4, 2)      # [row][pair][2]
+                offs = R[2048:].view(np.uint32).reshape(32, 2, 4)        # [row][half][4]
                 offs[:] = 8 * (wmask + 1)
                 for l, p in enumerate(parts):
                     for u in range(8):
                         sidx = 8 * bt + u
                         if sidx < len(p[4]):
-                            vals[u >> 1, l, u & 1] = p[5][sidx]
-                            offs[u >> 2, l, u & 3] = 8 * ((p[4][sidx] - blo) & wmask)
+                            vals[l, u >> 1, u & 1] = p[5][sidx]
+                            offs[l, u >> 2, u & 3] = 8 * ((p[4][sidx] - blo) & wmask)
             blobsA[g] = a
             # blob B
             order = sorted(range(32), key=lambda l: (-n_early[l], l))
