@@ -45,14 +45,30 @@ def log(*a):
 # problem construction (inputs of the hot path; cached on local disk so that the two arms share the factor)
 # ------------------------------------------------------------------------------------------------------------
 def build_problem(n: int, threads: int):
+    """A, G, part, b, P of the workload.  Generated once per box (reference factorization on the host, fixed seed) and
+    cached on local disk; under torchrun only local rank 0 generates, the other ranks wait for the cache and map it."""
     cache_root = os.environ.get("RCHOL_B200_CACHE", "/tmp/rchol_b200_cache")
     tag = os.path.join(cache_root, f"lap3d_{n}_T{threads}_s{SEED}")
     names = ["A_rp", "A_ci", "A_v", "G_rp", "G_ci", "G_v", "part", "b", "P"]
-    if all(os.path.exists(f"{tag}.{k}.npy") for k in names):
+    ready = f"{tag}.ready"
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    multi = int(os.environ.get("WORLD_SIZE", 1)) > 1
+
+    def load():
         t0 = time.time()
-        d = {k: np.load(f"{tag}.{k}.npy") for k in names}
+        d = {k: np.load(f"{tag}.{k}.npy", mmap_mode="r" if multi else None) for k in names}
         log(f"[bench] loaded cached problem {tag} in {time.time() - t0:.1f}s")
         return d, dict(cached=True)
+
+    if os.path.exists(ready) and all(os.path.exists(f"{tag}.{k}.npy") for k in names):
+        return load()
+    if multi and local_rank != 0:
+        t0 = time.time()
+        while not os.path.exists(ready):
+            if time.time() - t0 > 3600:
+                raise RuntimeError("timed out waiting for local rank 0 to generate the problem")
+            time.sleep(1.0)
+        return load()
     t0 = time.time()
     A = problems.laplace_3d(n)
     t1 = time.time()
@@ -70,10 +86,16 @@ def build_problem(n: int, threads: int):
         f"reorder {t3 - t2:.1f}s, nnzG={f.nnz}")
     try:
         os.makedirs(cache_root, exist_ok=True)
-        for k in names:
-            np.save(f"{tag}.{k}.npy", d[k])
-    except OSError as e:  # cache is an optimisation only
+        for k in names:                      # write-then-rename: a reader never sees a partial file
+            tmp = f"{tag}.{k}.tmp.npy"
+            np.save(tmp, d[k])
+            os.replace(tmp, f"{tag}.{k}.npy")
+        with open(ready, "w") as fh:
+            fh.write("ok\n")
+    except OSError as e:  # cache is an optimisation only (single process); the other ranks of a torchrun need it
         log(f"[bench] cache not written: {e}")
+        if multi:
+            raise
     return d, dict(cached=False, gen_s=t1 - t0, factor_s=t2 - t1, reorder_s=t3 - t2)
 
 

@@ -128,7 +128,7 @@ class Solver:
 
     def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
                  spmv_lanes: int = 0, chain_generic: bool = False, chain_mode: int = 0, backoff_ns: int = 0, dbg: int = 0, producers: int = 0,
-                 recent: int = 0, plain_launch: bool = False, sep_window: int = 0, early: int = 0):
+                 recent: int = 0, plain_launch: bool = False, sep_window: int = 0, early: int = 0, capb_quarters: int = 0, slots_a: int = 0):
         self._L = load()
         self._h = C.c_void_p()
         opt = Options()
@@ -142,6 +142,8 @@ class Solver:
         opt.reserved[3] = int(recent)
         opt.reserved[4] = int(sep_window)
         opt.reserved[5] = int(early)
+        opt.reserved[7] = int(capb_quarters)
+        opt.reserved[8] = int(slots_a)
         opt.reserved[6] = int(bool(plain_launch))
         rc = self._L.rcg_create_with_options(C.byref(self._h), int(device), C.byref(opt))
         if rc != 0:

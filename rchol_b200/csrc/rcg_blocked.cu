@@ -1002,9 +1002,18 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
       }
     } else if (warp == W_PRODA) {
       // ------------------------------ TMA producer, ring A -----------------------------------------------
+      // blob offsets of 32 chunks per load, the next batch in flight while this one is issued
+      int64_t O0n = 0, O1n = 0;
+      if (nch > 0) {
+        const uint32_t gl = b.chunk0 + min(lane, nch - 1u);
+        O0n = P.offA[gl]; O1n = P.offA[gl + 1];
+      }
       for (uint32_t base = 0; base < nch; base += 32u) {
-        const uint32_t gl = b.chunk0 + min(base + lane, nch - 1u);
-        const int64_t O0 = P.offA[gl], O1 = P.offA[gl + 1];
+        const int64_t O0 = O0n, O1 = O1n;
+        if (base + 32u < nch) {
+          const uint32_t gl = b.chunk0 + min(base + 32u + lane, nch - 1u);
+          O0n = P.offA[gl]; O1n = P.offA[gl + 1];
+        }
         for (uint32_t l = 0; l < 32u && base + l < nch; l++) {
           const uint32_t i = ia0 + base + l, slot = i % P.SA, use = i / P.SA;
           const int64_t e0 = __shfl_sync(0xffffffffu, O0, (int)l), e1 = __shfl_sync(0xffffffffu, O1, (int)l);
@@ -1019,9 +1028,18 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
       }
     } else if (warp == W_PRODB) {
       // ------------------------------ TMA producer, ring B -----------------------------------------------
+      // blob offsets of 32 chunks per load, the next batch in flight while this one is issued
+      int64_t O0n = 0, O1n = 0;
+      if (nch > 0) {
+        const uint32_t gl = b.chunk0 + min(lane, nch - 1u);
+        O0n = P.offB[gl]; O1n = P.offB[gl + 1];
+      }
       for (uint32_t base = 0; base < nch; base += 32u) {
-        const uint32_t gl = b.chunk0 + min(base + lane, nch - 1u);
-        const int64_t O0 = P.offB[gl], O1 = P.offB[gl + 1];
+        const int64_t O0 = O0n, O1 = O1n;
+        if (base + 32u < nch) {
+          const uint32_t gl = b.chunk0 + min(base + 32u + lane, nch - 1u);
+          O0n = P.offB[gl]; O1n = P.offB[gl + 1];
+        }
         for (uint32_t l = 0; l < 32u && base + l < nch; l++) {
           const uint32_t i = ia0 + base + l, slot = i % P.SB, use = i / P.SB;
           const int64_t e0 = __shfl_sync(0xffffffffu, O0, (int)l), e1 = __shfl_sync(0xffffffffu, O1, (int)l);
@@ -1303,13 +1321,17 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     BcLevel L;
     const int64_t meanB = nchl ? sumB / nchl : 0;
     L.capA = (uint32_t)((maxA + 127) & ~127ll);
-    int64_t capB = std::min<int64_t>(maxB, std::max<int64_t>(3 * meanB, 6144));
+    // staging slot of ring B: a multiple of the level's mean blob (reserved[7], in quarters; default 3x); larger blobs
+    // are read from HBM by their helper.  More, smaller slots put more chunks in flight (TMA latency cover).
+    const int64_t capq = h->opt.reserved[7] > 0 ? h->opt.reserved[7] : 12;
+    int64_t capB = std::min<int64_t>(maxB, std::max<int64_t>(capq * meanB / 4, 6144));
     capB = std::min<int64_t>(capB, 24576);
     L.capB = (uint32_t)((capB + 127) & ~127ll);
     const int64_t fixed = (int64_t)W * 8 + 128 + BC_TR * 32 * 8 + BC_SCR * 8 + BC_TR * 4 + 64 + 1024;
     int64_t avail = (int64_t)BC_SMEM_MAX - fixed;
     // ring A feeds one consumer (latency cover), ring B feeds BC_NH helpers that hold their slot while they work
     int64_t SA = std::max<int64_t>(3, std::min<int64_t>(10, (avail * 4 / 10) / L.capA));
+    if (h->opt.reserved[8] > 0) SA = std::max<int64_t>(2, std::min<int64_t>(10, h->opt.reserved[8]));   // tuning experiments
     int64_t SB = std::max<int64_t>(3, std::min<int64_t>(2 * BC_NH + 4, (avail - SA * L.capA) / (L.capB + 24)));
     while (SA > 3 && SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) SA--;
     while (SB > 3 && SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) SB--;

@@ -150,6 +150,16 @@ def assemble(pl: Plan, pieces):
 # ---------------------------------------------------------------------------------------------------------------------
 # N > 1 leg of bench.py
 # ---------------------------------------------------------------------------------------------------------------------
+def _roofline(value_gbs, world, B_iter, ms_per_iter):
+    """Iteration-level roofline of the sharded solve: aggregate algorithmic GB/s against world x the measured HBM peak
+    (the dominant kernel is k_bc_solve, as on one GPU; its per-launch figures are in the N = 1 line)."""
+    import bench as _bench
+    peak, src = _bench.measured_peak_gbs()
+    return dict(bound="hbm", kernel="PCG iteration (k_bc_solve dominates: see the N=1 line)", achieved=value_gbs,
+                peak=peak * world, unit="GB/s", frac=value_gbs / (peak * world), traffic=None, peak_source=src + f" x {world} GPUs",
+                bytes_per_iteration=B_iter, ms_per_iteration=ms_per_iter)
+
+
 def bench_main(args, d, B_iter, rank, world, config):
     import torch
     import torch.distributed as dist
@@ -192,6 +202,11 @@ def bench_main(args, d, B_iter, rank, world, config):
     dist.barrier(); torch.cuda.synchronize()
     launches0 = s.stats()["kernel_launches"]
     dev_ms, iters_total = 0.0, 0
+    sampler = None
+    if rank == 0:
+        import bench as _bench                      # the clock sampler and the measured peak live with the bench contract
+        sampler = _bench.ClockSampler(local_rank)
+        sampler.start()
     for k in range(args.steps):
         dist.barrier(); torch.cuda.synchronize()
         relres, itr = s.pcg_resident(1e-8, 500)
@@ -199,6 +214,7 @@ def bench_main(args, d, B_iter, rank, world, config):
         dev_ms += sync_max(s.stats()["solve_ms"])
         iters_total += itr
     launches = s.stats()["kernel_launches"] - launches0
+    clocks = sampler.stop() if sampler else None
     x_loc = s.solution()
     st = s.stats()
     s.close()
@@ -247,6 +263,7 @@ def bench_main(args, d, B_iter, rank, world, config):
                     e2e=dict(value=(B_iter * iters_total / args.steps / (e2e_ms * 1e-3) / 1e9) if e2e_ms else None,
                              unit="GB/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms,
                              note="per rank: upload of the local matrices, analysis, solve, download; max over ranks"),
+                    roofline=_roofline(value, world, B_iter, dev_ms / max(iters_total, 1)), clocks=clocks,
                     gpu_launches=int(launches), rank0_setup=dict(upload_ms=st["upload_ms"], analysis_ms=st["analysis_ms"]))
         print(json.dumps(line), flush=True)
     dist.barrier()

@@ -38,15 +38,17 @@ for cfg in cfgs:
     dbg = cfg[3] if len(cfg) > 3 else 0
     sepw = cfg[4] if len(cfg) > 4 else 0
     early = cfg[5] if len(cfg) > 5 else 0
-    s = capi.Solver(0, chain_window=win, recent=rec, chain_mode=mode, dbg=dbg, sep_window=sepw, early=early)
+    capq = cfg[6] if len(cfg) > 6 else 0
+    sa = cfg[7] if len(cfg) > 7 else 0
+    s = capi.Solver(0, chain_window=win, recent=rec, chain_mode=mode, dbg=dbg, sep_window=sepw, early=early, capb_quarters=capq, slots_a=sa)
     t = time.time(); s.set_matrix(*A); s.set_factor(*G, part); t_set = time.time() - t
     st = s.stats()
-    print(f"--- window={win} recent={rec} mode={mode} sep_window={sepw} early={early} dbg={dbg}: set-up wall {t_set:.2f}s upload {st['upload_ms']:.0f} analysis {st['analysis_ms']:.0f} ms", flush=True)
+    print(f"--- window={win} recent={rec} mode={mode} sep_window={sepw} early={early} capq={capq} SA={sa} dbg={dbg}: set-up wall {t_set:.2f}s upload {st['upload_ms']:.0f} analysis {st['analysis_ms']:.0f} ms", flush=True)
     if check:
         y = s.trsv(capi.TRSV_FORWARD, b); z = s.trsv(capi.TRSV_BACKWARD, yo); zz = s.precond(b)
         print(f"    fwd relerr {relerr(y, yo):.2e} bwd {relerr(z, zo):.2e} precond {relerr(zz, zo):.2e}", flush=True)
     s.set_rhs(b)
-    rr, it = s.pcg_resident(1e-8, 500)
+    rr, it = s.pcg_resident(1e-8, int(os.environ.get('RCHOL_PROBE_MAXIT', 500)))
     st = s.stats()
     ph = [s.time_phase(p, 3) for p in range(4)]
     print(f"    pcg it={it} relres={rr:.3e} solve_ms={st['solve_ms']:.2f} ms/it={st['solve_ms']/max(it,1):.3f} | spmv {ph[0]:.3f} fwd {ph[1]:.3f} bwd {ph[2]:.3f} vec {ph[3]:.3f} ms | launches/it {st['launches_per_iteration']}", flush=True)

@@ -60,7 +60,8 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
 @pytest.mark.parametrize("opts", [dict(), dict(recent=1), dict(recent=3), dict(chain_window=1024), dict(chain_window=2048, recent=1),
                                   dict(chain_window=8192), dict(plain_launch=True), dict(use_graph=False, chain_window=1024),
                                   dict(chain_mode=1), dict(chain_mode=3), dict(sep_window=4096), dict(chain_window=2048, sep_window=2048),
-                                  dict(early=6), dict(early=3, recent=2), dict(early=8, chain_mode=3)])
+                                  dict(early=6), dict(early=3, recent=2), dict(early=8, chain_mode=3),
+                                  dict(capb_quarters=4), dict(slots_a=2), dict(capb_quarters=5, slots_a=6, chain_window=2048)])
 @pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 33, 2), ("aniso2d", 160, 4), ("lap3d", 40, 0)])
 def test_blocked_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
