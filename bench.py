@@ -212,7 +212,8 @@ def workload_config(args, d, N):
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
-def run_ours_single(args, d, B_iter):
+def run_ours_single(args, d, B_iter, gen_info=None):
+    gen_info = gen_info or {}
     from rchol_b200 import capi
     A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
     part = d["part"] if args.threads > 0 else None
@@ -312,6 +313,22 @@ def run_ours_single(args, d, B_iter):
     e2e_value = B_iter * e2e_iters / (e2e_ms * 1e-3) / 1e9
     assert np.array_equal(x, x_dev), "one-shot and resident solves differ"
 
+    # ---- reorder(A, P) on the device (upload of the ORIGINAL A + permutation + per-row sort) ------------
+    reorder_info = None
+    if args.threads > 0:
+        try:
+            A0 = problems.laplace_3d(args.n)
+            with capi.Solver(0) as s3:
+                t0 = time.time()
+                s3.set_matrix_permuted(*A0, d["P"])
+                t_dev = time.time() - t0
+                same = all(np.array_equal(u, v) for u, v in zip(s3.get_matrix(), A))
+            reorder_info = dict(upload_plus_device_reorder_ms=1e3 * t_dev, bit_identical_to_reference_reorder=bool(same),
+                                reference_host_reorder_s=gen_info.get("reorder_s"))
+            del A0
+        except Exception as e:  # pragma: no cover - informational leg
+            reorder_info = dict(error=str(e))
+
     # ---- CPU baseline beside it (bounded sample, rank 0) ------------------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline:
@@ -329,7 +346,7 @@ def run_ours_single(args, d, B_iter):
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit="GB/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                          steps=e2e_steps, ms_per_step=e2e_ms / e2e_steps, host_memory="pageable (caller's SparseCSR arrays)"),
-                gpu_launches=int(launches), clocks=clocks,
+                gpu_launches=int(launches), clocks=clocks, device_reorder=reorder_info,
                 setup=dict(upload_ms=st0["upload_ms"], analysis_ms=st0["analysis_ms"], wall_s=setup_wall))
     print(json.dumps(line), flush=True)
 
@@ -361,7 +378,7 @@ def main():
     if world > 1 or args.gpus > 1:
         from rchol_b200 import multigpu
         return multigpu.bench_main(args, d, B_iter, rank, world, workload_config(args, d, N))
-    run_ours_single(args, d, B_iter)
+    run_ours_single(args, d, B_iter, info)
     return 0
 
 

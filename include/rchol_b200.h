@@ -98,6 +98,24 @@ int rcg_set_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint
 int rcg_set_factor_blocks(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                           const uint64_t *bounds, const int32_t *depth, uint64_t nblocks);
 
+/* ---- the permutation steps either side of the path, on the device --------------------------
+ * rcg_set_matrix_permuted: A is given in its ORIGINAL ordering together with the permutation P that rchol(A,G,P,threads)
+ * returned; the handle then holds B = A(P,P) with every row re-sorted by column, exactly what the reference's
+ * reorder(A, P, B) builds on the host (c++/util/util.cpp:16-57: B row i = A row P[i], column c -> inverse(P)[c]), and
+ * keeps P.  P must be a permutation of 0..N-1 (checked; RCG_ERR_INVALID otherwise).
+ * rcg_set_permutation: only records P (the caller's A is already permuted).
+ * rcg_permute_vector:   xp[i] = x[P[i]]   (util.hpp:147-155 reorder(x, P, xp))
+ * rcg_unpermute_vector: x[P[i]] = xp[i]   (python/ex_laplace_parallel.py:31-32  y[p] = x)
+ * rcg_pcg_original: the solve with b and x in the ORIGINAL ordering (b is permuted and x un-permuted on the device).
+ * rcg_get_matrix: downloads the handle's matrix in SparseCSR form (rowPtr N+1, colIdx/val nnz entries; testing). */
+int rcg_set_matrix_permuted(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                            const uint64_t *P);
+int rcg_set_permutation(rcg_handle *h, uint64_t N, const uint64_t *P);
+int rcg_permute_vector(rcg_handle *h, const double *x_host, double *xp_host);
+int rcg_unpermute_vector(rcg_handle *h, const double *xp_host, double *x_host);
+int rcg_pcg_original(rcg_handle *h, const double *b_host, double tol, int maxit, double *x_host, double *relres, int *itr);
+int rcg_get_matrix(rcg_handle *h, uint64_t *rowPtr, uint64_t *colIdx, double *val);
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ----------------------------------------
  * Rank r of 2^g owns the depth-g subtree r of the reference's nested-dissection tree (rchol_parallel.cpp:62-70) and
  * a replica of the 2^g - 1 separators above it.  The LOCAL index space of a rank is

@@ -27,9 +27,12 @@ EXPORTED = [
     "rcg_get_group_count", "rcg_get_group_info", "rcg_time_group",
     "rcg_set_factor_blocks", "rcg_nccl_unique_id", "rcg_dist_init", "rcg_dist_finalize",
     "rcg_debug_blocked_info", "rcg_debug_blocked_copy", "rcg_debug_counters",
+    "rcg_set_matrix_permuted", "rcg_set_permutation", "rcg_permute_vector", "rcg_unpermute_vector",
+    "rcg_pcg_original", "rcg_get_matrix",
 ]
 
 TRSV_FORWARD, TRSV_BACKWARD = 0, 1
+RCG_OK, RCG_ERR_CUDA, RCG_ERR_INVALID, RCG_ERR_STATE, RCG_ERR_STRUCTURE, RCG_ERR_NOMEM = 0, 1, 2, 3, 4, 5   # rchol_b200.h
 
 
 class Options(C.Structure):
@@ -107,6 +110,12 @@ def load():
     L.rcg_debug_blocked_info.argtypes = [H, C.c_int, C.POINTER(C.c_uint64)]
     L.rcg_debug_blocked_copy.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
     L.rcg_debug_counters.argtypes = [H, C.POINTER(C.c_uint64)]
+    L.rcg_set_matrix_permuted.argtypes = [H, C.c_uint64, _u64p, _u64p, _f64p, _u64p]
+    L.rcg_set_permutation.argtypes = [H, C.c_uint64, _u64p]
+    L.rcg_permute_vector.argtypes = [H, _f64p, _f64p]
+    L.rcg_unpermute_vector.argtypes = [H, _f64p, _f64p]
+    L.rcg_pcg_original.argtypes = [H, _f64p, C.c_double, C.c_int, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.rcg_get_matrix.argtypes = [H, _u64p, _u64p, _f64p]
     for name in EXPORTED:
         fn = getattr(L, name)
         if name not in ("rcg_last_error", "rcg_version"):
@@ -175,6 +184,41 @@ class Solver:
         rp = _u64(rowPtr)
         self.N = rp.shape[0] - 1
         self._check(self._L.rcg_set_matrix(self._h, self.N, rp, _u64(colIdx), _f64(val)))
+
+    # ---- permutation steps either side of the path, on the device (reference: util.cpp:16-57, util.hpp:147-155) ----
+    def set_matrix_permuted(self, rowPtr, colIdx, val, P):
+        """A in its ORIGINAL ordering + the permutation of rchol(A,G,P,threads): the handle holds A(P,P), rows re-sorted."""
+        rp = _u64(rowPtr)
+        self.N = rp.shape[0] - 1
+        self._check(self._L.rcg_set_matrix_permuted(self._h, self.N, rp, _u64(colIdx), _f64(val), _u64(P)))
+
+    def set_permutation(self, P):
+        p = _u64(P)
+        self.N = p.shape[0]
+        self._check(self._L.rcg_set_permutation(self._h, self.N, p))
+
+    def permute(self, x):
+        out = np.empty(self.N, np.float64)
+        self._check(self._L.rcg_permute_vector(self._h, _f64(x), out))
+        return out
+
+    def unpermute(self, xp):
+        out = np.empty(self.N, np.float64)
+        self._check(self._L.rcg_unpermute_vector(self._h, _f64(xp), out))
+        return out
+
+    def pcg_original(self, b, tol: float, maxit: int):
+        """b and x in the ORIGINAL ordering (permuted / un-permuted on the device)."""
+        x = np.empty(self.N, np.float64)
+        relres, itr = C.c_double(0), C.c_int(0)
+        self._check(self._L.rcg_pcg_original(self._h, _f64(b), float(tol), int(maxit), x, C.byref(relres), C.byref(itr)))
+        return x, relres.value, itr.value
+
+    def get_matrix(self):
+        st = self.stats()
+        rp = np.empty(self.N + 1, np.uint64); ci = np.empty(st["nnzA"], np.uint64); v = np.empty(st["nnzA"], np.float64)
+        self._check(self._L.rcg_get_matrix(self._h, rp, ci, v))
+        return rp, ci, v
 
     def set_factor(self, rowPtr, colIdx, val, part: Optional[np.ndarray] = None):
         rp = _u64(rowPtr)

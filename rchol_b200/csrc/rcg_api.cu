@@ -219,6 +219,7 @@ int rcg_destroy(rcg_handle *h) {
   free_vectors(h);
   if (h->haveA) rcg_free_csr(h->A);
   if (h->haveG) { rcg_free_direction(h->fwd); rcg_free_direction(h->bwd); }
+  cudaFree(h->perm);
   for (int i = 0; i < 2; i++) {
     if (h->stage_buf[i]) cudaFreeHost(h->stage_buf[i]);
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
@@ -235,6 +236,50 @@ int rcg_set_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint
   RCG_CUDA(h, cudaSetDevice(h->device));
   if (h->b && N != h->N) free_vectors(h);
   return rcg_setup_matrix(h, N, rowPtr, colIdx, val);
+}
+
+int rcg_set_matrix_permuted(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                            const uint64_t *P) {
+  if (!h) return RCG_ERR_INVALID;
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  if (h->b && N != h->N) free_vectors(h);
+  return rcg_setup_matrix_permuted(h, N, rowPtr, colIdx, val, P);
+}
+
+int rcg_set_permutation(rcg_handle *h, uint64_t N, const uint64_t *P) {
+  if (!h) return RCG_ERR_INVALID;
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  return rcg_setup_permutation(h, N, P);
+}
+
+int rcg_get_matrix(rcg_handle *h, uint64_t *rowPtr, uint64_t *colIdx, double *val) {
+  if (!h) return RCG_ERR_INVALID;
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  return rcg_download_matrix(h, rowPtr, colIdx, val);
+}
+
+// xp[i] = x[P[i]] (inverse = false) or x[P[i]] = xp[i] (inverse = true), host vectors through the device
+static int permute_host_vector(rcg_handle *h, const double *in_host, double *out_host, bool inverse) {
+  RCG_TRY(require(h, false, false));
+  if (!in_host || !out_host) { h->err = "null vector"; return RCG_ERR_INVALID; }
+  if (!h->perm) { h->err = "no permutation set (rcg_set_permutation / rcg_set_matrix_permuted)"; return RCG_ERR_STATE; }
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  const size_t bytes = sizeof(double) * h->N;
+  RCG_CUDA(h, cudaMemcpyAsync(h->io, in_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  RCG_TRY(rcg_apply_permutation(h, h->io, h->q, inverse));   // q is scratch outside a solve
+  RCG_CUDA(h, cudaMemcpyAsync(out_host, h->q, bytes, cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return RCG_OK;
+}
+
+int rcg_permute_vector(rcg_handle *h, const double *x_host, double *xp_host) {
+  if (!h) return RCG_ERR_INVALID;
+  return permute_host_vector(h, x_host, xp_host, false);
+}
+
+int rcg_unpermute_vector(rcg_handle *h, const double *xp_host, double *x_host) {
+  if (!h) return RCG_ERR_INVALID;
+  return permute_host_vector(h, xp_host, x_host, true);
 }
 
 int rcg_set_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
@@ -350,6 +395,30 @@ int rcg_pcg(rcg_handle *h, const double *b_host, double tol, int maxit, double *
   RCG_TRY(rcg_get_solution(h, x_host));
   h->stats.total_ms = wall_ms() - t0;
   h->stats.d2h_bytes += sizeof(double) * h->N;
+  return RCG_OK;
+}
+
+// b and x in the ORIGINAL ordering: bperm[i] = b[P[i]] (util.hpp:147-155), solve, y[P[i]] = x[i]
+// (python/ex_laplace_parallel.py:31-32), both on the device
+int rcg_pcg_original(rcg_handle *h, const double *b_host, double tol, int maxit, double *x_host, double *relres, int *itr) {
+  if (!h) return RCG_ERR_INVALID;
+  if (!b_host || !x_host) { h->err = "null vector"; return RCG_ERR_INVALID; }
+  RCG_TRY(require(h, true, true));
+  if (!h->perm) { h->err = "no permutation set (rcg_set_permutation / rcg_set_matrix_permuted)"; return RCG_ERR_STATE; }
+  if (h->dist.on) { h->err = "rcg_pcg_original is a single-GPU entry point"; return RCG_ERR_STATE; }
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  double t0 = wall_ms();
+  const size_t bytes = sizeof(double) * h->N;
+  RCG_CUDA(h, cudaMemcpyAsync(h->io, b_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  RCG_TRY(rcg_apply_permutation(h, h->io, h->b, false));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->haveB = true;
+  RCG_TRY(solve_resident(h, tol, maxit, relres, itr));
+  RCG_TRY(rcg_apply_permutation(h, h->x, h->io, true));
+  RCG_CUDA(h, cudaMemcpyAsync(x_host, h->io, bytes, cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->stats.total_ms = wall_ms() - t0;
+  h->stats.d2h_bytes += bytes;
   return RCG_OK;
 }
 

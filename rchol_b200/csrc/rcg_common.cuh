@@ -176,6 +176,8 @@ struct rcg_handle {
   rcg_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
+  uint32_t *perm = nullptr;   // device copy of the caller's permutation P (rcg_set_permutation / rcg_set_matrix_permuted)
+
   // two pinned staging buffers of the host->device upload (rcg_setup.cu), allocated at the first upload
   void *stage_buf[2] = {nullptr, nullptr};
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -205,6 +207,11 @@ struct rcg_handle {
 // ---------------------------------------------------------------------------------------------------------
 // rcg_setup.cu
 int rcg_setup_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val);
+int rcg_setup_permutation(rcg_handle *h, uint64_t N, const uint64_t *P);
+int rcg_setup_matrix_permuted(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                              const uint64_t *P);
+int rcg_download_matrix(rcg_handle *h, uint64_t *rowPtr, uint64_t *colIdx, double *val);
+int rcg_apply_permutation(rcg_handle *h, const double *src, double *dst, bool inverse);   // device vectors
 int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                      const uint64_t *part, uint64_t npart);
 int rcg_setup_factor_blocks(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,

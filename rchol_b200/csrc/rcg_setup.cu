@@ -1104,6 +1104,192 @@ int rcg_setup_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const ui
   return RCG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// permutation steps either side of the path: reorder(A, P, B) of the reference
+// (/root/reference/c++/util/util.cpp:16-57) and the vector permutations (util.hpp:147-155,
+// python/ex_laplace_parallel.py:31-32) on the device
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+// inv[P[i]] = i; err is set when P is not a permutation of 0..N-1 (out of range or a value taken twice)
+__global__ void k_perm_invert_checked(const uint32_t *__restrict__ P, uint32_t N, uint32_t *__restrict__ inv, int *err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; i < N; i += stride) {
+    const uint32_t v = P[i];
+    if (v >= N) { atomicExch(err, 1); continue; }
+    if (atomicExch(inv + v, i) != 0xFFFFFFFFu) atomicExch(err, 1);
+  }
+}
+
+// row lengths of B = A(P,P): len_B[i] = len_A[P[i]]
+__global__ void k_perm_row_lengths(const int64_t *__restrict__ rp, const uint32_t *__restrict__ P, uint32_t N,
+                                   int64_t *__restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; i < N; i += stride) {
+    const uint32_t s = P[i];
+    out[i] = rp[s + 1] - rp[s];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[N] = 0;
+}
+
+// B row i <- A row P[i] with the columns renamed by the inverse permutation; 8 lanes per row (rows of the path's
+// matrices hold 3-7 entries), unsorted: sort_segments() re-sorts every row afterwards like the reference does
+__global__ void k_perm_fill_rows(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col,
+                                 const double *__restrict__ val, const uint32_t *__restrict__ P,
+                                 const uint32_t *__restrict__ inv, const int64_t *__restrict__ nrp, uint32_t N,
+                                 uint32_t *__restrict__ ncol, double *__restrict__ nval) {
+  const uint32_t sub = threadIdx.x & 7u;
+  uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const uint32_t stride = (gridDim.x * blockDim.x) >> 3;
+  for (; i < N; i += stride) {
+    const uint32_t s = P[i];
+    const int64_t a0 = rp[s], a1 = rp[s + 1], b0 = nrp[i];
+    for (int64_t e = a0 + sub; e < a1; e += 8) {
+      ncol[b0 + (e - a0)] = inv[col[e]];
+      nval[b0 + (e - a0)] = val[e];
+    }
+  }
+}
+
+__global__ void k_vec_gather(const double *__restrict__ src, const uint32_t *__restrict__ P, uint32_t N,
+                             double *__restrict__ dst) {   // dst[i] = src[P[i]]
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; i < N; i += stride) dst[i] = src[P[i]];
+}
+
+__global__ void k_vec_scatter(const double *__restrict__ src, const uint32_t *__restrict__ P, uint32_t N,
+                              double *__restrict__ dst) {  // dst[P[i]] = src[i]
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (; i < N; i += stride) dst[P[i]] = src[i];
+}
+
+__global__ void k_widen_u32(const uint32_t *__restrict__ in, int64_t n, uint64_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = in[i];
+}
+
+// uploads P (narrowed to 32 bits) and builds the checked inverse; on success *dP (and *dinv if wanted) are device arrays
+int upload_permutation(rcg_handle *h, uint64_t N, const uint64_t *P, uint32_t **dP, uint32_t **dinv) {
+  if (!P) { h->err = "null permutation"; return RCG_ERR_INVALID; }
+  if (N == 0 || N >= 0xFFFFFFFFull) { h->err = "matrix dimension must be in [1, 2^32-2]"; return RCG_ERR_INVALID; }
+  const uint32_t n32 = (uint32_t)N;
+  uint32_t *p32 = nullptr, *inv = nullptr;
+  int *derr = nullptr;
+  RCG_CUDA(h, cudaMalloc(&p32, sizeof(uint32_t) * N));
+  RCG_CUDA(h, cudaMalloc(&inv, sizeof(uint32_t) * N));
+  RCG_CUDA(h, cudaMalloc(&derr, sizeof(int)));
+  RCG_CUDA(h, cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+  RCG_CUDA(h, cudaMemsetAsync(inv, 0xFF, sizeof(uint32_t) * N, h->stream));
+  bool bad = false;
+  double t0 = wall_ms();
+  RCG_TRY(staged_narrow(h, p32, P, (size_t)N, N, &bad));
+  h->stats.upload_ms += wall_ms() - t0;
+  h->stats.h2d_bytes += sizeof(uint32_t) * N;
+  int herr = 0;
+  if (!bad) {
+    k_perm_invert_checked<<<grid_for(h, n32, 256), 256, 0, h->stream>>>(p32, n32, inv, derr);
+    h->stats.kernel_launches += 1;
+    RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  }
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(derr);
+  if (bad || herr) {
+    cudaFree(p32); cudaFree(inv);
+    h->err = "P is not a permutation of 0..N-1";
+    return RCG_ERR_INVALID;
+  }
+  *dP = p32;
+  if (dinv) *dinv = inv; else cudaFree(inv);
+  return RCG_OK;
+}
+
+}  // namespace
+
+int rcg_setup_permutation(rcg_handle *h, uint64_t N, const uint64_t *P) {
+  if ((h->haveA || h->haveG) && N != h->N) { h->err = "permutation length differs from the matrix dimension"; return RCG_ERR_INVALID; }
+  uint32_t *dP = nullptr;
+  RCG_TRY(upload_permutation(h, N, P, &dP, nullptr));
+  cudaFree(h->perm);
+  h->perm = dP;
+  h->N = N;
+  return RCG_OK;
+}
+
+int rcg_setup_matrix_permuted(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                              const uint64_t *P) {
+  if (h->haveG && N != h->N) { h->err = "matrix dimension differs from the factor's"; return RCG_ERR_INVALID; }
+  uint32_t *dP = nullptr, *dinv = nullptr;
+  RCG_TRY(upload_permutation(h, N, P, &dP, &dinv));
+  CsrDev A0;
+  int rc = upload_csr(h, N, rowPtr, colIdx, val, A0);
+  if (rc != RCG_OK) { cudaFree(dP); cudaFree(dinv); return rc; }
+  double t0 = wall_ms();
+  const uint32_t n32 = (uint32_t)N;
+  CsrDev B;
+  B.nnz = A0.nnz;
+  RCG_CUDA(h, cudaMalloc(&B.rowptr, sizeof(int64_t) * (N + 1)));
+  RCG_CUDA(h, cudaMalloc(&B.col, sizeof(uint32_t) * (size_t)A0.nnz));
+  RCG_CUDA(h, cudaMalloc(&B.val, sizeof(double) * (size_t)A0.nnz));
+  k_perm_row_lengths<<<grid_for(h, n32, 256), 256, 0, h->stream>>>(A0.rowptr, dP, n32, B.rowptr);
+  h->stats.kernel_launches += 1;
+  RCG_TRY(exclusive_scan_inplace(h, B.rowptr, (int64_t)N + 1));
+  k_perm_fill_rows<<<grid_for(h, (int64_t)n32 * 8, 256), 256, 0, h->stream>>>(A0.rowptr, A0.col, A0.val, dP, dinv, B.rowptr,
+                                                                              n32, B.col, B.val);
+  h->stats.kernel_launches += 1;
+  RCG_CUDA(h, cudaGetLastError());
+  RCG_TRY(sort_segments(h, B.rowptr, B.col, B.val, n32));   // "sort elements" of util.cpp:40
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  rcg_free_csr(A0);
+  cudaFree(dinv);
+  if (h->haveA) { rcg_free_csr(h->A); h->haveA = false; }
+  cudaFree(h->perm);
+  h->perm = dP;
+  h->A = B;
+  h->N = N;
+  h->haveA = true;
+  h->stats.N = N;
+  h->stats.nnzA = (uint64_t)B.nnz;
+  if (h->opt.spmv_lanes > 0) {
+    h->spmv_lanes = h->opt.spmv_lanes;
+  } else {
+    double mean = (double)B.nnz / (double)N;
+    h->spmv_lanes = mean <= 2.5 ? 2 : mean <= 5.0 ? 4 : mean <= 12.0 ? 8 : mean <= 24.0 ? 16 : 32;
+  }
+  h->stats.analysis_ms += wall_ms() - t0;
+  return RCG_OK;
+}
+
+// device vectors: inverse = false: dst[i] = src[P[i]] ; inverse = true: dst[P[i]] = src[i]
+int rcg_apply_permutation(rcg_handle *h, const double *src, double *dst, bool inverse) {
+  if (!h->perm) { h->err = "no permutation set (rcg_set_permutation / rcg_set_matrix_permuted)"; return RCG_ERR_STATE; }
+  const uint32_t n32 = (uint32_t)h->N;
+  if (inverse) k_vec_scatter<<<grid_for(h, n32, 256), 256, 0, h->stream>>>(src, h->perm, n32, dst);
+  else k_vec_gather<<<grid_for(h, n32, 256), 256, 0, h->stream>>>(src, h->perm, n32, dst);
+  h->stats.kernel_launches += 1;
+  RCG_CUDA(h, cudaGetLastError());
+  return RCG_OK;
+}
+
+int rcg_download_matrix(rcg_handle *h, uint64_t *rowPtr, uint64_t *colIdx, double *val) {
+  if (!h->haveA) { h->err = "rcg_set_matrix has not been called"; return RCG_ERR_STATE; }
+  if (!rowPtr || !colIdx || !val) { h->err = "null output pointer"; return RCG_ERR_INVALID; }
+  uint64_t *c64 = nullptr;
+  RCG_CUDA(h, cudaMalloc(&c64, sizeof(uint64_t) * (size_t)h->A.nnz));
+  k_widen_u32<<<grid_for(h, h->A.nnz, 256), 256, 0, h->stream>>>(h->A.col, h->A.nnz, c64);
+  h->stats.kernel_launches += 1;
+  RCG_CUDA(h, cudaMemcpyAsync(rowPtr, h->A.rowptr, sizeof(int64_t) * (h->N + 1), cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(colIdx, c64, sizeof(uint64_t) * (size_t)h->A.nnz, cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(val, h->A.val, sizeof(double) * (size_t)h->A.nnz, cudaMemcpyDeviceToHost, h->stream));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(c64);
+  return RCG_OK;
+}
+
 static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                              const std::vector<uint32_t> &bounds, const TreeInfo &tree, bool strict_tree);
 

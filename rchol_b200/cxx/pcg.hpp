@@ -25,6 +25,13 @@ public:
   pcg(const SparseCSR &A, const std::vector<double> &b, double tol, int maxit, const SparseCSR &G,
       const std::vector<size_t> &part, std::vector<double> &x, double &relres, int &itr);
 
+  // Additive overload for the whole ex_laplace_parallel flow: A and b in their ORIGINAL ordering plus the permutation P
+  // that rchol(A,G,P,threads) returned.  reorder(A,P,Aperm) (util.cpp:16-57), reorder(b,P,bperm) (util.hpp:147-155) and
+  // the un-permutation of the solution (python/ex_laplace_parallel.py:31-32) run on the device; x comes back in the
+  // ORIGINAL ordering, so that ||A x - b|| / ||b|| can be checked against the caller's own A and b.
+  pcg(const SparseCSR &A, const std::vector<double> &b, double tol, int maxit, const SparseCSR &G,
+      const std::vector<size_t> &part, const std::vector<size_t> &P, std::vector<double> &x, double &relres, int &itr);
+
   // measurements of the last solve (milliseconds), for drivers that want to print them
   double upload_ms = 0, analysis_ms = 0, solve_ms = 0, total_ms = 0;
 

@@ -224,3 +224,6 @@ def test_cxx_driver_runs_like_the_reference_example(capi):
     itr = int(re.search(r"# CG iterations: (\d+)", out.stdout).group(1))
     relres = float(re.search(r"Relative residual: ([0-9.eE+-]+)", out.stdout).group(1))
     assert 10 <= itr <= 40 and relres <= 2e-8
+    # second solve of the driver: permutation steps on the device, same iterations, bit-identical solution
+    m = re.search(r"Device-permuted solve: (\d+) iterations, max \|y - unpermute\(x\)\| = ([0-9.eE+-]+)", out.stdout)
+    assert m and int(m.group(1)) == itr and float(m.group(2)) == 0.0
