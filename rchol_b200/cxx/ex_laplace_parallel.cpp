@@ -1,5 +1,7 @@
 // Example driver with the reference's command line (c++/ex_laplace_parallel.cpp:11-52): -n <grid> -t <leaves>.
 // Factorization = the reference code (host); solve = this repository's GPU path behind the reference's pcg API.
+// Factor once / solve many: -save <file> writes Aperm, G, P, part, bperm (io.hpp); -load <file> skips generation and
+// factorization and solves the stored problem.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -7,6 +9,7 @@
 #include <iomanip>
 #include <iostream>
 
+#include "io.hpp"
 #include "pcg.hpp"
 #include "rchol_ref.hpp"
 #include "sparse.hpp"
@@ -22,7 +25,25 @@ int main(int argc, char *argv[]) {
     if (!strcmp(argv[i], "-tol")) tol = atof(argv[i + 1]);
     if (!strcmp(argv[i], "-maxit")) maxit = atoi(argv[i + 1]);
   }
+  const char *save_path = nullptr, *load_path = nullptr;
+  for (int i = 1; i + 1 < argc; i++) {
+    if (!strcmp(argv[i], "-save")) save_path = argv[i + 1];
+    if (!strcmp(argv[i], "-load")) load_path = argv[i + 1];
+  }
   std::cout << std::setprecision(3);
+  if (load_path) {
+    rchol_b200::Problem pr;
+    rchol_b200::load_problem(load_path, pr);
+    double relres;
+    int itr;
+    std::vector<double> x;
+    pcg solver(pr.A, pr.b, tol, maxit, pr.G, pr.part, x, relres, itr);
+    std::cout << "Loaded " << load_path << ": N = " << pr.A.size() << ", blocks = " << (pr.part.empty() ? 1 : pr.part.size() - 1)
+              << std::endl;
+    std::cout << "# CG iterations: " << itr << std::endl;
+    std::cout << "Relative residual: " << relres << std::endl;
+    return 0;
+  }
   SparseCSR A;
   A = laplace_3d(n);
   std::vector<double> b(A.size());
@@ -30,16 +51,16 @@ int main(int argc, char *argv[]) {
 
   SparseCSR G;
   std::vector<size_t> P;
-  rchol(A, G, P, threads);
-  std::vector<uint64_t> part64(2 * (size_t)threads);
-  const uint64_t np = refprod_last_part(part64.data(), part64.size());
-  std::vector<size_t> part(part64.begin(), part64.begin() + np);
+  std::vector<size_t> part;
+  rchol(A, G, P, part, threads);   // additive overload of rchol_ref.hpp: also returns the block boundaries
   std::cout << "Fill-in ratio: " << 2. * G.nnz() / A.nnz() << std::endl;
 
   SparseCSR Aperm;
   reorder(A, P, Aperm);
   std::vector<double> bperm;
   reorder(b, P, bperm);
+
+  if (save_path) rchol_b200::save_problem(save_path, Aperm, G, P, part, bperm);
 
   double relres;
   int itr;

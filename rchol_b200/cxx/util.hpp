@@ -12,6 +12,12 @@ SparseCSR laplace_3d(int n);                                                   /
 void reorder(const SparseCSR &A, const std::vector<size_t> &P, SparseCSR &B);  // B = A(P,P), rows re-sorted
 void rand(std::vector<double> &x, uint64_t seed = 2024);                       // U(0,1); the reference is unseeded
 
+// SDD front-end (only the reference's MATLAB binding has it: matlab/rchol/sdd_to_sddm.m:2-17, ex_sdd.m:12-30):
+// Ae = [D + Neg, -Pos; -Pos, D + Neg] (2N x 2N SDDM, rows sorted), be = [b; -b], x = (xe[0:N] - xe[N:2N]) / 2
+void sdd_to_sddm(const SparseCSR &A, SparseCSR &Ae);
+void sdd_rhs(const std::vector<double> &b, std::vector<double> &be);
+void sdd_recover(const std::vector<double> &xe, std::vector<double> &x);
+
 template <typename T>
 void reorder(std::vector<T> &x, std::vector<size_t> &p, std::vector<T> &xp) {   // xp[i] = x[p[i]]
   xp.clear();

@@ -202,6 +202,55 @@ def test_properties_at_larger_size(capi):
 
 
 @needs_producer
+def test_baseline_config0_full_size(capi, oracle):
+    """BASELINE.json configs[0] at its full size: 3D 7-point Laplacian 64^3, SEQUENTIAL rchol (ex_laplace.cpp: natural
+    ordering, no partition) and pcg to 1e-8, against the oracle and -- where libpcg_ref.so travelled -- against the
+    unmodified reference pcg.cpp on real MKL."""
+    A, b, G, part, f = make_problem("lap3d", 64, 0)
+    assert part is None and f.N == 262144 and int(A[0][-1]) == 1810432          # SURVEY section 4 pin: nnz = 7n^3 - 6n^2
+    itr, relres = check_solve(capi, oracle, A, b, G, None)
+    assert 18 <= itr <= 30                                                       # SURVEY 8c loose regression bound [22, 26] +- slack
+    if oracle.have_reference_pcg():
+        r = oracle.reference_pcg(A, b, 1e-8, 500, G)
+        assert abs(itr - r["itr"]) <= 1 and r["relres"] <= 2e-8
+
+
+@needs_producer
+def test_config1_shape_at_128_cubed_vs_oracle(capi, oracle):
+    """The bench workload's shape (8-way METIS partition, leaves of 260 k rows, 4 tree levels) at a size the oracle
+    finishes in seconds: every kernel to 1e-12, iterations +-1, solution to 1e-9."""
+    A, b, G, part, f = make_problem("lap3d", 128, 8)
+    itr, relres = check_solve(capi, oracle, A, b, G, part)
+    assert relres <= 2e-8
+
+
+@needs_producer
+def test_factor_refresh_on_one_handle_and_many_right_hand_sides(capi, oracle):
+    """The reference's reuse flow (python/ex_reuse_partition.py): same matrix, permutation and partition, a NEW factor
+    (rchol samples a different pattern every time, so a refresh is a new rcg_set_factor on the same handle), several
+    right-hand sides per factor."""
+    from rchol_b200 import problems, producer
+    A0 = problems.laplace_3d(24)
+    f1 = producer.factor(*A0, threads=4, seed=1)
+    f2 = producer.factor(*A0, threads=4, seed=2)
+    assert np.array_equal(f1.P, f2.P) and np.array_equal(f1.part, f2.part)        # METIS is deterministic
+    assert f1.nnz != f2.nnz or not np.array_equal(f1.val, f2.val)                 # the factors differ
+    Ap = producer.ref_reorder(*A0, f1.P)
+    rng = np.random.default_rng(0)
+    with capi.Solver(0) as s:
+        s.set_matrix(*Ap)
+        for f in (f1, f2, f1):
+            G = (f.rowPtr, f.colIdx, f.val)
+            s.set_factor(*G, f.part)
+            for _ in range(2):
+                b = rng.random(f.N)
+                assert relerr(s.precond(b), oracle.precond(*G, b)) <= TRSV_TOL
+                x, relres, itr = s.pcg(b, 1e-8, 500)
+                o = oracle.pcg(Ap, b, 1e-8, 500, G)
+                assert abs(itr - o["itr"]) <= 1 and relres <= 2e-8
+
+
+@needs_producer
 def test_resident_solve_and_repeatability(capi):
     A, b, G, part, f = make_problem("lap3d", 32, 4)
     with capi.Solver(0) as s:
@@ -227,3 +276,24 @@ def test_cxx_driver_runs_like_the_reference_example(capi):
     # second solve of the driver: permutation steps on the device, same iterations, bit-identical solution
     m = re.search(r"Device-permuted solve: (\d+) iterations, max \|y - unpermute\(x\)\| = ([0-9.eE+-]+)", out.stdout)
     assert m and int(m.group(1)) == itr and float(m.group(2)) == 0.0
+
+
+@needs_producer
+def test_cxx_driver_factor_once_solve_many(capi, tmp_path):
+    """-save writes the factored problem (io.hpp), -load solves it again without the factorization; a Python reader of the
+    same file gets the same iteration count through the C ABI."""
+    from rchol_b200 import problems
+    exe = os.path.join(ROOT, "rchol_b200", "lib", "ex_laplace_parallel")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built (make driver)")
+    f = str(tmp_path / "p.rchb")
+    a = subprocess.run([exe, "-n", "14", "-t", "4", "-tol", "1e-8", "-maxit", "300", "-save", f], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0, a.stderr
+    b = subprocess.run([exe, "-tol", "1e-8", "-maxit", "300", "-load", f], capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0, b.stderr
+    it_a = int(re.search(r"# CG iterations: (\d+)", a.stdout).group(1))
+    it_b = int(re.search(r"# CG iterations: (\d+)", b.stdout).group(1))
+    assert it_a == it_b and "blocks = 7" in b.stdout
+    d = problems.load_problem(f)
+    x, relres, itr, st = capi.pcg(d["A"], d["b"], 1e-8, 300, d["G"], d["part"])
+    assert itr == it_a and relres <= 2e-8

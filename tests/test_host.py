@@ -168,3 +168,91 @@ int main() {
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-o", str(exe), str(src), "-I", os.path.join(ROOT, "rchol_b200", "cxx"),
                            "-L", lib, "-lrchol_b200_cxx", "-lrchol_b200", f"-Wl,-rpath,{lib}"])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_sdd_front_end_matches_the_matlab_definition_and_the_cxx_mirror(tmp_path):
+    """sdd_to_sddm (matlab/rchol/sdd_to_sddm.m:2-17): Ae = [D+Neg, -Pos; -Pos, D+Neg]; the numpy statement, a scipy
+    restatement of the MATLAB lines and the C++ mirror (rchol_b200/cxx/util.cpp) agree bit for bit; Ae is an SDDM."""
+    import scipy.sparse as sp
+    from rchol_b200 import problems
+    A = problems.sdd_3d(5)
+    N = A[0].shape[0] - 1
+    As = sp.csr_matrix((A[2], A[1].astype(np.int64), A[0].astype(np.int64)), shape=(N, N))
+    di = sp.diags(As.diagonal())
+    nod = As - di
+    pos, neg = nod.maximum(0), nod.minimum(0)
+    assert pos.nnz > 0                                                        # really SDD, not SDDM
+    ref = sp.bmat([[di + neg, -pos], [-pos, di + neg]]).tocsr()
+    ref.eliminate_zeros(); ref.sort_indices()
+    Ae = problems.sdd_to_sddm(*A)
+    assert np.array_equal(Ae[0], ref.indptr) and np.array_equal(Ae[1], ref.indices) and np.array_equal(Ae[2], ref.data)
+    off = ref - sp.diags(ref.diagonal())
+    assert off.nnz == 0 or off.data.max() <= 0                               # M-matrix pattern
+    assert np.asarray(ref.sum(axis=1)).min() >= -1e-12                       # diagonally dominant
+    b = problems.random_rhs(N)
+    assert np.array_equal(problems.sdd_recover(problems.sdd_rhs(b)), b)
+    # C++ mirror: dump what sdd_to_sddm builds for the same matrix
+    np.asarray(A[0]).tofile(tmp_path / "rp.bin"); np.asarray(A[1]).tofile(tmp_path / "ci.bin"); np.asarray(A[2]).tofile(tmp_path / "v.bin")
+    src = tmp_path / "sdd.cpp"
+    src.write_text('''
+#include <cstdio>
+#include <vector>
+#include "sparse.hpp"
+#include "util.hpp"
+template <class T> std::vector<T> rd(const char *p) { FILE *f = fopen(p, "rb"); fseek(f, 0, SEEK_END); long n = ftell(f); rewind(f);
+  std::vector<T> v(n / sizeof(T)); if (fread(v.data(), 1, n, f) != (size_t)n) return {}; fclose(f); return v; }
+template <class T> void wr(const char *p, const T *d, size_t n) { FILE *f = fopen(p, "wb"); fwrite(d, sizeof(T), n, f); fclose(f); }
+int main() {
+  auto rp = rd<size_t>("rp.bin"), ci = rd<size_t>("ci.bin"); auto v = rd<double>("v.bin");
+  SparseCSR A(rp, ci, v, true), Ae;
+  sdd_to_sddm(A, Ae);
+  wr("erp.bin", Ae.rowPtr, Ae.N + 1); wr("eci.bin", Ae.colIdx, Ae.nnz()); wr("ev.bin", Ae.val, Ae.nnz());
+  std::vector<double> b = {1, 2, 3}, be, x; sdd_rhs(b, be); sdd_recover(be, x);
+  return (be.size() == 6 && be[4] == -2 && x == b) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "sdd"
+    lib = os.path.join(ROOT, "rchol_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-o", str(exe), str(src), "-I", os.path.join(ROOT, "rchol_b200", "cxx"),
+                           "-L", lib, "-lrchol_b200_cxx", "-lrchol_b200", f"-Wl,-rpath,{lib}"])
+    assert subprocess.call([str(exe)], cwd=tmp_path) == 0
+    assert np.array_equal(np.fromfile(tmp_path / "erp.bin", np.uint64), Ae[0])
+    assert np.array_equal(np.fromfile(tmp_path / "eci.bin", np.uint64), Ae[1])
+    assert np.array_equal(np.fromfile(tmp_path / "ev.bin", np.float64), Ae[2])
+
+
+def test_problem_container_round_trips_between_python_and_cxx(tmp_path):
+    """rchol_b200/cxx/io.hpp <-> rchol_b200/problems.py (SURVEY 8f row 3): a golden problem written by Python is loaded
+    and re-written by C++ byte for byte, and read back identically."""
+    from conftest import load_golden
+    from rchol_b200 import problems
+    g = load_golden("lap3d_12_t4")
+    src_file, dst_file = tmp_path / "p.rchb", tmp_path / "q.rchb"
+    problems.save_problem(src_file, g["A"], g["G"], g["P"], g["part"], g["b"])
+    src = tmp_path / "io.cpp"
+    src.write_text('''
+#include "io.hpp"
+int main(int argc, char **argv) {
+  rchol_b200::Problem p;
+  rchol_b200::load_problem(argv[1], p);
+  if (p.A.size() != 1728 || p.G.size() != 1728 || p.P.size() != 1728 || p.b.size() != 1728 || p.part.size() != 8) return 2;
+  rchol_b200::save_problem(argv[2], p.A, p.G, p.P, p.part, p.b);
+  try { rchol_b200::load_problem(argv[0], p); return 3; } catch (const std::exception &) {}   // not a problem file
+  return 0;
+}
+''')
+    exe = tmp_path / "io"
+    lib = os.path.join(ROOT, "rchol_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-o", str(exe), str(src), "-I", os.path.join(ROOT, "rchol_b200", "cxx"),
+                           "-L", lib, "-lrchol_b200_cxx", "-lrchol_b200", f"-Wl,-rpath,{lib}"])
+    assert subprocess.call([str(exe), str(src_file), str(dst_file)]) == 0
+    assert open(src_file, "rb").read() == open(dst_file, "rb").read()
+    d = problems.load_problem(dst_file)
+    for k in range(3):
+        assert np.array_equal(d["A"][k], g["A"][k]) and np.array_equal(d["G"][k], g["G"][k])
+    assert np.array_equal(d["P"], g["P"]) and np.array_equal(d["part"], g["part"]) and np.array_equal(d["b"], g["b"])
+    problems.save_problem(src_file, g["A"], g["G"])                      # optional arrays absent
+    d = problems.load_problem(src_file)
+    assert d["P"] is None and d["part"] is None and d["b"] is None
+    with pytest.raises(ValueError):
+        problems.load_problem(src)                                       # not a problem file
