@@ -54,7 +54,9 @@ typedef struct rcg_options {
                               [3] blocked solve: recent chunk distance Kr (default 2), [4] window rows of the separator blocks
                               (default 1024), [5] blocked solve: distance E (chunks) that separates the "early" from the "late" entries
                               (default 16), [6] 1 = plain (non-cooperative) launch, [7] staging slot of the helpers' ring in quarters of
-                              the mean blob (default 12), [8] staging slots of the chain's ring (0 = automatic) */
+                              the mean blob (default 12), [8] staging slots of the chain's ring (0 = automatic), [9] bits 0-7: lanes per row of the
+                              far CTAs' in-block pass (8 default, 32); bits 8-15: chunks per far tile of the separator blocks
+                              (default 2; leaves use 8) */
 } rcg_options;
 
 /* Per-handle measurements, all device-side times from CUDA events on the handle's own stream. */

@@ -34,7 +34,7 @@ constexpr int BC_THREADS = 512;           // 16 warps: critical (alone on its sc
 constexpr uint32_t BC_NH = 9;            // near helpers of the single-critical-warp variant (the split variant has 8)
 constexpr uint32_t BC_SCR = 576;          // scratch doubles: [0,32) t vector(s), [32, 32+4*128) partial sums of the split chain
 constexpr uint32_t BC_TR = 32;            // ring of t' vectors between helpers and the critical warp
-constexpr uint32_t BC_TILE = 8;           // chunks per far tile
+constexpr uint32_t BC_TILE = 8;           // chunks per far tile of the leaf blocks (separator blocks: BlockedDev::tile_sep)
 constexpr uint32_t BC_WBYTES = 1024 * 8;  // Winv, full 32x32 (zeros above the diagonal): [column pair p][row] double2
 constexpr uint32_t BC_RBATCH = 3072;      // one batch of 8 recent slots: [32 rows][4 pairs] double2 values, then
                                           // [32 rows][2 halves] uint4 byte offsets into the window (row-major: the
@@ -165,6 +165,7 @@ __device__ __forceinline__ bool guard_poll(Guard &G, uint32_t code) {
 // ---------------------------------------------------------------------------------------------------------
 struct BcGeom {               // blocks in ascending solve order (device arrays of nb+1 entries)
   const uint32_t *bounds, *chunk0, *tile0, *dfar;   // dfar: per block (leaves keep a large window, separators a small one)
+  const uint32_t *tile;                             // chunks per far tile, per block
   int nb;
   uint32_t Kr, E;
 };
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     if (lane == 0) {
       sizeA[gc] = (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
       sizeB[gc] = (int64_t)(BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot) + 320u * nl);
-      if (need) atomicMax(&tile_need[g.tile0[b] + k / BC_TILE], need);
+      if (need) atomicMax(&tile_need[g.tile0[b] + k / g.tile[b]], need);
     }
   }
 }
@@ -393,7 +394,9 @@ struct BcArgs {
   int reversed;
   uint32_t Kr, E, Dfar, W;     // W = 32*Dfar window rows (power of two)
   uint32_t SA, SB, capA, capB;
-  uint32_t far_lpr;            // lanes per far row: 8 or 32
+  uint32_t tile;               // chunks per far tile of this level's blocks
+  uint32_t far_lpr;            // lanes per far row, pass 0 (entries of other blocks): 8 or 32
+  uint32_t far_lpr2;           // lanes per far row, pass 1 (entries >= window back in the own block): 8 or 32
   uint32_t col_min;            // multi-GPU top separators: far columns below col_min are left out ...
   const double *corr;          // ... their sum over all ranks arrives here (indexed by vector index - col_min)
   unsigned int *abort_g;
@@ -450,11 +453,14 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
     // far part.  Tiles without far entries inside the own block are complete after it and are released at once.
     // Pass 2: entries >= Dfar chunks back in the own block, tile by tile as the chain's published progress allows.
     const uint32_t hid = role - 1u;
-    const uint32_t lpr = P.far_lpr, rpw = 32u / lpr;   // lanes per row (8, or 32 for the long rows of separators), rows per warp
-    const uint32_t sub = lane & (lpr - 1u);
+    // lanes per row (8, or 32 for the long rows of separators) and rows per warp, per pass.  Pass 1 sits on the chain's
+    // critical path (its tile can start only when the chain is Dfar chunks away and must finish before the chain arrives;
+    // measured at 256^3: 16 rows per warp one after the other, ~2 us of dependent HBM round trips each = 32 us per
+    // tile, which bounded the separator levels at 2.2 us per chunk), so it uses few lanes per row and many rows at once.
+    const uint32_t lpr_pass[2] = {P.far_lpr, P.far_lpr2};
     for (uint32_t bi = grp; bi < P.nblocks; bi += P.ngroups) {
       const BcBlock b = P.blocks[bi];
-      const uint32_t nch = (b.hi - b.lo + 31u) >> 5, ntile = (nch + BC_TILE - 1u) / BC_TILE;
+      const uint32_t nch = (b.hi - b.lo + 31u) >> 5, ntile = (nch + P.tile - 1u) / P.tile;
       // own tiles t_i = hid + i*helpers; pass 1 of tile i runs after pass 0 of tile i + LA: the other-block work of the
       // next tiles is done before this CTA waits for the chain
       constexpr uint32_t LA = 2;
@@ -469,7 +475,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
             if (threadIdx.x == 0) BC_WAIT(ld_acquire_gpu(P.gprog + b.gidx) >= need, 0x100u, 200);
             __syncthreads();
           }
-          const uint32_t r0 = b.lo + t * (32u * BC_TILE), r1 = min(b.hi, r0 + 32u * BC_TILE);
+          const uint32_t lpr = lpr_pass[pass], rpw = 32u / lpr, sub = lane & (lpr - 1u);
+          const uint32_t r0 = b.lo + t * (32u * P.tile), r1 = min(b.hi, r0 + 32u * P.tile);
           for (uint32_t base = r0 + warp * rpw; base < r1; base += (BC_THREADS / 32) * rpw) {
             const uint32_t j = base + lane / lpr;
             const bool valid = j < r1;
@@ -865,8 +872,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
       uint32_t tiles_known = 0;
       double t0n = 0.0;
       if (hidx < nch) {
-        BC_WAIT(ld_acquire_gpu(P.tileflag + b.tile0 + hidx / BC_TILE) != 0u, 0x400u, 100);
-        tiles_known = hidx / BC_TILE + 1u;
+        BC_WAIT(ld_acquire_gpu(P.tileflag + b.tile0 + hidx / P.tile) != 0u, 0x400u, 100);
+        tiles_known = hidx / P.tile + 1u;
         const uint32_t j = b.lo + 32u * hidx + lane;
         t0n = j < b.hi ? __ldcg(P.w + j) : 0.0;
       }
@@ -875,7 +882,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
         long long h0 = 0;
         if (hprof) h0 = clock64();
         const double t0 = t0n;
-        const uint32_t kn = k + NH, tilen = kn / BC_TILE;
+        const uint32_t kn = k + NH, tilen = kn / P.tile;
         uint32_t fln = 1u;
         if (kn < nch && tilen >= tiles_known) fln = ld_acquire_gpu(P.tileflag + b.tile0 + tilen);
         long long h1 = 0;
@@ -917,6 +924,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
           base = b3 + n3;
         }
         ts += ts1;
+        long long hj = 0;
+        if (hprof) hj = clock64() + (ts == 1.25e-300 ? 1 : 0);   // (end of the jagged early entries)
         double t = __shfl_sync(0xffffffffu, ts, (int)rank);
         // late entries: columns in chunks k-E .. k-Kr-1.  Values and window slots of the first LB slots are loaded
         // before the wait; the t' slot and the window slot of chunk k must be free as well.
@@ -998,7 +1007,9 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bc_solve(const BcArgs P) {
           st_release_cta_s(trdy_s + 4u * tsl, k + 1u);
           if (!slot_done) mbar_arrive(emptyB + slot);
         }
-        if (hprof) { ph[0] += h1 - h0; ph[1] += h2 - h1; ph[2] += h3 - h2; ph[3] += h4 - h3; ph[4] += clock64() - h4; }
+        // ph[0]: tile flag / start vector of this chunk + late-entry loads and the NEXT own chunk's tile flag and start vector;
+        // ph[2]: wait for the chain to reach k-E + jagged early entries
+        if (hprof) { ph[0] += (h1 - h0) + (h3 - hj); ph[1] += h2 - h1; ph[2] += hj - h2; ph[3] += h4 - h3; ph[4] += clock64() - h4; }
       }
     } else if (warp == W_PRODA) {
       // ------------------------------ TMA producer, ring A -----------------------------------------------
@@ -1176,17 +1187,24 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   const uint32_t sep_rows = h->opt.reserved[4] > 0 ? (uint32_t)h->opt.reserved[4] : 1024u;
   B.Dfar_sep = std::min(B.Dfar, std::max(32u, floor_pow2_u32(std::max(32u, sep_rows) / 32u)));
   // ---- chunk / tile numbering ------------------------------------------------------------------------
-  std::vector<uint32_t> chunk0(nb + 1, 0), tile0(nb + 1, 0), dfar(nb + 1, B.Dfar);
+  // Far tiles: the unit in which the far CTAs hand the start vector to the chain.  A tile's in-block pass can start when
+  // the chain is a window away from it and is a chain of dependent HBM round trips (measured 26-50 us for 8 chunks of a
+  // separator), so the short-window separator blocks use small tiles: more tiles in flight, each one sweep of one CTA.
+  const int tile_opt = (h->opt.reserved[9] >> 8) & 0xFF;   // reserved[9] bits 8-15: chunks per far tile of the separator blocks
+  B.tile_sep = tile_opt > 0 ? (uint32_t)std::min(8, tile_opt) : 2u;
+  std::vector<uint32_t> chunk0(nb + 1, 0), tile0(nb + 1, 0), dfar(nb + 1, B.Dfar), tilesz(nb + 1, BC_TILE);
   for (int b = 0; b < nb; b++) dfar[b] = (depth[b] == max_depth) ? B.Dfar : B.Dfar_sep;
+  for (int b = 0; b < nb; b++) tilesz[b] = (depth[b] == max_depth) ? BC_TILE : B.tile_sep;
   for (int b = 0; b < nb; b++) {
     const uint32_t nch = (bounds[b + 1] - bounds[b] + 31u) / 32u;
     chunk0[b + 1] = chunk0[b] + nch;
-    tile0[b + 1] = tile0[b] + (nch + BC_TILE - 1u) / BC_TILE;
+    tile0[b + 1] = tile0[b] + (nch + tilesz[b] - 1u) / tilesz[b];
   }
   B.nchunks = chunk0[nb];
   B.ntiles = tile0[nb];
-  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0 | dfar
-  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 4 * (nb + 1)));
+  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0 | dfar | tile size
+  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 5 * (nb + 1)));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom + 4 * (nb + 1), tilesz.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 3 * (nb + 1), dfar.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom, bounds.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + (nb + 1), chunk0.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
@@ -1194,6 +1212,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   BcGeom g;
   g.bounds = dgeom; g.chunk0 = dgeom + (nb + 1); g.tile0 = dgeom + 2 * (nb + 1);
   g.dfar = dgeom + 3 * (nb + 1);
+  g.tile = dgeom + 4 * (nb + 1);
   g.nb = nb; g.Kr = B.Kr; g.E = B.E;
 
   // ---- sizes ---------------------------------------------------------------------------------------------
@@ -1259,6 +1278,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       bd.lo = bounds[b]; bd.hi = bounds[b + 1]; bd.chunk0 = chunk0[b]; bd.tile0 = tile0[b];
       bd.gidx = (uint32_t)B.blocks_host.size();
       bd.pad[0] = dfar[b];
+      bd.pad[1] = tilesz[b];
       B.blocks_host.push_back(bd);
       src_block.push_back(b);
       G.count++;
@@ -1423,7 +1443,9 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     a.N = (uint32_t)h->N; a.reversed = d.reversed ? 1 : 0;
     a.Kr = B.Kr; a.E = B.E; a.Dfar = L.Dfar; a.W = 32u * L.Dfar;
     a.SA = L.SA; a.SB = L.SB; a.capA = L.capA; a.capB = L.capB;
+    a.tile = B.blocks_host[G.first].pad[1];
     a.far_lpr = (G.rows > 0 && G.ext_nnz / G.rows > 64) ? 32u : 8u;
+    a.far_lpr2 = (h->opt.reserved[9] & 0xFF) == 32 ? 32u : 8u;   // reserved[9] bits 0-7: lanes per row of the in-block far pass
     a.col_min = top ? h->dist.n_sub : 0u;
     a.corr = top ? h->dist.sbuf : nullptr;
     a.abort_g = h->abort_flag;

@@ -47,7 +47,7 @@ def solve_from_layout(lay, rhs, reversed_):
     A, B = lay["blobA"], lay["blobB"]
     far_rp, far_col, far_val = lay["far_rp"], lay["far_col"].astype(np.int64), lay["far_val"]
     stats = dict(chunks=0, rec_slots=0, late_slots=0, early_max=0, early_tot=0)
-    for lo, hi, chunk0, tile0, gidx, dfar, *_ in lay["blocks"].astype(np.int64):
+    for lo, hi, chunk0, tile0, gidx, dfar, tile, *_ in lay["blocks"].astype(np.int64):
         nch = (hi - lo + 31) // 32
         wrows = 32 * dfar          # window of this block (leaves: Dfar, separators: Dfar_sep)
         wmask = wrows - 1
@@ -63,8 +63,8 @@ def solve_from_layout(lay, rhs, reversed_):
                 i = N - 1 - jj if reversed_ else jj
                 s, e = far_rp[jj], far_rp[jj + 1]
                 t0[l] = rhs[i] - np.dot(far_val[s:e], out[far_col[s:e]])
-            need = lay["tile_need"][tile0 + k // 8]
-            assert need <= 8 * (k // 8), "far tile would wait for a chunk of its own tile"
+            need = lay["tile_need"][tile0 + k // tile]
+            assert need <= tile * (k // tile), "far tile would wait for a chunk of its own tile"
             # ---- blob B: early (jagged diagonals) + late (ELL) --------------------------------------------
             b = B[lay["offB"][g]: lay["offB"][g + 1]]
             ne_max, ne_tot, nl = (int(v) for v in b[:12].view(np.uint32))

@@ -42,20 +42,21 @@ def direction_matrix(G, part, backward):
     return L, bounds, depth
 
 
-def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False):
+def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False, tile_sep=2, tile_leaf=8):
     N = L.shape[0]
     rp, col, val = L.indptr.astype(np.int64), L.indices.astype(np.int64), L.data
     nb = len(bounds) - 1
     max_depth = int(np.max(depth)) if nb else 0
     Dfar_sep = min(Dfar, Dfar_sep)
     dfar_of = [Dfar if depth[b] == max_depth else Dfar_sep for b in range(nb)]
+    tile_of = [tile_leaf if depth[b] == max_depth else tile_sep for b in range(nb)]   # chunks per far tile
     Dfar_leaf = Dfar
     chunk0 = np.zeros(nb + 1, np.int64)
     tile0 = np.zeros(nb + 1, np.int64)
     for b in range(nb):
         nch = (bounds[b + 1] - bounds[b] + 31) // 32
         chunk0[b + 1] = chunk0[b] + nch
-        tile0[b + 1] = tile0[b] + (nch + 7) // 8
+        tile0[b + 1] = tile0[b] + (nch + tile_of[b] - 1) // tile_of[b]
     nchunks, ntiles = int(chunk0[nb]), int(tile0[nb])
     blobsA, blobsB = [None] * nchunks, [None] * nchunks
     tile_need = np.zeros(ntiles, np.uint32)
@@ -90,7 +91,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
                 far_rows[j] = ((N - 1 - fc) if reversed_ else fc, vj[m_far])
                 loc = fc[fc >= blo]
                 if len(loc):
-                    t = int(tile0[b]) + k // 8
+                    t = int(tile0[b]) + k // tile_of[b]
                     tile_need[t] = max(tile_need[t], (int(loc[-1]) - blo) // 32 + 1)
             for l in range(nr, 32):
                 D[l, l] = 1.0
@@ -163,7 +164,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
         want = gl if root_first else max_depth - gl
         for b in range(nb):
             if depth[b] == want and bounds[b + 1] > bounds[b]:
-                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], 0, 0])
+                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], tile_of[b], 0])
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
     return dict(active=1, nchunks=nchunks, ntiles=ntiles, nblocks=len(blocks), N=N, Kr=Kr, E=E, Dfar=Dfar_leaf, Dfar_sep=Dfar_sep,
                 offA=offA, offB=offB, blobA=cat(blobsA, np.uint8), blobB=cat(blobsB, np.uint8), far_rp=far_rp,
