@@ -52,11 +52,11 @@ typedef struct rcg_options {
                               2 = level-space role-specialised kernel (experimental)                                 */
   int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2),
                               [3] blocked solve: recent chunk distance Kr (default 2), [4] window rows of the separator blocks
-                              (default 1024), [5] blocked solve: distance E (chunks) that separates the "early" from the "late" entries
-                              (default 16), [6] 1 = plain (non-cooperative) launch, [7] staging slot of the helpers' ring in quarters of
+                              (default 1024), [5] blocked solve: distance E (chunks) that separates the "early" from the "late" entries:
+                              bits 0-7 leaf blocks (default 16), bits 8-15 separator blocks (default 6), [6] 1 = plain (non-cooperative) launch, [7] staging slot of the helpers' ring in quarters of
                               the mean blob (default 12), [8] staging slots of the chain's ring (0 = automatic), [9] bits 0-7: lanes per row of the
                               far CTAs' in-block pass (8 default, 32); bits 8-15: chunks per far tile of the separator blocks
-                              (default 2; leaves use 8) */
+                              (default 1; leaves use 8) */
 } rcg_options;
 
 /* Per-handle measurements, all device-side times from CUDA events on the handle's own stream. */

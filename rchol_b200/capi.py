@@ -137,7 +137,7 @@ class Solver:
 
     def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
                  spmv_lanes: int = 0, chain_generic: bool = False, chain_mode: int = 0, backoff_ns: int = 0, dbg: int = 0, producers: int = 0,
-                 recent: int = 0, plain_launch: bool = False, sep_window: int = 0, early: int = 0, capb_quarters: int = 0, slots_a: int = 0, far_lanes2: int = 0, sep_tile: int = 0):
+                 recent: int = 0, plain_launch: bool = False, sep_window: int = 0, early: int = 0, capb_quarters: int = 0, slots_a: int = 0, far_lanes2: int = 0, sep_tile: int = 0, early_sep: int = 0):
         self._L = load()
         self._h = C.c_void_p()
         opt = Options()
@@ -150,7 +150,7 @@ class Solver:
         opt.reserved[2] = int(producers)
         opt.reserved[3] = int(recent)
         opt.reserved[4] = int(sep_window)
-        opt.reserved[5] = int(early)
+        opt.reserved[5] = int(early) | (int(early_sep) << 8)
         opt.reserved[7] = int(capb_quarters)
         opt.reserved[8] = int(slots_a)
         opt.reserved[9] = int(far_lanes2) | (int(sep_tile) << 8)
@@ -322,7 +322,7 @@ class Solver:
         """Raw copy of the blocked triangular-solve layout of one direction (tests/blocked_emulator.py interprets it)."""
         info = (C.c_uint64 * 16)()
         self._check(self._L.rcg_debug_blocked_info(self._h, int(direction), info))
-        keys = ["active", "nchunks", "ntiles", "nblocks", "bytesA", "bytesB", "far_nnz", "Kr", "E", "Dfar", "N", "nlevels", "Dfar_sep", "tile_sep"]
+        keys = ["active", "nchunks", "ntiles", "nblocks", "bytesA", "bytesB", "far_nnz", "Kr", "E", "Dfar", "N", "nlevels", "Dfar_sep", "tile_sep", "E_sep"]
         out = {k: int(info[i]) for i, k in enumerate(keys)}
         if not out["active"]:
             return out

@@ -562,6 +562,7 @@ int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16) {
   info16[11] = B.levels.size();
   info16[12] = B.Dfar_sep;
   info16[13] = B.tile_sep;
+  info16[14] = B.E_sep;
   return RCG_OK;
 }
 

@@ -166,6 +166,7 @@ __device__ __forceinline__ bool guard_poll(Guard &G, uint32_t code) {
 struct BcGeom {               // blocks in ascending solve order (device arrays of nb+1 entries)
   const uint32_t *bounds, *chunk0, *tile0, *dfar;   // dfar: per block (leaves keep a large window, separators a small one)
   const uint32_t *tile;                             // chunks per far tile, per block
+  const uint32_t *eblk;                             // early/late distance E, per block
   int nb;
   uint32_t Kr, E;
 };
@@ -184,13 +185,13 @@ __device__ __forceinline__ int find_le(const uint32_t *__restrict__ a, int n, ui
 struct RowSplit { int64_t s, p_far, p_early, p_late, p_rec, p_diag; };
 
 __device__ __forceinline__ RowSplit split_row(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, uint32_t j,
-                                              uint32_t blo, uint32_t k, const BcGeom &g, uint32_t Dfar) {
+                                              uint32_t blo, uint32_t k, const BcGeom &g, uint32_t Dfar, uint32_t E) {
   RowSplit r;
   r.s = rp[j];
   r.p_diag = rp[j + 1] - 1;
   const int ik = (int)k;
   const uint32_t c_far = blo + 32u * (uint32_t)max(0, ik + 1 - (int)Dfar);
-  const uint32_t c_early = blo + 32u * (uint32_t)max(0, ik - (int)g.E);
+  const uint32_t c_early = blo + 32u * (uint32_t)max(0, ik - (int)E);
   const uint32_t c_late = blo + 32u * (uint32_t)max(0, ik - (int)g.Kr);
   const uint32_t c_rec = blo + 32u * k;
   int64_t p = r.s;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     const uint32_t j = blo + 32u * k + lane;
     uint32_t n_rec = 0, n_late = 0, n_early = 0, need = 0;
     if (j < bhi) {
-      const RowSplit r = split_row(rp, col, j, blo, k, g, g.dfar[b]);
+      const RowSplit r = split_row(rp, col, j, blo, k, g, g.dfar[b], g.eblk[b]);
       if (col[r.p_diag] != j) atomicExch(err, 1);
       far_cnt[j] = r.p_far - r.s;
       n_early = (uint32_t)(r.p_early - r.p_far);
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
     RowSplit r;
     r.s = r.p_far = r.p_early = r.p_late = r.p_rec = r.p_diag = 0;
     const uint32_t wmask = 32u * g.dfar[b] - 1u;
-    if (valid) r = split_row(rp, col, j, blo, k, g, g.dfar[b]);
+    if (valid) r = split_row(rp, col, j, blo, k, g, g.dfar[b], g.eblk[b]);
     const uint32_t n_early = (uint32_t)(r.p_early - r.p_far), n_late = (uint32_t)(r.p_late - r.p_early);
     const uint32_t n_rec = (uint32_t)(r.p_rec - r.p_late), n_diag = (uint32_t)(r.p_diag - r.p_rec);
     const uint32_t nslots = warp_max_u32(n_rec), nl = warp_max_u32(n_late);
@@ -1179,7 +1180,13 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   B.Kr = h->opt.reserved[3] > 0 ? (uint32_t)std::min(h->opt.reserved[3], h->opt.chain_mode == 3 ? 4 : 2) : 2u;
   // chunks k-E .. k-Kr-1 are the "late" class (gathered by the near helper AFTER the chain reached chunk k-Kr);
   // older chunks inside the window are "early" (gathered before).  reserved[5] overrides (tuning experiments).
-  B.E = h->opt.reserved[5] > 0 ? (uint32_t)std::min(16, std::max<int>(h->opt.reserved[5], (int)B.Kr + 1)) : 16u;
+  {
+    const int e_leaf = h->opt.reserved[5] & 0xFF, e_sep = (h->opt.reserved[5] >> 8) & 0xFF;   // reserved[5]: leaves | separators << 8
+    B.E = e_leaf > 0 ? (uint32_t)std::min(16, std::max<int>(e_leaf, (int)B.Kr + 1)) : 16u;
+    // separator blocks are nearly dense next to the diagonal: with E = 16 their late ELL part has 35-50 slots, more than
+    // a helper keeps in registers, so the helper holds its staging slot through the late phase; E = 6 keeps it short
+    B.E_sep = e_sep > 0 ? (uint32_t)std::min(16, std::max<int>(e_sep, (int)B.Kr + 1)) : std::min(B.E, 6u);
+  }
   uint32_t win_rows = h->opt.chain_window > 0 ? (uint32_t)h->opt.chain_window : 4096u;
   B.Dfar = std::min(512u, std::max(32u, floor_pow2_u32(std::max(32u, win_rows) / 32u)));
   // Separator blocks are small, dense and have every far CTA of the launch to themselves: a short window sends most of
@@ -1191,10 +1198,11 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   // the chain is a window away from it and is a chain of dependent HBM round trips (measured 26-50 us for 8 chunks of a
   // separator), so the short-window separator blocks use small tiles: more tiles in flight, each one sweep of one CTA.
   const int tile_opt = (h->opt.reserved[9] >> 8) & 0xFF;   // reserved[9] bits 8-15: chunks per far tile of the separator blocks
-  B.tile_sep = tile_opt > 0 ? (uint32_t)std::min(8, tile_opt) : 2u;
-  std::vector<uint32_t> chunk0(nb + 1, 0), tile0(nb + 1, 0), dfar(nb + 1, B.Dfar), tilesz(nb + 1, BC_TILE);
+  B.tile_sep = tile_opt > 0 ? (uint32_t)std::min(8, tile_opt) : 1u;
+  std::vector<uint32_t> chunk0(nb + 1, 0), tile0(nb + 1, 0), dfar(nb + 1, B.Dfar), tilesz(nb + 1, BC_TILE), eblk(nb + 1, B.E);
   for (int b = 0; b < nb; b++) dfar[b] = (depth[b] == max_depth) ? B.Dfar : B.Dfar_sep;
   for (int b = 0; b < nb; b++) tilesz[b] = (depth[b] == max_depth) ? BC_TILE : B.tile_sep;
+  for (int b = 0; b < nb; b++) eblk[b] = (depth[b] == max_depth) ? B.E : B.E_sep;
   for (int b = 0; b < nb; b++) {
     const uint32_t nch = (bounds[b + 1] - bounds[b] + 31u) / 32u;
     chunk0[b + 1] = chunk0[b] + nch;
@@ -1202,8 +1210,9 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   }
   B.nchunks = chunk0[nb];
   B.ntiles = tile0[nb];
-  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0 | dfar | tile size
-  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 5 * (nb + 1)));
+  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0 | dfar | tile size | E
+  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 6 * (nb + 1)));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom + 5 * (nb + 1), eblk.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 4 * (nb + 1), tilesz.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 3 * (nb + 1), dfar.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom, bounds.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
@@ -1213,6 +1222,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   g.bounds = dgeom; g.chunk0 = dgeom + (nb + 1); g.tile0 = dgeom + 2 * (nb + 1);
   g.dfar = dgeom + 3 * (nb + 1);
   g.tile = dgeom + 4 * (nb + 1);
+  g.eblk = dgeom + 5 * (nb + 1);
   g.nb = nb; g.Kr = B.Kr; g.E = B.E;
 
   // ---- sizes ---------------------------------------------------------------------------------------------
@@ -1279,6 +1289,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       bd.gidx = (uint32_t)B.blocks_host.size();
       bd.pad[0] = dfar[b];
       bd.pad[1] = tilesz[b];
+      bd.pad[2] = eblk[b];
       B.blocks_host.push_back(bd);
       src_block.push_back(b);
       G.count++;
@@ -1441,7 +1452,7 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     a.w = B.w; a.rhs = rhs; a.out = out;
     a.dotvec = dotvec; a.dot_partials = dotvec ? rz_part : nullptr; a.dot_limit = dot_limit;
     a.N = (uint32_t)h->N; a.reversed = d.reversed ? 1 : 0;
-    a.Kr = B.Kr; a.E = B.E; a.Dfar = L.Dfar; a.W = 32u * L.Dfar;
+    a.Kr = B.Kr; a.E = B.blocks_host[G.first].pad[2]; a.Dfar = L.Dfar; a.W = 32u * L.Dfar;
     a.SA = L.SA; a.SB = L.SB; a.capA = L.capA; a.capB = L.capB;
     a.tile = B.blocks_host[G.first].pad[1];
     a.far_lpr = (G.rows > 0 && G.ext_nnz / G.rows > 64) ? 32u : 8u;

@@ -73,7 +73,7 @@ struct BcBlock {               // one nested-dissection block (device copy; orde
   uint32_t chunk0;             // global index of the block's first chunk
   uint32_t tile0;              // global index of the block's first far tile (8 chunks)
   uint32_t gidx;               // index of the block in the direction: progress counter, dot-partial slot
-  uint32_t pad[3];             // pad[0] = window of the block in chunks (Dfar), pad[1] = chunks per far tile
+  uint32_t pad[3];             // pad[0] = window of the block in chunks (Dfar), pad[1] = chunks per far tile, pad[2] = early/late distance E
 };
 
 struct BcLevel {               // per tree level: shared-memory plan of the launch
@@ -89,7 +89,8 @@ struct BlockedDev {
   bool on = false;
   uint32_t Kr = 2, E = 16, Dfar = 128;   // chunk-distance thresholds (see above); window = 32*Dfar rows (leaf blocks)
   uint32_t Dfar_sep = 32;                // window of the separator blocks
-  uint32_t tile_sep = 2;                 // chunks per far tile of the separator blocks (leaves: 8)
+  uint32_t E_sep = 6;                    // early/late distance of the separator blocks (leaves: E)
+  uint32_t tile_sep = 1;                 // chunks per far tile of the separator blocks (leaves: 8)
   uint32_t nchunks = 0, ntiles = 0, nblocks = 0;
   int64_t *offA = nullptr, *offB = nullptr;          // nchunks+1 byte offsets into the blobs
   unsigned char *blobA = nullptr, *blobB = nullptr;

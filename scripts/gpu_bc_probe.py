@@ -42,10 +42,11 @@ for cfg in cfgs:
     sa = cfg[7] if len(cfg) > 7 else 0
     fl2 = cfg[8] if len(cfg) > 8 else 0
     stile = cfg[9] if len(cfg) > 9 else 0
-    s = capi.Solver(0, chain_window=win, recent=rec, chain_mode=mode, dbg=dbg, sep_window=sepw, early=early, capb_quarters=capq, slots_a=sa, far_lanes2=fl2, sep_tile=stile)
+    esep = cfg[10] if len(cfg) > 10 else 0
+    s = capi.Solver(0, chain_window=win, recent=rec, chain_mode=mode, dbg=dbg, sep_window=sepw, early=early, capb_quarters=capq, slots_a=sa, far_lanes2=fl2, sep_tile=stile, early_sep=esep)
     t = time.time(); s.set_matrix(*A); s.set_factor(*G, part); t_set = time.time() - t
     st = s.stats()
-    print(f"--- window={win} recent={rec} mode={mode} sep_window={sepw} early={early} capq={capq} SA={sa} farlanes2={fl2} septile={stile} dbg={dbg}: set-up wall {t_set:.2f}s upload {st['upload_ms']:.0f} analysis {st['analysis_ms']:.0f} ms", flush=True)
+    print(f"--- window={win} recent={rec} mode={mode} sep_window={sepw} early={early} capq={capq} SA={sa} farlanes2={fl2} septile={stile} esep={esep} dbg={dbg}: set-up wall {t_set:.2f}s upload {st['upload_ms']:.0f} analysis {st['analysis_ms']:.0f} ms", flush=True)
     if check:
         y = s.trsv(capi.TRSV_FORWARD, b); z = s.trsv(capi.TRSV_BACKWARD, yo); zz = s.precond(b)
         print(f"    fwd relerr {relerr(y, yo):.2e} bwd {relerr(z, zo):.2e} precond {relerr(zz, zo):.2e}", flush=True)

@@ -42,7 +42,7 @@ def direction_matrix(G, part, backward):
     return L, bounds, depth
 
 
-def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False, tile_sep=2, tile_leaf=8):
+def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False, tile_sep=1, tile_leaf=8, E_sep=None):
     N = L.shape[0]
     rp, col, val = L.indptr.astype(np.int64), L.indices.astype(np.int64), L.data
     nb = len(bounds) - 1
@@ -50,6 +50,8 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
     Dfar_sep = min(Dfar, Dfar_sep)
     dfar_of = [Dfar if depth[b] == max_depth else Dfar_sep for b in range(nb)]
     tile_of = [tile_leaf if depth[b] == max_depth else tile_sep for b in range(nb)]   # chunks per far tile
+    E_sep = min(E, 6) if E_sep is None else E_sep
+    e_of = [E if depth[b] == max_depth else E_sep for b in range(nb)]                 # early/late distance
     Dfar_leaf = Dfar
     chunk0 = np.zeros(nb + 1, np.int64)
     tile0 = np.zeros(nb + 1, np.int64)
@@ -70,7 +72,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             rows = [j for j in range(blo + 32 * k, min(bhi, blo + 32 * k + 32))]
             nr = len(rows)
             c_far = blo + 32 * max(0, k + 1 - Dfar)
-            c_early = blo + 32 * max(0, k - E)
+            c_early = blo + 32 * max(0, k - e_of[b])
             c_late = blo + 32 * max(0, k - Kr)
             c_rec = blo + 32 * k
             parts = []
@@ -164,7 +166,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
         want = gl if root_first else max_depth - gl
         for b in range(nb):
             if depth[b] == want and bounds[b + 1] > bounds[b]:
-                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], tile_of[b], 0])
+                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], tile_of[b], e_of[b]])
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
     return dict(active=1, nchunks=nchunks, ntiles=ntiles, nblocks=len(blocks), N=N, Kr=Kr, E=E, Dfar=Dfar_leaf, Dfar_sep=Dfar_sep,
                 offA=offA, offB=offB, blobA=cat(blobsA, np.uint8), blobB=cat(blobsB, np.uint8), far_rp=far_rp,

@@ -35,7 +35,7 @@ def oracle():
                                                   ("lap3d", 33, 2, dict(chain_window=1024)),
                                                   ("lap3d", 40, 0, dict(chain_window=1024)),
                                                   ("lap3d", 33, 2, dict(chain_window=1024, early=6)),
-                                                  ("lap3d", 40, 8, dict(sep_tile=4)), ("aniso2d", 96, 4, dict(sep_tile=1))])
+                                                  ("lap3d", 40, 8, dict(sep_tile=4, early_sep=12)), ("aniso2d", 96, 4, dict(sep_tile=1))])
 def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
@@ -44,7 +44,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
         s.set_factor(*G, part)
         lay_f, lay_b = s.blocked_layout(capi.TRSV_FORWARD), s.blocked_layout(capi.TRSV_BACKWARD)
         assert lay_f["active"] and lay_b["active"]
-        kw = dict(Kr=lay_f["Kr"], E=lay_f["E"], Dfar=lay_f["Dfar"], Dfar_sep=lay_f["Dfar_sep"], tile_sep=lay_f["tile_sep"])
+        kw = dict(Kr=lay_f["Kr"], E=lay_f["E"], Dfar=lay_f["Dfar"], Dfar_sep=lay_f["Dfar_sep"], tile_sep=lay_f["tile_sep"], E_sep=lay_f["E_sep"])
         L, bounds, depth = direction_matrix(G, part, False)
         compare_layouts(lay_f, build_layout(L, bounds, depth, False, **kw))
         L, bounds, depth = direction_matrix(G, part, True)
@@ -62,7 +62,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
                                   dict(chain_window=8192), dict(plain_launch=True), dict(use_graph=False, chain_window=1024),
                                   dict(chain_mode=1), dict(chain_mode=3), dict(sep_window=4096), dict(chain_window=2048, sep_window=2048),
                                   dict(early=6), dict(early=3, recent=2), dict(early=8, chain_mode=3),
-                                  dict(capb_quarters=4), dict(slots_a=2), dict(sep_tile=1), dict(sep_tile=8, far_lanes2=32), dict(sep_tile=4, chain_window=1024), dict(capb_quarters=5, slots_a=6, chain_window=2048)])
+                                  dict(capb_quarters=4), dict(slots_a=2), dict(sep_tile=1), dict(sep_tile=8, far_lanes2=32), dict(early_sep=16), dict(early_sep=3, early=5), dict(sep_tile=4, chain_window=1024), dict(capb_quarters=5, slots_a=6, chain_window=2048)])
 @pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 33, 2), ("aniso2d", 160, 4), ("lap3d", 40, 0)])
 def test_blocked_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
