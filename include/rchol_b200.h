@@ -48,7 +48,8 @@ typedef struct rcg_options {
   int use_graph;           /* 1 = replay one CUDA graph per PCG iteration (default), 0 = plain launches   */
   int spmv_lanes;          /* lanes per row of the CSR SpMV (0 = choose from the row-length histogram)     */
   int chain_generic;       /* 1 = force the non-pipelined fallback kernel of the triangular solve (testing)  */
-  int chain_mode;          /* 0/3 = blocked-inverse chain (default), 1 = level-space sync-free polling kernel,
+  int chain_mode;          /* 0/3 = blocked-inverse chain (default), 4 = the same with the leaf level on the cluster chain (128-row chunks, 4 CTAs
+                              per leaf, DSMEM exchange), 1 = level-space sync-free polling kernel,
                               2 = level-space role-specialised kernel (experimental)                                 */
   int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2),
                               [3] blocked solve: recent chunk distance Kr (default 2), [4] window rows of the separator blocks

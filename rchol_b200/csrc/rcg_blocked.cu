@@ -1155,16 +1155,19 @@ uint32_t floor_pow2_u32(uint32_t v) {
   return p;
 }
 
+#include "rcg_cluster.cuh"
+
 }  // namespace
 
 bool rcg_use_blocked(const rcg_handle *h) {
-  return !h->opt.chain_generic && (h->opt.chain_mode == 0 || h->opt.chain_mode == 3);
+  return !h->opt.chain_generic && (h->opt.chain_mode == 0 || h->opt.chain_mode == 3 || h->opt.chain_mode == 4);
 }
 
 void rcg_free_blocked(BlockedDev &b) {
   cudaFree(b.offA); cudaFree(b.offB); cudaFree(b.blobA); cudaFree(b.blobB);
   rcg_free_csr(b.far);
   cudaFree(b.tile_need); cudaFree(b.flags); cudaFree(b.w); cudaFree(b.blocks); cudaFree(b.far_split);
+  cudaFree(b.cl.wslab); cudaFree(b.cl.blobN); cudaFree(b.cl.offN); cudaFree(b.cl.c0); cudaFree(b.cl.prog4);
   b = BlockedDev();
 }
 
@@ -1381,6 +1384,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   }
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   cudaFree(dgeom);
+  if (h->opt.chain_mode == 4) {   // cluster chain for the leaf level (128-row chunks, rcg_cluster.cuh)
+    const int rc = cl_build(h, d, comb, max_depth);
+    if (rc != RCG_OK) { rcg_free_csr(comb); return rc; }
+  }
   rcg_free_csr(comb);
   if (!h->abort_flag) {
     RCG_CUDA(h, cudaMalloc(&h->abort_flag, sizeof(unsigned int) * 4));
@@ -1418,6 +1425,7 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
   }
   if (only_kernel > 0) return RCG_OK;   // the level kernel is the only kernel of a group
   RCG_CUDA(h, cudaMemsetAsync(B.flags, 0, sizeof(uint32_t) * ((size_t)B.ntiles + B.nblocks), h->stream));
+  if (B.cl.on) RCG_CUDA(h, cudaMemsetAsync(B.cl.prog4, 0, sizeof(uint32_t) * 4 * (size_t)B.nblocks, h->stream));
   double *rz_part = h->partials + 2 * (size_t)h->partial_cap;
   const bool dist_fwd = h->dist.on && !d.reversed && h->N > h->dist.n_sub;
   const uint32_t dot_limit = h->dist.on ? h->dist.dot_limit : 0xFFFFFFFFu;
@@ -1462,6 +1470,10 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     a.abort_g = h->abort_flag;
     a.clk = h->clk_probe;
     a.dbg = (uint32_t)h->opt.reserved[1];
+    if (B.cl.on && B.cl.level_on[gi]) {   // leaf level on the cluster chain
+      RCG_TRY(cl_launch(h, B, a, G, gi));
+      continue;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L.groups * (1u + L.helpers));
     cfg.blockDim = dim3(BC_THREADS);

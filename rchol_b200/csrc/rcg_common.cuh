@@ -85,7 +85,27 @@ struct BcLevel {               // per tree level: shared-memory plan of the laun
   size_t smem = 0;
 };
 
+// Cluster chain (chain_mode 4, rcg_cluster.cuh): the leaf blocks' chain advances 128 rows per hop; the dense inverse of a
+// 128x128 diagonal block is split row-wise over a thread-block cluster of 4 CTAs and the solved rows are exchanged
+// through distributed shared memory.  Far entries (tile flags, start vector, progress words) are shared with the
+// 32-row layout above, so the far CTAs are the same.
+struct ClusterDev {
+  bool on = false;
+  uint32_t nchunks = 0;                  // 128-row chunks of all cluster-solved blocks
+  unsigned char *wslab = nullptr;        // nchunks x 80 KiB: four row slabs of the dense inverse (lower trapezoids)
+  unsigned char *blobN = nullptr;        // near entries (inside the window, outside the diagonal block), jagged diagonals
+  int64_t *offN = nullptr;               // nchunks+1 byte offsets into blobN
+  uint32_t *c0 = nullptr;                // per block of the direction (gidx): first 128-row chunk, 0xFFFFFFFF = not cluster-solved
+  uint32_t *prog4 = nullptr;             // per block (gidx) x cluster rank: published hops of the current solve
+  int64_t bytesN = 0;
+  std::vector<int> level_on;             // parallel to DirectionDev::groups: 1 = the level is launched as k_cl_solve
+  std::vector<uint32_t> level_cap;       // largest near blob of the level (bytes)
+  uint32_t ring = 0;                     // rows of the solution window ring (32*Dfar + 128)
+  int max_clusters = 0;                  // co-resident clusters of 4 CTAs (cudaOccupancyMaxActiveClusters)
+};
+
 struct BlockedDev {
+  ClusterDev cl;
   bool on = false;
   uint32_t Kr = 2, E = 16, Dfar = 128;   // chunk-distance thresholds (see above); window = 32*Dfar rows (leaf blocks)
   uint32_t Dfar_sep = 32;                // window of the separator blocks
