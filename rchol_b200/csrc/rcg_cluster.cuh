@@ -14,10 +14,11 @@
 //   far CTAs: identical to k_bc_solve's (tile flags, start vector P.w, progress words in 32-row units).
 constexpr uint32_t CL_S = 4;                 // CTAs per cluster
 constexpr uint32_t CL_NT = 256;              // compute threads
-constexpr uint32_t CL_THREADS = 320;         // + producer warp (8) + publisher warp (9)
+constexpr uint32_t CL_THREADS = 576;         // + producer warp (8) + publisher warp (9) + 8 helper warps (old entries, one hop ahead)
 constexpr uint32_t CL_WCHUNK = 81920;        // bytes of the four slabs of one chunk: 8 + 16 + 24 + 32 KiB
 constexpr uint32_t CL_WSTAGE = 32768;        // slab part of a staging slot
-constexpr uint32_t CL_NHDR = 784;            // near blob: 16 B header, perm_old[256], n_old[256], perm_rec[128], n_rec[128]
+constexpr uint32_t CL_NHDR = 1552;           // near blob: 16 B header, perm_old[512] (u16), n_old[512] (u8)
+constexpr uint32_t CL_RB = 6;                // recent ELL slots held in registers
 __host__ __device__ __forceinline__ uint32_t cl_slab_off(uint32_t q) { return 4096u * q * (q + 1u); }
 
 struct ClGeom {               // cluster-solved blocks in ascending chunk order
@@ -49,51 +50,60 @@ __device__ __forceinline__ ClRow cl_split(const int64_t *__restrict__ rp, const 
   return r;
 }
 
-// Jagged-diagonal bookkeeping of one chunk (CTA of 128 threads, thread = row).  Old entries: 256 lane-rows (row, half),
-// half h takes entries h, h+2, ...; recent entries: 128 lane-rows.  Lane-rows are sorted by descending count; `rank` is
-// the sorted position.  m[s] = lane-rows with more than s entries.
+// Jagged-diagonal bookkeeping of one chunk (CTA of 128 threads, thread = row).  Old entries: 512 lane-rows (row, quarter),
+// quarter h takes entries h, h+4, ...  Lane-rows are sorted by descending count; `rank` is the sorted position; diagonal s
+// holds the s-th entry of every lane-row with more than s entries.  The solve assigns sorted positions t and 511-t to
+// helper thread t (longest with shortest).
 struct ClJds {
-  uint32_t n_old[2], rank_old[2], n_rec, rank_rec;
+  uint32_t n_old[4], rank_old[4];
+  uint32_t n_rec[2], rank_rec;        // recent entries: rows sorted by count, half h of a row takes entries h, h+2, ...
   uint32_t nd_old, nd_rec, tot_old, tot_rec;
 };
-__device__ __forceinline__ ClJds cl_jds(uint32_t cnt_old, uint32_t cnt_rec, uint32_t *s_cnt /*384*/, uint32_t *s_red /*4*/) {
+__device__ __forceinline__ ClJds cl_jds(uint32_t cnt_old, uint32_t cnt_rec, uint32_t *s_cnt /*512*/, uint32_t *s_red /*4*/) {
   const uint32_t i = threadIdx.x;
   ClJds J;
-  J.n_old[0] = (cnt_old + 1u) >> 1;
-  J.n_old[1] = cnt_old >> 1;
-  J.n_rec = cnt_rec;
   if (i < 4u) s_red[i] = 0u;
-  s_cnt[i] = J.n_old[0];
-  s_cnt[128u + i] = J.n_old[1];
-  s_cnt[256u + i] = J.n_rec;
-  __syncthreads();
-  J.rank_old[0] = J.rank_old[1] = J.rank_rec = 0u;
-  for (uint32_t l = 0; l < 256u; l++) {
-    const uint32_t o = s_cnt[l];
-    J.rank_old[0] += (o > J.n_old[0] || (o == J.n_old[0] && l < i)) ? 1u : 0u;
-    J.rank_old[1] += (o > J.n_old[1] || (o == J.n_old[1] && l < 128u + i)) ? 1u : 0u;
+#pragma unroll
+  for (uint32_t h = 0; h < 4u; h++) {
+    J.n_old[h] = (cnt_old + 3u - h) >> 2;
+    s_cnt[128u * h + i] = J.n_old[h];
+    J.rank_old[h] = 0u;
   }
-  for (uint32_t l = 0; l < 128u; l++) {
-    const uint32_t o = s_cnt[256u + l];
-    J.rank_rec += (o > J.n_rec || (o == J.n_rec && l < i)) ? 1u : 0u;
+  __syncthreads();
+  for (uint32_t l = 0; l < 512u; l++) {
+    const uint32_t o = s_cnt[l];
+#pragma unroll
+    for (uint32_t h = 0; h < 4u; h++) J.rank_old[h] += (o > J.n_old[h] || (o == J.n_old[h] && l < 128u * h + i)) ? 1u : 0u;
   }
   atomicMax(&s_red[0], J.n_old[0]);
-  atomicMax(&s_red[1], J.n_rec);
-  atomicAdd(&s_red[2], J.n_old[0] + J.n_old[1]);
-  atomicAdd(&s_red[3], J.n_rec);
+  atomicMax(&s_red[1], (cnt_rec + 1u) >> 1);
+  atomicAdd(&s_red[2], cnt_old);
+  atomicAdd(&s_red[3], cnt_rec);
   __syncthreads();
   J.nd_old = s_red[0]; J.nd_rec = s_red[1]; J.tot_old = s_red[2]; J.tot_rec = s_red[3];
   __syncthreads();
+  s_cnt[i] = cnt_rec;
+  __syncthreads();
+  J.n_rec[0] = (cnt_rec + 1u) >> 1;
+  J.n_rec[1] = cnt_rec >> 1;
+  J.rank_rec = 0u;
+  for (uint32_t l = 0; l < 128u; l++) {
+    const uint32_t o = s_cnt[l];
+    J.rank_rec += (o > cnt_rec || (o == cnt_rec && l < i)) ? 1u : 0u;
+  }
+  __syncthreads();
   return J;
 }
+// near blob: header | old: bases[nd_old] u16, values, window slots | recent: perm[128] u8, counts[256] u8 (2*rank + half),
+// bases[2][nd_rec] u16, values, window slots
 __host__ __device__ __forceinline__ uint32_t cl_near_bytes(uint32_t nd_old, uint32_t nd_rec, uint32_t tot_old, uint32_t tot_rec) {
-  return CL_NHDR + r16(2u * nd_old) + r16(2u * nd_rec) + r16(8u * tot_old) + r16(2u * tot_old) + r16(8u * tot_rec) + r16(2u * tot_rec);
+  return CL_NHDR + r16(2u * nd_old) + r16(8u * tot_old) + r16(2u * tot_old) + 384u + r16(4u * nd_rec) + r16(8u * tot_rec) + r16(2u * tot_rec);
 }
 
 // CTA (128 threads) per chunk: size of the near blob
 __global__ void __launch_bounds__(128) k_cl_count(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, ClGeom g,
                                                   uint32_t nchunks, int64_t *__restrict__ sizeN, int *err) {
-  __shared__ uint32_t s_cnt[384], s_red[4];
+  __shared__ uint32_t s_cnt[512], s_red[4];
   for (uint32_t gc = blockIdx.x; gc < nchunks; gc += gridDim.x) {
     const int b = find_le(g.c0, g.nb, gc);
     const uint32_t K = gc - g.c0[b], blo = g.lo[b], bhi = g.hi[b];
@@ -104,16 +114,19 @@ __global__ void __launch_bounds__(128) k_cl_count(const int64_t *__restrict__ rp
       cnt_old = (uint32_t)(r.p_old - r.p_far);
       cnt_rec = (uint32_t)(r.p_rec - r.p_old);
     }
-    if (cnt_old > 510u || cnt_rec > 255u) atomicExch(err, 2);
+    if (cnt_old > 1020u || cnt_rec > 510u) atomicExch(err, 2);
     const ClJds J = cl_jds(cnt_old, cnt_rec, s_cnt, s_red);
-    if (threadIdx.x == 0) sizeN[gc] = (int64_t)cl_near_bytes(J.nd_old, J.nd_rec, J.tot_old, J.tot_rec);
+    if (threadIdx.x == 0) {
+      if (J.tot_old > 60000u || J.tot_rec > 60000u) atomicExch(err, 2);   // diagonal bases are 16-bit
+      sizeN[gc] = (int64_t)cl_near_bytes(J.nd_old, J.nd_rec, J.tot_old, J.tot_rec);
+    }
   }
 }
 
 // CTA (128 threads) per chunk: dense inverse of the 128x128 diagonal block -> four row slabs; near blob
 constexpr uint32_t CL_OWNCAP = 6144;   // staged own-block entries of a chunk (more: read from global memory)
 // W | oval | dval | ooff (130 words) | s_cnt | s_red | m_old | m_rec | ocolb
-constexpr int CL_FILL_SMEM = 128 * 128 * 8 + CL_OWNCAP * 8 + 128 * 8 + 130 * 4 + 384 * 4 + 16 + 512 * 2 + 512 * 2 + CL_OWNCAP;
+constexpr int CL_FILL_SMEM = 128 * 128 * 8 + CL_OWNCAP * 8 + 128 * 8 + 130 * 4 + 512 * 4 + 16 + 512 * 2 + 512 * 2 + CL_OWNCAP;
 __global__ void __launch_bounds__(128) k_cl_fill(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col,
                                                  const double *__restrict__ val, ClGeom g, uint32_t nchunks,
                                                  const int64_t *__restrict__ offN, unsigned char *__restrict__ wslab,
@@ -123,8 +136,8 @@ __global__ void __launch_bounds__(128) k_cl_fill(const int64_t *__restrict__ rp,
   double *oval = W + 128 * 128;                                        // [CL_OWNCAP] staged own-block values
   double *dval = oval + CL_OWNCAP;                                     // [128] diagonal
   uint32_t *ooff = reinterpret_cast<uint32_t *>(dval + 128);           // [129] prefix of own-entry counts (130 words reserved)
-  uint32_t *s_cnt = ooff + 130;                                        // [384]
-  uint32_t *s_red = s_cnt + 384;                                       // [4]
+  uint32_t *s_cnt = ooff + 130;                                        // [512]
+  uint32_t *s_red = s_cnt + 512;                                       // [4]
   uint16_t *m_old = reinterpret_cast<uint16_t *>(s_red + 4);           // [512] diagonal lengths, then bases
   uint16_t *m_rec = m_old + 512;                                       // [512]
   unsigned char *ocolb = reinterpret_cast<unsigned char *>(m_rec + 512);   // [CL_OWNCAP] staged own-block columns (0..127)
@@ -188,54 +201,59 @@ __global__ void __launch_bounds__(128) k_cl_fill(const int64_t *__restrict__ rp,
     __syncthreads();
     // diagonal lengths (shared-memory atomics on 32-bit words: two u16 per word, counts stay below 65536)
     {
-      uint32_t *mo32 = reinterpret_cast<uint32_t *>(m_old), *mr32 = reinterpret_cast<uint32_t *>(m_rec);
-      for (uint32_t h = 0; h < 2u; h++)
+      uint32_t *mo32 = reinterpret_cast<uint32_t *>(m_old);
+      for (uint32_t h = 0; h < 4u; h++)
         for (uint32_t s = 0; s < J.n_old[h]; s++) atomicAdd(&mo32[s >> 1], (s & 1u) ? 65536u : 1u);
-      for (uint32_t s = 0; s < J.n_rec; s++) atomicAdd(&mr32[s >> 1], (s & 1u) ? 65536u : 1u);
+      uint32_t *mr32 = reinterpret_cast<uint32_t *>(m_rec);   // [2][256]: half h, diagonal s
+      for (uint32_t h = 0; h < 2u; h++)
+        for (uint32_t s = 0; s < J.n_rec[h]; s++) atomicAdd(&mr32[(256u * h + s) >> 1], (s & 1u) ? 65536u : 1u);
     }
     __syncthreads();
     if (i == 0u) {   // lengths -> bases (exclusive prefix)
       uint32_t a = 0;
       for (uint32_t s = 0; s < J.nd_old; s++) { const uint32_t m = m_old[s]; m_old[s] = (uint16_t)a; a += m; }
       a = 0;
-      for (uint32_t s = 0; s < J.nd_rec; s++) { const uint32_t m = m_rec[s]; m_rec[s] = (uint16_t)a; a += m; }
+      for (uint32_t h = 0; h < 2u; h++)
+        for (uint32_t s = 0; s < J.nd_rec; s++) { const uint32_t m = m_rec[256u * h + s]; m_rec[256u * h + s] = (uint16_t)a; a += m; }
       uint32_t *hd = reinterpret_cast<uint32_t *>(Nb);
       hd[0] = J.nd_old; hd[1] = J.nd_rec; hd[2] = J.tot_old; hd[3] = J.tot_rec;
     }
     __syncthreads();
-    {   // first entry of every diagonal
-      uint16_t *g_bold = reinterpret_cast<uint16_t *>(Nb + CL_NHDR);
-      uint16_t *g_brec = reinterpret_cast<uint16_t *>(Nb + CL_NHDR + r16(2u * J.nd_old));
-      for (uint32_t s2 = i; s2 < J.nd_old; s2 += 128u) g_bold[s2] = m_old[s2];
-      for (uint32_t s2 = i; s2 < J.nd_rec; s2 += 128u) g_brec[s2] = m_rec[s2];
-    }
     {
-      unsigned char *perm_old = Nb + 16u, *n_old = Nb + 272u, *perm_rec = Nb + 528u, *n_rec = Nb + 656u;
-      unsigned char *p = Nb + CL_NHDR + r16(2u * J.nd_old) + r16(2u * J.nd_rec);
+      uint16_t *g_bold = reinterpret_cast<uint16_t *>(Nb + CL_NHDR);   // first entry of every diagonal
+      for (uint32_t s2 = i; s2 < J.nd_old; s2 += 128u) g_bold[s2] = m_old[s2];
+      uint16_t *perm_old = reinterpret_cast<uint16_t *>(Nb + 16u);
+      unsigned char *n_old = Nb + 1040u;
+      unsigned char *p = Nb + CL_NHDR + r16(2u * J.nd_old);
       double *v_old = reinterpret_cast<double *>(p);
       p += r16(8u * J.tot_old);
       uint16_t *c_old = reinterpret_cast<uint16_t *>(p);
       p += r16(2u * J.tot_old);
+      unsigned char *perm_rec = p, *n_rec = p + 128u;                    // rank -> row; counts indexed 2*rank + half
+      uint16_t *g_brec = reinterpret_cast<uint16_t *>(p + 384u);           // [2][nd_rec]
+      p += 384u + r16(4u * J.nd_rec);
       double *v_rec = reinterpret_cast<double *>(p);
-      p += r16(8u * J.tot_rec);
-      uint16_t *c_rec = reinterpret_cast<uint16_t *>(p);
-      for (uint32_t h = 0; h < 2u; h++) {
-        perm_old[J.rank_old[h]] = (unsigned char)(i + 128u * h);   // lane-row id: row + 128*half (stored mod 256)
+      uint16_t *c_rec = reinterpret_cast<uint16_t *>(p + r16(8u * J.tot_rec));
+      for (uint32_t h = 0; h < 4u; h++) {
+        perm_old[J.rank_old[h]] = (uint16_t)(i + 128u * h);   // lane-row id: row + 128*quarter
         n_old[J.rank_old[h]] = (unsigned char)J.n_old[h];
         for (uint32_t s = 0; s < J.n_old[h]; s++) {
-          const int64_t e = r.p_far + h + 2u * s;
+          const int64_t e = r.p_far + h + 4u * s;
           const uint32_t pos = (uint32_t)m_old[s] + J.rank_old[h];
           v_old[pos] = val[e];
           c_old[pos] = (uint16_t)((col[e] - blo) % g.ring);
         }
       }
       perm_rec[J.rank_rec] = (unsigned char)i;
-      n_rec[J.rank_rec] = (unsigned char)J.n_rec;
-      for (uint32_t s = 0; s < J.n_rec; s++) {
-        const int64_t e = r.p_old + s;
-        const uint32_t pos = (uint32_t)m_rec[s] + J.rank_rec;
-        v_rec[pos] = val[e];
-        c_rec[pos] = (uint16_t)((col[e] - blo) % g.ring);
+      for (uint32_t h = 0; h < 2u; h++) {
+        n_rec[2u * J.rank_rec + h] = (unsigned char)J.n_rec[h];
+        for (uint32_t s = i; s < J.nd_rec; s += 128u) g_brec[h * J.nd_rec + s] = m_rec[256u * h + s];
+        for (uint32_t s = 0; s < J.n_rec[h]; s++) {
+          const int64_t e = r.p_old + h + 2u * s;
+          const uint32_t pos = (uint32_t)m_rec[256u * h + s] + J.rank_rec;
+          v_rec[pos] = val[e];
+          c_rec[pos] = (uint16_t)((col[e] - blo) % g.ring);
+        }
       }
     }
     __syncthreads();
@@ -282,7 +300,7 @@ struct ClArgs {
   const uint32_t *c0;             // per block (gidx): first 128-row chunk
   uint32_t *prog4;                // per block (gidx) and cluster rank: published hops (the far CTAs wait for all four)
   uint32_t ring;                  // rows of the window ring
-  uint32_t NS, capN;              // staging slots, bytes of the near part of a slot
+  uint32_t smem_total, capN;      // dynamic shared memory of the launch, bytes of the near part of a staging slot
 };
 
 __device__ __forceinline__ bool cl_prog_reached(const uint32_t *p4, uint32_t hops) {
@@ -366,16 +384,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
   const BcArgs &P = A.f;
   extern __shared__ __align__(128) unsigned char smem[];
   // ---- shared-memory carve-up ------------------------------------------------------------------------------
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);            // [0,2) x, [2,2+NS) full, [2+NS,2+2NS) empty
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);            // [0,2) x, [2,4) told ready, [4,4+NS) full, [4+NS,4+2NS) empty
   uint32_t *ctl = reinterpret_cast<uint32_t *>(smem + 128);       // [0] hops landed in the window, [1] hops published, [2] abort
   double *dotbuf = reinterpret_cast<double *>(smem + 192);        // [4] fused dot product of the four ranks (rank 0's copy is used)
-  double *told = reinterpret_cast<double *>(smem + 256);          // [256] partial sums of the old entries per lane-row
-  double *tfull = told + 256;                                     // [128] t of the chunk
+  double *told = reinterpret_cast<double *>(smem + 256);          // [2][512] partial sums of the old entries per lane-row
+  double *tfull = told + 1024;                                    // [128] t of the chunk
   double *part = tfull + 128;                                     // [8][32] partial sums of the mat-vec
   double *dummy = part + 256;                                     // [128] target of the block-start round
-  double *win = dummy + 128;                                      // [ring] solution window (every CTA holds all of it)
+  double *win = dummy + 128;                                      // [ring] solution window (every CTA holds all of it); win[ring] = 0
   unsigned char *stages = reinterpret_cast<unsigned char *>(win + A.ring + 16);
-  const uint32_t stage_bytes = CL_WSTAGE + A.capN;
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   const uint32_t ring_hops = A.ring >> 7;   // a window slot is reused after this many hops
 
@@ -385,6 +402,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
   G.n = 0;
   G.t0 = 0;
   if (tid == 0) { ctl[0] = 0u; ctl[1] = 0u; ctl[2] = 0u; }
+  if (tid < 16u) win[A.ring + tid] = 0.0;
 
   if (blockIdx.x >= CL_S * P.ngroups) {
     // ======================================== far CTA ==========================================================
@@ -398,13 +416,20 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
   // ========================================== chain CTA ==========================================================
   const uint32_t q = cl_ctarank();
   const uint32_t grp = blockIdx.x / CL_S;
+  // staging slots of this rank: its slab is 8(q+1) KiB, so the low ranks get more slots than rank 3
+  const uint32_t wpart = 8192u * (q + 1u);
+  const uint32_t stage_bytes = wpart + A.capN;
+  const uint32_t NS = min(6u, (A.smem_total - (uint32_t)((const unsigned char *)stages - smem)) / stage_bytes);
+  uint64_t *tbar = bars + 2, *fullb = bars + 4, *emptyb = bars + 4 + NS;
   const uint32_t xbar0 = smem_u32(&bars[0]);
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
-    for (uint32_t s = 0; s < A.NS; s++) {
-      mbar_init(&bars[2 + s], 1);
-      mbar_init(&bars[2 + A.NS + s], CL_NT / 32);
+    mbar_init(&tbar[0], 8);
+    mbar_init(&tbar[1], 8);
+    for (uint32_t s = 0; s < NS; s++) {
+      mbar_init(&fullb[s], 1);
+      mbar_init(&emptyb[s], 16);   // 8 compute warps + 8 helper warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&bars[0], 1024);   // rounds 0 and 1
@@ -413,12 +438,19 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
   __syncthreads();
   cl_cluster_sync();
 
-  uint32_t step = 0;   // exchange rounds so far (compute threads): round n uses bars[n & 1], phase (n >> 1) & 1
-  uint32_t hs = 0;     // hops so far (staging ring position; compute threads and producer count alike)
+  uint32_t step = 0;   // exchange rounds before this block (round n: bars[n & 1], phase (n >> 1) & 1); compute threads count on
+  uint32_t hs = 0;     // hops before this block (staging ring / told buffers); every role counts alike
   const uint32_t ncol = 4u * (q + 1u);   // columns of the slab per column group (8 groups)
   const uint32_t wbytes = 8192u * (q + 1u);
-  const bool prof = (P.dbg & 1u) != 0u && P.clk != nullptr && blockIdx.x == 0 && tid == 0;
-  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles of thread 0: stage wait, old entries, barrier 1, x wait, recent, mat-vec, reduce+send, hops
+  const uint32_t prof_cta = (P.dbg & 2u) ? 3u : 0u;   // dbg bit 1: profile rank 3 of cluster 0 instead of rank 0
+  const bool prof_on = (P.dbg & 1u) != 0u && P.clk != nullptr && blockIdx.x == prof_cta;
+  const bool prof = prof_on && tid == 0;
+  long long ph[5] = {0, 0, 0, 0, 0};   // helper thread 0: stage wait, x wait, gathers; producer: tile flags, free slot
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles of thread 0: stage wait, loads, told wait, x wait, recent, mat-vec, reduce+send, hops
+  // remote addresses of the exchange: this thread's window slot and the x barriers in all four CTAs
+  uint32_t rbar[CL_S], rwin[CL_S];
+#pragma unroll
+  for (uint32_t p = 0; p < CL_S; p++) { rbar[p] = cl_mapa(xbar0, p); rwin[p] = cl_mapa(smem_u32(win), p); }
 
   for (uint32_t bi = grp; bi < P.nblocks; bi += P.ngroups) {
     const BcBlock b = P.blocks[bi];
@@ -428,27 +460,31 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
     if (tid < CL_NT) {
       // ------------------------------------------ compute threads ------------------------------------------------
       const uint32_t g = warp, r = lane;
+      const uint32_t rrank = tid >> 1, half = tid & 1u;   // recent entries: lane pair per row, rows in sorted order
       if (tid < 32u) {   // block-start round: nothing to wait for, but every round has the same shape
-        const uint32_t dst = smem_u32(&dummy[32u * q + tid]);
+        const uint32_t off = (uint32_t)((const unsigned char *)&dummy[32u * q + tid] - (const unsigned char *)win);
 #pragma unroll
-        for (uint32_t p = 0; p < CL_S; p++) cl_st_async(cl_mapa(dst, p), 0.0, cl_mapa(xbar0 + 8u * (step & 1u), p));
+        for (uint32_t p = 0; p < CL_S; p++) cl_st_async(rwin[p] + off, 0.0, rbar[p] + 8u * (step & 1u));
       }
-      for (uint32_t K = 0; K < nhop; K++, hs++) {
+      uint32_t pos = 32u * q + tid;   // window slot of this thread's row of the current chunk (threads 0..31)
+      for (uint32_t K = 0; K < nhop; K++) {
+        const uint32_t hp = hs + K;
         long long c_0 = 0, c_1 = 0, c_2 = 0, c_3 = 0, c_4 = 0, c_5 = 0, c_6 = 0;
         if (prof) c_0 = clock64();
-        const uint32_t slot = hs % A.NS;
+        const uint32_t slot = hp % NS;
         const unsigned char *St = stages + (size_t)slot * stage_bytes;
-        BC_WAIT(mbar_try(&bars[2 + slot], (hs / A.NS) & 1u), 0x1200u, 0);
+        BC_WAIT(mbar_try(&fullb[slot], (hp / NS) & 1u), 0x1200u, 0);
         if (prof) c_1 = clock64();
-        const unsigned char *Nb = St + CL_WSTAGE;
-        // start value of this thread's recent lane-row (threads 0..127): the global load flies during the old entries
-        uint32_t rr = 0, nrec = 0;
+        const unsigned char *Nb = St + wpart;
+        const uint32_t nd_old = reinterpret_cast<const uint32_t *>(Nb)[0], nd_rec = reinterpret_cast<const uint32_t *>(Nb)[1];
+        const uint32_t tot_old = reinterpret_cast<const uint32_t *>(Nb)[2], tot_rec = reinterpret_cast<const uint32_t *>(Nb)[3];
+        const unsigned char *prec = Nb + CL_NHDR + r16(2u * nd_old) + r16(8u * tot_old) + r16(2u * tot_old);
+        const uint32_t row = prec[rrank], nrec = prec[128u + tid];
+        // start value of the row (even lane of the pair): the global load flies during the other loads
         double wst = 0.0;
-        if (tid < 128u) {
-          rr = Nb[528u + tid];
-          nrec = Nb[656u + tid];
-          const uint32_t j = b.lo + 128u * K + rr;
-          if (j < b.hi) wst = __ldcg(P.w + j);
+        {
+          const uint32_t j = b.lo + 128u * K + row;
+          if (half == 0u && j < b.hi) wst = __ldcg(P.w + j);
         }
         // slab of Winv_K: this thread's columns [g*ncol, (g+1)*ncol), row r
         double wreg[16];
@@ -457,48 +493,23 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
 #pragma unroll
           for (uint32_t i = 0; i < 16u; i++) wreg[i] = i < ncol ? Ws[i * 32u] : 0.0;
         }
-        // old near entries: jagged diagonals, thread = sorted lane-row, b_old[s] = first entry of diagonal s
-        const uint32_t nd_old = reinterpret_cast<const uint32_t *>(Nb)[0], nd_rec = reinterpret_cast<const uint32_t *>(Nb)[1];
-        const uint32_t tot_old = reinterpret_cast<const uint32_t *>(Nb)[2], tot_rec = reinterpret_cast<const uint32_t *>(Nb)[3];
-        const uint16_t *b_old = reinterpret_cast<const uint16_t *>(Nb + CL_NHDR);
-        const uint16_t *b_rec = reinterpret_cast<const uint16_t *>(Nb + CL_NHDR + r16(2u * nd_old));
-        const unsigned char *pv = Nb + CL_NHDR + r16(2u * nd_old) + r16(2u * nd_rec);
-        const double *v_old = reinterpret_cast<const double *>(pv) + tid;
-        const uint16_t *c_old = reinterpret_cast<const uint16_t *>(pv + r16(8u * tot_old)) + tid;
-        const double *v_rec = reinterpret_cast<const double *>(pv + r16(8u * tot_old) + r16(2u * tot_old)) + tid;
-        const uint16_t *c_rec = reinterpret_cast<const uint16_t *>(pv + r16(8u * tot_old) + r16(2u * tot_old) + r16(8u * tot_rec)) + tid;
-        {
-          const uint32_t lr = Nb[16u + tid], n = Nb[272u + tid];
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-          uint32_t s = 0;
-          for (; s + 3u < n; s += 4u) {
-            const uint32_t e0 = b_old[s], e1 = b_old[s + 1u], e2 = b_old[s + 2u], e3 = b_old[s + 3u];
-            const uint32_t k0 = c_old[e0], k1 = c_old[e1], k2 = c_old[e2], k3 = c_old[e3];
-            const double v0 = v_old[e0], v1 = v_old[e1], v2 = v_old[e2], v3 = v_old[e3];
-            a0 = fma(v0, win[k0], a0);
-            a1 = fma(v1, win[k1], a1);
-            a2 = fma(v2, win[k2], a2);
-            a3 = fma(v3, win[k3], a3);
-          }
-          for (; s < n; s++) {
-            const uint32_t e0 = b_old[s];
-            a0 = fma(v_old[e0], win[c_old[e0]], a0);
-          }
-          told[lr] = (a0 + a1) + (a2 + a3);
-        }
-        // first recent entries into registers (their window values arrive with x of chunk K-1)
-        uint32_t rk0 = 0, rk1 = 0, rk2 = 0, rk3 = 0;
-        double rv0 = 0.0, rv1 = 0.0, rv2 = 0.0, rv3 = 0.0;
-        if (tid < 128u) {
-          if (nrec > 0u) { const uint32_t e = b_rec[0]; rk0 = c_rec[e]; rv0 = v_rec[e]; }
-          if (nrec > 1u) { const uint32_t e = b_rec[1]; rk1 = c_rec[e]; rv1 = v_rec[e]; }
-          if (nrec > 2u) { const uint32_t e = b_rec[2]; rk2 = c_rec[e]; rv2 = v_rec[e]; }
-          if (nrec > 3u) { const uint32_t e = b_rec[3]; rk3 = c_rec[e]; rv3 = v_rec[e]; }
+        // recent entries of the lane pair's row: values and window slots into registers
+        const uint16_t *b_rec = reinterpret_cast<const uint16_t *>(prec + 384u) + half * nd_rec;
+        const double *v_rec = reinterpret_cast<const double *>(prec + 384u + r16(4u * nd_rec)) + rrank;
+        const uint16_t *c_rec = reinterpret_cast<const uint16_t *>(prec + 384u + r16(4u * nd_rec) + r16(8u * tot_rec)) + rrank;
+        double rv[CL_RB];
+        uint32_t rk[CL_RB];
+#pragma unroll
+        for (uint32_t u = 0; u < CL_RB; u++) {
+          rv[u] = 0.0;
+          rk[u] = A.ring;
+          if (u < nrec) { const uint32_t e = b_rec[u]; rv[u] = v_rec[e]; rk[u] = c_rec[e]; }
         }
         if (prof) c_2 = clock64();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        double tb = 0.0;
-        if (tid < 128u) tb = wst - told[rr] - told[128u + rr];
+        // old entries of this chunk (helper warps, one hop ahead)
+        BC_WAIT(mbar_try(&tbar[hp & 1u], (hp >> 1) & 1u), 0x1900u, 0);
+        const double *to = told + 512u * (hp & 1u);
+        double tb = wst - ((to[row] + to[128u + row]) + (to[256u + row] + to[384u + row]));   // (odd lane: not used)
         // own rows of chunk K - ring_hops must have left the window (publisher of this CTA) before they are overwritten
         if (tid == 0u && K >= ring_hops) BC_WAIT(ld_acquire_cta_s(smem_u32(ctl + 1)) + ring_hops > K, 0x1800u, 0);
         if (prof) c_3 = clock64();
@@ -508,13 +519,20 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
         if (tid == 0u) st_release_cta_s(smem_u32(ctl), K);
         step++;
         if (prof) c_4 = clock64();
-        if (tid < 128u) {
-          double a0 = rv0 * win[rk0], a1 = rv1 * win[rk1], a2 = rv2 * win[rk2], a3 = rv3 * win[rk3];
-          for (uint32_t s = 4u; s < nrec; s++) {
-            const uint32_t e0 = b_rec[s];
-            a0 = fma(v_rec[e0], win[c_rec[e0]], a0);
+        {
+          double xv[CL_RB];
+#pragma unroll
+          for (uint32_t u = 0; u < CL_RB; u++) xv[u] = win[rk[u]];
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (uint32_t u = 0; u < CL_RB; u += 2u) {
+            a0 = fma(rv[u], xv[u], a0);
+            a1 = fma(rv[u + 1u], xv[u + 1u], a1);
           }
-          tfull[rr] = tb - ((a0 + a1) + (a2 + a3));
+          for (uint32_t u = CL_RB; u < nrec; u++) { const uint32_t e = b_rec[u]; a0 = fma(v_rec[e], win[c_rec[e]], a0); }
+          a0 += a1;
+          a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+          if (half == 0u) tfull[row] = tb - a0;
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (prof) c_5 = clock64();
@@ -532,17 +550,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
           part[g * 32u + r] = a0 + a1;
         }
         __syncwarp();
-        if (lane == 0u) mbar_arrive(&bars[2 + A.NS + slot]);   // every read of the staging slot is done
+        if (lane == 0u) mbar_arrive(&emptyb[slot]);   // every read of the staging slot by this warp is done
         asm volatile("bar.sync 3, 256;" ::: "memory");
         if (prof) c_6 = clock64();
         if (tid < 32u) {
-          double x = 0.0;
+          const double x = ((part[tid] + part[32u + tid]) + (part[64u + tid] + part[96u + tid])) +
+                           ((part[128u + tid] + part[160u + tid]) + (part[192u + tid] + part[224u + tid]));
+          const uint32_t nb8 = 8u * (step & 1u);
 #pragma unroll
-          for (uint32_t u = 0; u < 8u; u++) x += part[u * 32u + tid];
-          const uint32_t pos = (128u * K + 32u * q + tid) % A.ring;
-          const uint32_t dst = smem_u32(&win[pos]);
-#pragma unroll
-          for (uint32_t p = 0; p < CL_S; p++) cl_st_async(cl_mapa(dst, p), x, cl_mapa(xbar0 + 8u * (step & 1u), p));
+          for (uint32_t p = 0; p < CL_S; p++) cl_st_async(rwin[p] + 8u * pos, x, rbar[p] + nb8);
+          pos += 128u;
+          if (pos >= A.ring) pos -= A.ring;
         }
         if (prof) {
           pc[0] += c_1 - c_0; pc[1] += c_2 - c_1; pc[2] += c_3 - c_2; pc[3] += c_4 - c_3; pc[4] += c_5 - c_4; pc[5] += c_6 - c_5;
@@ -564,14 +582,16 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
         const int64_t o_mine = A.offN[c0 + min(base + lane, nhop)];
         for (uint32_t l = 0; l < 31u && base + l < nhop; l++, hp++) {
           const uint32_t K = base + l;
-          const uint32_t slot = hp % A.NS, use = hp / A.NS;
+          const uint32_t slot = hp % NS, use = hp / NS;
           const int64_t o0 = __shfl_sync(0xffffffffu, o_mine, (int)l), o1 = __shfl_sync(0xffffffffu, o_mine, (int)l + 1);
           // the start vector of the chunk's rows must be complete: far tiles covering 32-row chunks 4K .. 4K+3
           const uint32_t tl = min(4u * K + 3u, nch32 - 1u) / P.tile;
+          long long q0 = 0;
+          if (prof_on) q0 = clock64();
           while (tiles_known <= tl) {   // lanes look at consecutive tile flags, the leading run of set flags is taken
             const uint32_t t = tiles_known + lane;
             const bool set = t < ntile && ld_acquire_gpu(P.tileflag + b.tile0 + t) != 0u;
-            const uint32_t run = (uint32_t)__ffs((int)~__ballot_sync(0xffffffffu, set)) - 1u;   // 32 set flags: ffs(0) - 1 wraps, handled below
+            const uint32_t run = (uint32_t)__ffs((int)~__ballot_sync(0xffffffffu, set)) - 1u;   // all 32 set: ffs(0) - 1 wraps
             tiles_known += (run > 32u) ? 32u : run;
             if (tiles_known <= tl) {
               if (guard_poll(G, 0x1600u)) break;
@@ -579,19 +599,21 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
             }
           }
           G.n = 0;
+          long long q1 = 0;
+          if (prof_on) q1 = clock64();
           if (lane == 0u) {
-            if (use > 0u) BC_WAIT(mbar_try(&bars[2 + A.NS + slot], (use - 1u) & 1u), 0x1500u, 20);
+            if (use > 0u) BC_WAIT(mbar_try(&emptyb[slot], (use - 1u) & 1u), 0x1500u, 20);
+            if (prof_on) { ph[3] += q1 - q0; ph[4] += clock64() - q1; }
             const uint32_t nbytes = (uint32_t)(o1 - o0);
             unsigned char *St = stages + (size_t)slot * stage_bytes;
-            mbar_expect_tx(&bars[2 + slot], wbytes + nbytes);
-            bulk_g2s(St, A.wslab + (size_t)(c0 + K) * CL_WCHUNK + cl_slab_off(q), wbytes, &bars[2 + slot]);
-            bulk_g2s(St + CL_WSTAGE, A.blobN + o0, nbytes, &bars[2 + slot]);
+            mbar_expect_tx(&fullb[slot], wbytes + nbytes);
+            bulk_g2s(St, A.wslab + (size_t)(c0 + K) * CL_WCHUNK + cl_slab_off(q), wbytes, &fullb[slot]);
+            bulk_g2s(St + wpart, A.blobN + o0, nbytes, &fullb[slot]);
           }
           __syncwarp();
         }
       }
-      hs += nhop;
-    } else {
+    } else if (warp == 9u) {
       // ------------------------------------------ publisher: this rank's 32 rows of every chunk ------------------------
       uint32_t done = 0;
       double dot = 0.0;
@@ -633,8 +655,79 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
         const uint32_t dst = cl_mapa(smem_u32(&dotbuf[q]), 0u);
         asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst), "d"(dot) : "memory");
       }
-      hs += nhop;
+    } else {
+      // ------------------------------------------ helpers: old near entries, one hop ahead ---------------------------
+      // x of chunk K-2 is the newest value an old entry of chunk K can read: it has landed when round step + K - 1 is
+      // complete (round `step` is the block-start round), i.e. while the compute threads still work on chunk K-1
+      const uint32_t ht = tid - 320u;   // sorted lane-rows ht (long) and 511 - ht (short)
+      for (uint32_t K = 0; K < nhop; K++) {
+        const uint32_t hp = hs + K;
+        const uint32_t slot = hp % NS;
+        const unsigned char *Nb = stages + (size_t)slot * stage_bytes + wpart;
+        long long h0 = 0, h1 = 0, h2 = 0;
+        if (prof_on) h0 = clock64();
+        BC_WAIT(mbar_try(&fullb[slot], (hp / NS) & 1u), 0x1A00u, 0);
+        if (prof_on) h1 = clock64();
+        const uint32_t nd_old = reinterpret_cast<const uint32_t *>(Nb)[0], tot_old = reinterpret_cast<const uint32_t *>(Nb)[2];
+        const uint16_t *b_old = reinterpret_cast<const uint16_t *>(Nb + CL_NHDR);
+        const double *v_old = reinterpret_cast<const double *>(Nb + CL_NHDR + r16(2u * nd_old));
+        const uint16_t *c_old = reinterpret_cast<const uint16_t *>(Nb + CL_NHDR + r16(2u * nd_old) + r16(8u * tot_old));
+        const uint16_t *perm = reinterpret_cast<const uint16_t *>(Nb + 16u);
+        const uint32_t lrA = perm[ht], lrB = perm[511u - ht];
+        const uint32_t nA = Nb[1040u + ht], nB = Nb[1040u + 511u - ht];
+        constexpr uint32_t HB = 8;   // entries of the long lane-row held in registers before x arrives
+        double hv[HB];
+        uint32_t hk[HB];
+#pragma unroll
+        for (uint32_t u = 0; u < HB; u++) {
+          hv[u] = 0.0;
+          hk[u] = A.ring;
+          if (u < nA) { const uint32_t e = b_old[u] + ht; hv[u] = v_old[e]; hk[u] = c_old[e]; }
+        }
+        double bv = 0.0;
+        uint32_t bk = A.ring;
+        if (nB > 0u) { const uint32_t e = b_old[0] + 511u - ht; bv = v_old[e]; bk = c_old[e]; }
+        if (prof_on) h2 = clock64();
+        if (K >= 1u) {
+          const uint32_t rn = step + K - 1u;
+          BC_WAIT(cl_mbar_try_cluster(xbar0 + 8u * (rn & 1u), (rn >> 1) & 1u), 0x1B00u, 0);
+        }
+        long long h3 = 0;
+        if (prof_on) h3 = clock64();
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        {
+          double xv[HB];
+#pragma unroll
+          for (uint32_t u = 0; u < HB; u++) xv[u] = win[hk[u]];
+#pragma unroll
+          for (uint32_t u = 0; u < HB; u += 4u) {
+            a0 = fma(hv[u], xv[u], a0);
+            a1 = fma(hv[u + 1u], xv[u + 1u], a1);
+            a2 = fma(hv[u + 2u], xv[u + 2u], a2);
+            a3 = fma(hv[u + 3u], xv[u + 3u], a3);
+          }
+        }
+        double bsum = bv * win[bk];
+        for (uint32_t s = HB; s < nA; s++) {
+          const uint32_t e0 = b_old[s] + ht;
+          a0 = fma(v_old[e0], win[c_old[e0]], a0);
+        }
+        for (uint32_t s2 = 1; s2 < nB; s2++) {
+          const uint32_t e0 = b_old[s2] + 511u - ht;
+          bsum = fma(v_old[e0], win[c_old[e0]], bsum);
+        }
+        told[512u * (hp & 1u) + lrA] = (a0 + a1) + (a2 + a3);
+        told[512u * (hp & 1u) + lrB] = bsum;
+        __syncwarp();
+        if (lane == 0u) {
+          mbar_arrive(&tbar[hp & 1u]);
+          mbar_arrive(&emptyb[slot]);
+        }
+        if (prof_on) { ph[0] += h1 - h0; ph[1] += h3 - h2; ph[2] += (h2 - h1) + (clock64() - h3); }
+      }
+      step += nhop + 1u;
     }
+    hs += nhop;
     __syncthreads();
     cl_cluster_sync();
     if (tid == 0) {
@@ -647,7 +740,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
   }
   if (prof) {
     for (int i = 0; i < 8; i++) P.clk[3 + i] = (unsigned long long)pc[i];
+    P.clk[2] = NS;
   }
+  if (prof_on && tid == 320u)
+    for (int i = 0; i < 3; i++) P.clk[11 + i] = (unsigned long long)ph[i];
+  if (prof_on && tid == 256u) { P.clk[14] = (unsigned long long)ph[3]; P.clk[15] = (unsigned long long)ph[4]; }
   __syncthreads();
   cl_cluster_sync();   // nobody leaves while a peer may still write into its shared memory
 }
@@ -655,7 +752,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-constexpr int64_t CL_FIXED_SMEM = 6400;   // barriers, control words, told / tfull / part / dummy
+constexpr int64_t CL_FIXED_SMEM = 256 + 8 * (1024 + 128 + 256 + 128);   // barriers, control words, told / tfull / part / dummy
 
 static size_t cl_smem_bytes(uint32_t ring, uint32_t NS, uint32_t capN) {
   return (size_t)CL_FIXED_SMEM + ((size_t)ring + 16) * 8 + (size_t)NS * (CL_WSTAGE + capN);
@@ -758,10 +855,8 @@ static int cl_launch(rcg_handle *h, BlockedDev &B, BcArgs a, const GroupHost &G,
   A.wslab = C.wslab; A.blobN = C.blobN; A.offN = C.offN; A.c0 = C.c0; A.prog4 = C.prog4;
   A.ring = C.ring;
   A.capN = C.level_cap[gi];
-  uint32_t NS = 4;
-  while (NS > 2 && cl_smem_bytes(C.ring, NS, A.capN) > (size_t)BC_SMEM_MAX) NS--;
-  A.NS = NS;
-  const size_t smem = cl_smem_bytes(C.ring, NS, A.capN);
+  const size_t smem = (size_t)BC_SMEM_MAX;   // every rank fills it with as many staging slots as fit (at least two)
+  A.smem_total = (uint32_t)smem;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(CL_THREADS);
   cfg.dynamicSmemBytes = smem;

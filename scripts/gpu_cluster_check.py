@@ -31,9 +31,9 @@ for kind, n, T, opts in cases:
 for n in big:
     n = int(n)
     A, b, G, part, f = make_problem("lap3d", n, 8)
-    for mode in (0, 4):
+    for mode, kw in ((0, {}), (4, {}), (4, dict(chain_window=2048))):
         try:
-            with capi.Solver(0, chain_mode=mode) as s:
+            with capi.Solver(0, chain_mode=mode, **kw) as s:
                 s.set_matrix(*A); s.set_factor(*G, part)
                 z = s.precond(b)
                 line = []
@@ -42,18 +42,20 @@ for n in big:
                         line.append(f"{dn}{gi}[{g['blocks']}b,{g['rows']}r] {s.time_group(direction, gi, 0, 3):.3f}")
                 x, relres, itr = s.pcg(b, 1e-8, 500)
                 st = s.stats()
-                print(f"lap3d {n} T=8 mode {mode}: itr {itr} relres {relres:.2e} solve {st['solve_ms']:.1f} ms | " + " ".join(line), flush=True)
+                print(f"lap3d {n} T=8 mode {mode} {kw}: itr {itr} relres {relres:.2e} solve {st['solve_ms']:.1f} ms | " + " ".join(line), flush=True)
                 if mode == 0: z0 = z
                 else: print("   precond mode4 vs mode0:", relerr(z, z0))
             if mode == 4:
-                with capi.Solver(0, chain_mode=4, dbg=1) as s:
-                    s.set_matrix(*A); s.set_factor(*G, part)
-                    for direction, dn in ((capi.TRSV_FORWARD, "fwd"), (capi.TRSV_BACKWARD, "bwd")):
-                        gi = 0 if direction == capi.TRSV_FORWARD else len(s.groups(direction)) - 1
-                        ms = s.time_group(direction, gi, 0, 1)
-                        c = s.counters()
-                        hops = max(c[10], 1)
-                        names = ["stage wait", "old", "bar1+pub", "x wait", "recent", "matvec", "reduce+send"]
-                        print(f"   {dn} leaf level {ms:.3f} ms, {hops} hops of CTA 0: " + ", ".join(f"{nm} {c[3 + i] / hops:.0f}" for i, nm in enumerate(names)), flush=True)
+                for dbg in (1, 3):
+                    with capi.Solver(0, chain_mode=4, dbg=dbg, **kw) as s:
+                        s.set_matrix(*A); s.set_factor(*G, part)
+                        for direction, dn in ((capi.TRSV_FORWARD, "fwd"), (capi.TRSV_BACKWARD, "bwd")):
+                            gi = 0 if direction == capi.TRSV_FORWARD else len(s.groups(direction)) - 1
+                            ms = s.time_group(direction, gi, 0, 1)
+                            c = s.counters()
+                            hops = max(c[10], 1)
+                            names = ["stage wait", "loads", "told wait", "x wait", "recent", "matvec", "reduce+send"]
+                            print(f"   rank {0 if dbg == 1 else 3} {dn} leaf level {ms:.3f} ms, {hops} hops, NS {c[2]}: " + ", ".join(f"{nm} {c[3 + i] / hops:.0f}" for i, nm in enumerate(names))
+                                  + f" | helper: stage {c[11] / hops:.0f}, x {c[12] / hops:.0f}, gather {c[13] / hops:.0f} | producer: tiles {c[14] / hops:.0f}, slot {c[15] / hops:.0f}", flush=True)
         except Exception as e:
             print(f"lap3d {n} mode {mode}: FAILED {e}", flush=True)

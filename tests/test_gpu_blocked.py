@@ -62,7 +62,8 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
                                   dict(chain_window=8192), dict(plain_launch=True), dict(use_graph=False, chain_window=1024),
                                   dict(chain_mode=1), dict(chain_mode=3), dict(sep_window=4096), dict(chain_window=2048, sep_window=2048),
                                   dict(early=6), dict(early=3, recent=2), dict(early=8, chain_mode=3),
-                                  dict(capb_quarters=4), dict(slots_a=2), dict(sep_tile=1), dict(sep_tile=8, far_lanes2=32), dict(early_sep=16), dict(early_sep=3, early=5), dict(sep_tile=4, chain_window=1024), dict(capb_quarters=5, slots_a=6, chain_window=2048)])
+                                  dict(capb_quarters=4), dict(slots_a=2), dict(sep_tile=1), dict(sep_tile=8, far_lanes2=32), dict(early_sep=16), dict(early_sep=3, early=5), dict(sep_tile=4, chain_window=1024), dict(capb_quarters=5, slots_a=6, chain_window=2048),
+                                  dict(chain_mode=4), dict(chain_mode=4, chain_window=1024), dict(chain_mode=4, use_graph=False, chain_window=2048)])
 @pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 33, 2), ("aniso2d", 160, 4), ("lap3d", 40, 0)])
 def test_blocked_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
@@ -91,3 +92,28 @@ def test_many_leaves_more_blocks_than_chain_ctas(capi, oracle):
         s.set_factor(*G, part)
         assert relerr(s.trsv(capi.TRSV_FORWARD, b), yo) <= TRSV_TOL
         assert relerr(s.precond(b), zo) <= TRSV_TOL
+
+
+@needs_producer
+@pytest.mark.parametrize("kind,n,threads", [("lap3d", 48, 256), ("lap3d", 64, 8), ("lap3d", 5, 2)])
+def test_cluster_chain_vs_oracle_and_32_row_chain(capi, oracle, kind, n, threads):
+    """chain_mode 4 (rcg_cluster.cuh): leaf blocks on the cluster chain (128-row chunks, 4 CTAs per leaf, DSMEM exchange).
+    Many small leaves (every cluster walks several blocks), leaves longer than the window (far tiles inside the own
+    block, publisher back-pressure), and blocks shorter than one chunk; PCG with the fused r.z must converge like the
+    oracle, and reruns must be bit-identical."""
+    A, b, G, part, f = make_problem(kind, n, threads)
+    yo = oracle.trsv_forward(*G, b)
+    zo = oracle.trsv_backward(*G, yo)
+    with capi.Solver(0, chain_mode=4) as s:
+        s.set_matrix(*A)
+        s.set_factor(*G, part)
+        assert relerr(s.trsv(capi.TRSV_FORWARD, b), yo) <= TRSV_TOL
+        assert relerr(s.trsv(capi.TRSV_BACKWARD, yo), zo) <= TRSV_TOL
+        z1 = s.precond(b)
+        z2 = s.precond(b)
+        assert relerr(z1, zo) <= TRSV_TOL and np.array_equal(z1, z2)
+        x, relres, itr = s.pcg(b, 1e-8, 500)
+        x2, relres2, itr2 = s.pcg(b, 1e-8, 500)
+        o = oracle.pcg(A, b, 1e-8, 500, G)
+        assert abs(itr - o["itr"]) <= 1 and relres <= 2e-8
+        assert itr2 == itr and np.array_equal(x, x2)
