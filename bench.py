@@ -337,6 +337,16 @@ def run_ours_single(args, d, B_iter, gen_info=None):
                    sample=f"{it} PCG iterations (of {iters_total // args.steps} to convergence) on the full {args.n}^3 problem, "
                           f"{dt:.1f} s", ms_per_iter=1e3 * dt / it, detail=detail)
 
+    # ---- informational: the same workload with the leaf level on the cluster chain (chain_mode 4) -----------
+    cluster = None
+    if not args.no_cluster_leg:
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "cluster_leg.py"), str(args.n), str(args.threads), "2"],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
+            cluster = json.loads(p.stdout.strip().splitlines()[-1]) if p.returncode == 0 else dict(error=p.stderr[-300:])
+        except Exception as e:  # pragma: no cover - informational leg
+            cluster = dict(error=str(e)[:300])
+
     line = dict(metric="pcg_gbps_per_iter", value=value, unit="GB/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
                 ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                 dtype="f64", data="synthetic", config=workload_config(args, d, N),
@@ -346,7 +356,7 @@ def run_ours_single(args, d, B_iter, gen_info=None):
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit="GB/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                          steps=e2e_steps, ms_per_step=e2e_ms / e2e_steps, host_memory="pageable (caller's SparseCSR arrays)"),
-                gpu_launches=int(launches), clocks=clocks, device_reorder=reorder_info,
+                gpu_launches=int(launches), clocks=clocks, device_reorder=reorder_info, cluster_chain_opt_in=cluster,
                 setup=dict(upload_ms=st0["upload_ms"], analysis_ms=st0["analysis_ms"], wall_s=setup_wall))
     print(json.dumps(line), flush=True)
 
@@ -362,6 +372,7 @@ def main():
     ap.add_argument("--sample-iters", type=int, default=4, help="PCG iterations per CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cluster-leg", action="store_true", help="skip the informational chain_mode 4 run")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))

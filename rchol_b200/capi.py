@@ -318,6 +318,12 @@ class Solver:
         self._check(self._L.rcg_debug_counters(self._h, out))
         return [int(v) for v in out]
 
+    def cluster_levels(self, direction: int) -> int:
+        """Tree levels of one direction that are launched on the cluster chain (chain_mode 4); 0 = 32-row chain everywhere."""
+        info = (C.c_uint64 * 16)()
+        self._check(self._L.rcg_debug_blocked_info(self._h, int(direction), info))
+        return int(info[15])
+
     def blocked_layout(self, direction: int) -> dict:
         """Raw copy of the blocked triangular-solve layout of one direction (tests/blocked_emulator.py interprets it)."""
         info = (C.c_uint64 * 16)()

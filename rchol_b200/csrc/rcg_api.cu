@@ -563,6 +563,11 @@ int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16) {
   info16[12] = B.Dfar_sep;
   info16[13] = B.tile_sep;
   info16[14] = B.E_sep;
+  {   // levels launched on the cluster chain (chain_mode 4)
+    uint64_t n = 0;
+    if (B.cl.on) for (int v : B.cl.level_on) n += v ? 1 : 0;
+    info16[15] = n;
+  }
   return RCG_OK;
 }
 

@@ -18,7 +18,8 @@ constexpr uint32_t CL_THREADS = 576;         // + producer warp (8) + publisher 
 constexpr uint32_t CL_WCHUNK = 81920;        // bytes of the four slabs of one chunk: 8 + 16 + 24 + 32 KiB
 constexpr uint32_t CL_WSTAGE = 32768;        // slab part of a staging slot
 constexpr uint32_t CL_NHDR = 1552;           // near blob: 16 B header, perm_old[512] (u16), n_old[512] (u8)
-constexpr uint32_t CL_RB = 6;                // recent ELL slots held in registers
+constexpr uint32_t CL_RB = 6;                // recent entries per lane held in registers
+constexpr uint32_t CL_SV = 1040;             // start vector of a chunk inside a staging slot: 130 doubles (16-byte aligned source)
 __host__ __device__ __forceinline__ uint32_t cl_slab_off(uint32_t q) { return 4096u * q * (q + 1u); }
 
 struct ClGeom {               // cluster-solved blocks in ascending chunk order
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
   const uint32_t grp = blockIdx.x / CL_S;
   // staging slots of this rank: its slab is 8(q+1) KiB, so the low ranks get more slots than rank 3
   const uint32_t wpart = 8192u * (q + 1u);
-  const uint32_t stage_bytes = wpart + A.capN;
+  const uint32_t stage_bytes = wpart + CL_SV + A.capN;
   const uint32_t NS = min(6u, (A.smem_total - (uint32_t)((const unsigned char *)stages - smem)) / stage_bytes);
   uint64_t *tbar = bars + 2, *fullb = bars + 4, *emptyb = bars + 4 + NS;
   const uint32_t xbar0 = smem_u32(&bars[0]);
@@ -475,16 +476,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
         const unsigned char *St = stages + (size_t)slot * stage_bytes;
         BC_WAIT(mbar_try(&fullb[slot], (hp / NS) & 1u), 0x1200u, 0);
         if (prof) c_1 = clock64();
-        const unsigned char *Nb = St + wpart;
+        const double *sv = reinterpret_cast<const double *>(St + wpart);   // start vector, staged by the producer
+        const unsigned char *Nb = St + wpart + CL_SV;
         const uint32_t nd_old = reinterpret_cast<const uint32_t *>(Nb)[0], nd_rec = reinterpret_cast<const uint32_t *>(Nb)[1];
         const uint32_t tot_old = reinterpret_cast<const uint32_t *>(Nb)[2], tot_rec = reinterpret_cast<const uint32_t *>(Nb)[3];
         const unsigned char *prec = Nb + CL_NHDR + r16(2u * nd_old) + r16(8u * tot_old) + r16(2u * tot_old);
         const uint32_t row = prec[rrank], nrec = prec[128u + tid];
-        // start value of the row (even lane of the pair): the global load flies during the other loads
+        // start value of the row (even lane of the pair)
         double wst = 0.0;
         {
-          const uint32_t j = b.lo + 128u * K + row;
-          if (half == 0u && j < b.hi) wst = __ldcg(P.w + j);
+          const uint32_t j0 = b.lo + 128u * K;
+          if (half == 0u && j0 + row < b.hi) wst = sv[(j0 & 1u) + row];
         }
         // slab of Winv_K: this thread's columns [g*ncol, (g+1)*ncol), row r
         double wreg[16];
@@ -606,9 +608,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
             if (prof_on) { ph[3] += q1 - q0; ph[4] += clock64() - q1; }
             const uint32_t nbytes = (uint32_t)(o1 - o0);
             unsigned char *St = stages + (size_t)slot * stage_bytes;
-            mbar_expect_tx(&fullb[slot], wbytes + nbytes);
+            // start vector of the chunk's rows: written by the far CTAs (generic proxy, released with the tile flags that
+            // were acquired above), read here through the async proxy; 16-byte aligned source, even number of doubles
+            const uint32_t j0 = b.lo + 128u * K, al = j0 & 1u;
+            const uint32_t svbytes = 8u * ((min(128u, b.hi - j0) + al + 1u) & ~1u);
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            mbar_expect_tx(&fullb[slot], wbytes + nbytes + svbytes);
             bulk_g2s(St, A.wslab + (size_t)(c0 + K) * CL_WCHUNK + cl_slab_off(q), wbytes, &fullb[slot]);
-            bulk_g2s(St + wpart, A.blobN + o0, nbytes, &fullb[slot]);
+            bulk_g2s(St + wpart, P.w + (j0 - al), svbytes, &fullb[slot]);
+            bulk_g2s(St + wpart + CL_SV, A.blobN + o0, nbytes, &fullb[slot]);
           }
           __syncwarp();
         }
@@ -663,7 +671,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
       for (uint32_t K = 0; K < nhop; K++) {
         const uint32_t hp = hs + K;
         const uint32_t slot = hp % NS;
-        const unsigned char *Nb = stages + (size_t)slot * stage_bytes + wpart;
+        const unsigned char *Nb = stages + (size_t)slot * stage_bytes + wpart + CL_SV;
         long long h0 = 0, h1 = 0, h2 = 0;
         if (prof_on) h0 = clock64();
         BC_WAIT(mbar_try(&fullb[slot], (hp / NS) & 1u), 0x1A00u, 0);
@@ -755,7 +763,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cl_solve(const ClArgs A) {
 constexpr int64_t CL_FIXED_SMEM = 256 + 8 * (1024 + 128 + 256 + 128);   // barriers, control words, told / tfull / part / dummy
 
 static size_t cl_smem_bytes(uint32_t ring, uint32_t NS, uint32_t capN) {
-  return (size_t)CL_FIXED_SMEM + ((size_t)ring + 16) * 8 + (size_t)NS * (CL_WSTAGE + capN);
+  return (size_t)CL_FIXED_SMEM + ((size_t)ring + 16) * 8 + (size_t)NS * (CL_WSTAGE + CL_SV + capN);
 }
 
 // Builds the cluster layout of the leaf-level blocks (called from rcg_build_blocked while `comb` is alive).
