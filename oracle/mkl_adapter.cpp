@@ -2,7 +2,9 @@
 // against MKL's ILP64 interface, `#define MKL_INT size_t`, /root/reference/c++/util/pcg.cpp:3) and the
 // genuine oneMKL 2024.2 LP64 sparse kernels exported by libtorch_cpu.so.  The arithmetic of SpMV and of
 // both triangular solves is MKL's own; only the five CBLAS level-1 routines are restated here because
-// libtorch_cpu.so does not export them.
+// libtorch_cpu.so does not export them; they are OpenMP loops, because the CBLAS of a threaded MKL (what the
+// reference links, /root/reference/c++/Makefile:6) runs them on all cores - a serial stand-in would make the
+// reference arm of bench.py slower than the real thing.
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -36,7 +38,9 @@ int rchol_b200_mkl_create_csr(sparse_matrix_t *A, int indexing, size_t rows, siz
   h->rs = (int *)malloc((rows + 1) * sizeof(int));
   h->re = (int *)malloc((rows + 1) * sizeof(int));
   h->ci = (int *)malloc((nnz + 1) * sizeof(int));
+#pragma omp parallel for schedule(static)
   for (size_t i = 0; i < rows; i++) { h->rs[i] = (int)rows_start[i]; h->re[i] = (int)rows_end[i]; }
+#pragma omp parallel for schedule(static)
   for (size_t k = 0; k < nnz; k++) h->ci[k] = (int)col_indx[k];
   int st = mkl_sparse_d_create_csr(&h->mkl, indexing, (int)rows, (int)cols, h->rs, h->re, h->ci, values);
   *A = h;
@@ -59,22 +63,27 @@ int rchol_b200_mkl_destroy(sparse_matrix_t A) {
 }
 
 void rchol_b200_cblas_dcopy(size_t n, const double *x, size_t, double *y, size_t) {
+#pragma omp parallel for schedule(static)
   for (size_t i = 0; i < n; i++) y[i] = x[i];
 }
 double rchol_b200_cblas_ddot(size_t n, const double *x, size_t, const double *y, size_t) {
   double s = 0;
+#pragma omp parallel for schedule(static) reduction(+ : s)
   for (size_t i = 0; i < n; i++) s += x[i] * y[i];
   return s;
 }
 double rchol_b200_cblas_dnrm2(size_t n, const double *x, size_t) {
   double s = 0;
+#pragma omp parallel for schedule(static) reduction(+ : s)
   for (size_t i = 0; i < n; i++) s += x[i] * x[i];
   return std::sqrt(s);
 }
 void rchol_b200_cblas_dscal(size_t n, double a, double *x, size_t) {
+#pragma omp parallel for schedule(static)
   for (size_t i = 0; i < n; i++) x[i] *= a;
 }
 void rchol_b200_cblas_daxpy(size_t n, double a, const double *x, size_t, double *y, size_t) {
+#pragma omp parallel for schedule(static)
   for (size_t i = 0; i < n; i++) y[i] += a * x[i];
 }
 
