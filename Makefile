@@ -31,5 +31,15 @@ driver: rchol_b200/cxx/ex_laplace_parallel.cpp $(CXXLIB)
 	$(HOSTCXX) -O2 -std=c++17 -o rchol_b200/lib/ex_laplace_parallel $< -Irchol_b200/cxx -Lrchol_b200/lib -lrchol_b200_cxx -lrchol_b200 \
 	    -Lbaseline/_ref -lrchol_producer -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../../baseline/_ref'
 
+# Drop-in proof: the reference's own example mains, UNMODIFIED and compiled where they lie (fed through stdin so that
+# their `#include "sparse.hpp" / "util.hpp" / "pcg.hpp"` resolve to rchol_b200/cxx instead of the file's own directory),
+# linked against our pcg class and the reference factorization.  Outputs into baseline/_ref (git-ignored, travels).
+REF ?= /root/reference/c++
+refmains: $(CXXLIB)
+	for m in ex_laplace ex_laplace_parallel; do \
+	  $(HOSTCXX) -O2 -std=c++17 -w -x c++ - -o baseline/_ref/ref_$$m -Irchol_b200/cxx -I$(REF)/rchol \
+	    -Lrchol_b200/lib -lrchol_b200_cxx -lrchol_b200 -Lbaseline/_ref -lrchol_producer \
+	    -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../../rchol_b200/lib' < $(REF)/$$m.cpp || exit 1; done
+
 clean:
-	rm -f $(OBJ) $(LIB) $(CXXLIB) rchol_b200/lib/ex_laplace_parallel
+	rm -f $(OBJ) $(LIB) $(CXXLIB) rchol_b200/lib/ex_laplace_parallel baseline/_ref/ref_ex_laplace baseline/_ref/ref_ex_laplace_parallel

@@ -256,3 +256,21 @@ int main(int argc, char **argv) {
     assert d["P"] is None and d["part"] is None and d["b"] is None
     with pytest.raises(ValueError):
         problems.load_problem(src)                                       # not a problem file
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/c++"), reason="reference sources not mounted")
+def test_unmodified_reference_mains_build_on_our_pcg_and_fail_loudly_without_a_gpu():
+    """Drop-in boundary: /root/reference/c++/ex_laplace.cpp and ex_laplace_parallel.cpp compile UNCHANGED
+    against rchol_b200/cxx/{sparse,util,pcg}.hpp (`make refmains`) and link our pcg class + the reference factorization.
+    Without a GPU the pcg call must end in an error that names the missing device: there is no CPU fallback."""
+    subprocess.check_call(["make", "refmains"], cwd=ROOT, stdout=subprocess.DEVNULL)
+    import torch
+    for exe, args in (("ref_ex_laplace", ["-n", "6"]), ("ref_ex_laplace_parallel", ["-n", "8", "-t", "2"])):
+        path = os.path.join(ROOT, "baseline", "_ref", exe)
+        assert os.path.exists(path)
+        out = subprocess.run([path] + args, capture_output=True, text=True, timeout=300)
+        assert "Fill-in ratio" in out.stdout                     # the reference factorization ran
+        if not torch.cuda.is_available():
+            assert out.returncode != 0 and "no CPU fallback" in out.stderr, (out.returncode, out.stderr[-300:])
+        else:
+            assert out.returncode == 0 and "Relative residual" in out.stdout, out.stderr[-300:]
