@@ -61,3 +61,52 @@ def test_oracle_vs_live_reference_pcg():
     assert relerr(o["x"], ref["x"]) < 1e-12
     Ar, y, z = oracle.reference_mkl_kernels(A, G, b)
     assert relerr(oracle.trsv_forward(*G, b), y) < 1e-13 and relerr(oracle.precond(*G, b), z) < 1e-13
+
+
+def _random_upper(n, density, rng):
+    """Random upper-triangular CSR with the layout the reference factor has: diagonal first (> 0), then sorted columns."""
+    import scipy.sparse as sp
+    M = sp.random(n, n, density=density, random_state=rng, format="csr", data_rvs=lambda k: -rng.uniform(0.05, 1.0, k))
+    U = sp.triu(M, k=1).tocsr()
+    U.sort_indices()
+    rowsum = np.abs(U).sum(axis=1).A1 + np.abs(U).sum(axis=0).A1
+    U = (U + sp.diags(rowsum + rng.uniform(0.5, 1.5, n))).tocsr()
+    U.sort_indices()                                         # diagonal is the smallest column of an upper-triangular row
+    return U
+
+
+@pytest.mark.parametrize("n,density,seed", [(1, 1.0, 0), (2, 1.0, 1), (7, 0.0, 2), (50, 0.2, 3), (400, 0.02, 4), (400, 0.3, 5)])
+def test_triangular_solves_and_spmv_against_scipy(n, density, seed):
+    """Third statement of the three kernels (SciPy), independent of MKL and of the C restatement: random upper-triangular
+    factors including the edge cases N = 1, a dense 2 x 2, and a diagonal-only factor (empty off-diagonal rows)."""
+    from scipy.sparse.linalg import spsolve_triangular
+    rng = np.random.default_rng(seed)
+    U = _random_upper(n, density, rng)
+    G = (U.indptr.astype(np.uint64), U.indices.astype(np.uint64), U.data.astype(np.float64))
+    b = rng.standard_normal(n)
+    y_ref = spsolve_triangular(U.T.tocsr(), b, lower=True)
+    z_ref = spsolve_triangular(U, y_ref, lower=False)
+    y = oracle.trsv_forward(*G, b)
+    assert relerr(y, y_ref) < 1e-13
+    assert relerr(oracle.trsv_backward(*G, y), z_ref) < 1e-13
+    assert relerr(oracle.precond(*G, b), z_ref) < 1e-13
+    assert relerr(oracle.spmv(*G, b), U @ b) < 1e-14
+    # the preconditioner is symmetric positive definite: <u, M^-1 v> = <M^-1 u, v>
+    u, v = rng.standard_normal(n), rng.standard_normal(n)
+    assert abs(u @ oracle.precond(*G, v) - oracle.precond(*G, u) @ v) <= 1e-12 * (np.linalg.norm(u) * np.linalg.norm(v) + 1)
+
+
+def test_pcg_with_exact_factor_converges_in_one_iteration():
+    """With G = chol(A)^T the preconditioner is A^-1: one iteration, whatever the tolerance (pcg.cpp:82-112)."""
+    import scipy.sparse as sp
+    from rchol_b200 import problems
+    rp, ci, v = problems.laplace_3d(4)
+    N = rp.shape[0] - 1
+    A = sp.csr_matrix((v, ci.astype(np.int64), rp.astype(np.int64)), shape=(N, N))
+    U = sp.csr_matrix(np.triu(np.linalg.cholesky(A.toarray()).T))
+    U.eliminate_zeros(); U.sort_indices()
+    G = (U.indptr.astype(np.uint64), U.indices.astype(np.uint64), U.data)
+    b = problems.random_rhs(N)
+    o = oracle.pcg((rp, ci, v), b, 1e-10, 50, G)
+    assert o["itr"] == 1 and o["relres"] < 1e-13
+    assert relerr(o["x"], np.linalg.solve(A.toarray(), b)) < 1e-12
