@@ -161,26 +161,63 @@ def measured_peak_gbs():
 # ------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the path, bounded sample
 # ------------------------------------------------------------------------------------------------------------
+def _reference_sample_in_child(d, iters: int):
+    """One timed call of the UNMODIFIED reference pcg in a forked child.  Why a child: the reference leaks its set-up
+    copies by design (pcg.cpp:31-54, the `delete[]` is commented out: 16 B per entry of A and G, ~10 GB per call at
+    256^3), so repeated calls in one process run the host out of memory.  The child shares the problem copy-on-write,
+    warms MKL's thread pool on a tiny problem, runs `iters` iterations and reports the seconds spent inside
+    pcg::iteration (marks in oracle/mkl_adapter.cpp: end of the last create_csr -> first destroy), i.e. without the
+    set-up copies that a real solve spreads over ~37 iterations."""
+    rfd, wfd = os.pipe()
+    pid = os.fork()
+    if pid == 0:                                             # child: nothing but the reference call
+        status = 1
+        try:
+            os.close(rfd)
+            from oracle import oracle
+            w = problems.laplace_3d(6)
+            oracle.reference_pcg(w, np.ones(w[0].shape[0] - 1), 1e-30, 2, w)          # warm-up (threads, MKL init)
+            A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
+            t0 = time.time()
+            r = oracle.reference_pcg(A, d["b"], 1e-30, iters, G)                       # tol unreachable: `iters` iterations
+            out = dict(iteration_s=r["iteration_s"], call_s=time.time() - t0, itr=int(r["itr"]))
+            os.write(wfd, json.dumps(out).encode())
+            status = 0
+        except BaseException as e:  # pragma: no cover
+            try:
+                os.write(wfd, json.dumps(dict(error=repr(e)[:300])).encode())
+            except OSError:
+                pass
+        finally:
+            os._exit(status)
+    os.close(wfd)
+    buf = b""
+    while True:
+        chunk = os.read(rfd, 65536)
+        if not chunk:
+            break
+        buf += chunk
+    os.close(rfd)
+    _, st = os.waitpid(pid, 0)
+    if st != 0 or not buf:
+        raise RuntimeError(f"reference child ended with status {st}: {buf[-300:]!r}")
+    out = json.loads(buf.decode())
+    if "error" in out or out["iteration_s"] <= 0:
+        raise RuntimeError(f"reference child: {out}")
+    return out
+
+
 def cpu_sample(d, iters: int, prefer_reference: bool):
     """Runs `iters` PCG iterations on the host cores; returns (seconds, iterations, kind, cores, detail)."""
     from oracle import oracle
     A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
     if prefer_reference and oracle.have_reference_pcg() and int(d["G_rp"][-1]) < 2 ** 31 - 1:
         try:
-            # tol unreachable: exactly maxit iterations.  The constructor is monolithic (create_sparse copies + the
-            # iteration, pcg.cpp:14-28), so the per-iteration time is the difference of a (1 + iters)- and a 1-iteration
-            # call: the set-up is not charged to a 4-iteration sample that a real solve would spread over ~37.
-            t0 = time.time()
-            r1 = oracle.reference_pcg(A, d["b"], 1e-30, 1, G)
-            t1 = time.time()
-            r = oracle.reference_pcg(A, d["b"], 1e-30, 1 + iters, G)
-            t2 = time.time()
-            dt, its = (t2 - t1) - (t1 - t0), r["itr"] - r1["itr"]
-            if dt < 0.1 * (t2 - t1):       # timer noise on a tiny problem: charge the whole longer call instead
-                dt, its = t2 - t1, r["itr"]
-            return dt, its, "reference", os.cpu_count(), dict(
-                what="unmodified reference pcg.cpp + oneMKL SpMV/SpTRSV (libtorch_cpu), OpenMP CBLAS-1 stand-ins",
-                call_1_iteration_s=t1 - t0, call_1_plus_n_iterations_s=t2 - t1)
+            o = _reference_sample_in_child(d, iters)
+            return o["iteration_s"], o["itr"], "reference", os.cpu_count(), dict(
+                what="unmodified reference pcg.cpp + oneMKL SpMV/SpTRSV (libtorch_cpu), OpenMP CBLAS-1 stand-ins; seconds "
+                     "inside pcg::iteration, one forked child per step (the reference leaks its set-up copies)",
+                whole_call_s=o["call_s"])
         except Exception as e:  # pragma: no cover
             log(f"[bench] reference pcg unavailable ({e}); using the oracle port")
     t0 = time.time()
@@ -210,8 +247,8 @@ def run_reference_arm(args, d, B_iter, rank, world):
                 scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                 config=workload_config(args, d, N),
                 cpu_baseline=dict(value=value, unit="GB/s", cores=cores, kind=kind,
-                                  sample=f"{iters} PCG iterations per step on the full {args.n}^3 problem, timed as the difference "
-                                         f"of a {1 + iters}- and a 1-iteration call of the reference pcg (set-up excluded)"),
+                                  sample=f"{iters} PCG iterations per step on the full {args.n}^3 problem; seconds inside the "
+                                         f"reference's pcg::iteration (its set-up copies excluded)"),
                 e2e=dict(value=value, unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0, detail=detail)
     print(json.dumps(line), flush=True)

@@ -5,6 +5,7 @@
 // libtorch_cpu.so does not export them; they are OpenMP loops, because the CBLAS of a threaded MKL (what the
 // reference links, /root/reference/c++/Makefile:6) runs them on all cores - a serial stand-in would make the
 // reference arm of bench.py slower than the real thing.
+#include <chrono>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -28,7 +29,20 @@ struct rchol_b200_ilp64_handle {
 typedef rchol_b200_ilp64_handle *sparse_matrix_t;
 struct matrix_descr { int type, mode, diag; };
 
+// Wall-clock marks around the reference's iteration: pcg::pcg (pcg.cpp:14-28) is create, create, iteration, destroy,
+// destroy - so "end of the last create" to "start of the first destroy after it" is exactly pcg::iteration, without
+// touching the reference source.  Read by bench.py's reference arm (set-up copies are not part of a PCG iteration).
+static double g_mark_create_end = 0.0, g_mark_destroy_start = 0.0;
+static double now_s() {
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
 extern "C" {
+
+double rchol_b200_mkl_iteration_seconds(void) {
+  return g_mark_destroy_start > g_mark_create_end ? g_mark_destroy_start - g_mark_create_end : -1.0;
+}
 
 int rchol_b200_mkl_create_csr(sparse_matrix_t *A, int indexing, size_t rows, size_t cols, size_t *rows_start,
                               size_t *rows_end, size_t *col_indx, double *values) {
@@ -44,6 +58,8 @@ int rchol_b200_mkl_create_csr(sparse_matrix_t *A, int indexing, size_t rows, siz
   for (size_t k = 0; k < nnz; k++) h->ci[k] = (int)col_indx[k];
   int st = mkl_sparse_d_create_csr(&h->mkl, indexing, (int)rows, (int)cols, h->rs, h->re, h->ci, values);
   *A = h;
+  g_mark_create_end = now_s();
+  g_mark_destroy_start = 0.0;
   return st;
 }
 int rchol_b200_mkl_mv(int op, double alpha, const sparse_matrix_t A, matrix_descr d, const double *x,
@@ -56,6 +72,7 @@ int rchol_b200_mkl_trsv(int op, double alpha, const sparse_matrix_t A, matrix_de
   return mkl_sparse_d_trsv(op, alpha, A->mkl, dd, x, y);
 }
 int rchol_b200_mkl_destroy(sparse_matrix_t A) {
+  if (g_mark_destroy_start == 0.0) g_mark_destroy_start = now_s();
   int st = mkl_sparse_destroy(A->mkl);
   free(A->rs); free(A->re); free(A->ci);
   delete A;

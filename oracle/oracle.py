@@ -149,4 +149,7 @@ def reference_pcg(A, b, tol, maxit, G):
     _load_ref().refpcg_run(N, _c(A[0], np.uint64), _c(A[1], np.uint64), _c(A[2], np.float64), _c(b, np.float64),
                        float(tol), int(maxit), _c(G[0], np.uint64), _c(G[1], np.uint64), _c(G[2], np.float64),
                        x, C.byref(relres), C.byref(itr))
-    return dict(x=x, relres=relres.value, itr=itr.value)
+    L = _load_ref()
+    L.rchol_b200_mkl_iteration_seconds.restype = C.c_double
+    # seconds inside pcg::iteration alone (marks in mkl_adapter.cpp); the constructor's set-up copies are outside
+    return dict(x=x, relres=relres.value, itr=itr.value, iteration_s=float(L.rchol_b200_mkl_iteration_seconds()))
