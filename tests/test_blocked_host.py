@@ -52,3 +52,33 @@ def test_blocked_algorithm_with_every_entry_class():
     y, st = solve_from_layout(lay, b, False)
     assert relerr(y, yo) <= 1e-12
     assert st["early_tot"] > 0 and st["late_slots"] > 0 and st["rec_slots"] > 0 and lay["tile_need"].max() > 0
+
+
+def _solve_with_inverted_diagonal_blocks(L, bounds, b, C):
+    """x = L^-1 b block by block (bounds = nested-dissection blocks), every block cut into chunks of C rows whose C x C
+    diagonal block is inverted EXPLICITLY (what the GPU set-up stores) and everything left of it applied as a sparse panel."""
+    x = np.zeros(L.shape[0])
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        for s in range(int(lo), int(hi), C):
+            e = min(s + C, int(hi))
+            Dinv = np.linalg.inv(L[s:e, s:e].toarray())
+            x[s:e] = Dinv @ (b[s:e] - L[s:e, :s] @ x[:s])
+    return x
+
+
+@needs_producer
+@pytest.mark.parametrize("C", [32, 128, 256, 1024])
+def test_numerics_gate_of_large_inverted_chunks(C):
+    """Gate for the kernels DESIGN.md (g) plans (128/256-row cluster chain, 1024-row dense-inverse separators): solving
+    through explicitly inverted C x C diagonal blocks stays inside the 1e-12 bar of BASELINE.json in both directions - the
+    factor is strongly diagonally dominant (profiles/r01_separator_study_256_T8.txt: 4e-16 on the real 256^3 factor)."""
+    from oracle import oracle
+    for kind, n, threads in (("lap3d", 28, 4), ("aniso2d", 160, 4)):
+        A, b, G, part, f = make_problem(kind, n, threads)
+        yo = oracle.trsv_forward(*G, b)
+        zo = oracle.trsv_backward(*G, yo)
+        L, bounds, depth = direction_matrix(G, part, False)
+        assert relerr(_solve_with_inverted_diagonal_blocks(L, bounds, b, C), yo) <= 1e-13
+        Lb, bb, db = direction_matrix(G, part, True)
+        zb = _solve_with_inverted_diagonal_blocks(Lb, bb, yo[::-1].copy(), C)
+        assert relerr(zb[::-1], zo) <= 1e-13
