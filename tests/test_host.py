@@ -274,3 +274,25 @@ def test_unmodified_reference_mains_build_on_our_pcg_and_fail_loudly_without_a_g
             assert out.returncode != 0 and "no CPU fallback" in out.stderr, (out.returncode, out.stderr[-300:])
         else:
             assert out.returncode == 0 and "Relative residual" in out.stdout, out.stderr[-300:]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpcg_ref.so")) and not os.path.isdir("/root/reference/c++"),
+                    reason="reference pcg not built")
+@needs_producer
+def test_bench_reference_arm_prints_the_contract_line(tmp_path):
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line on stdout with the contract's keys,
+    kind "reference" (the unmodified pcg in a forked child), zero host<->device bytes, no GPU launches."""
+    import json
+    import sys
+    env = dict(os.environ, RCHOL_B200_CACHE=str(tmp_path))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "20", "--threads", "4",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "pcg_gbps_per_iter" and j["unit"] == "GB/s" and j["higher_is_better"]
+    assert j["value"] > 0 and j["steps"] == 2 and j["warmup"] == 1 and j["n_gpus"] == 1 and j["gpu_launches"] == 0
+    assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"] == dict(value=j["value"], unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    assert j["config"]["workload"] == "lap3d_20^3_rchol_T4_pcg_tol1e-8"
