@@ -161,6 +161,9 @@ def measured_peak_gbs():
 # ------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the path, bounded sample
 # ------------------------------------------------------------------------------------------------------------
+_reference_child_failed = False
+
+
 def _reference_sample_in_child(d, iters: int):
     """One timed call of the UNMODIFIED reference pcg in a forked child.  Why a child: the reference leaks its set-up
     copies by design (pcg.cpp:31-54, the `delete[]` is commented out: 16 B per entry of A and G, ~10 GB per call at
@@ -211,7 +214,9 @@ def cpu_sample(d, iters: int, prefer_reference: bool):
     """Runs `iters` PCG iterations on the host cores; returns (seconds, iterations, kind, cores, detail)."""
     from oracle import oracle
     A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
-    if prefer_reference and oracle.have_reference_pcg() and int(d["G_rp"][-1]) < 2 ** 31 - 1:
+    global _reference_child_failed
+    if (prefer_reference and not _reference_child_failed and oracle.have_reference_pcg()
+            and int(d["G_rp"][-1]) < 2 ** 31 - 1):
         try:
             o = _reference_sample_in_child(d, iters)
             return o["iteration_s"], o["itr"], "reference", os.cpu_count(), dict(
@@ -219,6 +224,8 @@ def cpu_sample(d, iters: int, prefer_reference: bool):
                      "inside pcg::iteration, one forked child per step (the reference leaks its set-up copies)",
                 whole_call_s=o["call_s"])
         except Exception as e:  # pragma: no cover
+            # sticky: the port below starts an OpenMP pool in THIS process, after which forking again is not safe
+            _reference_child_failed = True
             log(f"[bench] reference pcg unavailable ({e}); using the oracle port")
     t0 = time.time()
     o = oracle.pcg(A, d["b"], 1e-30, iters, G)
