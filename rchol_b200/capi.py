@@ -322,7 +322,7 @@ class Solver:
         """Tree levels of one direction that are launched on the cluster chain (chain_mode 4); 0 = 32-row chain everywhere."""
         info = (C.c_uint64 * 16)()
         self._check(self._L.rcg_debug_blocked_info(self._h, int(direction), info))
-        return int(info[15])
+        return int(info[15]) & 0xFFFFFFFF
 
     def blocked_layout(self, direction: int) -> dict:
         """Raw copy of the blocked triangular-solve layout of one direction (tests/blocked_emulator.py interprets it)."""
@@ -330,6 +330,7 @@ class Solver:
         self._check(self._L.rcg_debug_blocked_info(self._h, int(direction), info))
         keys = ["active", "nchunks", "ntiles", "nblocks", "bytesA", "bytesB", "far_nnz", "Kr", "E", "Dfar", "N", "nlevels", "Dfar_sep", "tile_sep", "E_sep"]
         out = {k: int(info[i]) for i, k in enumerate(keys)}
+        out["fold"] = int(info[15]) >> 32
         if not out["active"]:
             return out
 

@@ -566,7 +566,7 @@ int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16) {
   {   // levels launched on the cluster chain (chain_mode 4)
     uint64_t n = 0;
     if (B.cl.on) for (int v : B.cl.level_on) n += v ? 1 : 0;
-    info16[15] = n;
+    info16[15] = n | ((uint64_t)(B.fold ? 1 : 0) << 32);   // bit 32: folded layout (chain_mode 5)
   }
   return RCG_OK;
 }

@@ -51,6 +51,21 @@ __host__ __device__ __forceinline__ uint32_t r16(uint32_t v) { return (v + 15u) 
 __host__ __device__ __forceinline__ uint32_t w_pair_off(uint32_t p, uint32_t row) { return 512u * p + 16u * row; }
 __host__ __device__ __forceinline__ uint32_t rec_batches(uint32_t nslots) { return nslots <= 8u ? 1u : (nslots + 7u) / 8u; }
 
+// ---- folded layout (chain_mode 5, rcg_fold.cuh) ---------------------------------------------------------------------
+// The recent entries (chunks k-1 .. k-Kr) are folded with the inverse of the diagonal block at set-up:
+//     x_k = Winv_k (t'_k - L_rec x_rec) = u_k - M_k x_rec ,   u_k = Winv_k t'_k ,   M_k = Winv_k L_rec  (32 x ncol, dense)
+// so the chain's hop is ONE dense panel apply by one warp; the mat-vec with Winv_k moves off the chain to the near helper.
+// Blob A: 16 B header {batches, rows, columns, 0} | batches x 4 window byte offsets (u32) | batches x 1024 B of panel
+// values, batch-wise [column pair q][row] double2.  Columns ascending (oldest first); padding columns have value 0 and
+// point at the zero slot behind the window.  Blob B: as before, then Winv_k as a packed lower triangle.
+constexpr uint32_t FC_MINB = 4;              // every chunk has at least this many batches (the register-resident tail)
+constexpr uint32_t FC_KRMAX = 8;             // fold depth limit (bitmap of 32*Kr candidate columns)
+constexpr uint32_t FC_WPACK = 4352;          // packed Winv: pair p holds rows 2p..31 -> 16 * sum(32 - 2p) bytes
+__host__ __device__ __forceinline__ uint32_t fold_batches(uint32_t ncol) { return ncol <= 4u * FC_MINB ? FC_MINB : (ncol + 3u) / 4u; }
+__host__ __device__ __forceinline__ uint32_t fold_bytesA(uint32_t ncb) { return 16u + 1040u * ncb; }
+// byte offset of the double2 {Winv[row][2p], Winv[row][2p+1]} (row >= 2p) inside the packed triangle
+__host__ __device__ __forceinline__ uint32_t wp_pair_off(uint32_t p, uint32_t row) { return 16u * (p * (33u - p) + row - 2u * p); }
+
 // ---------------------------------------------------------------------------------------------------------
 // memory-model primitives
 // ---------------------------------------------------------------------------------------------------------
@@ -169,6 +184,7 @@ struct BcGeom {               // blocks in ascending solve order (device arrays 
   const uint32_t *eblk;                             // early/late distance E, per block
   int nb;
   uint32_t Kr, E;
+  uint32_t fold;                                    // 1: folded layout (panels in blob A, Winv in blob B)
 };
 
 __device__ __forceinline__ int find_le(const uint32_t *__restrict__ a, int n, uint32_t v) {   // largest i < n with a[i] <= v
@@ -213,16 +229,29 @@ __device__ __forceinline__ uint32_t warp_add_u32(uint32_t v) { return __reduce_a
 __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, BcGeom g,
                                                   uint32_t nchunks, int64_t *__restrict__ sizeA, int64_t *__restrict__ sizeB,
                                                   int64_t *__restrict__ far_cnt, uint32_t *__restrict__ tile_need, int *err) {
+  __shared__ uint32_t bm_all[8][FC_KRMAX];
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t wpc = blockDim.x >> 5;
+  uint32_t *bm = bm_all[threadIdx.x >> 5];
   for (uint32_t gc = blockIdx.x * wpc + (threadIdx.x >> 5); gc < nchunks; gc += gridDim.x * wpc) {
     const int b = find_le(g.chunk0, g.nb, gc);
     const uint32_t k = gc - g.chunk0[b], blo = g.bounds[b], bhi = g.bounds[b + 1];
     const uint32_t j = blo + 32u * k + lane;
     uint32_t n_rec = 0, n_late = 0, n_early = 0, need = 0;
+    if (g.fold) {
+      if (lane < FC_KRMAX) bm[lane] = 0u;
+      __syncwarp();
+    }
     if (j < bhi) {
       const RowSplit r = split_row(rp, col, j, blo, k, g, g.dfar[b], g.eblk[b]);
       if (col[r.p_diag] != j) atomicExch(err, 1);
+      if (g.fold) {   // distinct columns of the chunk's recent entries
+        const uint32_t c_late = blo + 32u * (uint32_t)max(0, (int)k - (int)g.Kr);
+        for (int64_t p = r.p_late; p < r.p_rec; p++) {
+          const uint32_t lc = col[p] - c_late;
+          atomicOr(&bm[lc >> 5], 1u << (lc & 31u));
+        }
+      }
       far_cnt[j] = r.p_far - r.s;
       n_early = (uint32_t)(r.p_early - r.p_far);
       n_late = (uint32_t)(r.p_late - r.p_early);
@@ -235,9 +264,16 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     const uint32_t nslots = warp_max_u32(n_rec), nl = warp_max_u32(n_late);
     const uint32_t ne_max = warp_max_u32(n_early), ne_tot = warp_add_u32(n_early);
     need = warp_max_u32(need);
+    uint32_t ncol = 0;
+    if (g.fold) {
+      __syncwarp();
+      ncol = warp_add_u32(lane < FC_KRMAX ? (uint32_t)__popc(bm[lane]) : 0u);
+      __syncwarp();
+    }
     if (lane == 0) {
-      sizeA[gc] = (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
-      sizeB[gc] = (int64_t)(BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot) + 320u * nl);
+      const uint32_t bbytes = BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot) + 320u * nl;
+      sizeA[gc] = g.fold ? (int64_t)fold_bytesA(fold_batches(ncol)) : (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
+      sizeB[gc] = (int64_t)(bbytes + (g.fold ? FC_WPACK : 0u));
       if (need) atomicMax(&tile_need[g.tile0[b] + k / g.tile[b]], need);
     }
   }
@@ -251,6 +287,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
                                                  const int64_t *__restrict__ far_rp, uint32_t *__restrict__ far_col,
                                                  double *__restrict__ far_val, uint32_t *__restrict__ far_split) {
   __shared__ double Wm_all[4][32][33];
+  __shared__ uint32_t bm_all[4][FC_KRMAX];
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double(*Wm)[33] = Wm_all[wib];
   const uint32_t wpc = blockDim.x >> 5;
@@ -300,7 +337,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
       Wm[i][lane] = s;
       __syncwarp();
     }
-    {
+    if (!g.fold) {
       unsigned char *Wp = A + BC_AHDR;
       for (uint32_t pp = 0; pp < 16u; pp++) {
         double *dst = reinterpret_cast<double *>(Wp + w_pair_off(pp, lane));
@@ -311,11 +348,9 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
         uint32_t *hd = reinterpret_cast<uint32_t *>(A);
         hd[0] = rec_batches(nslots); hd[1] = nr; hd[2] = nslots; hd[3] = 0;
       }
-    }
-    __syncwarp();
-    // ---- recent entries: batches of 8 slots; values [32 rows][4 pairs] double2, window byte offsets
-    //      [32 rows][2 halves] uint4.  Padding: value 0, offset of the slot behind the window that always holds 0.0
-    {
+      __syncwarp();
+      // ---- recent entries: batches of 8 slots; values [32 rows][4 pairs] double2, window byte offsets
+      //      [32 rows][2 halves] uint4.  Padding: value 0, offset of the slot behind the window that always holds 0.0
       const uint32_t nbt = rec_batches(nslots);
       for (uint32_t bt = 0; bt < nbt; bt++) {
         unsigned char *R = A + BC_AHDR + BC_WBYTES + (size_t)BC_RBATCH * bt;
@@ -325,6 +360,50 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
           reinterpret_cast<double *>(R + 64u * lane + 16u * (u >> 1))[u & 1u] = have ? val[r.p_late + sidx] : 0.0;
           reinterpret_cast<uint32_t *>(R + 2048u + 32u * lane + 16u * (u >> 2))[u & 3u] =
               8u * (have ? ((col[r.p_late + sidx] - blo) & wmask) : (wmask + 1u));
+        }
+      }
+    } else {
+      // ---- folded panel M = Winv * L_rec, one dense column per distinct recent column (ascending) ----------
+      const uint32_t c_late = blo + 32u * (uint32_t)max(0, (int)k - (int)g.Kr);
+      uint32_t *bm = bm_all[wib];
+      if (lane < FC_KRMAX) bm[lane] = 0u;
+      __syncwarp();
+      if (valid)
+        for (int64_t p = r.p_late; p < r.p_rec; p++) {
+          const uint32_t lc = col[p] - c_late;
+          atomicOr(&bm[lc >> 5], 1u << (lc & 31u));
+        }
+      __syncwarp();
+      const uint32_t ncol = warp_add_u32(lane < FC_KRMAX ? (uint32_t)__popc(bm[lane]) : 0u);
+      const uint32_t ncb = fold_batches(ncol);
+      uint32_t *offs = reinterpret_cast<uint32_t *>(A + 16u);
+      unsigned char *vals = A + 16u + 16u * ncb;
+      if (lane == 0) {
+        uint32_t *hd = reinterpret_cast<uint32_t *>(A);
+        hd[0] = ncb; hd[1] = nr; hd[2] = ncol; hd[3] = 0;
+      }
+      for (uint32_t i = lane; i < 4u * ncb; i += 32u) offs[i] = 8u * (wmask + 1u);   // padding columns: the zero slot
+      __syncwarp();
+      int64_t pcur = r.p_late;   // this row's next recent entry (rows are sorted by column)
+      uint32_t ci = 0;
+      for (uint32_t wd = 0; wd < FC_KRMAX; wd++) {
+        uint32_t bits = bm[wd];
+        while (bits) {
+          const uint32_t bpos = (uint32_t)__ffs((int)bits) - 1u;
+          bits &= bits - 1u;
+          const uint32_t c = c_late + 32u * wd + bpos;
+          double lval = 0.0;
+          if (valid && pcur < r.p_rec && col[pcur] == c) { lval = val[pcur]; pcur++; }
+          uint32_t nz = __ballot_sync(0xffffffffu, lval != 0.0);
+          double m = 0.0;
+          while (nz) {
+            const int i = __ffs((int)nz) - 1;
+            nz &= nz - 1u;
+            m = fma(Wm[lane][i], __shfl_sync(0xffffffffu, lval, i), m);   // Winv[row][i] * L[i][c]
+          }
+          reinterpret_cast<double *>(vals + 1024u * (ci >> 2) + 512u * ((ci >> 1) & 1u) + 16u * lane)[ci & 1u] = m;
+          if (lane == 0) offs[ci] = 8u * ((c - blo) & wmask);
+          ci++;
         }
       }
     }
@@ -360,6 +439,15 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
         const bool have = s < n_late;
         lv[s * 32u + lane] = have ? val[r.p_early + s] : 0.0;
         lc[s * 32u + lane] = have ? (uint16_t)((col[r.p_early + s] - blo) & wmask) : (uint16_t)(wmask + 1u);
+      }
+      if (g.fold) {   // Winv, packed lower triangle, behind the late entries
+        unsigned char *Wq = reinterpret_cast<unsigned char *>(lv) + 320u * nl;
+        for (uint32_t pp = 0; pp < 16u; pp++)
+          if (lane >= 2u * pp) {
+            double *dst = reinterpret_cast<double *>(Wq + wp_pair_off(pp, lane));
+            dst[0] = Wm[lane][2u * pp];
+            dst[1] = Wm[lane][2u * pp + 1u];
+          }
       }
     }
     __syncwarp();
@@ -1156,11 +1244,12 @@ uint32_t floor_pow2_u32(uint32_t v) {
 }
 
 #include "rcg_cluster.cuh"
+#include "rcg_fold.cuh"
 
 }  // namespace
 
 bool rcg_use_blocked(const rcg_handle *h) {
-  return !h->opt.chain_generic && (h->opt.chain_mode == 0 || h->opt.chain_mode == 3 || h->opt.chain_mode == 4);
+  return !h->opt.chain_generic && (h->opt.chain_mode == 0 || h->opt.chain_mode == 3 || h->opt.chain_mode == 4 || h->opt.chain_mode == 5);
 }
 
 void rcg_free_blocked(BlockedDev &b) {
@@ -1180,7 +1269,11 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   const int nb = (int)bounds.size() - 1;
   // ---- thresholds ------------------------------------------------------------------------------------
   // (the split chain keeps the solution of two chunks in its partial-sum buffers: recent distance at most 2)
+  B.fold = h->opt.chain_mode == 5;
   B.Kr = h->opt.reserved[3] > 0 ? (uint32_t)std::min(h->opt.reserved[3], h->opt.chain_mode == 3 ? 4 : 2) : 2u;
+  // folded chain: Kr is the fold depth (chunks whose entries become dense panel columns); it is also the slack, in hops,
+  // that the near helper has to deliver u_k after the chain solved chunk k-Kr-1
+  if (B.fold) B.Kr = h->opt.reserved[3] > 0 ? (uint32_t)std::min<int>(h->opt.reserved[3], (int)FC_KRMAX) : 3u;
   // chunks k-E .. k-Kr-1 are the "late" class (gathered by the near helper AFTER the chain reached chunk k-Kr);
   // older chunks inside the window are "early" (gathered before).  reserved[5] overrides (tuning experiments).
   {
@@ -1227,6 +1320,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   g.tile = dgeom + 4 * (nb + 1);
   g.eblk = dgeom + 5 * (nb + 1);
   g.nb = nb; g.Kr = B.Kr; g.E = B.E;
+  g.fold = B.fold ? 1u : 0u;
 
   // ---- sizes ---------------------------------------------------------------------------------------------
   int *derr = nullptr;
@@ -1357,14 +1451,15 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     L.capA = (uint32_t)((maxA + 127) & ~127ll);
     // staging slot of ring B: a multiple of the level's mean blob (reserved[7], in quarters; default 3x); larger blobs
     // are read from HBM by their helper.  More, smaller slots put more chunks in flight (TMA latency cover).
-    const int64_t capq = h->opt.reserved[7] > 0 ? h->opt.reserved[7] : 12;
+    // (folded chain: the blobs carry the packed inverse, 4.3 KB each, so the slot is a smaller multiple of the mean: 1.5x)
+    const int64_t capq = h->opt.reserved[7] > 0 ? h->opt.reserved[7] : (B.fold ? 6 : 12);
     int64_t capB = std::min<int64_t>(maxB, std::max<int64_t>(capq * meanB / 4, 6144));
     capB = std::min<int64_t>(capB, 24576);
     L.capB = (uint32_t)((capB + 127) & ~127ll);
-    const int64_t fixed = (int64_t)W * 8 + 128 + BC_TR * 32 * 8 + BC_SCR * 8 + BC_TR * 4 + 64 + 1024;
+    const int64_t fixed = (int64_t)W * 8 + 128 + BC_TR * 32 * 8 + (B.fold ? FC_SCR : BC_SCR) * 8 + BC_TR * 4 + 64 + 1024;
     int64_t avail = (int64_t)BC_SMEM_MAX - fixed;
     // ring A feeds one consumer (latency cover), ring B feeds BC_NH helpers that hold their slot while they work
-    int64_t SA = std::max<int64_t>(3, std::min<int64_t>(10, (avail * 4 / 10) / L.capA));
+    int64_t SA = std::max<int64_t>(3, std::min<int64_t>(10, (avail * (B.fold ? 3 : 4) / 10) / L.capA));
     if (h->opt.reserved[8] > 0) SA = std::max<int64_t>(2, std::min<int64_t>(10, h->opt.reserved[8]));   // tuning experiments
     int64_t SB = std::max<int64_t>(3, std::min<int64_t>(2 * BC_NH + 4, (avail - SA * L.capA) / (L.capB + 24)));
     while (SA > 3 && SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) SA--;
@@ -1415,13 +1510,14 @@ int rcg_check_abort(rcg_handle *h) {
 int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double *out, const double *dotvec, int only_group,
                        int only_kernel) {
   BlockedDev &B = d.bc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->smem_optin_blocked) {   // per handle = per device: the attribute belongs to the device's instance of the kernel
     RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
     RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
     RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
     RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
-    attr_set = true;
+    RCG_CUDA(h, cudaFuncSetAttribute(k_fc_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
+    RCG_CUDA(h, cudaFuncSetAttribute(k_fc_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
+    h->smem_optin_blocked = true;
   }
   if (only_kernel > 0) return RCG_OK;   // the level kernel is the only kernel of a group
   RCG_CUDA(h, cudaMemsetAsync(B.flags, 0, sizeof(uint32_t) * ((size_t)B.ntiles + B.nblocks), h->stream));
@@ -1476,7 +1572,7 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L.groups * (1u + L.helpers));
-    cfg.blockDim = dim3(BC_THREADS);
+    cfg.blockDim = dim3(B.fold ? FC_THREADS : BC_THREADS);
     cfg.dynamicSmemBytes = L.smem;
     cfg.stream = h->stream;
     cudaLaunchAttribute at[1];
@@ -1487,6 +1583,7 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     const bool split = h->opt.chain_mode != 3;   // default: four critical warps
     void (*kern)(const BcArgs) = (a.dbg & 1u) ? (split ? k_bc_solve<4, true> : k_bc_solve<1, true>)
                                               : (split ? k_bc_solve<4, false> : k_bc_solve<1, false>);
+    if (B.fold) kern = (a.dbg & 1u) ? k_fc_solve<true> : k_fc_solve<false>;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
     if (e != cudaSuccess && cfg.numAttrs == 1) {
       // co-residency is what the cooperative attribute guarantees; a context that cannot give it (or cannot capture it)

@@ -107,6 +107,7 @@ struct ClusterDev {
 struct BlockedDev {
   ClusterDev cl;
   bool on = false;
+  bool fold = false;                     // folded layout (chain_mode 5, rcg_fold.cuh): dense panels in blob A, packed Winv in blob B
   uint32_t Kr = 2, E = 16, Dfar = 128;   // chunk-distance thresholds (see above); window = 32*Dfar rows (leaf blocks)
   uint32_t Dfar_sep = 32;                // window of the separator blocks
   uint32_t E_sep = 6;                    // early/late distance of the separator blocks (leaves: E)
@@ -191,6 +192,7 @@ struct rcg_handle {
   uint32_t *trace = nullptr;                 // diagnostics: per-row timing trace of the chain kernel (rcg_debug_trace)
   unsigned long long *clk_probe = nullptr;   // device {cycles, ns} written by CTA 0 of the chain kernel
   unsigned int *abort_flag = nullptr;        // device: non-zero when a dependency wait of the blocked solve timed out
+  bool smem_optin_blocked = false;           // large dynamic shared memory enabled for this handle's device (rcg_blocked.cu)
   cudaGraphExec_t iter_graph = nullptr;
   std::vector<double> history;
 

@@ -1,0 +1,541 @@
+// rchol_b200 -- folded chain (chain_mode 5): the blocked-inverse triangular solve of rcg_blocked.cu with the recent entries
+// folded into dense panels at set-up, so that the chain's hop is ONE panel apply by ONE warp:
+//
+//     x_k = u_k - M_k x_rec          M_k = Winv_k L_rec   (32 x ncol, columns = the distinct recent columns, set-up)
+//     u_k = Winv_k t'_k              t'_k = start_k - early - late entries                     (near helper, off the chain)
+//
+// The old chain did  t = t' - L_rec x_rec (sparse gather, shuffle reduction)  THEN  x = Winv t (dense mat-vec, four warps,
+// one named barrier): two dependent stages, ~790 cycles per 32 rows.  Here the only dependent work per hop is: 16 shared-
+// memory loads of x (addresses and panel values already in registers), 4 dependent DFMA, 2 DADD, one store.
+// Included by rcg_blocked.cu inside its anonymous namespace (shares Guard/BC_WAIT, BcArgs, the memory-model primitives,
+// the far tiles / start vector / progress words).
+//
+// CTA = 12 warps (384 threads, 168 registers each):
+//   warp 0        chain (critical) warp, alone on scheduler 0 apart from the two TMA producers, which sleep in mbarrier waits
+//   warp 1        publisher: window -> out[], fused dot product, progress published with release semantics
+//   warp 4 / 8    TMA producers of ring A (panels) / ring B (early + late entries + packed Winv)
+//   warps 2,3,5,6,7,9,10,11   near helpers: chunk k -> helper k % 8, running up to 8 chunks ahead
+constexpr int FC_THREADS = 384;
+constexpr uint32_t FC_NH = 8;
+constexpr uint32_t FC_SCR = FC_NH * 32u;   // scratch doubles: one t vector per helper (broadcast for the Winv mat-vec)
+
+__device__ __forceinline__ void mbar_arrive_after3(uint64_t *bar, uint32_t a, double b, double c) {
+  asm volatile(
+      "{\n\t.reg .b32 lo, hi, lo2, hi2, z;\n\t"
+      "mov.b64 {lo, hi}, %2;\n\t"
+      "mov.b64 {lo2, hi2}, %3;\n\t"
+      "or.b32 z, lo, %1;\n\t"
+      "or.b32 z, z, lo2;\n\t"
+      "and.b32 z, z, 0;\n\t"
+      "add.u32 z, z, %0;\n\t"
+      "mbarrier.arrive.shared::cta.b64 _, [z];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(a), "d"(b), "d"(c)
+      : "memory");
+}
+
+// PROF: cycle counters of the chain warp and of near helper 0 (dbg bit 0) -- a separate instantiation.
+template <bool PROF>
+__global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t per = 1u + P.helpers;
+  const uint32_t grp = blockIdx.x / per, role = blockIdx.x % per;
+
+  double *win = reinterpret_cast<double *>(smem);
+  double *uring = win + P.W + 16;   // win[W] holds 0.0: the slot padding columns / entries point at
+  double *scratch = uring + BC_TR * 32u;
+  unsigned char *ringA = reinterpret_cast<unsigned char *>(scratch + FC_SCR);
+  unsigned char *ringB = ringA + (size_t)P.SA * P.capA;
+  uint64_t *fullA = reinterpret_cast<uint64_t *>(ringB + (size_t)P.SB * P.capB);
+  uint64_t *emptyA = fullA + P.SA;
+  uint64_t *fullB = emptyA + P.SA;
+  uint64_t *emptyB = fullB + P.SB;
+  unsigned long long *ptrB = reinterpret_cast<unsigned long long *>(emptyB + P.SB);
+  uint32_t *seqB = reinterpret_cast<uint32_t *>(ptrB + P.SB);
+  uint32_t *tready = seqB + P.SB;
+  uint32_t *ctl = tready + BC_TR;   // [0] prog: solved chunks of the current block, [1] published chunks, [2] abort
+
+  if (threadIdx.x < P.SA) { mbar_init(fullA + threadIdx.x, 1); mbar_init(emptyA + threadIdx.x, 1); }
+  if (threadIdx.x < P.SB) { mbar_init(fullB + threadIdx.x, 1); mbar_init(emptyB + threadIdx.x, 1); seqB[threadIdx.x] = 0xFFFFFFFFu; }
+  if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = 0; ctl[2] = 0; }
+  if (threadIdx.x < 16) win[P.W + threadIdx.x] = 0.0;
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  Guard G;
+  G.abort_s = smem_u32(ctl + 2);
+  G.abort_g = P.abort_g;
+  G.n = 0;
+  G.t0 = 0;
+  const uint32_t prog_s = smem_u32(ctl), pub_s = smem_u32(ctl + 1);
+
+  if (role > 0) {
+    // =========================== far CTA: start vector of the chain, tile by tile ===========================
+    // (same protocol as k_bc_solve: pass 0 = entries of other, already solved blocks, never waits; pass 1 = entries
+    //  >= Dfar chunks back in the own block, tile by tile as the chain's published progress allows)
+    const uint32_t hid = role - 1u;
+    const uint32_t lpr_pass[2] = {P.far_lpr, P.far_lpr2};
+    for (uint32_t bi = grp; bi < P.nblocks; bi += P.ngroups) {
+      const BcBlock b = P.blocks[bi];
+      const uint32_t nch = (b.hi - b.lo + 31u) >> 5, ntile = (nch + P.tile - 1u) / P.tile;
+      constexpr uint32_t LA = 2;
+      const uint32_t nown = hid < ntile ? (ntile - hid + P.helpers - 1u) / P.helpers : 0u;
+      for (uint32_t it = 0; it < nown + LA; it++) {
+        for (uint32_t pass = 0; pass < 2u; pass++) {
+          if (pass == 0u ? it >= nown : it < LA) continue;
+          const uint32_t t = hid + (pass == 0u ? it : it - LA) * P.helpers;
+          const uint32_t need = P.tile_need[b.tile0 + t];
+          if (pass == 1u) {
+            if (need == 0u) continue;
+            if (threadIdx.x == 0) BC_WAIT(ld_acquire_gpu(P.gprog + b.gidx) >= need, 0x100u, 200);
+            __syncthreads();
+          }
+          const uint32_t lpr = lpr_pass[pass], rpw = 32u / lpr, sub = lane & (lpr - 1u);
+          const uint32_t r0 = b.lo + t * (32u * P.tile), r1 = min(b.hi, r0 + 32u * P.tile);
+          for (uint32_t base = r0 + warp * rpw; base < r1; base += (FC_THREADS / 32) * rpw) {
+            const uint32_t j = base + lane / lpr;
+            const bool valid = j < r1;
+            double acc = 0.0;
+            if (valid) {
+              const int64_t es = P.far_rp[j] + P.far_split[j];   // [rp, es) other blocks, [es, rp1) own block
+              const int64_t e0 = pass == 0u ? P.far_rp[j] : es, e1 = pass == 0u ? es : P.far_rp[j + 1];
+              double acc1 = 0.0;
+              int64_t e = e0 + sub;
+              for (; e + lpr < e1; e += 2u * lpr) {
+                const uint32_t c = P.far_col[e], c2 = P.far_col[e + lpr];
+                if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
+                if (c2 >= P.col_min) acc1 = fma(P.far_val[e + lpr], __ldcg(P.out + c2), acc1);
+              }
+              if (e < e1) {
+                const uint32_t c = P.far_col[e];
+                if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
+              }
+              acc += acc1;
+            }
+            if (lpr == 32u) {
+              acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+              acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (valid && sub == 0u) {
+              double s;
+              if (pass == 0u) {
+                const uint32_t i = P.reversed ? P.N - 1u - j : j;
+                s = P.rhs[i];
+                if (P.corr) s -= P.corr[i - P.col_min];
+              } else {
+                s = __ldcg(P.w + j);   // written by this very thread in pass 0
+              }
+              __stcg(P.w + j, s - acc);
+            }
+          }
+          if (pass == 1u || need == 0u) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+              __threadfence();
+              st_release_gpu(P.tileflag + b.tile0 + t, 1u);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================= chain CTA ============================================================
+  const uint32_t wmask = P.W - 1u;
+  const uint32_t win_s = smem_u32(win), u_s = smem_u32(uring), sc_s = smem_u32(scratch), trdy_s = smem_u32(tready);
+  uint32_t ia0 = 0;   // chunks of the blocks this CTA has finished: running index of the staging rings
+  long long pc[4] = {0, 0, 0, 0};   // chain warp of CTA 0 (dbg bit 0): cycles waiting for ring A / for u, chunks, failed polls of u
+  long long ph[5] = {0, 0, 0, 0, 0};   // near helper 0 of CTA 0: start vector, blob B, early, wait for the chain, late + mat-vec
+  long long clk0 = 0;
+  if (P.clk && blockIdx.x == 0 && threadIdx.x == 0) clk0 = clock64();
+
+  for (uint32_t bi = grp; bi < P.nblocks; bi += P.ngroups) {
+    const BcBlock b = P.blocks[bi];
+    const uint32_t nch = (b.hi - b.lo + 31u) >> 5;
+    if (threadIdx.x < BC_TR) tready[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) { ctl[0] = 0u; ctl[1] = 0u; }
+    __syncthreads();
+
+    if (warp == 0) {
+      // ------------------------------ chain warp ---------------------------------------------------------
+      // Two register sets (E / O): the tail of chunk k+1 (offsets + panel values of its newest 16 columns) is loaded
+      // while the x loads of chunk k are in flight.  All shared-memory loads are volatile asm: their program order IS
+      // the schedule of the lone warp.
+      const bool prof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0;
+      const uint32_t fullA_s = smem_u32(fullA), ringA_s = smem_u32(ringA);
+      uint32_t slot = ia0 % P.SA, par = (ia0 / P.SA) & 1u;
+      uint32_t oE[16], oO[16];
+      double mE[16], mO[16];
+      uint32_t ncbE = FC_MINB, ncbO = FC_MINB, asE = 0, asO = 0;
+      uint32_t tpf = 0u, spins = 0u;
+#define FC_SPIN(cond_, code_)                                                                                             \
+      while (__builtin_expect(!(cond_), 0)) {                                                                             \
+        if (++spins > (1u << 24)) { atomicCAS(P.abort_g, 0u, (code_)); sts_volatile_u32(G.abort_s, 1u); break; }          \
+      }
+      // offsets + values of the last FC_MINB batches of the chunk staged in `slot`
+#define FC_PRELOAD(O_, M_, NCB_, AS_)                                                                                     \
+      do {                                                                                                                \
+        AS_ = ringA_s + slot * P.capA;                                                                                    \
+        NCB_ = lds_u32(AS_);                                                                                              \
+        const uint32_t nb_ = NCB_ - FC_MINB;                                                                              \
+        const uint32_t ob_ = AS_ + 16u + 16u * nb_, vb_ = AS_ + 16u + 16u * NCB_ + 1024u * nb_ + 16u * lane;              \
+        _Pragma("unroll") for (uint32_t q_ = 0; q_ < FC_MINB; q_++) {                                                     \
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"                                                         \
+                       : "=r"(O_[4 * q_]), "=r"(O_[4 * q_ + 1]), "=r"(O_[4 * q_ + 2]), "=r"(O_[4 * q_ + 3]) : "r"(ob_ + 16u * q_) : "memory"); \
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(M_[4 * q_]), "=d"(M_[4 * q_ + 1]) : "r"(vb_ + 1024u * q_) : "memory"); \
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(M_[4 * q_ + 2]), "=d"(M_[4 * q_ + 3]) : "r"(vb_ + 1024u * q_ + 512u) : "memory"); \
+        }                                                                                                                 \
+      } while (0)
+#define FC_CHUNK(O_, M_, NCB_, AS_, On_, Mn_, NCBn_, ASn_)                                                                \
+      do {                                                                                                                \
+        long long c0_ = 0;                                                                                                \
+        if (prof) c0_ = clock64();                                                                                        \
+        if (__builtin_expect(tpf != k + 1u, 0)) {                                                                         \
+          FC_SPIN((tpf = ld_acquire_cta_s(trdy_s + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);                          \
+          if (prof) { pc[3] += 1; pc[1] += clock64() - c0_; }                                                             \
+        }                                                                                                                 \
+        /* u_k through an address that depends on the flag (cannot be hoisted above it) */                                \
+        double a0_ = lds_f64(u_s + 8u * ((k & (BC_TR - 1u)) * 32u + lane) + ((tpf ^ (k + 1u)) & 0x7u) * 8u);              \
+        double a1_ = 0.0, a2_ = 0.0, a3_ = 0.0;                                                                           \
+        /* body: the older batches of a wide panel */                                                                     \
+        {                                                                                                                 \
+          const uint32_t nb_ = NCB_ - FC_MINB;                                                                            \
+          const uint32_t vb_ = AS_ + 16u + 16u * NCB_ + 16u * lane;                                                       \
+          _Pragma("unroll 1") for (uint32_t bb_ = 0; bb_ < nb_; bb_++) {                                                  \
+            uint32_t q0_, q1_, q2_, q3_;                                                                                  \
+            double m0_, m1_, m2_, m3_;                                                                                    \
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q0_), "=r"(q1_), "=r"(q2_), "=r"(q3_) : "r"(AS_ + 16u + 16u * bb_) : "memory"); \
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m0_), "=d"(m1_) : "r"(vb_ + 1024u * bb_) : "memory");   \
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m2_), "=d"(m3_) : "r"(vb_ + 1024u * bb_ + 512u) : "memory"); \
+            const double x0_ = lds_f64(win_s + q0_), x1_ = lds_f64(win_s + q1_), x2_ = lds_f64(win_s + q2_), x3_ = lds_f64(win_s + q3_); \
+            a0_ = fma(-m0_, x0_, a0_);                                                                                    \
+            a1_ = fma(-m1_, x1_, a1_);                                                                                    \
+            a2_ = fma(-m2_, x2_, a2_);                                                                                    \
+            a3_ = fma(-m3_, x3_, a3_);                                                                                    \
+          }                                                                                                               \
+        }                                                                                                                 \
+        /* tail: x of the newest 16 columns (the only loads that depend on the previous hop) */                           \
+        double x_[16];                                                                                                    \
+        _Pragma("unroll") for (uint32_t i_ = 0; i_ < 16u; i_++) x_[i_] = lds_f64(win_s + O_[i_]);                         \
+        /* chain-independent loads of the next chunk, in flight behind the x loads */                                     \
+        const uint32_t oslot_ = slot;                                                                                     \
+        if (k + 1u < nch) {                                                                                               \
+          if (++slot == P.SA) { slot = 0; par ^= 1u; }                                                                    \
+          if (__builtin_expect(!mbar_test(fullA + slot, par), 0)) {                                                       \
+            long long c1_ = 0;                                                                                            \
+            if (prof) c1_ = clock64();                                                                                    \
+            FC_SPIN(mbar_try(fullA + slot, par), 0x200u);                                                                 \
+            if (prof) pc[0] += clock64() - c1_;                                                                           \
+          }                                                                                                               \
+          FC_PRELOAD(On_, Mn_, NCBn_, ASn_);                                                                              \
+          tpf = lds_volatile_u32(trdy_s + 4u * ((k + 1u) & (BC_TR - 1u)));                                                \
+        }                                                                                                                 \
+        _Pragma("unroll") for (uint32_t i_ = 0; i_ < 16u; i_ += 4u) {                                                     \
+          a0_ = fma(-M_[i_], x_[i_], a0_);                                                                                \
+          a1_ = fma(-M_[i_ + 1u], x_[i_ + 1u], a1_);                                                                      \
+          a2_ = fma(-M_[i_ + 2u], x_[i_ + 2u], a2_);                                                                      \
+          a3_ = fma(-M_[i_ + 3u], x_[i_ + 3u], a3_);                                                                      \
+        }                                                                                                                 \
+        const double xk_ = (a0_ + a1_) + (a2_ + a3_);                                                                     \
+        sts_f64(win_s + 8u * ((32u * k + lane) & wmask), xk_);                                                            \
+        __syncwarp();                                                                                                     \
+        if (lane == 0) {                                                                                                  \
+          st_release_cta_s(prog_s, k + 1u);                                                                               \
+          mbar_arrive(emptyA + oslot_);                                                                                   \
+        }                                                                                                                 \
+        if (prof) pc[2] += 1;                                                                                             \
+        k++;                                                                                                              \
+      } while (0)
+      uint32_t k = 0;
+      if (nch > 0) {
+        FC_SPIN(mbar_try(fullA + slot, par), 0x200u);
+        FC_PRELOAD(oE, mE, ncbE, asE);
+        tpf = lds_volatile_u32(trdy_s);
+      }
+      while (k < nch) {
+        FC_CHUNK(oE, mE, ncbE, asE, oO, mO, ncbO, asO);
+        if (k >= nch) break;
+        FC_CHUNK(oO, mO, ncbO, asO, oE, mE, ncbE, asE);
+      }
+      (void)fullA_s;
+#undef FC_CHUNK
+#undef FC_PRELOAD
+#undef FC_SPIN
+    } else if (warp == 4u) {
+      // ------------------------------ TMA producer, ring A -----------------------------------------------
+      int64_t O0n = 0, O1n = 0;
+      if (nch > 0) {
+        const uint32_t gl = b.chunk0 + min(lane, nch - 1u);
+        O0n = P.offA[gl]; O1n = P.offA[gl + 1];
+      }
+      for (uint32_t base = 0; base < nch; base += 32u) {
+        const int64_t O0 = O0n, O1 = O1n;
+        if (base + 32u < nch) {
+          const uint32_t gl = b.chunk0 + min(base + 32u + lane, nch - 1u);
+          O0n = P.offA[gl]; O1n = P.offA[gl + 1];
+        }
+        for (uint32_t l = 0; l < 32u && base + l < nch; l++) {
+          const uint32_t i = ia0 + base + l, slot = i % P.SA, use = i / P.SA;
+          const int64_t e0 = __shfl_sync(0xffffffffu, O0, (int)l), e1 = __shfl_sync(0xffffffffu, O1, (int)l);
+          if (use > 0u) BC_WAIT(mbar_try(emptyA + slot, (use - 1u) & 1u), 0x900u, 20);
+          if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(e1 - e0);
+            mbar_expect_tx(fullA + slot, bytes);
+            bulk_g2s(ringA + (size_t)slot * P.capA, P.blobA + e0, bytes, fullA + slot);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp == 8u) {
+      // ------------------------------ TMA producer, ring B -----------------------------------------------
+      int64_t O0n = 0, O1n = 0;
+      if (nch > 0) {
+        const uint32_t gl = b.chunk0 + min(lane, nch - 1u);
+        O0n = P.offB[gl]; O1n = P.offB[gl + 1];
+      }
+      for (uint32_t base = 0; base < nch; base += 32u) {
+        const int64_t O0 = O0n, O1 = O1n;
+        if (base + 32u < nch) {
+          const uint32_t gl = b.chunk0 + min(base + 32u + lane, nch - 1u);
+          O0n = P.offB[gl]; O1n = P.offB[gl + 1];
+        }
+        for (uint32_t l = 0; l < 32u && base + l < nch; l++) {
+          const uint32_t i = ia0 + base + l, slot = i % P.SB, use = i / P.SB;
+          const int64_t e0 = __shfl_sync(0xffffffffu, O0, (int)l), e1 = __shfl_sync(0xffffffffu, O1, (int)l);
+          if (use > 0u) BC_WAIT(mbar_try(emptyB + slot, (use - 1u) & 1u), 0xA00u, 20);
+          if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(e1 - e0);
+            if (e1 - e0 <= (int64_t)P.capB) {
+              unsigned char *dst = ringB + (size_t)slot * P.capB;
+              ptrB[slot] = (unsigned long long)dst;
+              sts_volatile_u32(smem_u32(seqB + slot), i);
+              mbar_expect_tx(fullB + slot, bytes);
+              bulk_g2s(dst, P.blobB + e0, bytes, fullB + slot);
+            } else {   // does not fit a staging slot: the helper reads it from HBM
+              ptrB[slot] = (unsigned long long)(P.blobB + e0);
+              sts_volatile_u32(smem_u32(seqB + slot), i);
+              mbar_arrive(fullB + slot);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp == 1u) {
+      // ------------------------------ publisher ----------------------------------------------------------
+      uint32_t done = 0;
+      double dot = 0.0;
+      while (done < nch) {
+        uint32_t p = done;
+        BC_WAIT((p = ld_acquire_cta_s(prog_s)) > done, 0xB00u, 400);
+        if (p <= done) break;   // aborted
+        for (uint32_t k = done; k < p; k += 4u) {
+          double x[4], dv[4];
+          uint32_t idx[4];
+          bool ok[4];
+#pragma unroll
+          for (uint32_t u = 0; u < 4u; u++) {
+            const uint32_t j = b.lo + 32u * (k + u) + lane;
+            ok[u] = (k + u < p) && j < b.hi;
+            idx[u] = P.reversed ? P.N - 1u - j : j;
+            x[u] = lds_f64(win_s + 8u * ((32u * (k + u) + lane) & wmask));
+            dv[u] = (ok[u] && P.dotvec && idx[u] < P.dot_limit) ? P.dotvec[idx[u]] : 0.0;
+          }
+#pragma unroll
+          for (uint32_t u = 0; u < 4u; u++) {
+            if (ok[u]) {
+              P.out[idx[u]] = x[u];
+              dot = fma(x[u], dv[u], dot);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          st_release_gpu(P.gprog + b.gidx, p);
+          st_release_cta_s(pub_s, p);
+        }
+        done = p;
+      }
+      dot = warp_sum(dot);
+      if (lane == 0 && P.dot_partials) P.dot_partials[b.gidx] = dot;
+    } else {
+      // ------------------------------ near helpers: warps 2,3,5,6,7,9,10,11 ------------------------------
+      const uint32_t hidx = warp - 2u - (warp > 4u ? 1u : 0u) - (warp > 8u ? 1u : 0u);
+      const bool hprof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0 && hidx == 0u;
+      const uint32_t hs_s = sc_s + 256u * hidx;
+      uint32_t tiles_known = 0;
+      double t0n = 0.0;
+      if (hidx < nch) {
+        BC_WAIT(ld_acquire_gpu(P.tileflag + b.tile0 + hidx / P.tile) != 0u, 0x400u, 100);
+        tiles_known = hidx / P.tile + 1u;
+        const uint32_t j = b.lo + 32u * hidx + lane;
+        t0n = j < b.hi ? __ldcg(P.w + j) : 0.0;
+      }
+      for (uint32_t k = hidx; k < nch; k += FC_NH) {
+        const uint32_t i = ia0 + k, slot = i % P.SB;
+        long long h0 = 0;
+        if (hprof) h0 = clock64();
+        const double t0 = t0n;
+        const uint32_t kn = k + FC_NH, tilen = kn / P.tile;
+        uint32_t fln = 1u;
+        if (kn < nch && tilen >= tiles_known) fln = ld_acquire_gpu(P.tileflag + b.tile0 + tilen);
+        long long h1 = 0;
+        if (hprof) h1 = clock64();
+        BC_WAIT(lds_volatile_u32(smem_u32(seqB + slot)) == i && mbar_try(fullB + slot, (i / P.SB) & 1u), 0x500u, 200);
+        const unsigned char *bp = reinterpret_cast<const unsigned char *>(ptrB[slot]);
+        const uint32_t *hd = reinterpret_cast<const uint32_t *>(bp);
+        const uint32_t ne_max = hd[0], ne_tot = hd[1], nl = hd[2];
+        const uint32_t perm = bp[16u + lane], rank = bp[48u + lane];
+        const unsigned char *cnt = bp + BC_BHDR;
+        const double *ev = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max));
+        const uint16_t *ec = reinterpret_cast<const uint16_t *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot));
+        const double *lv = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot));
+        const uint16_t *lc = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(lv) + 256u * nl);
+        const unsigned char *wq = reinterpret_cast<const unsigned char *>(lv) + 320u * nl;   // packed Winv
+        // early entries: columns in chunks <= k-E-1 (jagged diagonals, four per trip)
+        const uint32_t need1 = k > P.E ? k - P.E : 0u;
+        long long h2 = 0;
+        if (hprof) h2 = clock64();
+        BC_WAIT(ld_acquire_cta_s(prog_s) >= need1, 0x600u, 200);
+        double ts = __shfl_sync(0xffffffffu, t0, (int)perm), ts1 = 0.0;
+        uint32_t base = 0;
+        for (uint32_t s = 0; s < ne_max; s += 4u) {
+          const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cnt + s);
+          const uint32_t n0 = c4 & 255u, n1 = (c4 >> 8) & 255u, n2 = (c4 >> 16) & 255u, n3 = c4 >> 24;
+          const uint32_t b1 = base + n0, b2 = b1 + n1, b3 = b2 + n2;
+          double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+          if (lane < n0) { v0 = ev[base + lane]; x0 = win[ec[base + lane]]; }
+          if (lane < n1) { v1 = ev[b1 + lane]; x1 = win[ec[b1 + lane]]; }
+          if (lane < n2) { v2 = ev[b2 + lane]; x2 = win[ec[b2 + lane]]; }
+          if (lane < n3) { v3 = ev[b3 + lane]; x3 = win[ec[b3 + lane]]; }
+          ts = fma(-v0, x0, ts);
+          ts1 = fma(-v1, x1, ts1);
+          ts = fma(-v2, x2, ts);
+          ts1 = fma(-v3, x3, ts1);
+          base = b3 + n3;
+        }
+        ts += ts1;
+        long long hj = 0;
+        if (hprof) hj = clock64() + (ts == 1.25e-300 ? 1 : 0);
+        double t = __shfl_sync(0xffffffffu, ts, (int)rank);
+        // late entries (chunks k-E .. k-Kr-1): values and window slots of the first LB slots, and the packed Winv of the
+        // chunk, are loaded BEFORE the wait for the chain; the staging slot is free once they are in registers
+        constexpr uint32_t LB = 8;
+        uint32_t lcr[LB];
+        double lvr[LB];
+#pragma unroll
+        for (uint32_t u = 0; u < LB; u++) {
+          lcr[u] = 0;
+          lvr[u] = 0.0;
+          if (u < nl) { lcr[u] = lc[u * 32u + lane]; lvr[u] = lv[u * 32u + lane]; }
+        }
+        double wv[32];
+#pragma unroll
+        for (uint32_t pp = 0; pp < 16u; pp++) {
+          const uint32_t rr = lane >= 2u * pp ? lane - 2u * pp : 0u;   // rows above the diagonal pair: clamped, then zeroed
+          const double2 w2 = *reinterpret_cast<const double2 *>(wq + 16u * (pp * (33u - pp) + rr));
+          wv[2 * pp] = lane >= 2u * pp ? w2.x : 0.0;
+          wv[2 * pp + 1] = lane >= 2u * pp ? w2.y : 0.0;
+        }
+        const bool slot_done = nl <= LB;
+        if (slot_done && lane == 0) mbar_arrive_after3(emptyB + slot, lcr[LB - 1u], lvr[LB - 1u], wv[0] + wv[31]);
+        if (kn < nch) {
+          if (fln == 0u) BC_WAIT(ld_acquire_gpu(P.tileflag + b.tile0 + tilen) != 0u, 0x400u, 100);
+          tiles_known = tilen + 1u;
+          const uint32_t jn = b.lo + 32u * kn + lane;
+          t0n = jn < b.hi ? __ldcg(P.w + jn) : 0.0;
+        }
+        uint32_t need2 = k > P.Kr ? k - P.Kr : 0u;
+        if (k + 1u > BC_TR) need2 = max(need2, k + 1u - BC_TR);
+        long long h3 = 0;
+        if (hprof) h3 = clock64();
+        {
+          uint32_t pnow = 0;
+          G.n = 0;
+          while ((pnow = ld_acquire_cta_s(prog_s)) < need2) {
+            if (guard_poll(G, 0x700u)) break;
+            if (need2 - pnow > 1u) __nanosleep(200);
+          }
+        }
+        if (k >= P.Dfar) BC_WAIT(ld_acquire_cta_s(pub_s) >= k - P.Dfar + 1u, 0x800u, 100);
+        long long h4 = 0;
+        if (hprof) h4 = clock64();
+        {
+          double xv[LB], q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+          for (uint32_t u = 0; u < LB; u++) {
+            xv[u] = 0.0;
+            lds_f64_if(xv[u], win_s + 8u * lcr[u], u < nl);
+          }
+#pragma unroll
+          for (uint32_t u = 0; u < LB; u += 4u) {
+            t = fma(-lvr[u], xv[u], t);
+            q1 = fma(-lvr[u + 1u], xv[u + 1u], q1);
+            q2 = fma(-lvr[u + 2u], xv[u + 2u], q2);
+            q3 = fma(-lvr[u + 3u], xv[u + 3u], q3);
+          }
+          for (uint32_t s0 = LB; s0 < nl; s0 += 8u) {   // long late rows (separator blocks): batches of 8, loads first
+            uint32_t cc[8];
+            double vv[8], xx[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u++) {
+              const bool have = s0 + u < nl;
+              cc[u] = have ? lc[(s0 + u) * 32u + lane] : P.W;
+              vv[u] = have ? lv[(s0 + u) * 32u + lane] : 0.0;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u++) xx[u] = win[cc[u]];
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u += 4u) {
+              t = fma(-vv[u], xx[u], t);
+              q1 = fma(-vv[u + 1u], xx[u + 1u], q1);
+              q2 = fma(-vv[u + 2u], xx[u + 2u], q2);
+              q3 = fma(-vv[u + 3u], xx[u + 3u], q3);
+            }
+          }
+          t = (t + q1) + (q2 + q3);
+        }
+        // u = Winv t : t broadcast through the helper's scratch row, lane = row of the result
+        sts_f64(hs_s + 8u * lane, t);
+        __syncwarp();
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+        for (uint32_t pp = 0; pp < 16u; pp += 2u) {
+          double ta, tb, tc, td;
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ta), "=d"(tb) : "r"(hs_s + 16u * pp) : "memory");
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc), "=d"(td) : "r"(hs_s + 16u * pp + 16u) : "memory");
+          u0 = fma(wv[2 * pp], ta, u0);
+          u1 = fma(wv[2 * pp + 1], tb, u1);
+          u2 = fma(wv[2 * pp + 2], tc, u2);
+          u3 = fma(wv[2 * pp + 3], td, u3);
+        }
+        const double uk = (u0 + u1) + (u2 + u3);
+        const uint32_t tsl = k & (BC_TR - 1u);
+        sts_f64(u_s + 8u * (tsl * 32u + lane), uk);
+        __syncwarp();
+        if (lane == 0) {
+          st_release_cta_s(trdy_s + 4u * tsl, k + 1u);
+          if (!slot_done) mbar_arrive(emptyB + slot);
+        }
+        if (hprof) { ph[0] += (h1 - h0) + (h3 - hj); ph[1] += h2 - h1; ph[2] += hj - h2; ph[3] += h4 - h3; ph[4] += clock64() - h4; }
+      }
+    }
+    __syncthreads();
+    ia0 += nch;
+  }
+  if (P.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    P.clk[0] = (unsigned long long)(clock64() - clk0);
+    if (P.dbg & 1u) {
+      P.clk[3] = (unsigned long long)pc[0];    // cycles waiting for ring A
+      P.clk[4] = (unsigned long long)pc[1];    // cycles waiting for u
+      P.clk[6] = (unsigned long long)pc[2];    // chunks
+      P.clk[15] = (unsigned long long)pc[3];   // failed first polls of u
+    }
+  }
+  if (P.clk && (P.dbg & 1u) && blockIdx.x == 0 && threadIdx.x == 64u)   // near helper 0 = warp 2
+    for (int q = 0; q < 5; q++) P.clk[8 + q] = (unsigned long long)ph[q];
+}

@@ -7,6 +7,41 @@
 import numpy as np
 
 AHDR, BHDR, WBYTES, RBATCH = 16, 80, 1024 * 8, 3072
+FC_MINB, FC_WPACK = 4, 4352          # folded layout (chain_mode 5, rcg_fold.cuh)
+
+
+def fold_batches(ncol):
+    return FC_MINB if ncol <= 4 * FC_MINB else (ncol + 3) // 4
+
+
+def fold_bytesA(ncb):
+    return 16 + 1040 * ncb
+
+
+def wp_pair_off(p, row):
+    """Byte offset of {Winv[row][2p], Winv[row][2p+1]} (row >= 2p) in the packed lower triangle of blob B."""
+    return 16 * (p * (33 - p) + row - 2 * p)
+
+
+def unpack_winv_packed(raw_bytes):
+    W = np.zeros((32, 32))
+    d = raw_bytes.view(np.float64)
+    for p in range(16):
+        for row in range(2 * p, 32):
+            o = wp_pair_off(p, row) // 8
+            W[row, 2 * p], W[row, 2 * p + 1] = d[o], d[o + 1]
+    return W
+
+
+def unpack_panel(a):
+    """Folded blob A -> (ncb, nr, ncol, window slots [4*ncb], panel values [32, 4*ncb])."""
+    ncb, nr, ncol = (int(v) for v in a[:12].view(np.uint32))
+    assert len(a) == fold_bytesA(ncb) and ncb == fold_batches(ncol)
+    offs = a[16:16 + 16 * ncb].view(np.uint32).astype(np.int64)
+    assert np.all(offs % 8 == 0)
+    vals = a[16 + 16 * ncb:].view(np.float64).reshape(ncb, 2, 32, 2)      # [batch][pair][row][2]
+    M = vals.transpose(2, 0, 1, 3).reshape(32, 4 * ncb)
+    return ncb, nr, ncol, offs // 8, M
 
 
 def r16(v):
@@ -46,7 +81,8 @@ def solve_from_layout(lay, rhs, reversed_):
     out = np.zeros(N)
     A, B = lay["blobA"], lay["blobB"]
     far_rp, far_col, far_val = lay["far_rp"], lay["far_col"].astype(np.int64), lay["far_val"]
-    stats = dict(chunks=0, rec_slots=0, late_slots=0, early_max=0, early_tot=0)
+    fold = bool(lay.get("fold", 0))
+    stats = dict(chunks=0, rec_slots=0, late_slots=0, early_max=0, early_tot=0, panel_cols=0)
     for lo, hi, chunk0, tile0, gidx, dfar, tile, *_ in lay["blocks"].astype(np.int64):
         nch = (hi - lo + 31) // 32
         wrows = 32 * dfar          # window of this block (leaves: Dfar, separators: Dfar_sep)
@@ -78,7 +114,7 @@ def solve_from_layout(lay, rhs, reversed_):
             o += r16(2 * ne_tot)
             lv = b[o: o + 256 * nl].view(np.float64).reshape(nl, 32)
             lc = b[o + 256 * nl: o + 320 * nl].view(np.uint16).astype(np.int64).reshape(nl, 32)
-            assert o + 320 * nl == len(b) and cnt.sum() == ne_tot
+            assert o + 320 * nl + (FC_WPACK if fold else 0) == len(b) and cnt.sum() == ne_tot
             ts = t0[perm]
             base = 0
             for s in range(ne_max):
@@ -88,8 +124,24 @@ def solve_from_layout(lay, rhs, reversed_):
             t = ts[rank]
             for s in range(nl):
                 t -= lv[s] * win[lc[s]]
-            # ---- blob A: Winv + recent (ELL) ------------------------------------------------------------
             a = A[lay["offA"][g]: lay["offA"][g + 1]]
+            if fold:
+                # ---- helper: u = Winv t ; chain: x = u - M x_rec (dense panel, blob A) ---------------------
+                W = unpack_winv_packed(b[o + 320 * nl:])
+                ncb, nr, ncol, slots, M = unpack_panel(a)
+                assert nr == int(valid.sum())
+                assert np.all(slots[ncol:] == wrows) and not M[:, ncol:].any(), "padding columns"
+                x = W @ t - M @ win[slots]
+                win[(32 * k + np.arange(32)) & wmask] = x
+                jv = j[valid]
+                out[(N - 1 - jv) if reversed_ else jv] = x[valid]
+                stats["chunks"] += 1
+                stats["panel_cols"] += ncol
+                stats["late_slots"] += nl
+                stats["early_max"] += ne_max
+                stats["early_tot"] += ne_tot
+                continue
+            # ---- blob A: Winv + recent (ELL) ------------------------------------------------------------
             nbt, nr, nslots = (int(v) for v in a[:12].view(np.uint32))
             assert nr == int(valid.sum()) and nbt == rec_batches(nslots) and len(a) == AHDR + WBYTES + RBATCH * nbt
             W = unpack_winv(a[AHDR: AHDR + WBYTES].view(np.float64))

@@ -4,7 +4,7 @@ tests/blocked_emulator.py, to exercise the algorithm on the CPU (-m "not gpu")."
 import numpy as np
 import scipy.sparse as sp
 
-from blocked_emulator import AHDR, BHDR, WBYTES, RBATCH, r16, w_pair_off, rec_batches
+from blocked_emulator import AHDR, BHDR, WBYTES, RBATCH, FC_WPACK, r16, w_pair_off, rec_batches, fold_batches, fold_bytesA, wp_pair_off
 
 
 def tree_depths(nb):
@@ -42,7 +42,8 @@ def direction_matrix(G, part, backward):
     return L, bounds, depth
 
 
-def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False, tile_sep=1, tile_leaf=8, E_sep=None):
+def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False, tile_sep=1, tile_leaf=8, E_sep=None,
+                 fold=False):
     N = L.shape[0]
     rp, col, val = L.indptr.astype(np.int64), L.indices.astype(np.int64), L.data
     nb = len(bounds) - 1
@@ -108,6 +109,26 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             n_rec = np.array([len(p[4]) for p in parts])
             nslots, nl, ne_max, ne_tot = int(n_rec.max()), int(n_late.max()), int(n_early.max()), int(n_early.sum())
             # blob A
+            if fold:
+                # dense panel M = Winv L_rec over the distinct recent columns (ascending)
+                cols = sorted(set(int(c) for p in parts for c in p[4]))
+                ncol = len(cols)
+                ncb = fold_batches(ncol)
+                pos = {c: i for i, c in enumerate(cols)}
+                Lrec = np.zeros((32, ncol))
+                for l, p in enumerate(parts):
+                    for c, v in zip(p[4], p[5]):
+                        Lrec[l, pos[int(c)]] = v
+                M = W @ Lrec
+                a = np.zeros(fold_bytesA(ncb), np.uint8)
+                a[:12].view(np.uint32)[:] = [ncb, nr, ncol]
+                offs = a[16:16 + 16 * ncb].view(np.uint32)
+                offs[:] = 8 * (wmask + 1)
+                offs[:ncol] = [8 * ((c - blo) & wmask) for c in cols]
+                vals = a[16 + 16 * ncb:].view(np.float64).reshape(ncb, 2, 32, 2)
+                for i in range(ncol):
+                    vals[i >> 2, (i >> 1) & 1, :, i & 1] = M[:, i]
+                blobsA[g] = a
             nbt = rec_batches(nslots)
             a = np.zeros(AHDR + WBYTES + RBATCH * nbt, np.uint8)
             a[:12].view(np.uint32)[:] = [nbt, nr, nslots]
@@ -128,12 +149,13 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
                         if sidx < len(p[4]):
                             vals[l, u >> 1, u & 1] = p[5][sidx]
                             offs[l, u >> 2, u & 3] = 8 * ((p[4][sidx] - blo) & wmask)
-            blobsA[g] = a
+            if not fold:
+                blobsA[g] = a
             # blob B
             order = sorted(range(32), key=lambda l: (-n_early[l], l))
             rank = np.zeros(32, np.int64)
             rank[order] = np.arange(32)
-            bb = np.zeros(BHDR + r16(ne_max) + r16(8 * ne_tot) + r16(2 * ne_tot) + 320 * nl, np.uint8)
+            bb = np.zeros(BHDR + r16(ne_max) + r16(8 * ne_tot) + r16(2 * ne_tot) + 320 * nl + (FC_WPACK if fold else 0), np.uint8)
             bb[:12].view(np.uint32)[:] = [ne_max, ne_tot, nl]
             bb[16:48] = order
             bb[48:80] = rank
@@ -143,7 +165,13 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             ec = bb[o: o + 2 * ne_tot].view(np.uint16)
             o += r16(2 * ne_tot)
             lv = bb[o: o + 256 * nl].view(np.float64).reshape(nl, 32)
-            lc = bb[o + 256 * nl:].view(np.uint16).reshape(nl, 32)
+            lc = bb[o + 256 * nl: o + 320 * nl].view(np.uint16).reshape(nl, 32)
+            if fold:
+                wq = bb[o + 320 * nl:].view(np.float64)
+                for pp in range(16):
+                    for row in range(2 * pp, 32):
+                        wq[wp_pair_off(pp, row) // 8] = W[row, 2 * pp]
+                        wq[wp_pair_off(pp, row) // 8 + 1] = W[row, 2 * pp + 1]
             base = 0
             for s in range(ne_max):
                 cs = int((n_early > s).sum())
@@ -168,7 +196,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             if depth[b] == want and bounds[b + 1] > bounds[b]:
                 blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], tile_of[b], e_of[b]])
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
-    return dict(active=1, nchunks=nchunks, ntiles=ntiles, nblocks=len(blocks), N=N, Kr=Kr, E=E, Dfar=Dfar_leaf, Dfar_sep=Dfar_sep,
+    return dict(fold=int(fold), active=1, nchunks=nchunks, ntiles=ntiles, nblocks=len(blocks), N=N, Kr=Kr, E=E, Dfar=Dfar_leaf, Dfar_sep=Dfar_sep,
                 offA=offA, offB=offB, blobA=cat(blobsA, np.uint8), blobB=cat(blobsB, np.uint8), far_rp=far_rp,
                 far_col=cat([r[0] for r in far_rows], np.uint32), far_val=cat([r[1] for r in far_rows], np.float64),
                 tile_need=tile_need, blocks=np.array(blocks, np.uint32).reshape(-1, 8))
@@ -188,10 +216,16 @@ def compare_layouts(dev, ref, val_tol=1e-12):
     for g in range(ref["nchunks"]):
         a, r = dev["blobA"][ref["offA"][g]: ref["offA"][g + 1]], ref["blobA"][ref["offA"][g]: ref["offA"][g + 1]]
         assert np.array_equal(a[:12], r[:12]), ("A header", g)
-        nslots = int(r[:12].view(np.uint32)[2])
-        wd, wr = a[AHDR:AHDR + WBYTES].view(np.float64), r[AHDR:AHDR + WBYTES].view(np.float64)
-        assert np.abs(wd - wr).max() <= val_tol * max(1.0, np.abs(wr).max()), ("Winv", g)
-        assert np.array_equal(a[AHDR + WBYTES:], r[AHDR + WBYTES:]), ("recent", g, nslots)
+        if ref.get("fold"):
+            ncb = int(r[:12].view(np.uint32)[0])
+            assert np.array_equal(a[16:16 + 16 * ncb], r[16:16 + 16 * ncb]), ("panel columns", g)
+            md, mr = a[16 + 16 * ncb:].view(np.float64), r[16 + 16 * ncb:].view(np.float64)
+            assert np.abs(md - mr).max() <= val_tol * max(1.0, np.abs(mr).max()), ("panel", g)
+        else:
+            nslots = int(r[:12].view(np.uint32)[2])
+            wd, wr = a[AHDR:AHDR + WBYTES].view(np.float64), r[AHDR:AHDR + WBYTES].view(np.float64)
+            assert np.abs(wd - wr).max() <= val_tol * max(1.0, np.abs(wr).max()), ("Winv", g)
+            assert np.array_equal(a[AHDR + WBYTES:], r[AHDR + WBYTES:]), ("recent", g, nslots)
         b, rb = dev["blobB"][ref["offB"][g]: ref["offB"][g + 1]], ref["blobB"][ref["offB"][g]: ref["offB"][g + 1]]
         assert np.array_equal(b[:12], rb[:12]) and np.array_equal(b[16:80], rb[16:80]), ("B header", g)
         ne_max, ne_tot, nl = (int(v) for v in rb[:12].view(np.uint32))
@@ -201,4 +235,8 @@ def compare_layouts(dev, ref, val_tol=1e-12):
         o += r16(8 * ne_tot)
         assert np.array_equal(b[o:o + 2 * ne_tot], rb[o:o + 2 * ne_tot]), ("early col", g)
         o += r16(2 * ne_tot)
-        assert np.array_equal(b[o:], rb[o:]), ("late", g)
+        assert np.array_equal(b[o:o + 320 * nl], rb[o:o + 320 * nl]), ("late", g)
+        if ref.get("fold"):
+            wd, wr = b[o + 320 * nl:].view(np.float64), rb[o + 320 * nl:].view(np.float64)
+            assert len(wd) == len(wr) == FC_WPACK // 8
+            assert np.abs(wd - wr).max() <= val_tol * max(1.0, np.abs(wr).max()), ("Winv packed", g)

@@ -28,7 +28,8 @@ def test_tree_depths_follow_the_reference_post_order():
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-@pytest.mark.parametrize("kw", [dict(), dict(Kr=1, Dfar=32)])
+@pytest.mark.parametrize("kw", [dict(), dict(Kr=1, Dfar=32), dict(fold=True, Kr=3), dict(fold=True, Kr=1, Dfar=32),
+                                dict(fold=True, Kr=8, E=10)])
 def test_blocked_algorithm_on_goldens(name, kw):
     g = load_golden(name)
     part = g["part"] if len(g["part"]) > 2 else None
@@ -52,6 +53,11 @@ def test_blocked_algorithm_with_every_entry_class():
     y, st = solve_from_layout(lay, b, False)
     assert relerr(y, yo) <= 1e-12
     assert st["early_tot"] > 0 and st["late_slots"] > 0 and st["rec_slots"] > 0 and lay["tile_need"].max() > 0
+    # folded layout: the recent entries become dense panel columns, the inverse moves to the helper's blob
+    lay = build_layout(L, bounds, depth, False, Dfar=32, fold=True, Kr=3)
+    y, st = solve_from_layout(lay, b, False)
+    assert relerr(y, yo) <= 1e-12
+    assert st["early_tot"] > 0 and st["late_slots"] > 0 and st["panel_cols"] > 0 and lay["tile_need"].max() > 0
 
 
 def _solve_with_inverted_diagonal_blocks(L, bounds, b, C):
