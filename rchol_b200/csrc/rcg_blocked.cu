@@ -55,13 +55,18 @@ __host__ __device__ __forceinline__ uint32_t rec_batches(uint32_t nslots) { retu
 // The recent entries (chunks k-1 .. k-Kr) are folded with the inverse of the diagonal block at set-up:
 //     x_k = Winv_k (t'_k - L_rec x_rec) = u_k - M_k x_rec ,   u_k = Winv_k t'_k ,   M_k = Winv_k L_rec  (32 x ncol, dense)
 // so the chain's hop is ONE dense panel apply by one warp; the mat-vec with Winv_k moves off the chain to the near helper.
-// Blob A: 16 B header {batches, rows, columns, 0} | batches x 4 window byte offsets (u32) | batches x 1024 B of panel
-// values, batch-wise [column pair q][row] double2.  Columns ascending (oldest first); padding columns have value 0 and
-// point at the zero slot behind the window.  Blob B: as before, then Winv_k as a packed lower triangle.
-constexpr uint32_t FC_MINB = 4;              // every chunk has at least this many batches (the register-resident tail)
+// Blob A: 16 B header {batches, rows, columns, 0} | TAIL = the 4 batches of the newest 16 columns: 4 x 4 window byte
+// offsets (u32), 4 x 1024 B of panel values, batch-wise [column pair q][row] double2 | BODY = the older batches (an even
+// number): offsets, then values.  Column order is ascending over body-then-tail; padding columns come FIRST (value 0,
+// offset of the zero slot behind the window), so the tail always holds the newest columns at fixed offsets.
+// Blob B: as before, then Winv_k as a packed lower triangle.
+constexpr uint32_t FC_MINB = 4;              // tail batches (register-resident in the chain warp)
+constexpr uint32_t FC_TAILB = 16u + 1040u * FC_MINB;   // header + tail: byte offset of the body
 constexpr uint32_t FC_KRMAX = 8;             // fold depth limit (bitmap of 32*Kr candidate columns)
 constexpr uint32_t FC_WPACK = 4352;          // packed Winv: pair p holds rows 2p..31 -> 16 * sum(32 - 2p) bytes
-__host__ __device__ __forceinline__ uint32_t fold_batches(uint32_t ncol) { return ncol <= 4u * FC_MINB ? FC_MINB : (ncol + 3u) / 4u; }
+__host__ __device__ __forceinline__ uint32_t fold_batches(uint32_t ncol) {   // tail + an even number of body batches
+  return ncol <= 4u * FC_MINB ? FC_MINB : FC_MINB + 2u * ((ncol - 4u * FC_MINB + 7u) / 8u);
+}
 __host__ __device__ __forceinline__ uint32_t fold_bytesA(uint32_t ncb) { return 16u + 1040u * ncb; }
 // byte offset of the double2 {Winv[row][2p], Winv[row][2p+1]} (row >= 2p) inside the packed triangle
 __host__ __device__ __forceinline__ uint32_t wp_pair_off(uint32_t p, uint32_t row) { return 16u * (p * (33u - p) + row - 2u * p); }
@@ -376,16 +381,26 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
       __syncwarp();
       const uint32_t ncol = warp_add_u32(lane < FC_KRMAX ? (uint32_t)__popc(bm[lane]) : 0u);
       const uint32_t ncb = fold_batches(ncol);
-      uint32_t *offs = reinterpret_cast<uint32_t *>(A + 16u);
-      unsigned char *vals = A + 16u + 16u * ncb;
+      // column slot ci (0 .. 4 ncb - 1, padding first): batch = ci / 4; body batches come first in column order
+      const uint32_t nbody = ncb - FC_MINB, npad = 4u * ncb - ncol;
+      auto off_ptr = [&](uint32_t ci_) -> uint32_t * {
+        const uint32_t bt = ci_ >> 2;
+        unsigned char *o = bt < nbody ? A + FC_TAILB + 16u * bt : A + 16u + 16u * (bt - nbody);
+        return reinterpret_cast<uint32_t *>(o) + (ci_ & 3u);
+      };
+      auto val_ptr = [&](uint32_t ci_, uint32_t row_) -> double * {
+        const uint32_t bt = ci_ >> 2;
+        unsigned char *v = bt < nbody ? A + FC_TAILB + 16u * nbody + 1024u * bt : A + 16u + 16u * FC_MINB + 1024u * (bt - nbody);
+        return reinterpret_cast<double *>(v + 512u * ((ci_ >> 1) & 1u) + 16u * row_) + (ci_ & 1u);
+      };
       if (lane == 0) {
         uint32_t *hd = reinterpret_cast<uint32_t *>(A);
         hd[0] = ncb; hd[1] = nr; hd[2] = ncol; hd[3] = 0;
       }
-      for (uint32_t i = lane; i < 4u * ncb; i += 32u) offs[i] = 8u * (wmask + 1u);   // padding columns: the zero slot
+      for (uint32_t i = lane; i < npad; i += 32u) *off_ptr(i) = 8u * (wmask + 1u);   // padding columns: the zero slot
       __syncwarp();
       int64_t pcur = r.p_late;   // this row's next recent entry (rows are sorted by column)
-      uint32_t ci = 0;
+      uint32_t ci = npad;
       for (uint32_t wd = 0; wd < FC_KRMAX; wd++) {
         uint32_t bits = bm[wd];
         while (bits) {
@@ -401,8 +416,8 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
             nz &= nz - 1u;
             m = fma(Wm[lane][i], __shfl_sync(0xffffffffu, lval, i), m);   // Winv[row][i] * L[i][c]
           }
-          reinterpret_cast<double *>(vals + 1024u * (ci >> 2) + 512u * ((ci >> 1) & 1u) + 16u * lane)[ci & 1u] = m;
-          if (lane == 0) offs[ci] = 8u * ((c - blo) & wmask);
+          *val_ptr(ci, lane) = m;
+          if (lane == 0) *off_ptr(ci) = 8u * ((c - blo) & wmask);
           ci++;
         }
       }

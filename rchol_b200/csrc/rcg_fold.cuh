@@ -33,6 +33,19 @@ __device__ __forceinline__ void mbar_arrive_after3(uint64_t *bar, uint32_t a, do
       : "memory");
 }
 
+__device__ __forceinline__ uint32_t mbar_test_s(uint32_t bar_s, uint32_t par) {   // non-blocking, 32-bit shared address
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar_s), "r"(par) : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint32_t mbar_try_s(uint32_t bar_s, uint32_t par) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar_s), "r"(par) : "memory");
+  return ok;
+}
+
 // PROF: cycle counters of the chain warp and of near helper 0 (dbg bit 0) -- a separate instantiation.
 template <bool PROF>
 __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
@@ -55,7 +68,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
   uint32_t *tready = seqB + P.SB;
   uint32_t *ctl = tready + BC_TR;   // [0] prog: solved chunks of the current block, [1] published chunks, [2] abort
 
-  if (threadIdx.x < P.SA) { mbar_init(fullA + threadIdx.x, 1); mbar_init(emptyA + threadIdx.x, 1); }
+  if (threadIdx.x < P.SA) mbar_init(fullA + threadIdx.x, 1);   // (ring A has no empty barriers: the producer polls prog)
   if (threadIdx.x < P.SB) { mbar_init(fullB + threadIdx.x, 1); mbar_init(emptyB + threadIdx.x, 1); seqB[threadIdx.x] = 0xFFFFFFFFu; }
   if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = 0; ctl[2] = 0; }
   if (threadIdx.x < 16) win[P.W + threadIdx.x] = 0.0;
@@ -162,108 +175,146 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
 
     if (warp == 0) {
       // ------------------------------ chain warp ---------------------------------------------------------
-      // Two register sets (E / O): the tail of chunk k+1 (offsets + panel values of its newest 16 columns) is loaded
-      // while the x loads of chunk k are in flight.  All shared-memory loads are volatile asm: their program order IS
-      // the schedule of the lone warp.
+      // A lone warp is bound by the number of instructions between two hops (measured: 4-8 cycles per dependent
+      // instruction, 150 for a synchronous mbarrier test, 160-410 for a divergent branch, a MEMBAR for st.release), so:
+      // 32-bit shared addresses only, no divergent branch (lane 0's stores are predicated), the progress word is a
+      // volatile store behind the window store (same warp, same LSU queue: program order), the staging barrier of
+      // chunk k+2 is tested at the top of chunk k and its answer is consumed a chunk later, and two register sets
+      // (E / O) hold the tail of the next chunk (fixed offsets in the blob) while this one's x loads are in flight.
       const bool prof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0;
-      const uint32_t fullA_s = smem_u32(fullA), ringA_s = smem_u32(ringA);
-      uint32_t slot = ia0 % P.SA, par = (ia0 / P.SA) & 1u;
-      uint32_t oE[16], oO[16];
-      double mE[16], mO[16];
-      uint32_t ncbE = FC_MINB, ncbO = FC_MINB, asE = 0, asO = 0;
+      uint32_t fullA_s = smem_u32(fullA), ringA_s = smem_u32(ringA);
+      uint32_t SA = P.SA, capA = P.capA, wm8 = 8u * wmask, win_r = win_s, trdy_r = trdy_s, prog_r = prog_s;
+      uint32_t xst_s = win_s + 8u * lane;            // window slot of this lane's row: + ((256 k) & wm8)
+      uint32_t ul_s = u_s + 8u * lane;
+      uint32_t lane16 = 16u * lane;
+      // opaque to the compiler: kept in registers instead of being re-derived from the constant bank / special
+      // registers inside the loop (the lone warp pays for every instruction)
+      asm volatile("" : "+r"(fullA_s), "+r"(ringA_s), "+r"(SA), "+r"(capA), "+r"(wm8));
+      asm volatile("" : "+r"(win_r), "+r"(trdy_r), "+r"(prog_r), "+r"(xst_s), "+r"(ul_s), "+r"(lane16));
+      uint32_t slot0 = ia0 % SA, par0 = (ia0 / SA) & 1u;   // staging slot of chunk k
+      uint32_t slot1 = slot0 + 1u, par1 = par0;            // ... of chunk k+1
+      if (slot1 == SA) { slot1 = 0u; par1 ^= 1u; }
+      uint32_t ok1 = 0u;                                   // "chunk k+1 is staged", tested one chunk ahead
+      uint32_t oE[16], oO[16];                             // tail columns: shared addresses of x (two sets, chunk parity)
+      double mt[16];                                       // tail panel values (one set: reloaded behind the FMAs)
+      uint32_t ncb = FC_MINB, ncb_n = FC_MINB, as_c = 0, as_n = 0;
       uint32_t tpf = 0u, spins = 0u;
+      double un = 0.0;                                     // u of the next chunk, loaded behind its flag
 #define FC_SPIN(cond_, code_)                                                                                             \
       while (__builtin_expect(!(cond_), 0)) {                                                                             \
         if (++spins > (1u << 24)) { atomicCAS(P.abort_g, 0u, (code_)); sts_volatile_u32(G.abort_s, 1u); break; }          \
       }
-      // offsets + values of the last FC_MINB batches of the chunk staged in `slot`
-#define FC_PRELOAD(O_, M_, NCB_, AS_)                                                                                     \
-      do {                                                                                                                \
-        AS_ = ringA_s + slot * P.capA;                                                                                    \
-        NCB_ = lds_u32(AS_);                                                                                              \
-        const uint32_t nb_ = NCB_ - FC_MINB;                                                                              \
-        const uint32_t ob_ = AS_ + 16u + 16u * nb_, vb_ = AS_ + 16u + 16u * NCB_ + 1024u * nb_ + 16u * lane;              \
-        _Pragma("unroll") for (uint32_t q_ = 0; q_ < FC_MINB; q_++) {                                                     \
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"                                                         \
-                       : "=r"(O_[4 * q_]), "=r"(O_[4 * q_ + 1]), "=r"(O_[4 * q_ + 2]), "=r"(O_[4 * q_ + 3]) : "r"(ob_ + 16u * q_) : "memory"); \
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(M_[4 * q_]), "=d"(M_[4 * q_ + 1]) : "r"(vb_ + 1024u * q_) : "memory"); \
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(M_[4 * q_ + 2]), "=d"(M_[4 * q_ + 3]) : "r"(vb_ + 1024u * q_ + 512u) : "memory"); \
-        }                                                                                                                 \
-      } while (0)
-#define FC_CHUNK(O_, M_, NCB_, AS_, On_, Mn_, NCBn_, ASn_)                                                                \
+      // tail of the chunk staged at AS_: window offsets of its newest 16 columns (fixed place in the blob) ...
+#define FC_LOAD_OFFS(O_, AS_)                                                                                             \
+      _Pragma("unroll") for (uint32_t q_ = 0; q_ < FC_MINB; q_++)                                                         \
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"                                                           \
+                     : "=r"(O_[4 * q_]), "=r"(O_[4 * q_ + 1]), "=r"(O_[4 * q_ + 2]), "=r"(O_[4 * q_ + 3]) : "r"((AS_) + 16u + 16u * q_) : "memory")
+      // ... and their panel values
+#define FC_LOAD_VALS(AS_)                                                                                                 \
+      _Pragma("unroll") for (uint32_t q_ = 0; q_ < FC_MINB; q_++) {                                                       \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mt[4 * q_]), "=d"(mt[4 * q_ + 1]) : "r"((AS_) + 80u + lane16 + 1024u * q_) : "memory"); \
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mt[4 * q_ + 2]), "=d"(mt[4 * q_ + 3]) : "r"((AS_) + 592u + lane16 + 1024u * q_) : "memory"); \
+      }
+#define FC_CHUNK(O_, On_)                                                                                                 \
       do {                                                                                                                \
         long long c0_ = 0;                                                                                                \
         if (prof) c0_ = clock64();                                                                                        \
+        /* staging barrier of chunk k+2: asked now, answered (ok2_) while this chunk computes */                          \
+        uint32_t slot2_ = slot1 + 1u, par2_ = par1;                                                                       \
+        if (slot2_ == SA) { slot2_ = 0u; par2_ ^= 1u; }                                                                   \
+        const uint32_t ok2_ = mbar_test_s(fullA_s + 8u * slot2_, par2_);                                                  \
         if (__builtin_expect(tpf != k + 1u, 0)) {                                                                         \
-          FC_SPIN((tpf = ld_acquire_cta_s(trdy_s + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);                          \
+          FC_SPIN((tpf = ld_acquire_cta_s(trdy_r + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);                          \
+          un = lds_f64(ul_s + ((k & (BC_TR - 1u)) << 8));                                                                 \
           if (prof) { pc[3] += 1; pc[1] += clock64() - c0_; }                                                             \
         }                                                                                                                 \
-        /* u_k through an address that depends on the flag (cannot be hoisted above it) */                                \
-        double a0_ = lds_f64(u_s + 8u * ((k & (BC_TR - 1u)) * 32u + lane) + ((tpf ^ (k + 1u)) & 0x7u) * 8u);              \
-        double a1_ = 0.0, a2_ = 0.0, a3_ = 0.0;                                                                           \
-        /* body: the older batches of a wide panel */                                                                     \
-        {                                                                                                                 \
-          const uint32_t nb_ = NCB_ - FC_MINB;                                                                            \
-          const uint32_t vb_ = AS_ + 16u + 16u * NCB_ + 16u * lane;                                                       \
-          _Pragma("unroll 1") for (uint32_t bb_ = 0; bb_ < nb_; bb_++) {                                                  \
-            uint32_t q0_, q1_, q2_, q3_;                                                                                  \
-            double m0_, m1_, m2_, m3_;                                                                                    \
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q0_), "=r"(q1_), "=r"(q2_), "=r"(q3_) : "r"(AS_ + 16u + 16u * bb_) : "memory"); \
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m0_), "=d"(m1_) : "r"(vb_ + 1024u * bb_) : "memory");   \
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m2_), "=d"(m3_) : "r"(vb_ + 1024u * bb_ + 512u) : "memory"); \
-            const double x0_ = lds_f64(win_s + q0_), x1_ = lds_f64(win_s + q1_), x2_ = lds_f64(win_s + q2_), x3_ = lds_f64(win_s + q3_); \
-            a0_ = fma(-m0_, x0_, a0_);                                                                                    \
-            a1_ = fma(-m1_, x1_, a1_);                                                                                    \
-            a2_ = fma(-m2_, x2_, a2_);                                                                                    \
-            a3_ = fma(-m3_, x3_, a3_);                                                                                    \
+        double a0_ = un, a1_ = 0.0, a2_ = 0.0, a3_ = 0.0;                                                                           \
+        /* body: the older batches of a wide panel, two per trip (eight independent gathers in flight) */                 \
+        if (__builtin_expect(ncb != FC_MINB, 0)) {                                                                        \
+          const uint32_t nb_ = ncb - FC_MINB;                                                                             \
+          const uint32_t ob_ = as_c + FC_TAILB, vb_ = ob_ + 16u * nb_ + lane16;                                           \
+          _Pragma("unroll 1") for (uint32_t bb_ = 0; bb_ < nb_; bb_ += 2u) {                                              \
+            uint32_t q_[8];                                                                                               \
+            double m_[8], y_[8];                                                                                          \
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q_[0]), "=r"(q_[1]), "=r"(q_[2]), "=r"(q_[3]) : "r"(ob_ + 16u * bb_) : "memory"); \
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q_[4]), "=r"(q_[5]), "=r"(q_[6]), "=r"(q_[7]) : "r"(ob_ + 16u * bb_ + 16u) : "memory"); \
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m_[0]), "=d"(m_[1]) : "r"(vb_ + 1024u * bb_) : "memory");     \
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m_[2]), "=d"(m_[3]) : "r"(vb_ + 1024u * bb_ + 512u) : "memory"); \
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m_[4]), "=d"(m_[5]) : "r"(vb_ + 1024u * bb_ + 1024u) : "memory"); \
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m_[6]), "=d"(m_[7]) : "r"(vb_ + 1024u * bb_ + 1536u) : "memory"); \
+            _Pragma("unroll") for (uint32_t i_ = 0; i_ < 8u; i_++) y_[i_] = lds_f64(win_r + q_[i_]);                      \
+            a0_ = fma(-m_[0], y_[0], a0_);                                                                                \
+            a1_ = fma(-m_[1], y_[1], a1_);                                                                                \
+            a2_ = fma(-m_[2], y_[2], a2_);                                                                                \
+            a3_ = fma(-m_[3], y_[3], a3_);                                                                                \
+            a0_ = fma(-m_[4], y_[4], a0_);                                                                                \
+            a1_ = fma(-m_[5], y_[5], a1_);                                                                                \
+            a2_ = fma(-m_[6], y_[6], a2_);                                                                                \
+            a3_ = fma(-m_[7], y_[7], a3_);                                                                                \
           }                                                                                                               \
         }                                                                                                                 \
-        /* tail: x of the newest 16 columns (the only loads that depend on the previous hop) */                           \
+        /* tail: x of the newest 16 columns (the only loads that depend on the previous hop); O_ holds addresses */       \
         double x_[16];                                                                                                    \
-        _Pragma("unroll") for (uint32_t i_ = 0; i_ < 16u; i_++) x_[i_] = lds_f64(win_s + O_[i_]);                         \
-        /* chain-independent loads of the next chunk, in flight behind the x loads */                                     \
-        const uint32_t oslot_ = slot;                                                                                     \
-        if (k + 1u < nch) {                                                                                               \
-          if (++slot == P.SA) { slot = 0; par ^= 1u; }                                                                    \
-          if (__builtin_expect(!mbar_test(fullA + slot, par), 0)) {                                                       \
+        _Pragma("unroll") for (uint32_t i_ = 0; i_ < 16u; i_++) x_[i_] = lds_f64(O_[i_]);                                 \
+        /* chain-independent loads of the next chunk, in flight behind the x loads: offsets, batch count, flag of u */    \
+        const bool more_ = k + 1u < nch;                                                                                  \
+        if (more_) {                                                                                                      \
+          if (__builtin_expect(ok1 == 0u, 0)) {                                                                           \
             long long c1_ = 0;                                                                                            \
             if (prof) c1_ = clock64();                                                                                    \
-            FC_SPIN(mbar_try(fullA + slot, par), 0x200u);                                                                 \
+            FC_SPIN((ok1 = mbar_try_s(fullA_s + 8u * slot1, par1)) != 0u, 0x200u);                                        \
             if (prof) pc[0] += clock64() - c1_;                                                                           \
           }                                                                                                               \
-          FC_PRELOAD(On_, Mn_, NCBn_, ASn_);                                                                              \
-          tpf = lds_volatile_u32(trdy_s + 4u * ((k + 1u) & (BC_TR - 1u)));                                                \
+          as_n = ringA_s + slot1 * capA;                                                                                  \
+          FC_LOAD_OFFS(On_, as_n);                                                                                        \
+          ncb_n = lds_u32(as_n);                                                                                          \
+          /* flag of u_{k+1}, then the value: shared-memory loads of one warp complete in order, so a value read       \
+             behind a set flag is the published one; a clear flag is polled at the top of the next chunk */              \
+          tpf = lds_volatile_u32(trdy_r + 4u * ((k + 1u) & (BC_TR - 1u)));                                                \
+          un = lds_f64(ul_s + (((k + 1u) & (BC_TR - 1u)) << 8));                                                          \
         }                                                                                                                 \
         _Pragma("unroll") for (uint32_t i_ = 0; i_ < 16u; i_ += 4u) {                                                     \
-          a0_ = fma(-M_[i_], x_[i_], a0_);                                                                                \
-          a1_ = fma(-M_[i_ + 1u], x_[i_ + 1u], a1_);                                                                      \
-          a2_ = fma(-M_[i_ + 2u], x_[i_ + 2u], a2_);                                                                      \
-          a3_ = fma(-M_[i_ + 3u], x_[i_ + 3u], a3_);                                                                      \
+          a0_ = fma(-mt[i_], x_[i_], a0_);                                                                                \
+          a1_ = fma(-mt[i_ + 1u], x_[i_ + 1u], a1_);                                                                      \
+          a2_ = fma(-mt[i_ + 2u], x_[i_ + 2u], a2_);                                                                      \
+          a3_ = fma(-mt[i_ + 3u], x_[i_ + 3u], a3_);                                                                      \
         }                                                                                                                 \
+        /* panel values of the next chunk's tail, into the registers the FMAs above have just read */                     \
+        if (more_) { FC_LOAD_VALS(as_n); }                                                                                \
         const double xk_ = (a0_ + a1_) + (a2_ + a3_);                                                                     \
-        sts_f64(win_s + 8u * ((32u * k + lane) & wmask), xk_);                                                            \
-        __syncwarp();                                                                                                     \
-        if (lane == 0) {                                                                                                  \
-          st_release_cta_s(prog_s, k + 1u);                                                                               \
-          mbar_arrive(emptyA + oslot_);                                                                                   \
+        sts_f64(xst_s + ((k << 8) & wm8), xk_);                                                                           \
+        /* progress word: a volatile store behind the window store, by ALL lanes (same word, same value: no divergent    \
+           branch).  It also frees the staging slot: the producer of ring A polls it. */                                 \
+        sts_volatile_u32(prog_r, k + 1u);                                                                                 \
+        if (more_) {                                                                                                      \
+          _Pragma("unroll") for (uint32_t i_ = 0; i_ < 16u; i_++) On_[i_] += win_r;   /* offsets -> addresses */          \
         }                                                                                                                 \
+        slot0 = slot1; slot1 = slot2_; par1 = par2_; ok1 = ok2_;                                                          \
+        as_c = as_n; ncb = ncb_n;                                                                                         \
         if (prof) pc[2] += 1;                                                                                             \
         k++;                                                                                                              \
       } while (0)
       uint32_t k = 0;
       if (nch > 0) {
-        FC_SPIN(mbar_try(fullA + slot, par), 0x200u);
-        FC_PRELOAD(oE, mE, ncbE, asE);
-        tpf = lds_volatile_u32(trdy_s);
+        FC_SPIN(mbar_try_s(fullA_s + 8u * slot0, par0) != 0u, 0x200u);
+        as_c = ringA_s + slot0 * capA;
+        FC_LOAD_OFFS(oE, as_c);
+        FC_LOAD_VALS(as_c);
+        ncb = lds_u32(as_c);
+#pragma unroll
+        for (uint32_t i = 0; i < 16u; i++) oE[i] += win_r;
+        tpf = lds_volatile_u32(trdy_r);
+        un = lds_f64(ul_s);
+        if (nch > 1u) ok1 = mbar_test_s(fullA_s + 8u * slot1, par1);
       }
       while (k < nch) {
-        FC_CHUNK(oE, mE, ncbE, asE, oO, mO, ncbO, asO);
+        FC_CHUNK(oE, oO);
         if (k >= nch) break;
-        FC_CHUNK(oO, mO, ncbO, asO, oE, mE, ncbE, asE);
+        FC_CHUNK(oO, oE);
       }
-      (void)fullA_s;
 #undef FC_CHUNK
-#undef FC_PRELOAD
+#undef FC_LOAD_VALS
+#undef FC_LOAD_OFFS
 #undef FC_SPIN
     } else if (warp == 4u) {
       // ------------------------------ TMA producer, ring A -----------------------------------------------
@@ -281,7 +332,10 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         for (uint32_t l = 0; l < 32u && base + l < nch; l++) {
           const uint32_t i = ia0 + base + l, slot = i % P.SA, use = i / P.SA;
           const int64_t e0 = __shfl_sync(0xffffffffu, O0, (int)l), e1 = __shfl_sync(0xffffffffu, O1, (int)l);
-          if (use > 0u) BC_WAIT(mbar_try(emptyA + slot, (use - 1u) & 1u), 0x900u, 20);
+          // the slot's previous tenant is chunk base + l - SA of this block (earlier blocks are finished: block barrier);
+          // the chain warp has read it completely when it publishes that chunk's progress
+          (void)use;
+          if (base + l >= P.SA) BC_WAIT(ld_acquire_cta_s(prog_s) >= base + l - P.SA + 1u, 0x900u, 40);
           if (lane == 0) {
             const uint32_t bytes = (uint32_t)(e1 - e0);
             mbar_expect_tx(fullA + slot, bytes);

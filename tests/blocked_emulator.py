@@ -10,8 +10,12 @@ AHDR, BHDR, WBYTES, RBATCH = 16, 80, 1024 * 8, 3072
 FC_MINB, FC_WPACK = 4, 4352          # folded layout (chain_mode 5, rcg_fold.cuh)
 
 
+FC_TAILB = 16 + 1040 * FC_MINB       # header + tail (the newest 16 columns): byte offset of the body
+
+
 def fold_batches(ncol):
-    return FC_MINB if ncol <= 4 * FC_MINB else (ncol + 3) // 4
+    """Tail (4 batches) + an even number of body batches."""
+    return FC_MINB if ncol <= 4 * FC_MINB else FC_MINB + 2 * ((ncol - 4 * FC_MINB + 7) // 8)
 
 
 def fold_bytesA(ncb):
@@ -37,10 +41,12 @@ def unpack_panel(a):
     """Folded blob A -> (ncb, nr, ncol, window slots [4*ncb], panel values [32, 4*ncb])."""
     ncb, nr, ncol = (int(v) for v in a[:12].view(np.uint32))
     assert len(a) == fold_bytesA(ncb) and ncb == fold_batches(ncol)
-    offs = a[16:16 + 16 * ncb].view(np.uint32).astype(np.int64)
+    nbody = ncb - FC_MINB
+    # column order: body batches first (oldest, padding in front), then the tail; the tail sits first in the blob
+    offs = np.concatenate([a[FC_TAILB:FC_TAILB + 16 * nbody], a[16:16 + 16 * FC_MINB]]).view(np.uint32).astype(np.int64)
     assert np.all(offs % 8 == 0)
-    vals = a[16 + 16 * ncb:].view(np.float64).reshape(ncb, 2, 32, 2)      # [batch][pair][row][2]
-    M = vals.transpose(2, 0, 1, 3).reshape(32, 4 * ncb)
+    vals = np.concatenate([a[FC_TAILB + 16 * nbody:], a[16 + 16 * FC_MINB:FC_TAILB]]).view(np.float64).reshape(ncb, 2, 32, 2)
+    M = vals.transpose(2, 0, 1, 3).reshape(32, 4 * ncb)                    # [batch][pair][row][2] -> [row][column]
     return ncb, nr, ncol, offs // 8, M
 
 
@@ -130,7 +136,8 @@ def solve_from_layout(lay, rhs, reversed_):
                 W = unpack_winv_packed(b[o + 320 * nl:])
                 ncb, nr, ncol, slots, M = unpack_panel(a)
                 assert nr == int(valid.sum())
-                assert np.all(slots[ncol:] == wrows) and not M[:, ncol:].any(), "padding columns"
+                npad = 4 * ncb - ncol
+                assert np.all(slots[:npad] == wrows) and not M[:, :npad].any(), "padding columns come first"
                 x = W @ t - M @ win[slots]
                 win[(32 * k + np.arange(32)) & wmask] = x
                 jv = j[valid]

@@ -4,7 +4,7 @@ tests/blocked_emulator.py, to exercise the algorithm on the CPU (-m "not gpu")."
 import numpy as np
 import scipy.sparse as sp
 
-from blocked_emulator import AHDR, BHDR, WBYTES, RBATCH, FC_WPACK, r16, w_pair_off, rec_batches, fold_batches, fold_bytesA, wp_pair_off
+from blocked_emulator import AHDR, BHDR, WBYTES, RBATCH, FC_WPACK, FC_MINB, FC_TAILB, r16, w_pair_off, rec_batches, fold_batches, fold_bytesA, wp_pair_off
 
 
 def tree_depths(nb):
@@ -122,12 +122,18 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
                 M = W @ Lrec
                 a = np.zeros(fold_bytesA(ncb), np.uint8)
                 a[:12].view(np.uint32)[:] = [ncb, nr, ncol]
-                offs = a[16:16 + 16 * ncb].view(np.uint32)
-                offs[:] = 8 * (wmask + 1)
-                offs[:ncol] = [8 * ((c - blo) & wmask) for c in cols]
-                vals = a[16 + 16 * ncb:].view(np.float64).reshape(ncb, 2, 32, 2)
+                nbody, npad = ncb - FC_MINB, 4 * ncb - ncol
+                offs = np.full(4 * ncb, 8 * (wmask + 1), np.uint32)         # column slots, padding first
+                offs[npad:] = [8 * ((c - blo) & wmask) for c in cols]
+                vals = np.zeros((ncb, 2, 32, 2))
                 for i in range(ncol):
-                    vals[i >> 2, (i >> 1) & 1, :, i & 1] = M[:, i]
+                    ci = npad + i
+                    vals[ci >> 2, (ci >> 1) & 1, :, ci & 1] = M[:, i]
+                # blob: header | tail offsets | tail values | body offsets | body values
+                a[16:16 + 16 * FC_MINB] = offs[4 * nbody:].view(np.uint8)
+                a[16 + 16 * FC_MINB:FC_TAILB] = vals[nbody:].reshape(-1).view(np.uint8)
+                a[FC_TAILB:FC_TAILB + 16 * nbody] = offs[:4 * nbody].view(np.uint8)
+                a[FC_TAILB + 16 * nbody:] = vals[:nbody].reshape(-1).view(np.uint8)
                 blobsA[g] = a
             nbt = rec_batches(nslots)
             a = np.zeros(AHDR + WBYTES + RBATCH * nbt, np.uint8)
@@ -218,9 +224,13 @@ def compare_layouts(dev, ref, val_tol=1e-12):
         assert np.array_equal(a[:12], r[:12]), ("A header", g)
         if ref.get("fold"):
             ncb = int(r[:12].view(np.uint32)[0])
-            assert np.array_equal(a[16:16 + 16 * ncb], r[16:16 + 16 * ncb]), ("panel columns", g)
-            md, mr = a[16 + 16 * ncb:].view(np.float64), r[16 + 16 * ncb:].view(np.float64)
-            assert np.abs(md - mr).max() <= val_tol * max(1.0, np.abs(mr).max()), ("panel", g)
+            nbody = ncb - FC_MINB
+            for lo_, hi_ in ((16, 16 + 16 * FC_MINB), (FC_TAILB, FC_TAILB + 16 * nbody)):
+                assert np.array_equal(a[lo_:hi_], r[lo_:hi_]), ("panel columns", g)
+            for lo_, hi_ in ((16 + 16 * FC_MINB, FC_TAILB), (FC_TAILB + 16 * nbody, len(r))):
+                md, mr = a[lo_:hi_].view(np.float64), r[lo_:hi_].view(np.float64)
+                if len(mr):
+                    assert np.abs(md - mr).max() <= val_tol * max(1.0, np.abs(mr).max()), ("panel", g)
         else:
             nslots = int(r[:12].view(np.uint32)[2])
             wd, wr = a[AHDR:AHDR + WBYTES].view(np.float64), r[AHDR:AHDR + WBYTES].view(np.float64)
