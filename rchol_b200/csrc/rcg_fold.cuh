@@ -181,138 +181,130 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
       // volatile store behind the window store (same warp, same LSU queue: program order), the staging barrier of
       // chunk k+2 is tested at the top of chunk k and its answer is consumed a chunk later, and two register sets
       // (E / O) hold the tail of the next chunk (fixed offsets in the blob) while this one's x loads are in flight.
+      // The loop body is ONE copy of straight-line code of ~90 instructions (1.5 KB): a lone warp has nobody to hide
+      // its instruction fetches behind, and a body larger than the scheduler's L0 instruction cache (two unrolled
+      // copies were 6.7 KB) costs more than everything else in it.
       const bool prof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0;
-      uint32_t fullA_s = smem_u32(fullA), ringA_s = smem_u32(ringA);
-      uint32_t SA = P.SA, capA = P.capA, wm8 = 8u * wmask, win_r = win_s, trdy_r = trdy_s, prog_r = prog_s;
+      uint32_t ringA_s = smem_u32(ringA), ringA_e = ringA_s + P.SA * P.capA, capA = P.capA;
+      uint32_t fullA_s = smem_u32(fullA), fullA_e = fullA_s + 8u * P.SA;
+      uint32_t wm8 = 8u * wmask, lane16 = 16u * lane;
       uint32_t xst_s = win_s + 8u * lane;            // window slot of this lane's row: + ((256 k) & wm8)
       uint32_t ul_s = u_s + 8u * lane;
-      uint32_t lane16 = 16u * lane;
       // opaque to the compiler: kept in registers instead of being re-derived from the constant bank / special
       // registers inside the loop (the lone warp pays for every instruction)
-      asm volatile("" : "+r"(fullA_s), "+r"(ringA_s), "+r"(SA), "+r"(capA), "+r"(wm8));
-      asm volatile("" : "+r"(win_r), "+r"(trdy_r), "+r"(prog_r), "+r"(xst_s), "+r"(ul_s), "+r"(lane16));
-      uint32_t slot0 = ia0 % SA, par0 = (ia0 / SA) & 1u;   // staging slot of chunk k
-      uint32_t slot1 = slot0 + 1u, par1 = par0;            // ... of chunk k+1
-      if (slot1 == SA) { slot1 = 0u; par1 ^= 1u; }
-      uint32_t ok1 = 0u;                                   // "chunk k+1 is staged", tested one chunk ahead
-      uint32_t oE[16], oO[16];                             // tail columns: shared addresses of x (two sets, chunk parity)
-      double mt[16];                                       // tail panel values (one set: reloaded behind the FMAs)
-      uint32_t ncb = FC_MINB, ncb_n = FC_MINB, as_c = 0, as_n = 0;
+      asm volatile("" : "+r"(ringA_s), "+r"(ringA_e), "+r"(capA), "+r"(fullA_s), "+r"(fullA_e), "+r"(wm8));
+      asm volatile("" : "+r"(xst_s), "+r"(ul_s), "+r"(lane16));
+      const uint32_t slot0 = ia0 % P.SA;
+      uint32_t par1 = (ia0 / P.SA) & 1u;                   // parity of the staging barrier of chunk k+1 ...
+      uint32_t bar1 = fullA_s + 8u * slot0 + 8u;           // ... its address ...
+      uint32_t as_n = ringA_s + slot0 * capA + capA;       // ... and its staging slot
+      if (bar1 == fullA_e) { bar1 = fullA_s; as_n = ringA_s; par1 ^= 1u; }
+      uint32_t ok1 = 0u;                                   // "chunk k+1 is staged", asked one chunk ahead
+      uint32_t o[16];                                      // tail columns of chunk k: window byte offsets of x
+      double mt[16];                                       // tail panel values
+      uint32_t ncb = FC_MINB, as_c = ringA_s + slot0 * capA;
       uint32_t tpf = 0u, spins = 0u;
       double un = 0.0;                                     // u of the next chunk, loaded behind its flag
 #define FC_SPIN(cond_, code_)                                                                                             \
       while (__builtin_expect(!(cond_), 0)) {                                                                             \
         if (++spins > (1u << 24)) { atomicCAS(P.abort_g, 0u, (code_)); sts_volatile_u32(G.abort_s, 1u); break; }          \
       }
-      // tail of the chunk staged at AS_: window offsets of its newest 16 columns (fixed place in the blob) ...
-#define FC_LOAD_OFFS(O_, AS_)                                                                                             \
+#define FC_LOAD_OFFS(AS_)                                                                                                 \
       _Pragma("unroll") for (uint32_t q_ = 0; q_ < FC_MINB; q_++)                                                         \
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"                                                           \
-                     : "=r"(O_[4 * q_]), "=r"(O_[4 * q_ + 1]), "=r"(O_[4 * q_ + 2]), "=r"(O_[4 * q_ + 3]) : "r"((AS_) + 16u + 16u * q_) : "memory")
-      // ... and their panel values
+                     : "=r"(o[4 * q_]), "=r"(o[4 * q_ + 1]), "=r"(o[4 * q_ + 2]), "=r"(o[4 * q_ + 3]) : "r"((AS_) + 16u + 16u * q_) : "memory")
 #define FC_LOAD_VALS(AS_)                                                                                                 \
       _Pragma("unroll") for (uint32_t q_ = 0; q_ < FC_MINB; q_++) {                                                       \
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mt[4 * q_]), "=d"(mt[4 * q_ + 1]) : "r"((AS_) + 80u + lane16 + 1024u * q_) : "memory"); \
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mt[4 * q_ + 2]), "=d"(mt[4 * q_ + 3]) : "r"((AS_) + 592u + lane16 + 1024u * q_) : "memory"); \
       }
-#define FC_CHUNK(O_, On_)                                                                                                 \
-      do {                                                                                                                \
-        long long c0_ = 0;                                                                                                \
-        if (prof) c0_ = clock64();                                                                                        \
-        /* staging barrier of chunk k+2: asked now, answered (ok2_) while this chunk computes */                          \
-        uint32_t slot2_ = slot1 + 1u, par2_ = par1;                                                                       \
-        if (slot2_ == SA) { slot2_ = 0u; par2_ ^= 1u; }                                                                   \
-        const uint32_t ok2_ = mbar_test_s(fullA_s + 8u * slot2_, par2_);                                                  \
-        if (__builtin_expect(tpf != k + 1u, 0)) {                                                                         \
-          FC_SPIN((tpf = ld_acquire_cta_s(trdy_r + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);                          \
-          un = lds_f64(ul_s + ((k & (BC_TR - 1u)) << 8));                                                                 \
-          if (prof) { pc[3] += 1; pc[1] += clock64() - c0_; }                                                             \
-        }                                                                                                                 \
-        double a0_ = un, a1_ = 0.0, a2_ = 0.0, a3_ = 0.0;                                                                           \
-        /* body: the older batches of a wide panel, two per trip (eight independent gathers in flight) */                 \
-        if (__builtin_expect(ncb != FC_MINB, 0)) {                                                                        \
-          const uint32_t nb_ = ncb - FC_MINB;                                                                             \
-          const uint32_t ob_ = as_c + FC_TAILB, vb_ = ob_ + 16u * nb_ + lane16;                                           \
-          _Pragma("unroll 1") for (uint32_t bb_ = 0; bb_ < nb_; bb_ += 2u) {                                              \
-            uint32_t q_[8];                                                                                               \
-            double m_[8], y_[8];                                                                                          \
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q_[0]), "=r"(q_[1]), "=r"(q_[2]), "=r"(q_[3]) : "r"(ob_ + 16u * bb_) : "memory"); \
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q_[4]), "=r"(q_[5]), "=r"(q_[6]), "=r"(q_[7]) : "r"(ob_ + 16u * bb_ + 16u) : "memory"); \
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m_[0]), "=d"(m_[1]) : "r"(vb_ + 1024u * bb_) : "memory");     \
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m_[2]), "=d"(m_[3]) : "r"(vb_ + 1024u * bb_ + 512u) : "memory"); \
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m_[4]), "=d"(m_[5]) : "r"(vb_ + 1024u * bb_ + 1024u) : "memory"); \
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m_[6]), "=d"(m_[7]) : "r"(vb_ + 1024u * bb_ + 1536u) : "memory"); \
-            _Pragma("unroll") for (uint32_t i_ = 0; i_ < 8u; i_++) y_[i_] = lds_f64(win_r + q_[i_]);                      \
-            a0_ = fma(-m_[0], y_[0], a0_);                                                                                \
-            a1_ = fma(-m_[1], y_[1], a1_);                                                                                \
-            a2_ = fma(-m_[2], y_[2], a2_);                                                                                \
-            a3_ = fma(-m_[3], y_[3], a3_);                                                                                \
-            a0_ = fma(-m_[4], y_[4], a0_);                                                                                \
-            a1_ = fma(-m_[5], y_[5], a1_);                                                                                \
-            a2_ = fma(-m_[6], y_[6], a2_);                                                                                \
-            a3_ = fma(-m_[7], y_[7], a3_);                                                                                \
-          }                                                                                                               \
-        }                                                                                                                 \
-        /* tail: x of the newest 16 columns (the only loads that depend on the previous hop); O_ holds addresses */       \
-        double x_[16];                                                                                                    \
-        _Pragma("unroll") for (uint32_t i_ = 0; i_ < 16u; i_++) x_[i_] = lds_f64(O_[i_]);                                 \
-        /* chain-independent loads of the next chunk, in flight behind the x loads: offsets, batch count, flag of u */    \
-        const bool more_ = k + 1u < nch;                                                                                  \
-        if (more_) {                                                                                                      \
-          if (__builtin_expect(ok1 == 0u, 0)) {                                                                           \
-            long long c1_ = 0;                                                                                            \
-            if (prof) c1_ = clock64();                                                                                    \
-            FC_SPIN((ok1 = mbar_try_s(fullA_s + 8u * slot1, par1)) != 0u, 0x200u);                                        \
-            if (prof) pc[0] += clock64() - c1_;                                                                           \
-          }                                                                                                               \
-          as_n = ringA_s + slot1 * capA;                                                                                  \
-          FC_LOAD_OFFS(On_, as_n);                                                                                        \
-          ncb_n = lds_u32(as_n);                                                                                          \
-          /* flag of u_{k+1}, then the value: shared-memory loads of one warp complete in order, so a value read       \
-             behind a set flag is the published one; a clear flag is polled at the top of the next chunk */              \
-          tpf = lds_volatile_u32(trdy_r + 4u * ((k + 1u) & (BC_TR - 1u)));                                                \
-          un = lds_f64(ul_s + (((k + 1u) & (BC_TR - 1u)) << 8));                                                          \
-        }                                                                                                                 \
-        _Pragma("unroll") for (uint32_t i_ = 0; i_ < 16u; i_ += 4u) {                                                     \
-          a0_ = fma(-mt[i_], x_[i_], a0_);                                                                                \
-          a1_ = fma(-mt[i_ + 1u], x_[i_ + 1u], a1_);                                                                      \
-          a2_ = fma(-mt[i_ + 2u], x_[i_ + 2u], a2_);                                                                      \
-          a3_ = fma(-mt[i_ + 3u], x_[i_ + 3u], a3_);                                                                      \
-        }                                                                                                                 \
-        /* panel values of the next chunk's tail, into the registers the FMAs above have just read */                     \
-        if (more_) { FC_LOAD_VALS(as_n); }                                                                                \
-        const double xk_ = (a0_ + a1_) + (a2_ + a3_);                                                                     \
-        sts_f64(xst_s + ((k << 8) & wm8), xk_);                                                                           \
-        /* progress word: a volatile store behind the window store, by ALL lanes (same word, same value: no divergent    \
-           branch).  It also frees the staging slot: the producer of ring A polls it. */                                 \
-        sts_volatile_u32(prog_r, k + 1u);                                                                                 \
-        if (more_) {                                                                                                      \
-          _Pragma("unroll") for (uint32_t i_ = 0; i_ < 16u; i_++) On_[i_] += win_r;   /* offsets -> addresses */          \
-        }                                                                                                                 \
-        slot0 = slot1; slot1 = slot2_; par1 = par2_; ok1 = ok2_;                                                          \
-        as_c = as_n; ncb = ncb_n;                                                                                         \
-        if (prof) pc[2] += 1;                                                                                             \
-        k++;                                                                                                              \
-      } while (0)
-      uint32_t k = 0;
       if (nch > 0) {
-        FC_SPIN(mbar_try_s(fullA_s + 8u * slot0, par0) != 0u, 0x200u);
-        as_c = ringA_s + slot0 * capA;
-        FC_LOAD_OFFS(oE, as_c);
+        FC_SPIN(mbar_try_s(fullA_s + 8u * slot0, par1 ^ (bar1 == fullA_s ? 1u : 0u)) != 0u, 0x200u);
+        FC_LOAD_OFFS(as_c);
         FC_LOAD_VALS(as_c);
         ncb = lds_u32(as_c);
-#pragma unroll
-        for (uint32_t i = 0; i < 16u; i++) oE[i] += win_r;
-        tpf = lds_volatile_u32(trdy_r);
+        tpf = lds_volatile_u32(trdy_s);
         un = lds_f64(ul_s);
-        if (nch > 1u) ok1 = mbar_test_s(fullA_s + 8u * slot1, par1);
+        if (nch > 1u) ok1 = mbar_test_s(bar1, par1);
       }
-      while (k < nch) {
-        FC_CHUNK(oE, oO);
-        if (k >= nch) break;
-        FC_CHUNK(oO, oE);
+#pragma unroll 1
+      for (uint32_t k = 0; k < nch; k++) {
+        long long c0 = 0;
+        if (prof) c0 = clock64();
+        // staging barrier of chunk k+2: asked now, answered (ok2) while this chunk computes
+        uint32_t bar2 = bar1 + 8u, par2 = par1, as_2 = as_n + capA;
+        if (bar2 == fullA_e) { bar2 = fullA_s; as_2 = ringA_s; par2 ^= 1u; }
+        const uint32_t ok2 = mbar_test_s(bar2, par2);
+        if (__builtin_expect(tpf != k + 1u, 0)) {
+          FC_SPIN((tpf = ld_acquire_cta_s(trdy_s + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);
+          un = lds_f64(ul_s + ((k & (BC_TR - 1u)) << 8));
+          if (prof) { pc[3] += 1; pc[1] += clock64() - c0; }
+        }
+        double a0 = un, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        // body: the older batches of a wide panel, two per trip (eight independent gathers in flight)
+        if (__builtin_expect(ncb != FC_MINB, 0)) {
+          const uint32_t nb = ncb - FC_MINB;
+          const uint32_t ob = as_c + FC_TAILB, vb = ob + 16u * nb + lane16;
+#pragma unroll 1
+          for (uint32_t bb = 0; bb < nb; bb += 2u) {
+            uint32_t q[8];
+            double m[8], y[8];
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(ob + 16u * bb) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]) : "r"(ob + 16u * bb + 16u) : "memory");
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m[0]), "=d"(m[1]) : "r"(vb + 1024u * bb) : "memory");
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m[2]), "=d"(m[3]) : "r"(vb + 1024u * bb + 512u) : "memory");
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m[4]), "=d"(m[5]) : "r"(vb + 1024u * bb + 1024u) : "memory");
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m[6]), "=d"(m[7]) : "r"(vb + 1024u * bb + 1536u) : "memory");
+#pragma unroll
+            for (uint32_t i = 0; i < 8u; i++) y[i] = lds_f64(win_s + q[i]);
+            a0 = fma(-m[0], y[0], a0);
+            a1 = fma(-m[1], y[1], a1);
+            a2 = fma(-m[2], y[2], a2);
+            a3 = fma(-m[3], y[3], a3);
+            a0 = fma(-m[4], y[4], a0);
+            a1 = fma(-m[5], y[5], a1);
+            a2 = fma(-m[6], y[6], a2);
+            a3 = fma(-m[7], y[7], a3);
+          }
+        }
+        // tail: x of the newest 16 columns (the only loads that depend on the previous hop)
+        double x[16];
+#pragma unroll
+        for (uint32_t i = 0; i < 16u; i++) x[i] = lds_f64(win_s + o[i]);
+        // chain-independent loads of the next chunk, in flight behind the x loads: offsets (into the registers the
+        // x loads have just read), batch count, flag of u and u itself
+        const bool more = k + 1u < nch;
+        if (more) {
+          if (__builtin_expect(ok1 == 0u, 0)) {
+            long long c1 = 0;
+            if (prof) c1 = clock64();
+            FC_SPIN((ok1 = mbar_try_s(bar1, par1)) != 0u, 0x200u);
+            if (prof) pc[0] += clock64() - c1;
+          }
+          FC_LOAD_OFFS(as_n);
+          ncb = lds_u32(as_n);
+          // flag of u_{k+1}, then the value: shared-memory loads of one warp complete in order, so a value read behind a
+          // set flag is the published one; a clear flag is polled at the top of the next chunk
+          tpf = lds_volatile_u32(trdy_s + 4u * ((k + 1u) & (BC_TR - 1u)));
+          un = lds_f64(ul_s + (((k + 1u) & (BC_TR - 1u)) << 8));
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < 16u; i += 4u) {
+          a0 = fma(-mt[i], x[i], a0);
+          a1 = fma(-mt[i + 1u], x[i + 1u], a1);
+          a2 = fma(-mt[i + 2u], x[i + 2u], a2);
+          a3 = fma(-mt[i + 3u], x[i + 3u], a3);
+        }
+        // panel values of the next chunk's tail, into the registers the FMAs above have just read
+        if (more) { FC_LOAD_VALS(as_n); }
+        const double xk = (a0 + a1) + (a2 + a3);
+        sts_f64(xst_s + ((k << 8) & wm8), xk);
+        // progress word: a volatile store behind the window store, by ALL lanes (same word, same value: no divergent
+        // branch).  It also frees the staging slot: the producer of ring A polls it.
+        sts_volatile_u32(prog_s, k + 1u);
+        as_c = as_n; as_n = as_2; bar1 = bar2; par1 = par2; ok1 = ok2;
+        if (prof) pc[2] += 1;
       }
-#undef FC_CHUNK
 #undef FC_LOAD_VALS
 #undef FC_LOAD_OFFS
 #undef FC_SPIN
@@ -335,7 +327,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
           // the slot's previous tenant is chunk base + l - SA of this block (earlier blocks are finished: block barrier);
           // the chain warp has read it completely when it publishes that chunk's progress
           (void)use;
-          if (base + l >= P.SA) BC_WAIT(ld_acquire_cta_s(prog_s) >= base + l - P.SA + 1u, 0x900u, 40);
+          if (base + l >= P.SA) BC_WAIT(ld_acquire_cta_s(prog_s) >= base + l - P.SA + 1u, 0x900u, 100);
           if (lane == 0) {
             const uint32_t bytes = (uint32_t)(e1 - e0);
             mbar_expect_tx(fullA + slot, bytes);
