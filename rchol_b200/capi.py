@@ -137,7 +137,8 @@ class Solver:
 
     def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
                  spmv_lanes: int = 0, chain_generic: bool = False, chain_mode: int = 0, backoff_ns: int = 0, dbg: int = 0, producers: int = 0,
-                 recent: int = 0, plain_launch: bool = False, sep_window: int = 0, early: int = 0, capb_quarters: int = 0, slots_a: int = 0, far_lanes2: int = 0, sep_tile: int = 0, early_sep: int = 0):
+                 recent: int = 0, plain_launch: bool = False, sep_window: int = 0, early: int = 0, capb_quarters: int = 0, slots_a: int = 0, far_lanes2: int = 0, sep_tile: int = 0, early_sep: int = 0,
+                 wb_min: int = 0):
         self._L = load()
         self._h = C.c_void_p()
         opt = Options()
@@ -153,7 +154,8 @@ class Solver:
         opt.reserved[5] = int(early) | (int(early_sep) << 8)
         opt.reserved[7] = int(capb_quarters)
         opt.reserved[8] = int(slots_a)
-        opt.reserved[9] = int(far_lanes2) | (int(sep_tile) << 8)
+        # wb_min: tree levels with at least this many blocks are solved warp-per-block (0 = default 64, -1 = never)
+        opt.reserved[9] = int(far_lanes2) | (int(sep_tile) << 8) | ((0xFFFF if wb_min < 0 else int(wb_min)) << 16)
         opt.reserved[6] = int(bool(plain_launch))
         rc = self._L.rcg_create_with_options(C.byref(self._h), int(device), C.byref(opt))
         if rc != 0:
@@ -331,6 +333,9 @@ class Solver:
         keys = ["active", "nchunks", "ntiles", "nblocks", "bytesA", "bytesB", "far_nnz", "Kr", "E", "Dfar", "N", "nlevels", "Dfar_sep", "tile_sep", "E_sep"]
         out = {k: int(info[i]) for i, k in enumerate(keys)}
         out["fold"] = int(info[15]) >> 32
+        out["wb_min"] = (out["tile_sep"] >> 16) & 0xFFFFFF
+        out["Dfar_wb"] = out["tile_sep"] >> 40
+        out["tile_sep"] &= 0xFFFF
         if not out["active"]:
             return out
 

@@ -561,7 +561,7 @@ int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16) {
   info16[7] = B.Kr; info16[8] = B.E; info16[9] = B.Dfar; info16[10] = h->N;
   info16[11] = B.levels.size();
   info16[12] = B.Dfar_sep;
-  info16[13] = B.tile_sep;
+  info16[13] = (uint64_t)B.tile_sep | ((uint64_t)B.wb_min << 16) | ((uint64_t)B.Dfar_wb << 40);
   info16[14] = B.E_sep;
   {   // levels launched on the cluster chain (chain_mode 4)
     uint64_t n = 0;

@@ -187,6 +187,8 @@ struct BcGeom {               // blocks in ascending solve order (device arrays 
   const uint32_t *bounds, *chunk0, *tile0, *dfar;   // dfar: per block (leaves keep a large window, separators a small one)
   const uint32_t *tile;                             // chunks per far tile, per block
   const uint32_t *eblk;                             // early/late distance E, per block
+  const uint32_t *krblk;                            // recent / fold depth Kr, per block (0 for warp-per-block levels)
+  const uint32_t *wb;                               // 1: block of a warp-per-block level (k_wb_solve): blob A is a bare header
   int nb;
   uint32_t Kr, E;
   uint32_t fold;                                    // 1: folded layout (panels in blob A, Winv in blob B)
@@ -206,14 +208,14 @@ __device__ __forceinline__ int find_le(const uint32_t *__restrict__ a, int n, ui
 struct RowSplit { int64_t s, p_far, p_early, p_late, p_rec, p_diag; };
 
 __device__ __forceinline__ RowSplit split_row(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, uint32_t j,
-                                              uint32_t blo, uint32_t k, const BcGeom &g, uint32_t Dfar, uint32_t E) {
+                                              uint32_t blo, uint32_t k, uint32_t Kr, uint32_t Dfar, uint32_t E) {
   RowSplit r;
   r.s = rp[j];
   r.p_diag = rp[j + 1] - 1;
   const int ik = (int)k;
   const uint32_t c_far = blo + 32u * (uint32_t)max(0, ik + 1 - (int)Dfar);
   const uint32_t c_early = blo + 32u * (uint32_t)max(0, ik - (int)E);
-  const uint32_t c_late = blo + 32u * (uint32_t)max(0, ik - (int)g.Kr);
+  const uint32_t c_late = blo + 32u * (uint32_t)max(0, ik - (int)Kr);
   const uint32_t c_rec = blo + 32u * k;
   int64_t p = r.s;
   while (p < r.p_diag && col[p] < c_far) p++;
@@ -248,10 +250,10 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
       __syncwarp();
     }
     if (j < bhi) {
-      const RowSplit r = split_row(rp, col, j, blo, k, g, g.dfar[b], g.eblk[b]);
+      const RowSplit r = split_row(rp, col, j, blo, k, g.krblk[b], g.dfar[b], g.eblk[b]);
       if (col[r.p_diag] != j) atomicExch(err, 1);
       if (g.fold) {   // distinct columns of the chunk's recent entries
-        const uint32_t c_late = blo + 32u * (uint32_t)max(0, (int)k - (int)g.Kr);
+        const uint32_t c_late = blo + 32u * (uint32_t)max(0, (int)k - (int)g.krblk[b]);
         for (int64_t p = r.p_late; p < r.p_rec; p++) {
           const uint32_t lc = col[p] - c_late;
           atomicOr(&bm[lc >> 5], 1u << (lc & 31u));
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     }
     if (lane == 0) {
       const uint32_t bbytes = BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot) + 320u * nl;
-      sizeA[gc] = g.fold ? (int64_t)fold_bytesA(fold_batches(ncol)) : (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
+      sizeA[gc] = g.wb[b] ? 16 : g.fold ? (int64_t)fold_bytesA(fold_batches(ncol)) : (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
       sizeB[gc] = (int64_t)(bbytes + (g.fold ? FC_WPACK : 0u));
       if (need) atomicMax(&tile_need[g.tile0[b] + k / g.tile[b]], need);
     }
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
     RowSplit r;
     r.s = r.p_far = r.p_early = r.p_late = r.p_rec = r.p_diag = 0;
     const uint32_t wmask = 32u * g.dfar[b] - 1u;
-    if (valid) r = split_row(rp, col, j, blo, k, g, g.dfar[b], g.eblk[b]);
+    if (valid) r = split_row(rp, col, j, blo, k, g.krblk[b], g.dfar[b], g.eblk[b]);
     const uint32_t n_early = (uint32_t)(r.p_early - r.p_far), n_late = (uint32_t)(r.p_late - r.p_early);
     const uint32_t n_rec = (uint32_t)(r.p_rec - r.p_late), n_diag = (uint32_t)(r.p_diag - r.p_rec);
     const uint32_t nslots = warp_max_u32(n_rec), nl = warp_max_u32(n_late);
@@ -367,9 +369,15 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
               8u * (have ? ((col[r.p_late + sidx] - blo) & wmask) : (wmask + 1u));
         }
       }
+    } else if (g.wb[b]) {
+      // ---- warp-per-block level: no chain, no panel; the warp that owns the block applies everything ---------------
+      if (lane == 0) {
+        uint32_t *hd = reinterpret_cast<uint32_t *>(A);
+        hd[0] = 0; hd[1] = nr; hd[2] = 0; hd[3] = 0;
+      }
     } else {
       // ---- folded panel M = Winv * L_rec, one dense column per distinct recent column (ascending) ----------
-      const uint32_t c_late = blo + 32u * (uint32_t)max(0, (int)k - (int)g.Kr);
+      const uint32_t c_late = blo + 32u * (uint32_t)max(0, (int)k - (int)g.krblk[b]);
       uint32_t *bm = bm_all[wib];
       if (lane < FC_KRMAX) bm[lane] = 0u;
       __syncwarp();
@@ -1314,6 +1322,21 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   for (int b = 0; b < nb; b++) dfar[b] = (depth[b] == max_depth) ? B.Dfar : B.Dfar_sep;
   for (int b = 0; b < nb; b++) tilesz[b] = (depth[b] == max_depth) ? BC_TILE : B.tile_sep;
   for (int b = 0; b < nb; b++) eblk[b] = (depth[b] == max_depth) ? B.E : B.E_sep;
+  // Warp-per-block levels (k_wb_solve, rcg_fold.cuh): a tree level with many blocks has enough independent chains to fill
+  // the GPU with one WARP per block -- no chain CTA, no handshakes; every in-window entry is applied by the block's warp
+  // (Kr = 0: nothing folded, E = 0: one jagged class), older entries of the own block and the other blocks stay far.
+  std::vector<uint32_t> krblk(nb + 1, B.Kr), wbblk(nb + 1, 0);
+  {
+    const int wb_opt = (h->opt.reserved[9] >> 16) & 0xFFFF;   // reserved[9] bits 16-31: blocks per level from which the
+    B.wb_min = !B.fold || wb_opt == 0xFFFF ? 0u : wb_opt > 0 ? (uint32_t)wb_opt : 64u;   // level is warp-per-block (0xFFFF: never)
+    B.Dfar_wb = 32u;
+    std::vector<int> per_depth(max_depth + 2, 0);
+    for (int b = 0; b < nb; b++) if (bounds[b + 1] > bounds[b]) per_depth[depth[b]]++;
+    for (int b = 0; b < nb; b++)
+      if (B.wb_min > 0 && (uint32_t)per_depth[depth[b]] >= B.wb_min) {
+        wbblk[b] = 1; krblk[b] = 0; eblk[b] = 0; dfar[b] = B.Dfar_wb; tilesz[b] = B.tile_sep;
+      }
+  }
   for (int b = 0; b < nb; b++) {
     const uint32_t nch = (bounds[b + 1] - bounds[b] + 31u) / 32u;
     chunk0[b + 1] = chunk0[b] + nch;
@@ -1321,8 +1344,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   }
   B.nchunks = chunk0[nb];
   B.ntiles = tile0[nb];
-  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0 | dfar | tile size | E
-  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 6 * (nb + 1)));
+  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0 | dfar | tile size | E | Kr | warp-per-block flag
+  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 8 * (nb + 1)));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom + 7 * (nb + 1), wbblk.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom + 6 * (nb + 1), krblk.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 5 * (nb + 1), eblk.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 4 * (nb + 1), tilesz.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 3 * (nb + 1), dfar.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
@@ -1334,6 +1359,8 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   g.dfar = dgeom + 3 * (nb + 1);
   g.tile = dgeom + 4 * (nb + 1);
   g.eblk = dgeom + 5 * (nb + 1);
+  g.krblk = dgeom + 6 * (nb + 1);
+  g.wb = dgeom + 7 * (nb + 1);
   g.nb = nb; g.Kr = B.Kr; g.E = B.E;
   g.fold = B.fold ? 1u : 0u;
 
@@ -1401,7 +1428,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       bd.gidx = (uint32_t)B.blocks_host.size();
       bd.pad[0] = dfar[b];
       bd.pad[1] = tilesz[b];
-      bd.pad[2] = eblk[b];
+      bd.pad[2] = eblk[b] | (krblk[b] << 8) | (wbblk[b] << 16);   // E | Kr << 8 | warp-per-block << 16
       B.blocks_host.push_back(bd);
       src_block.push_back(b);
       G.count++;
@@ -1462,6 +1489,14 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     }
     G.max_stage = (uint32_t)maxA;
     BcLevel L;
+    if ((B.blocks_host[G.first].pad[2] >> 16) & 1u) {   // warp-per-block level: per-warp window + scratch, no rings
+      L.wb = true;
+      L.Dfar = B.blocks_host[G.first].pad[0];
+      L.smem = (size_t)WB_WARPS * (32u * L.Dfar + 48u) * 8u;
+      L.groups = (uint32_t)((G.count + WB_WARPS - 1) / WB_WARPS);
+      B.levels.push_back(L);
+      continue;
+    }
     const int64_t meanB = nchl ? sumB / nchl : 0;
     L.capA = (uint32_t)((maxA + 127) & ~127ll);
     // staging slot of ring B: a multiple of the level's mean blob (reserved[7], in quarters; default 3x); larger blobs
@@ -1532,6 +1567,7 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     RCG_CUDA(h, cudaFuncSetAttribute(k_bc_solve<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
     RCG_CUDA(h, cudaFuncSetAttribute(k_fc_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
     RCG_CUDA(h, cudaFuncSetAttribute(k_fc_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
+    RCG_CUDA(h, cudaFuncSetAttribute(k_wb_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
     h->smem_optin_blocked = true;
   }
   if (only_kernel > 0) return RCG_OK;   // the level kernel is the only kernel of a group
@@ -1571,7 +1607,7 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     a.w = B.w; a.rhs = rhs; a.out = out;
     a.dotvec = dotvec; a.dot_partials = dotvec ? rz_part : nullptr; a.dot_limit = dot_limit;
     a.N = (uint32_t)h->N; a.reversed = d.reversed ? 1 : 0;
-    a.Kr = B.Kr; a.E = B.blocks_host[G.first].pad[2]; a.Dfar = L.Dfar; a.W = 32u * L.Dfar;
+    a.Kr = (B.blocks_host[G.first].pad[2] >> 8) & 0xFFu; a.E = B.blocks_host[G.first].pad[2] & 0xFFu; a.Dfar = L.Dfar; a.W = 32u * L.Dfar;
     a.SA = L.SA; a.SB = L.SB; a.capA = L.capA; a.capB = L.capB;
     a.tile = B.blocks_host[G.first].pad[1];
     a.far_lpr = (G.rows > 0 && G.ext_nnz / G.rows > 64) ? 32u : 8u;
@@ -1581,6 +1617,14 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     a.abort_g = h->abort_flag;
     a.clk = h->clk_probe;
     a.dbg = (uint32_t)h->opt.reserved[1];
+    if (L.wb) {   // warp-per-block level: fully parallel pre-pass over the entries of other blocks, then one warp per block
+      const uint32_t pre_grid = std::min<uint32_t>((uint32_t)G.count, (uint32_t)h->sm_count * 8u);
+      k_wb_pre<<<pre_grid, 256, 0, h->stream>>>(a);
+      k_wb_solve<<<L.groups, WB_WARPS * 32, L.smem, h->stream>>>(a);
+      RCG_CUDA(h, cudaGetLastError());
+      h->stats.kernel_launches += 2;
+      continue;
+    }
     if (B.cl.on && B.cl.level_on[gi]) {   // leaf level on the cluster chain
       RCG_TRY(cl_launch(h, B, a, G, gi));
       continue;

@@ -82,6 +82,7 @@ struct BcLevel {               // per tree level: shared-memory plan of the laun
   uint32_t groups = 0;         // chain CTAs of the launch
   uint32_t helpers = 0;        // far CTAs per chain CTA
   uint32_t Dfar = 0;           // window of the level's blocks in chunks
+  bool wb = false;             // warp-per-block level: k_wb_pre + k_wb_solve instead of the chain kernel
   size_t smem = 0;
 };
 
@@ -112,6 +113,8 @@ struct BlockedDev {
   uint32_t Dfar_sep = 32;                // window of the separator blocks
   uint32_t E_sep = 6;                    // early/late distance of the separator blocks (leaves: E)
   uint32_t tile_sep = 1;                 // chunks per far tile of the separator blocks (leaves: 8)
+  uint32_t wb_min = 0;                   // tree levels with at least this many blocks are solved warp-per-block (0: none)
+  uint32_t Dfar_wb = 32;                 // window (chunks) of the warp-per-block levels
   uint32_t nchunks = 0, ntiles = 0, nblocks = 0;
   int64_t *offA = nullptr, *offB = nullptr;          // nchunks+1 byte offsets into the blobs
   unsigned char *blobA = nullptr, *blobB = nullptr;

@@ -585,3 +585,146 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
   if (P.clk && (P.dbg & 1u) && blockIdx.x == 0 && threadIdx.x == 64u)   // near helper 0 = warp 2
     for (int q = 0; q < 5; q++) P.clk[8 + q] = (unsigned long long)ph[q];
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-per-block levels.  A tree level with many blocks (hundreds of leaves, the lower separator levels) has more
+// independent dependency chains than the GPU has schedulers, so nothing is gained by making one chain fast: ONE WARP owns
+// a block and walks its chunks in order,  x_k = Winv_k (start_k - in-window entries),  with the solution window of the
+// block in the warp's own shared memory -- no flags, no staging rings, no roles.  Throughput comes from the number of
+// resident warps (4 per CTA, several CTAs per SM).
+//   k_wb_pre   : start[j] = rhs[j] - (entries of other, already solved blocks), all rows of the level in parallel
+//   k_wb_solve : per chunk: start - far entries of the own block (>= window back, read back through L2) - in-window
+//                entries (blob B: jagged diagonals + ELL) -> mat-vec with the packed inverse -> window, out[], fused dot
+// ---------------------------------------------------------------------------------------------------------
+constexpr int WB_WARPS = 4;
+
+__global__ void __launch_bounds__(256) k_wb_pre(const BcArgs P) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t sub = lane & 7u;   // 8 lanes per row, 4 rows per warp, 32 rows per CTA pass
+  for (uint32_t bi = blockIdx.x; bi < P.nblocks; bi += gridDim.x) {
+    const BcBlock b = P.blocks[bi];
+    for (uint32_t base = b.lo + 4u * warp; base < b.hi; base += 32u) {
+      const uint32_t j = base + (lane >> 3);
+      const bool valid = j < b.hi;
+      double acc = 0.0;
+      if (valid) {
+        const int64_t e0 = P.far_rp[j], e1 = e0 + P.far_split[j];   // [e0, e1): entries of other blocks
+        double acc1 = 0.0;
+        int64_t e = e0 + sub;
+        for (; e + 8 < e1; e += 16) {
+          const uint32_t c = P.far_col[e], c2 = P.far_col[e + 8];
+          if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
+          if (c2 >= P.col_min) acc1 = fma(P.far_val[e + 8], __ldcg(P.out + c2), acc1);
+        }
+        if (e < e1) {
+          const uint32_t c = P.far_col[e];
+          if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
+        }
+        acc += acc1;
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (valid && sub == 0u) {
+        const uint32_t i = P.reversed ? P.N - 1u - j : j;
+        double s = P.rhs[i];
+        if (P.corr) s -= P.corr[i - P.col_min];
+        __stcg(P.w + j, s - acc);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WB_WARPS * 32, 4) k_wb_solve(const BcArgs P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *win = reinterpret_cast<double *>(smem) + (size_t)warp * (P.W + 48u);   // window | zero slot (16) | t vector (32)
+  double *scr = win + P.W + 16u;
+  const uint32_t wmask = P.W - 1u;
+  const uint32_t scr_s = smem_u32(scr);
+  if (lane < 16u) win[P.W + lane] = 0.0;
+  __syncwarp();
+  const uint32_t nwarps = gridDim.x * WB_WARPS;
+  for (uint32_t bi = blockIdx.x * WB_WARPS + warp; bi < P.nblocks; bi += nwarps) {
+    const BcBlock b = P.blocks[bi];
+    const uint32_t nch = (b.hi - b.lo + 31u) >> 5;
+    double dot = 0.0;
+    int64_t offn = nch > 0u ? P.offB[b.chunk0] : 0;
+    for (uint32_t k = 0; k < nch; k++) {
+      const uint32_t j = b.lo + 32u * k + lane;
+      const bool valid = j < b.hi;
+      const uint32_t i = P.reversed ? P.N - 1u - j : j;
+      const unsigned char *bp = P.blobB + offn;
+      if (k + 1u < nch) offn = P.offB[b.chunk0 + k + 1u];   // next chunk's blob offset: in flight during this chunk
+      // start vector of the pre-pass minus the far entries of the own block (>= a window back; read back through L2)
+      double t0 = 0.0;
+      if (valid) {
+        t0 = __ldcg(P.w + j);
+        const int64_t e1 = P.far_rp[j + 1];
+        for (int64_t e = P.far_rp[j] + P.far_split[j]; e < e1; e++) t0 = fma(-P.far_val[e], __ldcg(P.out + P.far_col[e]), t0);
+      }
+      const uint32_t *hd = reinterpret_cast<const uint32_t *>(bp);
+      const uint32_t ne_max = hd[0], ne_tot = hd[1], nl = hd[2];
+      const uint32_t perm = bp[16u + lane], rank = bp[48u + lane];
+      const unsigned char *cnt = bp + BC_BHDR;
+      const double *ev = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max));
+      const uint16_t *ec = reinterpret_cast<const uint16_t *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot));
+      const double *lv = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot));
+      const uint16_t *lc = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(lv) + 256u * nl);
+      const unsigned char *wq = reinterpret_cast<const unsigned char *>(lv) + 320u * nl;   // packed Winv
+      // the inverse first: its loads do not depend on anything and cover the latency of the entry loads below
+      double wv[32];
+#pragma unroll
+      for (uint32_t pp = 0; pp < 16u; pp++) {
+        const uint32_t rr = lane >= 2u * pp ? lane - 2u * pp : 0u;
+        const double2 w2 = *reinterpret_cast<const double2 *>(wq + 16u * (pp * (33u - pp) + rr));
+        wv[2 * pp] = lane >= 2u * pp ? w2.x : 0.0;
+        wv[2 * pp + 1] = lane >= 2u * pp ? w2.y : 0.0;
+      }
+      // in-window entries, jagged diagonals (rows sorted by length), four per trip
+      double ts = __shfl_sync(0xffffffffu, t0, (int)perm), ts1 = 0.0;
+      uint32_t base = 0;
+      for (uint32_t s = 0; s < ne_max; s += 4u) {
+        const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cnt + s);
+        const uint32_t n0 = c4 & 255u, n1 = (c4 >> 8) & 255u, n2 = (c4 >> 16) & 255u, n3 = c4 >> 24;
+        const uint32_t b1 = base + n0, b2 = b1 + n1, b3 = b2 + n2;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+        if (lane < n0) { v0 = ev[base + lane]; x0 = win[ec[base + lane]]; }
+        if (lane < n1) { v1 = ev[b1 + lane]; x1 = win[ec[b1 + lane]]; }
+        if (lane < n2) { v2 = ev[b2 + lane]; x2 = win[ec[b2 + lane]]; }
+        if (lane < n3) { v3 = ev[b3 + lane]; x3 = win[ec[b3 + lane]]; }
+        ts = fma(-v0, x0, ts);
+        ts1 = fma(-v1, x1, ts1);
+        ts = fma(-v2, x2, ts);
+        ts1 = fma(-v3, x3, ts1);
+        base = b3 + n3;
+      }
+      ts += ts1;
+      double t = __shfl_sync(0xffffffffu, ts, (int)rank);
+      for (uint32_t s = 0; s < nl; s++) t = fma(-lv[s * 32u + lane], win[lc[s * 32u + lane]], t);   // ELL class (empty when E = 0)
+      // x = Winv t : t broadcast through the warp's scratch row, lane = row of the result
+      sts_f64(scr_s + 8u * lane, t);
+      __syncwarp();
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+      for (uint32_t pp = 0; pp < 16u; pp += 2u) {
+        double ta, tb, tc, td;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ta), "=d"(tb) : "r"(scr_s + 16u * pp) : "memory");
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc), "=d"(td) : "r"(scr_s + 16u * pp + 16u) : "memory");
+        u0 = fma(wv[2 * pp], ta, u0);
+        u1 = fma(wv[2 * pp + 1], tb, u1);
+        u2 = fma(wv[2 * pp + 2], tc, u2);
+        u3 = fma(wv[2 * pp + 3], td, u3);
+      }
+      const double x = (u0 + u1) + (u2 + u3);
+      win[(32u * k + lane) & wmask] = x;
+      if (valid) {
+        __stcg(P.out + i, x);
+        if (P.dotvec && i < P.dot_limit) dot = fma(x, P.dotvec[i], dot);
+      }
+      __syncwarp();
+    }
+    dot = warp_sum(dot);
+    if (lane == 0 && P.dot_partials) P.dot_partials[b.gidx] = dot;
+  }
+}

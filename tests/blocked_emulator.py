@@ -40,6 +40,9 @@ def unpack_winv_packed(raw_bytes):
 def unpack_panel(a):
     """Folded blob A -> (ncb, nr, ncol, window slots [4*ncb], panel values [32, 4*ncb])."""
     ncb, nr, ncol = (int(v) for v in a[:12].view(np.uint32))
+    if ncb == 0:                      # block of a warp-per-block level: bare header, nothing folded
+        assert len(a) == 16 and ncol == 0
+        return 0, nr, 0, np.zeros(0, np.int64), np.zeros((32, 0))
     assert len(a) == fold_bytesA(ncb) and ncb == fold_batches(ncol)
     nbody = ncb - FC_MINB
     # column order: body batches first (oldest, padding in front), then the tail; the tail sits first in the blob

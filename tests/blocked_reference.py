@@ -43,7 +43,7 @@ def direction_matrix(G, part, backward):
 
 
 def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False, tile_sep=1, tile_leaf=8, E_sep=None,
-                 fold=False):
+                 fold=False, wb_min=0, Dfar_wb=32):
     N = L.shape[0]
     rp, col, val = L.indptr.astype(np.int64), L.indices.astype(np.int64), L.data
     nb = len(bounds) - 1
@@ -53,6 +53,16 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
     tile_of = [tile_leaf if depth[b] == max_depth else tile_sep for b in range(nb)]   # chunks per far tile
     E_sep = min(E, 6) if E_sep is None else E_sep
     e_of = [E if depth[b] == max_depth else E_sep for b in range(nb)]                 # early/late distance
+    kr_of = [Kr] * nb
+    # warp-per-block levels (k_wb_solve): tree levels with at least wb_min non-empty blocks: nothing folded, one jagged class
+    per_depth = {}
+    for b in range(nb):
+        if bounds[b + 1] > bounds[b]:
+            per_depth[int(depth[b])] = per_depth.get(int(depth[b]), 0) + 1
+    wb_of = [1 if fold and wb_min > 0 and per_depth.get(int(depth[b]), 0) >= wb_min else 0 for b in range(nb)]
+    for b in range(nb):
+        if wb_of[b]:
+            kr_of[b], e_of[b], dfar_of[b], tile_of[b] = 0, 0, Dfar_wb, tile_sep
     Dfar_leaf = Dfar
     chunk0 = np.zeros(nb + 1, np.int64)
     tile0 = np.zeros(nb + 1, np.int64)
@@ -74,7 +84,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             nr = len(rows)
             c_far = blo + 32 * max(0, k + 1 - Dfar)
             c_early = blo + 32 * max(0, k - e_of[b])
-            c_late = blo + 32 * max(0, k - Kr)
+            c_late = blo + 32 * max(0, k - kr_of[b])
             c_rec = blo + 32 * k
             parts = []
             D = np.zeros((32, 32))
@@ -109,7 +119,11 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             n_rec = np.array([len(p[4]) for p in parts])
             nslots, nl, ne_max, ne_tot = int(n_rec.max()), int(n_late.max()), int(n_early.max()), int(n_early.sum())
             # blob A
-            if fold:
+            if wb_of[b]:
+                a = np.zeros(16, np.uint8)
+                a[:12].view(np.uint32)[:] = [0, nr, 0]
+                blobsA[g] = a
+            elif fold:
                 # dense panel M = Winv L_rec over the distinct recent columns (ascending)
                 cols = sorted(set(int(c) for p in parts for c in p[4]))
                 ncol = len(cols)
@@ -155,7 +169,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
                         if sidx < len(p[4]):
                             vals[l, u >> 1, u & 1] = p[5][sidx]
                             offs[l, u >> 2, u & 3] = 8 * ((p[4][sidx] - blo) & wmask)
-            if not fold:
+            if not fold and not wb_of[b]:
                 blobsA[g] = a
             # blob B
             order = sorted(range(32), key=lambda l: (-n_early[l], l))
@@ -200,7 +214,8 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
         want = gl if root_first else max_depth - gl
         for b in range(nb):
             if depth[b] == want and bounds[b + 1] > bounds[b]:
-                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], tile_of[b], e_of[b]])
+                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], tile_of[b],
+                               e_of[b] | (kr_of[b] << 8) | (wb_of[b] << 16)])
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
     return dict(fold=int(fold), active=1, nchunks=nchunks, ntiles=ntiles, nblocks=len(blocks), N=N, Kr=Kr, E=E, Dfar=Dfar_leaf, Dfar_sep=Dfar_sep,
                 offA=offA, offB=offB, blobA=cat(blobsA, np.uint8), blobB=cat(blobsB, np.uint8), far_rp=far_rp,
@@ -222,7 +237,9 @@ def compare_layouts(dev, ref, val_tol=1e-12):
     for g in range(ref["nchunks"]):
         a, r = dev["blobA"][ref["offA"][g]: ref["offA"][g + 1]], ref["blobA"][ref["offA"][g]: ref["offA"][g + 1]]
         assert np.array_equal(a[:12], r[:12]), ("A header", g)
-        if ref.get("fold"):
+        if ref.get("fold") and len(r) == 16:
+            assert len(a) == 16
+        elif ref.get("fold"):
             ncb = int(r[:12].view(np.uint32)[0])
             nbody = ncb - FC_MINB
             for lo_, hi_ in ((16, 16 + 16 * FC_MINB), (FC_TAILB, FC_TAILB + 16 * nbody)):

@@ -36,7 +36,9 @@ def oracle():
 @pytest.mark.parametrize("kind,n,threads,opts", [("lap3d", 14, 4, dict()), ("lap3d", 20, 0, dict(chain_window=1024, recent=1)),
                                                   ("aniso2d", 64, 8, dict(chain_window=1024, recent=8)),
                                                   ("lap3d", 33, 2, dict(chain_window=1024, early=6)),
-                                                  ("lap3d", 40, 8, dict(sep_tile=4, early_sep=12, recent=2))])
+                                                  ("lap3d", 40, 8, dict(sep_tile=4, early_sep=12, recent=2)),
+                                                  ("lap3d", 14, 4, dict(wb_min=2)), ("lap3d", 40, 8, dict(wb_min=4, recent=2)),
+                                                  ("aniso2d", 64, 8, dict(wb_min=1, chain_window=1024))])
 def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
@@ -46,7 +48,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
         lay_f, lay_b = s.blocked_layout(capi.TRSV_FORWARD), s.blocked_layout(capi.TRSV_BACKWARD)
         assert lay_f["active"] and lay_b["active"] and lay_f["fold"] == 1 and lay_b["fold"] == 1
         kw = dict(Kr=lay_f["Kr"], E=lay_f["E"], Dfar=lay_f["Dfar"], Dfar_sep=lay_f["Dfar_sep"], tile_sep=lay_f["tile_sep"],
-                  E_sep=lay_f["E_sep"], fold=True)
+                  E_sep=lay_f["E_sep"], fold=True, wb_min=lay_f["wb_min"], Dfar_wb=lay_f["Dfar_wb"])
         L, bounds, depth = direction_matrix(G, part, False)
         compare_layouts(lay_f, build_layout(L, bounds, depth, False, **kw))
         L, bounds, depth = direction_matrix(G, part, True)
@@ -64,7 +66,8 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
                                   dict(chain_window=2048, recent=1), dict(chain_window=8192), dict(plain_launch=True),
                                   dict(use_graph=False, chain_window=1024), dict(sep_window=4096), dict(chain_window=2048, sep_window=2048),
                                   dict(early=6), dict(early=4, recent=3), dict(capb_quarters=4), dict(slots_a=2), dict(slots_a=8, capb_quarters=5),
-                                  dict(sep_tile=8, far_lanes2=32), dict(early_sep=16), dict(early_sep=4, early=5), dict(sep_tile=4, chain_window=1024)])
+                                  dict(sep_tile=8, far_lanes2=32), dict(early_sep=16), dict(early_sep=4, early=5), dict(sep_tile=4, chain_window=1024),
+                                  dict(wb_min=1), dict(wb_min=2), dict(wb_min=4, recent=2), dict(wb_min=-1), dict(wb_min=2, use_graph=False)])
 @pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 33, 2), ("aniso2d", 160, 4), ("lap3d", 40, 0)])
 def test_folded_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
@@ -83,15 +86,19 @@ def test_folded_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
 
 
 @needs_producer
-@pytest.mark.parametrize("kind,n,threads", [("lap3d", 48, 256), ("lap3d", 64, 8), ("lap3d", 5, 2), ("aniso2d", 256, 64)])
-def test_folded_chain_many_blocks_long_leaves_and_repeatability(capi, oracle, kind, n, threads):
-    """More blocks than chain CTAs (the rings run across block boundaries), leaves longer than the window (far tiles
+@pytest.mark.parametrize("kind,n,threads,opts", [("lap3d", 48, 256, dict()), ("lap3d", 64, 8, dict()), ("lap3d", 5, 2, dict()), ("aniso2d", 256, 64, dict()),
+                                                 ("lap3d", 48, 256, dict(wb_min=-1)), ("lap3d", 64, 8, dict(wb_min=8)),
+                                                 ("lap3d", 64, 0, dict(wb_min=1)), ("aniso2d", 256, 64, dict(wb_min=16))])
+def test_folded_chain_many_blocks_long_leaves_and_repeatability(capi, oracle, kind, n, threads, opts):
+    """Warp-per-block levels (T=256: the leaf level and the lower separator levels by default; forced on / off elsewhere;
+    a single 262144-row block walked by one warp, far entries of the own block read back through L2).
+    More blocks than chain CTAs (the rings run across block boundaries), leaves longer than the window (far tiles
     inside the own block, publisher back-pressure), blocks shorter than one chunk; bit-identical reruns; PCG converges
     like the oracle."""
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
     zo = oracle.trsv_backward(*G, yo)
-    with capi.Solver(0, chain_mode=5) as s:
+    with capi.Solver(0, chain_mode=5, **opts) as s:
         s.set_matrix(*A)
         s.set_factor(*G, part)
         assert relerr(s.trsv(capi.TRSV_FORWARD, b), yo) <= TRSV_TOL
