@@ -63,6 +63,7 @@ __host__ __device__ __forceinline__ uint32_t rec_batches(uint32_t nslots) { retu
 constexpr uint32_t FC_MINB = 4;              // tail batches (register-resident in the chain warp)
 constexpr uint32_t FC_TAILB = 16u + 1040u * FC_MINB;   // header + tail: byte offset of the body
 constexpr uint32_t FC_KRMAX = 8;             // fold depth limit (bitmap of 32*Kr candidate columns)
+constexpr uint32_t FC_COLCAP = 32;           // panel columns per chunk beyond the previous chunk's (chunk_fold_depth)
 constexpr uint32_t FC_WPACK = 4352;          // packed Winv: pair p holds rows 2p..31 -> 16 * sum(32 - 2p) bytes
 __host__ __device__ __forceinline__ uint32_t fold_batches(uint32_t ncol) {   // tail + an even number of body batches
   return ncol <= 4u * FC_MINB ? FC_MINB : FC_MINB + 2u * ((ncol - 4u * FC_MINB + 7u) / 8u);
@@ -232,6 +233,37 @@ __device__ __forceinline__ RowSplit split_row(const int64_t *__restrict__ rp, co
 __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
 __device__ __forceinline__ uint32_t warp_add_u32(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 
+// Fold depth of one chunk (warp-collective, folded layout): the largest D <= Kr such that the chunk's rows reference at
+// most FC_COLCAP distinct columns in the D previous chunks (D >= 1 whenever there is a previous chunk).  It bounds the
+// panel (blob A <= 16 + 1040 * 8 bytes: many staging slots, short chain hops); entries older than D chunks stay with the
+// near helper as "late" entries.  The helper reads D from its blob's header.  ncol = columns of the panel.
+__device__ __forceinline__ uint32_t chunk_fold_depth(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, uint32_t j,
+                                                     bool valid, uint32_t blo, uint32_t k, uint32_t Kr, uint32_t Dfar, uint32_t E,
+                                                     uint32_t *bm, uint32_t lane, uint32_t &ncol) {
+  const uint32_t ng = min(k, Kr);
+  if (lane < FC_KRMAX) bm[lane] = 0u;
+  __syncwarp();
+  if (valid && ng) {
+    const RowSplit r = split_row(rp, col, j, blo, k, Kr, Dfar, E);
+    const uint32_t c_late = blo + 32u * (k - ng);
+    for (int64_t p = r.p_late; p < r.p_rec; p++) {
+      const uint32_t lc = col[p] - c_late;
+      atomicOr(&bm[lc >> 5], 1u << (lc & 31u));
+    }
+  }
+  __syncwarp();
+  uint32_t cum = 0, D = 0;
+  for (uint32_t d = 1; d <= ng; d++) {   // word ng - d holds the columns of the chunk at distance d
+    const uint32_t c = (uint32_t)__popc(bm[ng - d]);
+    if (d > 1u && cum + c > FC_COLCAP) break;
+    cum += c;
+    D = d;
+  }
+  __syncwarp();
+  ncol = cum;
+  return D;
+}
+
 // warp per chunk: blob sizes, far row lengths, far-tile requirements
 __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, BcGeom g,
                                                   uint32_t nchunks, int64_t *__restrict__ sizeA, int64_t *__restrict__ sizeB,
@@ -245,20 +277,11 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     const uint32_t k = gc - g.chunk0[b], blo = g.bounds[b], bhi = g.bounds[b + 1];
     const uint32_t j = blo + 32u * k + lane;
     uint32_t n_rec = 0, n_late = 0, n_early = 0, need = 0;
-    if (g.fold) {
-      if (lane < FC_KRMAX) bm[lane] = 0u;
-      __syncwarp();
-    }
+    uint32_t ncol = 0, Dk = g.krblk[b];
+    if (g.fold && !g.wb[b]) Dk = chunk_fold_depth(rp, col, j, j < bhi, blo, k, g.krblk[b], g.dfar[b], g.eblk[b], bm, lane, ncol);
     if (j < bhi) {
-      const RowSplit r = split_row(rp, col, j, blo, k, g.krblk[b], g.dfar[b], g.eblk[b]);
+      const RowSplit r = split_row(rp, col, j, blo, k, Dk, g.dfar[b], g.eblk[b]);
       if (col[r.p_diag] != j) atomicExch(err, 1);
-      if (g.fold) {   // distinct columns of the chunk's recent entries
-        const uint32_t c_late = blo + 32u * (uint32_t)max(0, (int)k - (int)g.krblk[b]);
-        for (int64_t p = r.p_late; p < r.p_rec; p++) {
-          const uint32_t lc = col[p] - c_late;
-          atomicOr(&bm[lc >> 5], 1u << (lc & 31u));
-        }
-      }
       far_cnt[j] = r.p_far - r.s;
       n_early = (uint32_t)(r.p_early - r.p_far);
       n_late = (uint32_t)(r.p_late - r.p_early);
@@ -271,12 +294,6 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     const uint32_t nslots = warp_max_u32(n_rec), nl = warp_max_u32(n_late);
     const uint32_t ne_max = warp_max_u32(n_early), ne_tot = warp_add_u32(n_early);
     need = warp_max_u32(need);
-    uint32_t ncol = 0;
-    if (g.fold) {
-      __syncwarp();
-      ncol = warp_add_u32(lane < FC_KRMAX ? (uint32_t)__popc(bm[lane]) : 0u);
-      __syncwarp();
-    }
     if (lane == 0) {
       const uint32_t bbytes = BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot) + 320u * nl;
       sizeA[gc] = g.wb[b] ? 16 : g.fold ? (int64_t)fold_bytesA(fold_batches(ncol)) : (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
@@ -307,7 +324,9 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
     RowSplit r;
     r.s = r.p_far = r.p_early = r.p_late = r.p_rec = r.p_diag = 0;
     const uint32_t wmask = 32u * g.dfar[b] - 1u;
-    if (valid) r = split_row(rp, col, j, blo, k, g.krblk[b], g.dfar[b], g.eblk[b]);
+    uint32_t ncol_fold = 0, Dk = g.krblk[b];
+    if (g.fold && !g.wb[b]) Dk = chunk_fold_depth(rp, col, j, valid, blo, k, g.krblk[b], g.dfar[b], g.eblk[b], bm_all[wib], lane, ncol_fold);
+    if (valid) r = split_row(rp, col, j, blo, k, Dk, g.dfar[b], g.eblk[b]);
     const uint32_t n_early = (uint32_t)(r.p_early - r.p_far), n_late = (uint32_t)(r.p_late - r.p_early);
     const uint32_t n_rec = (uint32_t)(r.p_rec - r.p_late), n_diag = (uint32_t)(r.p_diag - r.p_rec);
     const uint32_t nslots = warp_max_u32(n_rec), nl = warp_max_u32(n_late);
@@ -377,7 +396,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
       }
     } else {
       // ---- folded panel M = Winv * L_rec, one dense column per distinct recent column (ascending) ----------
-      const uint32_t c_late = blo + 32u * (uint32_t)max(0, (int)k - (int)g.krblk[b]);
+      const uint32_t c_late = blo + 32u * (uint32_t)max(0, (int)k - (int)Dk);
       uint32_t *bm = bm_all[wib];
       if (lane < FC_KRMAX) bm[lane] = 0u;
       __syncwarp();
@@ -439,7 +458,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
       }
       if (lane == 0) {
         uint32_t *hd = reinterpret_cast<uint32_t *>(B);
-        hd[0] = ne_max; hd[1] = ne_tot; hd[2] = nl; hd[3] = 0;
+        hd[0] = ne_max; hd[1] = ne_tot; hd[2] = nl; hd[3] = Dk;   // Dk: fold depth of the chunk (the helper's late wait)
       }
       B[16u + rank] = (unsigned char)lane;   // perm: sorted position -> row
       B[48u + lane] = (unsigned char)rank;   // rank: row -> sorted position
@@ -1492,7 +1511,11 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     if ((B.blocks_host[G.first].pad[2] >> 16) & 1u) {   // warp-per-block level: per-warp window + scratch, no rings
       L.wb = true;
       L.Dfar = B.blocks_host[G.first].pad[0];
-      L.smem = (size_t)WB_WARPS * (32u * L.Dfar + 48u) * 8u;
+      const uint32_t Wwb = 32u * L.Dfar;
+      const int64_t per_warp = ((int64_t)BC_SMEM_MAX / WB_WARPS) & ~15ll;
+      const int64_t cap_max = ((per_warp - (int64_t)(Wwb + 48u) * 8 - 16) / 2) & ~127ll;   // two staging buffers per warp
+      L.capB = (uint32_t)std::min<int64_t>((maxB + 127) & ~127ll, cap_max);                 // larger blobs are read from HBM
+      L.smem = (size_t)WB_WARPS * wb_warp_bytes(Wwb, L.capB);
       L.groups = (uint32_t)((G.count + WB_WARPS - 1) / WB_WARPS);
       B.levels.push_back(L);
       continue;
@@ -1509,7 +1532,9 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     const int64_t fixed = (int64_t)W * 8 + 128 + BC_TR * 32 * 8 + (B.fold ? FC_SCR : BC_SCR) * 8 + BC_TR * 4 + 64 + 1024;
     int64_t avail = (int64_t)BC_SMEM_MAX - fixed;
     // ring A feeds one consumer (latency cover), ring B feeds BC_NH helpers that hold their slot while they work
-    int64_t SA = std::max<int64_t>(3, std::min<int64_t>(10, (avail * (B.fold ? 3 : 4) / 10) / L.capA));
+    // (folded chain: the panel is capped at 8.3 KB per chunk -- chunk_fold_depth -- and a bulk copy from HBM takes 1-2 us,
+    //  i.e. several hops: up to 12 slots)
+    int64_t SA = std::max<int64_t>(3, std::min<int64_t>(B.fold ? 12 : 10, (avail * (B.fold ? 35 : 40) / 100) / L.capA));
     if (h->opt.reserved[8] > 0) SA = std::max<int64_t>(2, std::min<int64_t>(10, h->opt.reserved[8]));   // tuning experiments
     int64_t SB = std::max<int64_t>(3, std::min<int64_t>(2 * BC_NH + 4, (avail - SA * L.capA) / (L.capB + 24)));
     while (SA > 3 && SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) SA--;

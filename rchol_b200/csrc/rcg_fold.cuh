@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         BC_WAIT(lds_volatile_u32(smem_u32(seqB + slot)) == i && mbar_try(fullB + slot, (i / P.SB) & 1u), 0x500u, 200);
         const unsigned char *bp = reinterpret_cast<const unsigned char *>(ptrB[slot]);
         const uint32_t *hd = reinterpret_cast<const uint32_t *>(bp);
-        const uint32_t ne_max = hd[0], ne_tot = hd[1], nl = hd[2];
+        const uint32_t ne_max = hd[0], ne_tot = hd[1], nl = hd[2], Dk = hd[3];
         const uint32_t perm = bp[16u + lane], rank = bp[48u + lane];
         const unsigned char *cnt = bp + BC_BHDR;
         const double *ev = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max));
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
           const uint32_t jn = b.lo + 32u * kn + lane;
           t0n = jn < b.hi ? __ldcg(P.w + jn) : 0.0;
         }
-        uint32_t need2 = k > P.Kr ? k - P.Kr : 0u;
+        uint32_t need2 = k > Dk ? k - Dk : 0u;   // Dk: this chunk's fold depth (blob header)
         if (k + 1u > BC_TR) need2 = max(need2, k + 1u - BC_TR);
         long long h3 = 0;
         if (hprof) h3 = clock64();
@@ -635,33 +635,68 @@ __global__ void __launch_bounds__(256) k_wb_pre(const BcArgs P) {
   }
 }
 
-__global__ void __launch_bounds__(WB_WARPS * 32, 4) k_wb_solve(const BcArgs P) {
-  extern __shared__ __align__(16) unsigned char smem[];
+// Per-warp shared memory: window (W + 16 doubles) | t vector (32 doubles) | two staging buffers of capB bytes | two mbarriers.
+__host__ __device__ __forceinline__ uint32_t wb_warp_bytes(uint32_t W, uint32_t capB) { return (W + 48u) * 8u + 2u * capB + 16u; }
+
+__global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
+  extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *win = reinterpret_cast<double *>(smem) + (size_t)warp * (P.W + 48u);   // window | zero slot (16) | t vector (32)
+  unsigned char *mine = smem + (size_t)warp * wb_warp_bytes(P.W, P.capB);
+  double *win = reinterpret_cast<double *>(mine);
   double *scr = win + P.W + 16u;
+  unsigned char *buf = reinterpret_cast<unsigned char *>(scr + 32u);
+  uint64_t *full = reinterpret_cast<uint64_t *>(buf + 2u * (size_t)P.capB);
   const uint32_t wmask = P.W - 1u;
-  const uint32_t scr_s = smem_u32(scr);
+  const uint32_t scr_s = smem_u32(scr), full_s = smem_u32(full);
   if (lane < 16u) win[P.W + lane] = 0.0;
+  if (lane < 2u) mbar_init(full + lane, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
+  uint32_t phase = 0u;   // bit q: parity of the next phase of staging barrier q
   const uint32_t nwarps = gridDim.x * WB_WARPS;
   for (uint32_t bi = blockIdx.x * WB_WARPS + warp; bi < P.nblocks; bi += nwarps) {
     const BcBlock b = P.blocks[bi];
     const uint32_t nch = (b.hi - b.lo + 31u) >> 5;
     double dot = 0.0;
-    int64_t offn = nch > 0u ? P.offB[b.chunk0] : 0;
+    // blob of chunk kk -> staging buffer kk & 1 (bulk copy, completion on the buffer's barrier); blobs larger than a
+    // buffer are read from HBM directly
+    int64_t o0 = nch > 0u ? P.offB[b.chunk0] : 0, o1 = nch > 0u ? P.offB[b.chunk0 + 1u] : 0;
+    if (nch > 0u && lane == 0u && o1 - o0 <= (int64_t)P.capB) {
+      mbar_expect_tx(full, (uint32_t)(o1 - o0));
+      bulk_g2s(buf, P.blobB + o0, (uint32_t)(o1 - o0), full);
+    }
     for (uint32_t k = 0; k < nch; k++) {
       const uint32_t j = b.lo + 32u * k + lane;
       const bool valid = j < b.hi;
       const uint32_t i = P.reversed ? P.N - 1u - j : j;
-      const unsigned char *bp = P.blobB + offn;
-      if (k + 1u < nch) offn = P.offB[b.chunk0 + k + 1u];   // next chunk's blob offset: in flight during this chunk
+      const uint32_t cur = k & 1u;
+      const int64_t c0 = o0, c1 = o1;
+      // next chunk's blob into the other buffer (every lane has finished reading it: __syncwarp at the end of chunk k-1)
+      if (k + 1u < nch) {
+        o0 = o1;
+        o1 = P.offB[b.chunk0 + k + 2u];
+        if (lane == 0u && o1 - o0 <= (int64_t)P.capB) {
+          mbar_expect_tx(full + (cur ^ 1u), (uint32_t)(o1 - o0));
+          bulk_g2s(buf + (size_t)(cur ^ 1u) * P.capB, P.blobB + o0, (uint32_t)(o1 - o0), full + (cur ^ 1u));
+        }
+      }
       // start vector of the pre-pass minus the far entries of the own block (>= a window back; read back through L2)
       double t0 = 0.0;
       if (valid) {
         t0 = __ldcg(P.w + j);
         const int64_t e1 = P.far_rp[j + 1];
         for (int64_t e = P.far_rp[j] + P.far_split[j]; e < e1; e++) t0 = fma(-P.far_val[e], __ldcg(P.out + P.far_col[e]), t0);
+      }
+      const unsigned char *bp;
+      if (c1 - c0 <= (int64_t)P.capB) {
+        uint32_t spins = 0;
+        while (!mbar_try_s(full_s + 8u * cur, (phase >> cur) & 1u)) {
+          if (++spins > (1u << 22)) { atomicCAS(P.abort_g, 0u, 0xC00u); break; }
+        }
+        phase ^= 1u << cur;
+        bp = buf + (size_t)cur * P.capB;
+      } else {
+        bp = P.blobB + c0;
       }
       const uint32_t *hd = reinterpret_cast<const uint32_t *>(bp);
       const uint32_t ne_max = hd[0], ne_tot = hd[1], nl = hd[2];
@@ -672,15 +707,6 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 4) k_wb_solve(const BcArgs P) {
       const double *lv = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot));
       const uint16_t *lc = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(lv) + 256u * nl);
       const unsigned char *wq = reinterpret_cast<const unsigned char *>(lv) + 320u * nl;   // packed Winv
-      // the inverse first: its loads do not depend on anything and cover the latency of the entry loads below
-      double wv[32];
-#pragma unroll
-      for (uint32_t pp = 0; pp < 16u; pp++) {
-        const uint32_t rr = lane >= 2u * pp ? lane - 2u * pp : 0u;
-        const double2 w2 = *reinterpret_cast<const double2 *>(wq + 16u * (pp * (33u - pp) + rr));
-        wv[2 * pp] = lane >= 2u * pp ? w2.x : 0.0;
-        wv[2 * pp + 1] = lane >= 2u * pp ? w2.y : 0.0;
-      }
       // in-window entries, jagged diagonals (rows sorted by length), four per trip
       double ts = __shfl_sync(0xffffffffu, t0, (int)perm), ts1 = 0.0;
       uint32_t base = 0;
@@ -711,10 +737,11 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 4) k_wb_solve(const BcArgs P) {
         double ta, tb, tc, td;
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ta), "=d"(tb) : "r"(scr_s + 16u * pp) : "memory");
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc), "=d"(td) : "r"(scr_s + 16u * pp + 16u) : "memory");
-        u0 = fma(wv[2 * pp], ta, u0);
-        u1 = fma(wv[2 * pp + 1], tb, u1);
-        u2 = fma(wv[2 * pp + 2], tc, u2);
-        u3 = fma(wv[2 * pp + 3], td, u3);
+        const uint32_t r0 = lane >= 2u * pp ? lane - 2u * pp : 0u, r1 = lane >= 2u * pp + 2u ? lane - 2u * pp - 2u : 0u;
+        const double2 wa = *reinterpret_cast<const double2 *>(wq + 16u * (pp * (33u - pp) + r0));
+        const double2 wb = *reinterpret_cast<const double2 *>(wq + 16u * ((pp + 1u) * (32u - pp) + r1));
+        if (lane >= 2u * pp) { u0 = fma(wa.x, ta, u0); u1 = fma(wa.y, tb, u1); }
+        if (lane >= 2u * pp + 2u) { u2 = fma(wb.x, tc, u2); u3 = fma(wb.y, td, u3); }
       }
       const double x = (u0 + u1) + (u2 + u3);
       win[(32u * k + lane) & wmask] = x;

@@ -8,6 +8,7 @@ import numpy as np
 
 AHDR, BHDR, WBYTES, RBATCH = 16, 80, 1024 * 8, 3072
 FC_MINB, FC_WPACK = 4, 4352          # folded layout (chain_mode 5, rcg_fold.cuh)
+FC_COLCAP = 32                       # panel columns per chunk beyond the previous chunk's (chunk_fold_depth)
 
 
 FC_TAILB = 16 + 1040 * FC_MINB       # header + tail (the newest 16 columns): byte offset of the body

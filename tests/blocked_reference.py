@@ -4,7 +4,7 @@ tests/blocked_emulator.py, to exercise the algorithm on the CPU (-m "not gpu")."
 import numpy as np
 import scipy.sparse as sp
 
-from blocked_emulator import AHDR, BHDR, WBYTES, RBATCH, FC_WPACK, FC_MINB, FC_TAILB, r16, w_pair_off, rec_batches, fold_batches, fold_bytesA, wp_pair_off
+from blocked_emulator import AHDR, BHDR, WBYTES, RBATCH, FC_WPACK, FC_MINB, FC_TAILB, FC_COLCAP, r16, w_pair_off, rec_batches, fold_batches, fold_bytesA, wp_pair_off
 
 
 def tree_depths(nb):
@@ -84,7 +84,24 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             nr = len(rows)
             c_far = blo + 32 * max(0, k + 1 - Dfar)
             c_early = blo + 32 * max(0, k - e_of[b])
-            c_late = blo + 32 * max(0, k - kr_of[b])
+            Dk = kr_of[b]
+            if fold and not wb_of[b]:
+                # fold depth of the chunk (chunk_fold_depth): the largest D <= Kr with at most FC_COLCAP distinct columns in
+                # the D previous chunks; the previous chunk is always folded
+                ng = min(k, kr_of[b])
+                by_dist = [set() for _ in range(ng + 1)]
+                for j in rows:
+                    s_, e_ = rp[j], rp[j + 1]
+                    for c in col[s_:e_ - 1]:
+                        if blo + 32 * (k - ng) <= c < blo + 32 * k:
+                            by_dist[k - (int(c) - blo) // 32].add(int(c))
+                Dk, cum = 0, 0
+                for dd in range(1, ng + 1):
+                    if dd > 1 and cum + len(by_dist[dd]) > FC_COLCAP:
+                        break
+                    cum += len(by_dist[dd])
+                    Dk = dd
+            c_late = blo + 32 * max(0, k - Dk)
             c_rec = blo + 32 * k
             parts = []
             D = np.zeros((32, 32))
@@ -176,7 +193,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             rank = np.zeros(32, np.int64)
             rank[order] = np.arange(32)
             bb = np.zeros(BHDR + r16(ne_max) + r16(8 * ne_tot) + r16(2 * ne_tot) + 320 * nl + (FC_WPACK if fold else 0), np.uint8)
-            bb[:12].view(np.uint32)[:] = [ne_max, ne_tot, nl]
+            bb[:16].view(np.uint32)[:] = [ne_max, ne_tot, nl, Dk]
             bb[16:48] = order
             bb[48:80] = rank
             o = BHDR + r16(ne_max)
