@@ -1320,10 +1320,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   // older chunks inside the window are "early" (gathered before).  reserved[5] overrides (tuning experiments).
   {
     const int e_leaf = h->opt.reserved[5] & 0xFF, e_sep = (h->opt.reserved[5] >> 8) & 0xFF;   // reserved[5]: leaves | separators << 8
-    B.E = e_leaf > 0 ? (uint32_t)std::min(16, std::max<int>(e_leaf, (int)B.Kr + 1)) : 16u;
+    B.E = e_leaf > 0 ? (uint32_t)std::min(255, std::max<int>(e_leaf, (int)B.Kr + 1)) : 16u;   // (E >= window: no early class)
     // separator blocks are nearly dense next to the diagonal: with E = 16 their late ELL part has 35-50 slots, more than
     // a helper keeps in registers, so the helper holds its staging slot through the late phase; E = 6 keeps it short
-    B.E_sep = e_sep > 0 ? (uint32_t)std::min(16, std::max<int>(e_sep, (int)B.Kr + 1)) : std::min(B.E, 6u);
+    B.E_sep = e_sep > 0 ? (uint32_t)std::min(255, std::max<int>(e_sep, (int)B.Kr + 1)) : std::min(B.E, 6u);
   }
   uint32_t win_rows = h->opt.chain_window > 0 ? (uint32_t)h->opt.chain_window : 4096u;
   B.Dfar = std::min(512u, std::max(32u, floor_pow2_u32(std::max(32u, win_rows) / 32u)));
@@ -1353,7 +1353,9 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     for (int b = 0; b < nb; b++) if (bounds[b + 1] > bounds[b]) per_depth[depth[b]]++;
     for (int b = 0; b < nb; b++)
       if (B.wb_min > 0 && (uint32_t)per_depth[depth[b]] >= B.wb_min) {
-        wbblk[b] = 1; krblk[b] = 0; eblk[b] = 0; dfar[b] = B.Dfar_wb; tilesz[b] = B.tile_sep;
+        // in-window entries as ONE class: ELL (E = window; lane = row, independent loads, no divergence) by default,
+        // jagged diagonals (E = 0; fewer bytes, dependent loads) with reserved[2] = 1
+        wbblk[b] = 1; krblk[b] = 0; eblk[b] = h->opt.reserved[2] == 1 ? 0u : B.Dfar_wb; dfar[b] = B.Dfar_wb; tilesz[b] = B.tile_sep;
       }
   }
   for (int b = 0; b < nb; b++) {

@@ -727,7 +727,29 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
       }
       ts += ts1;
       double t = __shfl_sync(0xffffffffu, ts, (int)rank);
-      for (uint32_t s = 0; s < nl; s++) t = fma(-lv[s * 32u + lane], win[lc[s * 32u + lane]], t);   // ELL class (empty when E = 0)
+      {   // ELL class (lane = row; padding slots point at the zero slot): eight independent gathers per trip
+        double q1 = 0.0, q2 = 0.0, q3 = 0.0;
+        for (uint32_t s0 = 0; s0 < nl; s0 += 8u) {
+          uint32_t cc[8];
+          double vv[8], xx[8];
+#pragma unroll
+          for (uint32_t u = 0; u < 8u; u++) {
+            const bool have = s0 + u < nl;
+            cc[u] = have ? lc[(s0 + u) * 32u + lane] : P.W;
+            vv[u] = have ? lv[(s0 + u) * 32u + lane] : 0.0;
+          }
+#pragma unroll
+          for (uint32_t u = 0; u < 8u; u++) xx[u] = win[cc[u]];
+#pragma unroll
+          for (uint32_t u = 0; u < 8u; u += 4u) {
+            t = fma(-vv[u], xx[u], t);
+            q1 = fma(-vv[u + 1u], xx[u + 1u], q1);
+            q2 = fma(-vv[u + 2u], xx[u + 2u], q2);
+            q3 = fma(-vv[u + 3u], xx[u + 3u], q3);
+          }
+        }
+        t = (t + q1) + (q2 + q3);
+      }
       // x = Winv t : t broadcast through the warp's scratch row, lane = row of the result
       sts_f64(scr_s + 8u * lane, t);
       __syncwarp();

@@ -43,7 +43,7 @@ def direction_matrix(G, part, backward):
 
 
 def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False, tile_sep=1, tile_leaf=8, E_sep=None,
-                 fold=False, wb_min=0, Dfar_wb=32):
+                 fold=False, wb_min=0, Dfar_wb=32, wb_jagged=False):
     N = L.shape[0]
     rp, col, val = L.indptr.astype(np.int64), L.indices.astype(np.int64), L.data
     nb = len(bounds) - 1
@@ -62,7 +62,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
     wb_of = [1 if fold and wb_min > 0 and per_depth.get(int(depth[b]), 0) >= wb_min else 0 for b in range(nb)]
     for b in range(nb):
         if wb_of[b]:
-            kr_of[b], e_of[b], dfar_of[b], tile_of[b] = 0, 0, Dfar_wb, tile_sep
+            kr_of[b], e_of[b], dfar_of[b], tile_of[b] = 0, (0 if wb_jagged else Dfar_wb), Dfar_wb, tile_sep
     Dfar_leaf = Dfar
     chunk0 = np.zeros(nb + 1, np.int64)
     tile0 = np.zeros(nb + 1, np.int64)
