@@ -16,11 +16,20 @@ cores on a bounded sample (a fixed number of iterations per step).
 """
 from __future__ import annotations
 
+import os
+import sys
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # The reference arm runs the reference's CPU code on ALL host cores.  torchrun exports OMP_NUM_THREADS=1 to every
+    # rank; the OpenMP / MKL runtimes read the environment when they load, so it is overridden here, before numpy,
+    # torch or the oracle libraries are imported.
+    _n = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_k] = _n
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -183,7 +192,9 @@ def _reference_sample_in_child(d, iters: int):
             A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
             t0 = time.time()
             r = oracle.reference_pcg(A, d["b"], 1e-30, iters, G)                       # tol unreachable: `iters` iterations
-            out = dict(iteration_s=r["iteration_s"], call_s=time.time() - t0, itr=int(r["itr"]))
+            import torch
+            out = dict(iteration_s=r["iteration_s"], call_s=time.time() - t0, itr=int(r["itr"]),
+                       omp_threads=int(oracle.num_threads()), mkl_threads=int(torch.get_num_threads()))
             os.write(wfd, json.dumps(out).encode())
             status = 0
         except BaseException as e:  # pragma: no cover
@@ -219,10 +230,12 @@ def cpu_sample(d, iters: int, prefer_reference: bool):
             and int(d["G_rp"][-1]) < 2 ** 31 - 1):
         try:
             o = _reference_sample_in_child(d, iters)
-            return o["iteration_s"], o["itr"], "reference", os.cpu_count(), dict(
+            return o["iteration_s"], o["itr"], "reference", min(o["omp_threads"], o["mkl_threads"]), dict(
                 what="unmodified reference pcg.cpp + oneMKL SpMV/SpTRSV (libtorch_cpu), OpenMP CBLAS-1 stand-ins; seconds "
-                     "inside pcg::iteration, one forked child per step (the reference leaks its set-up copies)",
-                whole_call_s=o["call_s"])
+                     "inside pcg::iteration (its six zero-filled work vectors and the final true-residual SpMV included, "
+                     "its set-up copies not), one forked child per step (the reference leaks its set-up copies)",
+                whole_call_s=o["call_s"], omp_threads=o["omp_threads"], mkl_threads=o["mkl_threads"],
+                env_omp_num_threads=os.environ.get("OMP_NUM_THREADS"))
         except Exception as e:  # pragma: no cover
             # sticky: the port below starts an OpenMP pool in THIS process, after which forking again is not safe
             _reference_child_failed = True

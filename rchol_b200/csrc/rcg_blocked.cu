@@ -1348,7 +1348,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   {
     const int wb_opt = (h->opt.reserved[9] >> 16) & 0xFFFF;   // reserved[9] bits 16-31: blocks per level from which the
     B.wb_min = !B.fold || wb_opt == 0xFFFF ? 0u : wb_opt > 0 ? (uint32_t)wb_opt : 64u;   // level is warp-per-block (0xFFFF: never)
-    B.Dfar_wb = 32u;
+    // window of a warp-per-block level: 2048 rows.  Older entries of the own block are gathered from HBM/L2 by the block's
+    // warp, one dependent round trip after the other (measured at 256^3 / T=512 with a 1024-row window: the plane
+    // neighbours of a 32^3 leaf sit ~1024 rows back, 40 % of the factor was "far" and a chunk took 9600 cycles)
+    B.Dfar_wb = 64u;
     std::vector<int> per_depth(max_depth + 2, 0);
     for (int b = 0; b < nb; b++) if (bounds[b + 1] > bounds[b]) per_depth[depth[b]]++;
     for (int b = 0; b < nb; b++)
@@ -1536,10 +1539,13 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     // ring A feeds one consumer (latency cover), ring B feeds BC_NH helpers that hold their slot while they work
     // (folded chain: the panel is capped at 8.3 KB per chunk -- chunk_fold_depth -- and a bulk copy from HBM takes 1-2 us,
     //  i.e. several hops: up to 12 slots)
-    int64_t SA = std::max<int64_t>(3, std::min<int64_t>(B.fold ? 12 : 10, (avail * (B.fold ? 35 : 40) / 100) / L.capA));
-    if (h->opt.reserved[8] > 0) SA = std::max<int64_t>(2, std::min<int64_t>(10, h->opt.reserved[8]));   // tuning experiments
-    int64_t SB = std::max<int64_t>(3, std::min<int64_t>(2 * BC_NH + 4, (avail - SA * L.capA) / (L.capB + 24)));
-    while (SA > 3 && SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) SA--;
+    // (folded chain: three chain warps take turns and each preloads its next chunk, 3 ahead: at least 4 slots, 7 wanted)
+    const int64_t SA_min = B.fold ? 4 : 3;
+    int64_t SA = std::max<int64_t>(B.fold ? 7 : 3, std::min<int64_t>(B.fold ? 12 : 10, (avail * (B.fold ? 35 : 40) / 100) / L.capA));
+    if (h->opt.reserved[8] > 0) SA = std::max<int64_t>(B.fold ? SA_min : 2, std::min<int64_t>(12, h->opt.reserved[8]));   // tuning experiments
+    const int64_t NHELP = B.fold ? FC_NH : BC_NH;
+    int64_t SB = std::max<int64_t>(3, std::min<int64_t>(2 * NHELP + 4, (avail - SA * L.capA) / (L.capB + 24)));
+    while (SA > SA_min && SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) SA--;
     while (SB > 3 && SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) SB--;
     if (SA * L.capA + SB * (L.capB + 24) + SA * 16 > avail) {
       cudaFree(dgeom);

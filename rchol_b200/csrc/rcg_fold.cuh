@@ -11,12 +11,16 @@
 // the far tiles / start vector / progress words).
 //
 // CTA = 12 warps (384 threads, 168 registers each):
-//   warp 0        chain (critical) warp, alone on scheduler 0 apart from the two TMA producers, which sleep in mbarrier waits
+//   warps 0,4,8   chain warps, the only warps of scheduler 0.  Chunk k belongs to chain warp k % 3.  A lone warp needs
+//                 ~700 cycles for the ~110 instructions of a chunk (measured), but only the x loads, 4 dependent DFMA, 2
+//                 DADD and two stores depend on the previous chunk: with three warps taking turns, the bookkeeping of
+//                 chunk k (staging barrier, next tail into registers, flag of u) overlaps the critical section of k+1, k+2.
 //   warp 1        publisher: window -> out[], fused dot product, progress published with release semantics
-//   warp 4 / 8    TMA producers of ring A (panels) / ring B (early + late entries + packed Winv)
-//   warps 2,3,5,6,7,9,10,11   near helpers: chunk k -> helper k % 8, running up to 8 chunks ahead
+//   warp 2 / 3    TMA producers of ring A (panels) / ring B (early + late entries + packed Winv)
+//   warps 5,6,7,9,10,11   near helpers: chunk k -> helper k % 6, running up to 6 chunks ahead
 constexpr int FC_THREADS = 384;
-constexpr uint32_t FC_NH = 8;
+constexpr uint32_t FC_NC = 3;
+constexpr uint32_t FC_NH = 6;
 constexpr uint32_t FC_SCR = FC_NH * 32u;   // scratch doubles: one t vector per helper (broadcast for the Winv mat-vec)
 
 __device__ __forceinline__ void mbar_arrive_after3(uint64_t *bar, uint32_t a, double b, double c) {
@@ -173,8 +177,9 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
     if (threadIdx.x == 0) { ctl[0] = 0u; ctl[1] = 0u; }
     __syncthreads();
 
-    if (warp == 0) {
-      // ------------------------------ chain warp ---------------------------------------------------------
+    if ((warp & 3u) == 0u) {
+      // ------------------------------ chain warps (0, 4, 8) ----------------------------------------------
+      const uint32_t cw = warp >> 2;   // this warp's turn: chunks cw, cw + 3, ...
       // A lone warp is bound by the number of instructions between two hops (measured: 4-8 cycles per dependent
       // instruction, 150 for a synchronous mbarrier test, 160-410 for a divergent branch, a MEMBAR for st.release), so:
       // 32-bit shared addresses only, no divergent branch (lane 0's stores are predicated), the progress word is a
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
       // The loop body is ONE copy of straight-line code of ~90 instructions (1.5 KB): a lone warp has nobody to hide
       // its instruction fetches behind, and a body larger than the scheduler's L0 instruction cache (two unrolled
       // copies were 6.7 KB) costs more than everything else in it.
-      const bool prof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0;
+      const bool prof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0 && warp == 0u;
       uint32_t ringA_s = smem_u32(ringA), ringA_e = ringA_s + P.SA * P.capA, capA = P.capA;
       uint32_t fullA_s = smem_u32(fullA), fullA_e = fullA_s + 8u * P.SA;
       uint32_t wm8 = 8u * wmask, lane16 = 16u * lane;
@@ -194,17 +199,19 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
       // registers inside the loop (the lone warp pays for every instruction)
       asm volatile("" : "+r"(ringA_s), "+r"(ringA_e), "+r"(capA), "+r"(fullA_s), "+r"(fullA_e), "+r"(wm8));
       asm volatile("" : "+r"(xst_s), "+r"(ul_s), "+r"(lane16));
-      const uint32_t slot0 = ia0 % P.SA;
-      uint32_t par1 = (ia0 / P.SA) & 1u;                   // parity of the staging barrier of chunk k+1 ...
-      uint32_t bar1 = fullA_s + 8u * slot0 + 8u;           // ... its address ...
-      uint32_t as_n = ringA_s + slot0 * capA + capA;       // ... and its staging slot
-      if (bar1 == fullA_e) { bar1 = fullA_s; as_n = ringA_s; par1 ^= 1u; }
-      uint32_t ok1 = 0u;                                   // "chunk k+1 is staged", asked one chunk ahead
+      const uint32_t step8 = 8u * FC_NC, stepA = FC_NC * capA;
+      const uint32_t i0 = ia0 + cw, slot0 = i0 % P.SA;     // ring index / staging slot of this warp's first chunk
+      const uint32_t par0 = (i0 / P.SA) & 1u;
+      uint32_t par1 = par0;                                // parity of the staging barrier of this warp's next chunk (k + 3) ...
+      uint32_t bar1 = fullA_s + 8u * slot0 + step8;        // ... its address ...
+      uint32_t as_n = ringA_s + slot0 * capA + stepA;      // ... and its staging slot
+      if (bar1 >= fullA_e) { bar1 -= 8u * P.SA; as_n -= P.SA * capA; par1 ^= 1u; }
+      uint32_t ok1 = 0u;                                   // "chunk k+3 is staged", asked one own chunk ahead
       uint32_t o[16];                                      // tail columns of chunk k: window byte offsets of x
       double mt[16];                                       // tail panel values
       uint32_t ncb = FC_MINB, as_c = ringA_s + slot0 * capA;
       uint32_t tpf = 0u, spins = 0u;
-      double un = 0.0;                                     // u of the next chunk, loaded behind its flag
+      double un = 0.0;                                     // u of this warp's next chunk, loaded behind its flag
 #define FC_SPIN(cond_, code_)                                                                                             \
       while (__builtin_expect(!(cond_), 0)) {                                                                             \
         if (++spins > (1u << 24)) { atomicCAS(P.abort_g, 0u, (code_)); sts_volatile_u32(G.abort_s, 1u); break; }          \
@@ -218,29 +225,36 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mt[4 * q_]), "=d"(mt[4 * q_ + 1]) : "r"((AS_) + 80u + lane16 + 1024u * q_) : "memory"); \
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mt[4 * q_ + 2]), "=d"(mt[4 * q_ + 3]) : "r"((AS_) + 592u + lane16 + 1024u * q_) : "memory"); \
       }
-      if (nch > 0) {
-        FC_SPIN(mbar_try_s(fullA_s + 8u * slot0, par1 ^ (bar1 == fullA_s ? 1u : 0u)) != 0u, 0x200u);
+      if (cw < nch) {
+        FC_SPIN(mbar_try_s(fullA_s + 8u * slot0, par0) != 0u, 0x200u);
         FC_LOAD_OFFS(as_c);
         FC_LOAD_VALS(as_c);
         ncb = lds_u32(as_c);
-        tpf = lds_volatile_u32(trdy_s);
-        un = lds_f64(ul_s);
-        if (nch > 1u) ok1 = mbar_test_s(bar1, par1);
+        tpf = lds_volatile_u32(trdy_s + 4u * cw);
+        un = lds_f64(ul_s + (cw << 8));
+        if (cw + FC_NC < nch) ok1 = mbar_test_s(bar1, par1);
       }
 #pragma unroll 1
-      for (uint32_t k = 0; k < nch; k++) {
+      for (uint32_t k = cw; k < nch; k += FC_NC) {
         long long c0 = 0;
         if (prof) c0 = clock64();
-        // staging barrier of chunk k+2: asked now, answered (ok2) while this chunk computes
-        uint32_t bar2 = bar1 + 8u, par2 = par1, as_2 = as_n + capA;
-        if (bar2 == fullA_e) { bar2 = fullA_s; as_2 = ringA_s; par2 ^= 1u; }
+        // staging barrier of this warp's chunk after next (k + 6): asked now, answered (ok2) while this chunk computes
+        uint32_t bar2 = bar1 + step8, par2 = par1, as_2 = as_n + stepA;
+        if (bar2 >= fullA_e) { bar2 -= 8u * P.SA; as_2 -= P.SA * capA; par2 ^= 1u; }
         const uint32_t ok2 = mbar_test_s(bar2, par2);
         if (__builtin_expect(tpf != k + 1u, 0)) {
           FC_SPIN((tpf = ld_acquire_cta_s(trdy_s + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);
           un = lds_f64(ul_s + ((k & (BC_TR - 1u)) << 8));
-          if (prof) { pc[3] += 1; pc[1] += clock64() - c0; }
+          if (prof) { pc[3] += 1; pc[0] += clock64() - c0; }
         }
         double a0 = un, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        // this warp's turn: the chain has to have solved chunk k-1 (everything above was bookkeeping ahead of it)
+        if (k > 0u) {
+          long long c2 = 0;
+          if (prof) c2 = clock64();
+          FC_SPIN(lds_volatile_u32(prog_s) >= k, 0xD00u);
+          if (prof) pc[1] += clock64() - c2;
+        }
         // body: the older batches of a wide panel, two per trip (eight independent gathers in flight)
         if (__builtin_expect(ncb != FC_MINB, 0)) {
           const uint32_t nb = ncb - FC_MINB;
@@ -273,20 +287,17 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         for (uint32_t i = 0; i < 16u; i++) x[i] = lds_f64(win_s + o[i]);
         // chain-independent loads of the next chunk, in flight behind the x loads: offsets (into the registers the
         // x loads have just read), batch count, flag of u and u itself
-        const bool more = k + 1u < nch;
+        const bool more = k + FC_NC < nch;
         if (more) {
           if (__builtin_expect(ok1 == 0u, 0)) {
-            long long c1 = 0;
-            if (prof) c1 = clock64();
             FC_SPIN((ok1 = mbar_try_s(bar1, par1)) != 0u, 0x200u);
-            if (prof) pc[0] += clock64() - c1;
           }
           FC_LOAD_OFFS(as_n);
           ncb = lds_u32(as_n);
           // flag of u_{k+1}, then the value: shared-memory loads of one warp complete in order, so a value read behind a
           // set flag is the published one; a clear flag is polled at the top of the next chunk
-          tpf = lds_volatile_u32(trdy_s + 4u * ((k + 1u) & (BC_TR - 1u)));
-          un = lds_f64(ul_s + (((k + 1u) & (BC_TR - 1u)) << 8));
+          tpf = lds_volatile_u32(trdy_s + 4u * ((k + FC_NC) & (BC_TR - 1u)));
+          un = lds_f64(ul_s + (((k + FC_NC) & (BC_TR - 1u)) << 8));
         }
 #pragma unroll
         for (uint32_t i = 0; i < 16u; i += 4u) {
@@ -308,7 +319,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
 #undef FC_LOAD_VALS
 #undef FC_LOAD_OFFS
 #undef FC_SPIN
-    } else if (warp == 4u) {
+    } else if (warp == 2u) {
       // ------------------------------ TMA producer, ring A -----------------------------------------------
       int64_t O0n = 0, O1n = 0;
       if (nch > 0) {
@@ -336,7 +347,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
           __syncwarp();
         }
       }
-    } else if (warp == 8u) {
+    } else if (warp == 3u) {
       // ------------------------------ TMA producer, ring B -----------------------------------------------
       int64_t O0n = 0, O1n = 0;
       if (nch > 0) {
@@ -409,8 +420,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
       dot = warp_sum(dot);
       if (lane == 0 && P.dot_partials) P.dot_partials[b.gidx] = dot;
     } else {
-      // ------------------------------ near helpers: warps 2,3,5,6,7,9,10,11 ------------------------------
-      const uint32_t hidx = warp - 2u - (warp > 4u ? 1u : 0u) - (warp > 8u ? 1u : 0u);
+      // ------------------------------ near helpers: warps 5,6,7,9,10,11 ----------------------------------
+      const uint32_t hidx = warp - 5u - (warp > 8u ? 1u : 0u);
       const bool hprof = PROF && (P.dbg & 1u) != 0u && blockIdx.x == 0 && hidx == 0u;
       const uint32_t hs_s = sc_s + 256u * hidx;
       uint32_t tiles_known = 0;
@@ -582,7 +593,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
       P.clk[15] = (unsigned long long)pc[3];   // failed first polls of u
     }
   }
-  if (P.clk && (P.dbg & 1u) && blockIdx.x == 0 && threadIdx.x == 64u)   // near helper 0 = warp 2
+  if (P.clk && (P.dbg & 1u) && blockIdx.x == 0 && threadIdx.x == 160u)   // near helper 0 = warp 5
     for (int q = 0; q < 5; q++) P.clk[8 + q] = (unsigned long long)ph[q];
 }
 
@@ -685,7 +696,16 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
       if (valid) {
         t0 = __ldcg(P.w + j);
         const int64_t e1 = P.far_rp[j + 1];
-        for (int64_t e = P.far_rp[j] + P.far_split[j]; e < e1; e++) t0 = fma(-P.far_val[e], __ldcg(P.out + P.far_col[e]), t0);
+        int64_t e = P.far_rp[j] + P.far_split[j];
+        double t1 = 0.0;
+        for (; e + 1 < e1; e += 2) {   // two independent gathers per trip
+          const uint32_t ca = P.far_col[e], cb = P.far_col[e + 1];
+          const double va = P.far_val[e], vb = P.far_val[e + 1];
+          t0 = fma(-va, __ldcg(P.out + ca), t0);
+          t1 = fma(-vb, __ldcg(P.out + cb), t1);
+        }
+        if (e < e1) t0 = fma(-P.far_val[e], __ldcg(P.out + P.far_col[e]), t0);
+        t0 += t1;
       }
       const unsigned char *bp;
       if (c1 - c0 <= (int64_t)P.capB) {

@@ -43,7 +43,7 @@ def direction_matrix(G, part, backward):
 
 
 def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32, reversed_=False, tile_sep=1, tile_leaf=8, E_sep=None,
-                 fold=False, wb_min=0, Dfar_wb=32, wb_jagged=False):
+                 fold=False, wb_min=0, Dfar_wb=64, wb_jagged=False):
     N = L.shape[0]
     rp, col, val = L.indptr.astype(np.int64), L.indices.astype(np.int64), L.data
     nb = len(bounds) - 1
