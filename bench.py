@@ -67,7 +67,7 @@ def build_problem(n: int, threads: int):
         t0 = time.time()
         d = {k: np.load(f"{tag}.{k}.npy", mmap_mode="r" if multi else None) for k in names}
         log(f"[bench] loaded cached problem {tag} in {time.time() - t0:.1f}s")
-        return d, dict(cached=True)
+        return d, dict(cached=True, tag=tag)
 
     if os.path.exists(ready) and all(os.path.exists(f"{tag}.{k}.npy") for k in names):
         return load()
@@ -105,7 +105,7 @@ def build_problem(n: int, threads: int):
         log(f"[bench] cache not written: {e}")
         if multi:
             raise
-    return d, dict(cached=False, gen_s=t1 - t0, factor_s=t2 - t1, reorder_s=t3 - t2)
+    return d, dict(cached=False, gen_s=t1 - t0, factor_s=t2 - t1, reorder_s=t3 - t2, tag=tag)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -283,15 +283,21 @@ def workload_config(args, d, N):
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
-def run_ours_single(args, d, B_iter, gen_info=None):
-    gen_info = gen_info or {}
+def _relerr(a, b):
+    nb = float(np.linalg.norm(b))
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0))
+
+
+def measure_resident(d, threads, steps, warmup, peak, levels=True):
+    """A, G, b resident in HBM: `warmup` untimed and `steps` timed PCG solves (CUDA events inside the library, on its own
+    stream), then the per-launch split of the triangular solves.  Returns (result dict, solver) -- the solver is still
+    open so that the caller can add parity checks on the same device copy."""
     from rchol_b200 import capi
     A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
-    part = d["part"] if args.threads > 0 else None
+    part = d["part"] if threads > 0 else None
     N = A[0].shape[0] - 1
     nnzA, nnzG = int(A[0][-1]), int(G[0][-1])
-    peak, peak_src = measured_peak_gbs()
-
+    B_iter = problems.algorithmic_bytes_per_iteration(N, nnzA, nnzG)
     s = capi.Solver(0)
     t0 = time.time()
     s.set_matrix(*A)
@@ -299,18 +305,16 @@ def run_ours_single(args, d, B_iter, gen_info=None):
     s.set_rhs(d["b"])
     setup_wall = time.time() - t0
     st0 = s.stats()
-    log(f"[bench] upload {st0['upload_ms']:.0f} ms, analysis {st0['analysis_ms']:.0f} ms, device bytes {st0['device_bytes'] / 1e9:.2f} GB")
-
-    for w in range(args.warmup):
+    log(f"[bench] T={threads}: upload {st0['upload_ms']:.0f} ms, analysis {st0['analysis_ms']:.0f} ms")
+    for w in range(warmup):
         relres, itr = s.pcg_resident(TOL, MAXIT)
-        log(f"[bench] warm-up {w}: {itr} iterations, relres {relres:.3e}, {s.stats()['solve_ms']:.1f} ms")
-
+        log(f"[bench] T={threads} warm-up {w}: {itr} iterations, relres {relres:.3e}, {s.stats()['solve_ms']:.1f} ms")
     sampler = ClockSampler(0)
     sampler.start()
     launches0 = s.stats()["kernel_launches"]
     dev_ms, iters_total = 0.0, 0
     wall0 = time.time()
-    for k in range(args.steps):
+    for k in range(steps):
         relres, itr = s.pcg_resident(TOL, MAXIT)
         dev_ms += s.stats()["solve_ms"]
         iters_total += itr
@@ -318,56 +322,112 @@ def run_ours_single(args, d, B_iter, gen_info=None):
     launches = s.stats()["kernel_launches"] - launches0
     clocks = sampler.stop()
     value = B_iter * iters_total / (dev_ms * 1e-3) / 1e9
-    x_dev = s.solution()
+    out = dict(B_iter=B_iter, N=N, nnzA=nnzA, nnzG=nnzG, value=value, dev_ms=dev_ms, iters_total=iters_total, relres=relres,
+               wall=wall, launches=int(launches), clocks=clocks, setup=dict(upload_ms=st0["upload_ms"], analysis_ms=st0["analysis_ms"],
+                                                                           wall_s=setup_wall))
+    if levels:
+        # The triangular solves run as ONE launch (warp-per-block levels: two) per tree level and direction: the dominant
+        # kernels.  Every level is timed with CUDA events on the library's stream (rcg_time_group).  Algorithmic bytes of a
+        # level: 12 B per factor entry of its rows, 4 B row pointer, right-hand side in and solution out (16 B).
+        prof = s.profile_iteration(3)
+        per_level, tot_ms, tot_bytes, nl, dom = {}, 0.0, 0, 0, None
+        for direction, dname in ((capi.TRSV_FORWARD, "fwd"), (capi.TRSV_BACKWARD, "bwd")):
+            for gi, g in enumerate(s.groups(direction)):
+                ms = s.time_group(direction, gi, 0, 3)
+                lbytes = 12 * (g["loc_nnz"] + g["ext_nnz"]) + 20 * g["rows"]
+                tot_ms += ms; tot_bytes += lbytes; nl += 1
+                per_level[f"{dname}:level{gi}:{g['blocks']}blocks"] = dict(
+                    rows=g["rows"], max_rows=g["max_rows"], entries=g["loc_nnz"] + g["ext_nnz"], ms=ms, algorithmic_bytes=lbytes,
+                    gbs=lbytes / ms / 1e6 if ms else 0.0)
+                if dom is None or ms > dom[1]:
+                    dom = (f"{dname} level {gi}: {g['blocks']} blocks, {g['rows']} rows", ms, lbytes)
+        spmv_ms = prof["spmv_ms"]
+        ach = tot_bytes / tot_ms / 1e6
+        out["roofline"] = dict(
+            bound="hbm", kernel="triangular-solve level launches (k_fc_solve / k_wb_solve): all launches of one forward + one backward solve",
+            achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, launches_per_solve_pair=nl, bytes_per_launch=tot_bytes / nl,
+            ms_per_launch=tot_ms / nl, trsv_kernel_ms_per_iteration=tot_ms,
+            largest_launch=dict(kernel=dom[0], ms=dom[1], gbs=dom[2] / dom[1] / 1e6),
+            iteration=dict(bytes=B_iter, ms=dev_ms / max(iters_total, 1), gbs=value, frac=value / peak, trsv_ms=prof["trsv_ms"],
+                           spmv_ms=spmv_ms, blas1_ms=prof["blas1_ms"],
+                           spmv_gbs=(12 * nnzA + 4 * N + 24 * N) / spmv_ms / 1e6 if spmv_ms else 0.0),
+            tree_levels=per_level)
+    return out, s
 
-    # ---- per-phase and per-kernel split (live CUDA events) ------------------------------------------------------
-    prof = s.profile_iteration(3)
-    # The triangular solves run as ONE launch per tree level and direction (k_bc_solve, rcg_blocked.cu): the dominant
-    # kernel.  Every launch is timed with CUDA events on the library's stream (rcg_time_group).
-    # Algorithmic bytes of a launch: 12 B per factor entry of the level's rows, 4 B row pointer per row,
-    # right-hand side in and solution out (16 B per row).
-    per_level = {}
-    chain_ms_total, chain_bytes_total, chain_launches, blob_bytes_total, far_nnz_total = 0.0, 0, 0, 0, 0
-    dom = None
-    for direction, dname in ((capi.TRSV_FORWARD, "fwd"), (capi.TRSV_BACKWARD, "bwd")):
-        for gi, g in enumerate(s.groups(direction)):
-            ms = s.time_group(direction, gi, 0, 3)
-            nnz_level = g["loc_nnz"] + g["ext_nnz"]
-            lbytes = 12 * nnz_level + 4 * g["rows"] + 16 * g["rows"]
-            chain_ms_total += ms; chain_bytes_total += lbytes; chain_launches += 1
-            blob_bytes_total += g["max_stage"]; far_nnz_total += g["ext_nnz"]
-            per_level[f"{dname}:level{gi}:{g['blocks']}blocks"] = dict(
-                rows=g["rows"], entries_chain_ctas=g["loc_nnz"], entries_far_ctas=g["ext_nnz"], chain_blob_bytes=g["max_stage"],
-                ms=ms, algorithmic_bytes=lbytes, gbs=lbytes / ms / 1e6 if ms else 0.0,
-                chunks_per_block_per_us=g["rows"] / 32 / max(g["blocks"], 1) / ms / 1e3 if ms else 0.0)
-            if dom is None or ms > dom[1]:
-                dom = (f"k_bc_solve[{dname} level {gi}: {g['blocks']} blocks, {g['rows']} rows]", ms, lbytes)
-    spmv_ms = prof["spmv_ms"]
-    ach = chain_bytes_total / chain_ms_total / 1e6
-    # bytes the launches actually stream: chain blobs (dense inverses included) + 12 B per far entry + vectors
-    moved = blob_bytes_total + 12 * far_nnz_total + 2 * (4 + 24) * N
-    traffic_ratio = None
+
+def parity_at_bench_config(s, d, tag):
+    """Parity AT THE BENCHMARKED SIZE, outside the timed region: both triangular solves and their composition against the
+    oracle's sequential substitution (oracle/pcg_oracle.c restating pcg.cpp:141-159) on the bench right-hand side, and
+    the iteration count of one converged CPU solve of the restated reference loop (cached beside the problem)."""
+    from oracle import oracle
+    from rchol_b200 import capi
+    A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
+    b = np.asarray(d["b"])
+    t0 = time.time()
+    yo = oracle.trsv_forward(*G, b)
+    zo = oracle.trsv_backward(*G, yo)
+    out = dict(fwd=_relerr(s.trsv(capi.TRSV_FORWARD, b), yo), bwd=_relerr(s.trsv(capi.TRSV_BACKWARD, yo), zo),
+               precond=_relerr(s.precond(b), zo), tolerance=1e-12, oracle_trsv_s=time.time() - t0)
+    cache = f"{tag}.parity.json" if tag else None
+    ref = None
+    if cache and os.path.exists(cache):
+        try:
+            ref = json.load(open(cache))
+        except Exception:
+            ref = None
+    if ref is None:
+        t0 = time.time()
+        o = oracle.pcg(A, b, TOL, MAXIT, G)
+        ref = dict(itr_ref=int(o["itr"]), relres_ref=float(o["relres"]), cpu_solve_s=time.time() - t0, threads=oracle.num_threads())
+        ref["x_norm"] = float(np.linalg.norm(o["x"]))
+        np.save(f"{tag}.xref.npy", o["x"]) if tag else None
+        if cache:
+            try:
+                json.dump(ref, open(cache, "w"))
+            except OSError:
+                pass
+    out.update(ref)
+    x = s.solution()
     try:
-        traffic_ratio = float(json.load(open(os.path.join(ROOT, "profiles", "r01_bc_traffic.json")))["dram_bytes_over_algorithmic"])
+        out["x_relerr_vs_cpu"] = _relerr(x, np.load(f"{tag}.xref.npy"))
     except Exception:
-        pass
-    roofline = dict(bound="hbm", kernel="k_bc_solve (one launch per tree level: all launches of one forward + one backward solve)",
-                    achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
-                    # dram__bytes_read+write of the dominant launch from the ncu --set full capture, scaled per launch
-                    traffic=(traffic_ratio * chain_bytes_total / chain_launches) if traffic_ratio else None,
-                    traffic_source="ncu --set full capture of the leaf-level launch, lap3d 128^3 (profiles/r01_bc_traffic.json)",
-                    peak_source=peak_src,
-                    launches_per_solve_pair=chain_launches, bytes_per_launch=chain_bytes_total / chain_launches,
-                    ms_per_launch=chain_ms_total / chain_launches, trsv_kernel_ms_per_iteration=chain_ms_total,
-                    streamed_bytes_per_iteration=moved, streamed_gbs=moved / chain_ms_total / 1e6,
-                    largest_launch=dict(kernel=dom[0], ms=dom[1], gbs=dom[2] / dom[1] / 1e6),
-                    note="dependency chain of the factor, one chain CTA per nested-dissection block: with T=8 leaves only 8 "
-                         "SMs carry the chain, so the kernel is bound by the per-chunk latency of the chain (DESIGN.md "
-                         "'SpTRSV'), not by HBM",
-                    iteration=dict(bytes=B_iter, ms=dev_ms / max(iters_total, 1), gbs=value, frac=value / peak,
-                                   trsv_ms=prof["trsv_ms"], spmv_ms=spmv_ms, blas1_ms=prof["blas1_ms"],
-                                   spmv_gbs=(12 * nnzA + 4 * N + 24 * N) / spmv_ms / 1e6 if spmv_ms else 0.0),
-                    tree_levels=per_level)
+        out["x_relerr_vs_cpu"] = None
+    return out
+
+
+def run_ours_single(args, d, B_iter, gen_info=None):
+    gen_info = gen_info or {}
+    from rchol_b200 import capi
+    A = (d["A_rp"], d["A_ci"], d["A_v"]); G = (d["G_rp"], d["G_ci"], d["G_v"])
+    part = d["part"] if args.threads > 0 else None
+    N = A[0].shape[0] - 1
+    peak, peak_src = measured_peak_gbs()
+
+    m, s = measure_resident(d, args.threads, args.steps, args.warmup, peak)
+    value, dev_ms, iters_total, relres = m["value"], m["dev_ms"], m["iters_total"], m["relres"]
+    x_dev = s.solution()
+    roofline = m["roofline"]
+    roofline["peak_source"] = peak_src
+    # dram__bytes_read+write of the level launches from an `ncu --set full` capture AT THE BENCH CONFIGURATION
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_trsv_traffic.json")))
+        if tr.get("workload") == workload_config(args, d, N)["workload"]:
+            roofline["traffic"] = tr["dram_bytes_per_solve_pair"] / roofline["launches_per_solve_pair"]
+            roofline["traffic_over_algorithmic"] = tr["dram_bytes_per_solve_pair"] / (roofline["bytes_per_launch"] * roofline["launches_per_solve_pair"])
+            roofline["traffic_source"] = tr.get("source")
+        else:
+            roofline["traffic"] = None
+    except Exception:
+        roofline["traffic"] = None
+
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_at_bench_config(s, d, gen_info.get("tag"))
+            parity["itr"] = iters_total // args.steps
+            log(f"[bench] parity at the bench configuration: {parity}")
+        except Exception as e:  # pragma: no cover
+            parity = dict(error=repr(e)[:300])
     s.close()
 
     # ---- end to end through the drop-in entry point, host buffers -------------------------------------------------
@@ -408,27 +468,33 @@ def run_ours_single(args, d, B_iter, gen_info=None):
                    sample=f"{it} PCG iterations (of {iters_total // args.steps} to convergence) on the full {args.n}^3 problem, "
                           f"{dt:.1f} s", ms_per_iter=1e3 * dt / it, detail=detail)
 
-    # ---- informational: the same workload with the leaf level on the cluster chain (chain_mode 4) -----------
-    cluster = None
-    if args.cluster_leg:
+    # ---- BASELINE.json configs[1] beside the headline: the same grid with the reference's 8-way partition --------------
+    configs1 = None
+    if args.configs1 and args.threads != 8:
         try:
-            p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "cluster_leg.py"), str(args.n), str(args.threads), "2"],
-                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
-            cluster = json.loads(p.stdout.strip().splitlines()[-1]) if p.returncode == 0 else dict(error=p.stderr[-300:])
+            d8, info8 = build_problem(args.n, 8)
+            m8, s8 = measure_resident(d8, 8, max(1, min(args.steps, 3)), 2, peak)
+            s8.close()
+            r8 = m8["roofline"]
+            configs1 = dict(workload=f"lap3d_{args.n}^3_rchol_T8_pcg_tol1e-8", nnzG=m8["nnzG"], iterations=m8["iters_total"] // max(1, min(args.steps, 3)),
+                            relres=m8["relres"], ms_per_iter=m8["dev_ms"] / max(m8["iters_total"], 1), value=m8["value"], unit="GB/s",
+                            frac_of_peak=m8["value"] / peak, trsv_frac_of_peak=r8["frac"], trsv_ms_per_iteration=r8["trsv_kernel_ms_per_iteration"],
+                            largest_launch=r8["largest_launch"], factor_s=info8.get("factor_s"))
+            del d8
         except Exception as e:  # pragma: no cover - informational leg
-            cluster = dict(error=str(e)[:300])
+            configs1 = dict(error=repr(e)[:300])
 
     line = dict(metric="pcg_gbps_per_iter", value=value, unit="GB/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
                 ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                 dtype="f64", data="synthetic", config=workload_config(args, d, N),
                 iterations=iters_total // args.steps, relres=relres, ms_per_iter=dev_ms / max(iters_total, 1),
                 time_to_solution_ms=dict(resident=dev_ms / args.steps, end_to_end=e2e_ms / e2e_steps, parts=setup_ms),
-                wall_ms_per_step=1e3 * wall / args.steps,
-                roofline=roofline, cpu_baseline=cpu,
+                wall_ms_per_step=1e3 * m["wall"] / args.steps,
+                roofline=roofline, cpu_baseline=cpu, parity=parity,
                 e2e=dict(value=e2e_value, unit="GB/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                          steps=e2e_steps, ms_per_step=e2e_ms / e2e_steps, host_memory="pageable (caller's SparseCSR arrays)"),
-                gpu_launches=int(launches), clocks=clocks, device_reorder=reorder_info, cluster_chain_opt_in=cluster,
-                setup=dict(upload_ms=st0["upload_ms"], analysis_ms=st0["analysis_ms"], wall_s=setup_wall))
+                gpu_launches=m["launches"], clocks=m["clocks"], device_reorder=reorder_info, configs1=configs1,
+                setup=m["setup"])
     print(json.dumps(line), flush=True)
 
 
@@ -443,9 +509,9 @@ def main():
     ap.add_argument("--sample-iters", type=int, default=4, help="PCG iterations per CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cluster-leg", action="store_true",
-                    help="also run the informational chain_mode 4 leg (own process, 420 s time-out); off by default so that "
-                         "the default run holds nothing but the measured path")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison at the bench configuration")
+    ap.add_argument("--no-configs1", dest="configs1", action="store_false",
+                    help="skip the BASELINE.json configs[1] leg (same grid, the reference's 8-way partition)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))

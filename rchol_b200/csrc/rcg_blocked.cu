@@ -1330,7 +1330,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   // Separator blocks are small, dense and have every far CTA of the launch to themselves: a short window sends most of
   // their entries to the far CTAs and keeps their chain blobs small enough for many staging slots.
   const uint32_t sep_rows = h->opt.reserved[4] > 0 ? (uint32_t)h->opt.reserved[4] : 1024u;
-  B.Dfar_sep = std::min(B.Dfar, std::max(32u, floor_pow2_u32(std::max(32u, sep_rows) / 32u)));
+  // (at least 4 chunks = 128 rows: the fold depth and the helpers' run-ahead have to fit inside the window)
+  B.Dfar_sep = std::min(B.Dfar, std::max(4u, floor_pow2_u32(std::max(128u, sep_rows) / 32u)));
+  if (B.fold) B.Kr = std::min(B.Kr, B.Dfar_sep - 1u);
+  B.E_sep = std::max(B.Kr, std::min(B.E_sep, B.Dfar_sep - 1u));   // Kr <= E <= window - 1
   // ---- chunk / tile numbering ------------------------------------------------------------------------
   // Far tiles: the unit in which the far CTAs hand the start vector to the chain.  A tile's in-block pass can start when
   // the chain is a window away from it and is a chain of dependent HBM round trips (measured 26-50 us for 8 chunks of a
@@ -1353,12 +1356,21 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     // neighbours of a 32^3 leaf sit ~1024 rows back, 40 % of the factor was "far" and a chunk took 9600 cycles)
     B.Dfar_wb = 64u;
     std::vector<int> per_depth(max_depth + 2, 0);
-    for (int b = 0; b < nb; b++) if (bounds[b + 1] > bounds[b]) per_depth[depth[b]]++;
+    std::vector<uint32_t> nch_depth(max_depth + 2, 0);   // longest block of a level, in chunks
+    for (int b = 0; b < nb; b++)
+      if (bounds[b + 1] > bounds[b]) {
+        per_depth[depth[b]]++;
+        nch_depth[depth[b]] = std::max(nch_depth[depth[b]], (bounds[b + 1] - bounds[b] + 31u) / 32u);
+      }
     for (int b = 0; b < nb; b++)
       if (B.wb_min > 0 && (uint32_t)per_depth[depth[b]] >= B.wb_min) {
         // in-window entries as ONE class: ELL (E = window; lane = row, independent loads, no divergence) by default,
         // jagged diagonals (E = 0; fewer bytes, dependent loads) with reserved[2] = 1
-        wbblk[b] = 1; krblk[b] = 0; eblk[b] = h->opt.reserved[2] == 1 ? 0u : B.Dfar_wb; dfar[b] = B.Dfar_wb; tilesz[b] = B.tile_sep;
+        // window of the level: the whole block when it is short (no far entries inside the own block at all), at most
+        // Dfar_wb chunks
+        uint32_t dw = 4u;
+        while (dw < nch_depth[depth[b]] && dw < B.Dfar_wb) dw <<= 1;
+        wbblk[b] = 1; krblk[b] = 0; eblk[b] = h->opt.reserved[2] == 1 ? 0u : dw; dfar[b] = dw; tilesz[b] = B.tile_sep;
       }
   }
   for (int b = 0; b < nb; b++) {
@@ -1517,11 +1529,16 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       L.wb = true;
       L.Dfar = B.blocks_host[G.first].pad[0];
       const uint32_t Wwb = 32u * L.Dfar;
-      const int64_t per_warp = ((int64_t)BC_SMEM_MAX / WB_WARPS) & ~15ll;
-      const int64_t cap_max = ((per_warp - (int64_t)(Wwb + 48u) * 8 - 16) / 2) & ~127ll;   // two staging buffers per warp
-      L.capB = (uint32_t)std::min<int64_t>((maxB + 127) & ~127ll, cap_max);                 // larger blobs are read from HBM
-      L.smem = (size_t)WB_WARPS * wb_warp_bytes(Wwb, L.capB);
-      L.groups = (uint32_t)((G.count + WB_WARPS - 1) / WB_WARPS);
+      // warps per CTA: as many (at most 4) as fit with two staging buffers of the level's largest blob each; blobs
+      // larger than 48 KB are read from HBM (slow path)
+      L.capB = (uint32_t)std::min<int64_t>((maxB + 127) & ~127ll, 49152);
+      uint32_t wbw = WB_WARPS;
+      while (wbw > 1u && (int64_t)wbw * wb_warp_bytes(Wwb, L.capB) > (int64_t)BC_SMEM_MAX) wbw--;
+      if ((int64_t)wb_warp_bytes(Wwb, L.capB) > (int64_t)BC_SMEM_MAX)
+        L.capB = (uint32_t)((((int64_t)BC_SMEM_MAX - (int64_t)(Wwb + 48u) * 8 - 16) / 2) & ~127ll);
+      L.SA = wbw;   // (warp-per-block levels have no ring A: the field carries the warps per CTA)
+      L.smem = (size_t)wbw * wb_warp_bytes(Wwb, L.capB);
+      L.groups = (uint32_t)((G.count + wbw - 1) / wbw);
       B.levels.push_back(L);
       continue;
     }
@@ -1653,7 +1670,7 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     if (L.wb) {   // warp-per-block level: fully parallel pre-pass over the entries of other blocks, then one warp per block
       const uint32_t pre_grid = std::min<uint32_t>((uint32_t)G.count, (uint32_t)h->sm_count * 8u);
       k_wb_pre<<<pre_grid, 256, 0, h->stream>>>(a);
-      k_wb_solve<<<L.groups, WB_WARPS * 32, L.smem, h->stream>>>(a);
+      k_wb_solve<<<L.groups, L.SA * 32, L.smem, h->stream>>>(a);
       RCG_CUDA(h, cudaGetLastError());
       h->stats.kernel_launches += 2;
       continue;

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
       asm volatile("" : "+r"(ringA_s), "+r"(ringA_e), "+r"(capA), "+r"(fullA_s), "+r"(fullA_e), "+r"(wm8));
       asm volatile("" : "+r"(xst_s), "+r"(ul_s), "+r"(lane16));
       const uint32_t step8 = 8u * FC_NC, stepA = FC_NC * capA;
+      const bool look2 = P.SA >= 2u * FC_NC + 1u;
       const uint32_t i0 = ia0 + cw, slot0 = i0 % P.SA;     // ring index / staging slot of this warp's first chunk
       const uint32_t par0 = (i0 / P.SA) & 1u;
       uint32_t par1 = par0;                                // parity of the staging barrier of this warp's next chunk (k + 3) ...
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         ncb = lds_u32(as_c);
         tpf = lds_volatile_u32(trdy_s + 4u * cw);
         un = lds_f64(ul_s + (cw << 8));
-        if (cw + FC_NC < nch) ok1 = mbar_test_s(bar1, par1);
+        if (cw + FC_NC < nch && P.SA >= FC_NC + 1u + cw) ok1 = mbar_test_s(bar1, par1);
       }
 #pragma unroll 1
       for (uint32_t k = cw; k < nch; k += FC_NC) {
@@ -241,7 +242,9 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         // staging barrier of this warp's chunk after next (k + 6): asked now, answered (ok2) while this chunk computes
         uint32_t bar2 = bar1 + step8, par2 = par1, as_2 = as_n + stepA;
         if (bar2 >= fullA_e) { bar2 -= 8u * P.SA; as_2 -= P.SA * capA; par2 ^= 1u; }
-        const uint32_t ok2 = mbar_test_s(bar2, par2);
+        // (only when the slot's previous tenant, chunk k + 6 - SA, is a finished chunk: with fewer than 7 slots the parity
+        //  of an older phase would answer for it)
+        const uint32_t ok2 = look2 ? mbar_test_s(bar2, par2) : 0u;
         if (__builtin_expect(tpf != k + 1u, 0)) {
           FC_SPIN((tpf = ld_acquire_cta_s(trdy_s + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);
           un = lds_f64(ul_s + ((k & (BC_TR - 1u)) << 8));
@@ -664,11 +667,24 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
   uint32_t phase = 0u;   // bit q: parity of the next phase of staging barrier q
-  const uint32_t nwarps = gridDim.x * WB_WARPS;
-  for (uint32_t bi = blockIdx.x * WB_WARPS + warp; bi < P.nblocks; bi += nwarps) {
+  const uint32_t wpc = blockDim.x >> 5, nwarps = gridDim.x * wpc;
+  for (uint32_t bi = blockIdx.x * wpc + warp; bi < P.nblocks; bi += nwarps) {
     const BcBlock b = P.blocks[bi];
     const uint32_t nch = (b.hi - b.lo + 31u) >> 5;
     double dot = 0.0;
+    // the first chunks' blobs towards L2 (the staging copy below then hits L2 instead of HBM)
+    if (lane == 0u && nch > 0u) {
+      const uint32_t la = min(nch, 3u);
+      const int64_t p0 = P.offB[b.chunk0], p1 = P.offB[b.chunk0 + la];
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.blobB + p0), "r"((uint32_t)(p1 - p0)) : "memory");
+    }
+    double wn = 0.0;          // start vector of the next chunk (pre-pass result), loaded one chunk ahead
+    int64_t fe0n = 0, fe1n = 0;   // its far entries of the own block
+    if (nch > 0u && b.lo + lane < b.hi) {
+      wn = __ldcg(P.w + b.lo + lane);
+      fe0n = P.far_rp[b.lo + lane] + P.far_split[b.lo + lane];
+      fe1n = P.far_rp[b.lo + lane + 1u];
+    }
     // blob of chunk kk -> staging buffer kk & 1 (bulk copy, completion on the buffer's barrier); blobs larger than a
     // buffer are read from HBM directly
     int64_t o0 = nch > 0u ? P.offB[b.chunk0] : 0, o1 = nch > 0u ? P.offB[b.chunk0 + 1u] : 0;
@@ -686,26 +702,49 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
       if (k + 1u < nch) {
         o0 = o1;
         o1 = P.offB[b.chunk0 + k + 2u];
-        if (lane == 0u && o1 - o0 <= (int64_t)P.capB) {
-          mbar_expect_tx(full + (cur ^ 1u), (uint32_t)(o1 - o0));
-          bulk_g2s(buf + (size_t)(cur ^ 1u) * P.capB, P.blobB + o0, (uint32_t)(o1 - o0), full + (cur ^ 1u));
+        if (lane == 0u) {
+          if (o1 - o0 <= (int64_t)P.capB) {
+            mbar_expect_tx(full + (cur ^ 1u), (uint32_t)(o1 - o0));
+            bulk_g2s(buf + (size_t)(cur ^ 1u) * P.capB, P.blobB + o0, (uint32_t)(o1 - o0), full + (cur ^ 1u));
+          }
+          if (k + 3u < nch) {   // chunk k+3 towards L2
+            const int64_t q0 = P.offB[b.chunk0 + k + 3u], q1 = P.offB[b.chunk0 + k + 4u];
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.blobB + q0), "r"((uint32_t)(q1 - q0)) : "memory");
+          }
         }
       }
-      // start vector of the pre-pass minus the far entries of the own block (>= a window back; read back through L2)
-      double t0 = 0.0;
-      if (valid) {
-        t0 = __ldcg(P.w + j);
-        const int64_t e1 = P.far_rp[j + 1];
-        int64_t e = P.far_rp[j] + P.far_split[j];
-        double t1 = 0.0;
-        for (; e + 1 < e1; e += 2) {   // two independent gathers per trip
-          const uint32_t ca = P.far_col[e], cb = P.far_col[e + 1];
-          const double va = P.far_val[e], vb = P.far_val[e + 1];
-          t0 = fma(-va, __ldcg(P.out + ca), t0);
-          t1 = fma(-vb, __ldcg(P.out + cb), t1);
+      // start vector of the pre-pass minus the far entries of the own block (>= a window back; read back through L2):
+      // four independent gathers per trip
+      double t0 = wn;
+      {
+        const int64_t e1 = fe1n;
+        int64_t e = fe0n;
+        const uint32_t jn = j + 32u;
+        if (k + 1u < nch && jn < b.hi) {   // next chunk's start vector and far range: in flight during this chunk
+          wn = __ldcg(P.w + jn);
+          fe0n = P.far_rp[jn] + P.far_split[jn];
+          fe1n = P.far_rp[jn + 1u];
+        } else {
+          wn = 0.0; fe0n = 0; fe1n = 0;
         }
-        if (e < e1) t0 = fma(-P.far_val[e], __ldcg(P.out + P.far_col[e]), t0);
-        t0 += t1;
+        double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        for (; e < e1; e += 4) {
+          uint32_t c[4];
+          double v[4], x[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const bool have = e + u < e1;
+            c[u] = have ? P.far_col[e + u] : 0u;
+            v[u] = have ? P.far_val[e + u] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) x[u] = v[u] != 0.0 ? __ldcg(P.out + c[u]) : 0.0;
+          t0 = fma(-v[0], x[0], t0);
+          t1 = fma(-v[1], x[1], t1);
+          t2 = fma(-v[2], x[2], t2);
+          t3 = fma(-v[3], x[3], t3);
+        }
+        t0 = (t0 + t1) + (t2 + t3);
       }
       const unsigned char *bp;
       if (c1 - c0 <= (int64_t)P.capB) {

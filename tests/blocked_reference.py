@@ -60,9 +60,16 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
         if bounds[b + 1] > bounds[b]:
             per_depth[int(depth[b])] = per_depth.get(int(depth[b]), 0) + 1
     wb_of = [1 if fold and wb_min > 0 and per_depth.get(int(depth[b]), 0) >= wb_min else 0 for b in range(nb)]
+    nch_depth = {}
+    for b in range(nb):
+        if bounds[b + 1] > bounds[b]:
+            nch_depth[int(depth[b])] = max(nch_depth.get(int(depth[b]), 0), (int(bounds[b + 1] - bounds[b]) + 31) // 32)
     for b in range(nb):
         if wb_of[b]:
-            kr_of[b], e_of[b], dfar_of[b], tile_of[b] = 0, (0 if wb_jagged else Dfar_wb), Dfar_wb, tile_sep
+            dw = 4                     # window of the level: the whole block when it is short, at most Dfar_wb chunks
+            while dw < nch_depth[int(depth[b])] and dw < Dfar_wb:
+                dw <<= 1
+            kr_of[b], e_of[b], dfar_of[b], tile_of[b] = 0, (0 if wb_jagged else dw), dw, tile_sep
     Dfar_leaf = Dfar
     chunk0 = np.zeros(nb + 1, np.int64)
     tile0 = np.zeros(nb + 1, np.int64)
