@@ -235,6 +235,8 @@ int rcg_set_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint
   if (!h) return RCG_ERR_INVALID;
   RCG_CUDA(h, cudaSetDevice(h->device));
   if (h->b && N != h->N) free_vectors(h);
+  // the captured iteration holds A's device pointers and the SpMV's lane template: a new A invalidates it
+  if (h->iter_graph) { cudaGraphExecDestroy(h->iter_graph); h->iter_graph = nullptr; }
   return rcg_setup_matrix(h, N, rowPtr, colIdx, val);
 }
 
@@ -243,6 +245,7 @@ int rcg_set_matrix_permuted(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, c
   if (!h) return RCG_ERR_INVALID;
   RCG_CUDA(h, cudaSetDevice(h->device));
   if (h->b && N != h->N) free_vectors(h);
+  if (h->iter_graph) { cudaGraphExecDestroy(h->iter_graph); h->iter_graph = nullptr; }
   return rcg_setup_matrix_permuted(h, N, rowPtr, colIdx, val, P);
 }
 

@@ -23,6 +23,7 @@
 // Every spin wait is bounded (clock64 time-out -> abort flag, all waits of all CTAs then fall through): corrupt input
 // or a scheduling accident cannot hang the GPU; the host turns the flag into an error.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -1330,8 +1331,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   // Separator blocks are small, dense and have every far CTA of the launch to themselves: a short window sends most of
   // their entries to the far CTAs and keeps their chain blobs small enough for many staging slots.
   const uint32_t sep_rows = h->opt.reserved[4] > 0 ? (uint32_t)h->opt.reserved[4] : 1024u;
-  // (at least 4 chunks = 128 rows: the fold depth and the helpers' run-ahead have to fit inside the window)
-  B.Dfar_sep = std::min(B.Dfar, std::max(4u, floor_pow2_u32(std::max(128u, sep_rows) / 32u)));
+  // (at least 32 chunks: the far CTAs' hand-off takes 10-20 us -- published progress, two dependent L2 gathers, tile flag --
+  //  and can only start when the chain is a window away; measured at 256^3 / T=512: a 512-row window doubles the root
+  //  separator's time, a 256-row window makes it 9x slower)
+  B.Dfar_sep = std::min(B.Dfar, std::max(32u, floor_pow2_u32(std::max(32u, sep_rows) / 32u)));
   if (B.fold) B.Kr = std::min(B.Kr, B.Dfar_sep - 1u);
   B.E_sep = std::max(B.Kr, std::min(B.E_sep, B.Dfar_sep - 1u));   // Kr <= E <= window - 1
   // ---- chunk / tile numbering ------------------------------------------------------------------------
@@ -1368,8 +1371,15 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
         // jagged diagonals (E = 0; fewer bytes, dependent loads) with reserved[2] = 1
         // window of the level: the whole block when it is short (no far entries inside the own block at all), at most
         // Dfar_wb chunks
+        // (leaves keep the natural order of a 3-D box: the plane neighbours sit rows^(2/3) back, two planes are kept;
+        //  separator blocks are dense and short: the whole block, at most 128 chunks)
+        uint32_t want = nch_depth[depth[b]], cap = 128u;
+        if (depth[b] == max_depth) {
+          want = (uint32_t)(2.0 * std::pow(32.0 * nch_depth[depth[b]], 2.0 / 3.0) / 32.0) + 1u;
+          cap = B.Dfar_wb;
+        }
         uint32_t dw = 4u;
-        while (dw < nch_depth[depth[b]] && dw < B.Dfar_wb) dw <<= 1;
+        while (dw < want && dw < cap) dw <<= 1;
         wbblk[b] = 1; krblk[b] = 0; eblk[b] = h->opt.reserved[2] == 1 ? 0u : dw; dfar[b] = dw; tilesz[b] = B.tile_sep;
       }
   }

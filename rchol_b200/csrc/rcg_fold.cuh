@@ -672,11 +672,20 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
     const BcBlock b = P.blocks[bi];
     const uint32_t nch = (b.hi - b.lo + 31u) >> 5;
     double dot = 0.0;
+    // blob offsets: one coalesced load per 32 chunks (this group and the next one), shuffles afterwards -- no
+    // global load of an offset on the per-chunk path
+    int64_t og0 = 0, og1 = 0;
+    if (nch > 0u) {
+      og0 = P.offB[b.chunk0 + min(lane, nch)];
+      og1 = P.offB[b.chunk0 + min(32u + lane, nch)];
+    }
+    uint32_t ogbase = 0;
+#define WB_OFF(idx_) ((idx_) - ogbase < 32u ? __shfl_sync(0xffffffffu, og0, (int)((idx_) - ogbase)) \
+                                            : __shfl_sync(0xffffffffu, og1, (int)((idx_) - ogbase - 32u)))
     // the first chunks' blobs towards L2 (the staging copy below then hits L2 instead of HBM)
-    if (lane == 0u && nch > 0u) {
-      const uint32_t la = min(nch, 3u);
-      const int64_t p0 = P.offB[b.chunk0], p1 = P.offB[b.chunk0 + la];
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.blobB + p0), "r"((uint32_t)(p1 - p0)) : "memory");
+    if (nch > 0u) {
+      const int64_t p0 = WB_OFF(0u), p1 = WB_OFF(min(nch, 3u));
+      if (lane == 0u) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.blobB + p0), "r"((uint32_t)(p1 - p0)) : "memory");
     }
     double wn = 0.0;          // start vector of the next chunk (pre-pass result), loaded one chunk ahead
     int64_t fe0n = 0, fe1n = 0;   // its far entries of the own block
@@ -687,7 +696,7 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
     }
     // blob of chunk kk -> staging buffer kk & 1 (bulk copy, completion on the buffer's barrier); blobs larger than a
     // buffer are read from HBM directly
-    int64_t o0 = nch > 0u ? P.offB[b.chunk0] : 0, o1 = nch > 0u ? P.offB[b.chunk0 + 1u] : 0;
+    int64_t o0 = nch > 0u ? WB_OFF(0u) : 0, o1 = nch > 0u ? WB_OFF(1u) : 0;
     if (nch > 0u && lane == 0u && o1 - o0 <= (int64_t)P.capB) {
       mbar_expect_tx(full, (uint32_t)(o1 - o0));
       bulk_g2s(buf, P.blobB + o0, (uint32_t)(o1 - o0), full);
@@ -699,18 +708,21 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
       const uint32_t cur = k & 1u;
       const int64_t c0 = o0, c1 = o1;
       // next chunk's blob into the other buffer (every lane has finished reading it: __syncwarp at the end of chunk k-1)
+      if ((k & 31u) == 0u && k > 0u) {   // next group of 32 offsets
+        ogbase = k;
+        og0 = og1;
+        og1 = P.offB[b.chunk0 + min(k + 32u + lane, nch)];
+      }
       if (k + 1u < nch) {
         o0 = o1;
-        o1 = P.offB[b.chunk0 + k + 2u];
+        o1 = WB_OFF(k + 2u);
+        const int64_t q0 = WB_OFF(min(k + 3u, nch)), q1 = WB_OFF(min(k + 4u, nch));
         if (lane == 0u) {
           if (o1 - o0 <= (int64_t)P.capB) {
             mbar_expect_tx(full + (cur ^ 1u), (uint32_t)(o1 - o0));
             bulk_g2s(buf + (size_t)(cur ^ 1u) * P.capB, P.blobB + o0, (uint32_t)(o1 - o0), full + (cur ^ 1u));
           }
-          if (k + 3u < nch) {   // chunk k+3 towards L2
-            const int64_t q0 = P.offB[b.chunk0 + k + 3u], q1 = P.offB[b.chunk0 + k + 4u];
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.blobB + q0), "r"((uint32_t)(q1 - q0)) : "memory");
-          }
+          if (q1 > q0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.blobB + q0), "r"((uint32_t)(q1 - q0)) : "memory");   // chunk k+3 towards L2
         }
       }
       // start vector of the pre-pass minus the far entries of the own block (>= a window back; read back through L2):
@@ -834,5 +846,6 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
     }
     dot = warp_sum(dot);
     if (lane == 0 && P.dot_partials) P.dot_partials[b.gidx] = dot;
+#undef WB_OFF
   }
 }

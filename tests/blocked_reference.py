@@ -66,8 +66,13 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             nch_depth[int(depth[b])] = max(nch_depth.get(int(depth[b]), 0), (int(bounds[b + 1] - bounds[b]) + 31) // 32)
     for b in range(nb):
         if wb_of[b]:
-            dw = 4                     # window of the level: the whole block when it is short, at most Dfar_wb chunks
-            while dw < nch_depth[int(depth[b])] and dw < Dfar_wb:
+            # window of the level: leaves two planes of a 3-D box (rows^(2/3) each, at most Dfar_wb chunks), separator
+            # blocks the whole block (at most 128 chunks)
+            want, cap = nch_depth[int(depth[b])], 128
+            if depth[b] == max_depth:
+                want, cap = int(2.0 * (32.0 * nch_depth[int(depth[b])]) ** (2.0 / 3.0) / 32.0) + 1, Dfar_wb
+            dw = 4
+            while dw < want and dw < cap:
                 dw <<= 1
             kr_of[b], e_of[b], dfar_of[b], tile_of[b] = 0, (0 if wb_jagged else dw), dw, tile_sep
     Dfar_leaf = Dfar

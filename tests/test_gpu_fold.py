@@ -39,8 +39,7 @@ def oracle():
                                                   ("lap3d", 40, 8, dict(sep_tile=4, early_sep=12, recent=2)),
                                                   ("lap3d", 14, 4, dict(wb_min=2)), ("lap3d", 40, 8, dict(wb_min=4, recent=2)),
                                                   ("aniso2d", 64, 8, dict(wb_min=1, chain_window=1024)), ("lap3d", 14, 4, dict(wb_min=2, wb_jagged=True)),
-                                                  ("lap3d", 33, 2, dict(chain_window=1024, early=255)), ("lap3d", 40, 8, dict(sep_window=128)),
-                                                  ("lap3d", 40, 8, dict(sep_window=256, wb_min=4))])
+                                                  ("lap3d", 33, 2, dict(chain_window=1024, early=255)), ("lap3d", 40, 8, dict(sep_window=2048, wb_min=4))])
 def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
@@ -71,7 +70,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
                                   dict(sep_tile=8, far_lanes2=32), dict(early_sep=16), dict(early_sep=4, early=5), dict(sep_tile=4, chain_window=1024),
                                   dict(wb_min=1), dict(wb_min=2), dict(wb_min=4, recent=2), dict(wb_min=-1), dict(wb_min=2, use_graph=False),
                                   dict(wb_min=2, wb_jagged=True), dict(early=255), dict(early=255, early_sep=255, recent=2),
-                                  dict(sep_window=128), dict(sep_window=256, recent=2), dict(sep_window=512, early_sep=4), dict(slots_a=5)])
+                                  dict(sep_window=2048), dict(slots_a=5)])
 @pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 33, 2), ("aniso2d", 160, 4), ("lap3d", 40, 0)])
 def test_folded_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)

@@ -251,6 +251,31 @@ def test_factor_refresh_on_one_handle_and_many_right_hand_sides(capi, oracle):
 
 
 @needs_producer
+def test_matrix_replaced_after_a_solve_same_size(capi, oracle):
+    """set_matrix(A1); pcg; set_matrix(A2: same N, different nnz and values); pcg -- the captured iteration (CUDA graph)
+    held A1's device pointers and SpMV template; it has to be rebuilt (advisor finding, round 1)."""
+    import scipy.sparse as sp
+    A, b, G, part, f = make_problem("lap3d", 20, 4)
+    N = f.N
+    M = sp.csr_matrix((A[2], A[1].astype(np.int64), A[0].astype(np.int64)), shape=(N, N))
+    E = sp.diags([np.full(N - 7, -0.05), np.full(N - 7, -0.05)], [7, -7], format="csr")     # extra symmetric couplings
+    M2 = (M + E + sp.diags(np.full(N, 0.2))).tocsr()
+    M2.sort_indices()
+    A2 = (M2.indptr.astype(np.uint64), M2.indices.astype(np.uint64), M2.data.astype(np.float64))
+    assert A2[0][-1] != A[0][-1]
+    with capi.Solver(0) as s:
+        s.set_matrix(*A); s.set_factor(*G, part)
+        x1, r1, i1 = s.pcg(b, 1e-8, 500)
+        o1 = oracle.pcg(A, b, 1e-8, 500, G)
+        assert abs(i1 - o1["itr"]) <= 1 and relerr(x1, o1["x"]) <= 1e-6
+        s.set_matrix(*A2)
+        assert relerr(s.spmv(b), oracle.spmv(*A2, b)) < 1e-14
+        x2, r2, i2 = s.pcg(b, 1e-8, 500)
+        o2 = oracle.pcg(A2, b, 1e-8, 500, G)
+        assert abs(i2 - o2["itr"]) <= 1 and r2 <= 2e-8 and relerr(x2, o2["x"]) <= 1e-6
+
+
+@needs_producer
 def test_resident_solve_and_repeatability(capi):
     A, b, G, part, f = make_problem("lap3d", 32, 4)
     with capi.Solver(0) as s:
