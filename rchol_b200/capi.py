@@ -138,7 +138,7 @@ class Solver:
     def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
                  spmv_lanes: int = 0, chain_generic: bool = False, chain_mode: int = 0, backoff_ns: int = 0, dbg: int = 0, producers: int = 0,
                  recent: int = 0, plain_launch: bool = False, sep_window: int = 0, early: int = 0, capb_quarters: int = 0, slots_a: int = 0, far_lanes2: int = 0, sep_tile: int = 0, early_sep: int = 0,
-                 wb_min: int = 0, wb_jagged: bool = False):
+                 wb_min: int = 0, wb_ell: bool = False):
         self._L = load()
         self._h = C.c_void_p()
         opt = Options()
@@ -148,7 +148,7 @@ class Solver:
         opt.chain_mode = int(chain_mode)
         opt.reserved[0] = int(backoff_ns)
         opt.reserved[1] = int(dbg)
-        opt.reserved[2] = 1 if wb_jagged else int(producers)
+        opt.reserved[2] = 1 if wb_ell else int(producers)
         opt.reserved[3] = int(recent)
         opt.reserved[4] = int(sep_window)
         opt.reserved[5] = int(early) | (int(early_sep) << 8)

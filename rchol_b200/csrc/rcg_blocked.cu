@@ -57,19 +57,22 @@ __host__ __device__ __forceinline__ uint32_t rec_batches(uint32_t nslots) { retu
 //     x_k = Winv_k (t'_k - L_rec x_rec) = u_k - M_k x_rec ,   u_k = Winv_k t'_k ,   M_k = Winv_k L_rec  (32 x ncol, dense)
 // so the chain's hop is ONE dense panel apply by one warp; the mat-vec with Winv_k moves off the chain to the near helper.
 // Blob A: 16 B header {batches, rows, columns, 0} | TAIL = the 4 batches of the newest 16 columns: 4 x 4 window byte
-// offsets (u32), 4 x 1024 B of panel values, batch-wise [column pair q][row] double2 | BODY = the older batches (an even
-// number): offsets, then values.  Column order is ascending over body-then-tail; padding columns come FIRST (value 0,
-// offset of the zero slot behind the window), so the tail always holds the newest columns at fixed offsets.
-// Blob B: as before, then Winv_k as a packed lower triangle.
+// offsets (u32), 4 x 1024 B of panel values, batch-wise [column pair q][row] double2 | Winv_k, full 32 x 32, [column pair]
+// [row] double2 (the chain warp that owns the chunk applies it to t'_k ahead of its turn) | BODY = the older batches (an
+// even number): offsets, then values.  Column order is ascending over body-then-tail; padding columns come FIRST (value
+// 0, offset of the zero slot behind the window), so the tail always holds the newest columns at fixed offsets.
+// Blob B: the near helper's entries (early jagged diagonals + late ELL) as before.  Warp-per-block levels: blob A is a
+// bare header and blob B ends with Winv_k as a packed lower triangle.
 constexpr uint32_t FC_MINB = 4;              // tail batches (register-resident in the chain warp)
-constexpr uint32_t FC_TAILB = 16u + 1040u * FC_MINB;   // header + tail: byte offset of the body
+constexpr uint32_t FC_WOFF = 16u + 1040u * FC_MINB;    // header + tail: byte offset of Winv
+constexpr uint32_t FC_TAILB = FC_WOFF + BC_WBYTES;     // byte offset of the body
 constexpr uint32_t FC_KRMAX = 8;             // fold depth limit (bitmap of 32*Kr candidate columns)
 constexpr uint32_t FC_COLCAP = 32;           // panel columns per chunk beyond the previous chunk's (chunk_fold_depth)
 constexpr uint32_t FC_WPACK = 4352;          // packed Winv: pair p holds rows 2p..31 -> 16 * sum(32 - 2p) bytes
 __host__ __device__ __forceinline__ uint32_t fold_batches(uint32_t ncol) {   // tail + an even number of body batches
   return ncol <= 4u * FC_MINB ? FC_MINB : FC_MINB + 2u * ((ncol - 4u * FC_MINB + 7u) / 8u);
 }
-__host__ __device__ __forceinline__ uint32_t fold_bytesA(uint32_t ncb) { return 16u + 1040u * ncb; }
+__host__ __device__ __forceinline__ uint32_t fold_bytesA(uint32_t ncb) { return 16u + 1040u * ncb + BC_WBYTES; }
 // byte offset of the double2 {Winv[row][2p], Winv[row][2p+1]} (row >= 2p) inside the packed triangle
 __host__ __device__ __forceinline__ uint32_t wp_pair_off(uint32_t p, uint32_t row) { return 16u * (p * (33u - p) + row - 2u * p); }
 
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     if (lane == 0) {
       const uint32_t bbytes = BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot) + 320u * nl;
       sizeA[gc] = g.wb[b] ? 16 : g.fold ? (int64_t)fold_bytesA(fold_batches(ncol)) : (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
-      sizeB[gc] = (int64_t)(bbytes + (g.fold ? FC_WPACK : 0u));
+      sizeB[gc] = (int64_t)(bbytes + (g.wb[b] ? FC_WPACK : 0u));
       if (need) atomicMax(&tile_need[g.tile0[b] + k / g.tile[b]], need);
     }
   }
@@ -421,6 +424,11 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
         unsigned char *v = bt < nbody ? A + FC_TAILB + 16u * nbody + 1024u * bt : A + 16u + 16u * FC_MINB + 1024u * (bt - nbody);
         return reinterpret_cast<double *>(v + 512u * ((ci_ >> 1) & 1u) + 16u * row_) + (ci_ & 1u);
       };
+      for (uint32_t pp = 0; pp < 16u; pp++) {   // Winv for the chain warp that owns the chunk
+        double *dst = reinterpret_cast<double *>(A + FC_WOFF + w_pair_off(pp, lane));
+        dst[0] = Wm[lane][2u * pp];
+        dst[1] = Wm[lane][2u * pp + 1u];
+      }
       if (lane == 0) {
         uint32_t *hd = reinterpret_cast<uint32_t *>(A);
         hd[0] = ncb; hd[1] = nr; hd[2] = ncol; hd[3] = 0;
@@ -483,7 +491,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
         lv[s * 32u + lane] = have ? val[r.p_early + s] : 0.0;
         lc[s * 32u + lane] = have ? (uint16_t)((col[r.p_early + s] - blo) & wmask) : (uint16_t)(wmask + 1u);
       }
-      if (g.fold) {   // Winv, packed lower triangle, behind the late entries
+      if (g.wb[b]) {   // warp-per-block levels: Winv, packed lower triangle, behind the late entries
         unsigned char *Wq = reinterpret_cast<unsigned char *>(lv) + 320u * nl;
         for (uint32_t pp = 0; pp < 16u; pp++)
           if (lane >= 2u * pp) {
@@ -1367,8 +1375,8 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       }
     for (int b = 0; b < nb; b++)
       if (B.wb_min > 0 && (uint32_t)per_depth[depth[b]] >= B.wb_min) {
-        // in-window entries as ONE class: ELL (E = window; lane = row, independent loads, no divergence) by default,
-        // jagged diagonals (E = 0; fewer bytes, dependent loads) with reserved[2] = 1
+        // in-window entries as ONE class: jagged diagonals (E = 0; rows sorted by length, no padding) by default -- measured
+        // at 256^3 / T=4096: 2.16 ms per leaf level against 2.91 ms for ELL (E = window, reserved[2] = 1: lane = row, padded)
         // window of the level: the whole block when it is short (no far entries inside the own block at all), at most
         // Dfar_wb chunks
         // (leaves keep the natural order of a 3-D box: the plane neighbours sit rows^(2/3) back, two planes are kept;
@@ -1380,7 +1388,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
         }
         uint32_t dw = 4u;
         while (dw < want && dw < cap) dw <<= 1;
-        wbblk[b] = 1; krblk[b] = 0; eblk[b] = h->opt.reserved[2] == 1 ? 0u : dw; dfar[b] = dw; tilesz[b] = B.tile_sep;
+        wbblk[b] = 1; krblk[b] = 0; eblk[b] = h->opt.reserved[2] == 1 ? dw : 0u; dfar[b] = dw; tilesz[b] = B.tile_sep;
       }
   }
   for (int b = 0; b < nb; b++) {
@@ -1539,15 +1547,23 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       L.wb = true;
       L.Dfar = B.blocks_host[G.first].pad[0];
       const uint32_t Wwb = 32u * L.Dfar;
-      // warps per CTA: as many (at most 4) as fit with two staging buffers of the level's largest blob each; blobs
-      // larger than 48 KB are read from HBM (slow path)
+      // warps per CTA and staging buffers per warp: as many warps as possible (their turns hide each other's latencies;
+      // measured at 256^3 / T=4096: one warp per scheduler needs ~5400 cycles per chunk), then two buffers if they fit;
+      // blobs larger than 48 KB are read from HBM (slow path)
       L.capB = (uint32_t)std::min<int64_t>((maxB + 127) & ~127ll, 49152);
-      uint32_t wbw = WB_WARPS;
-      while (wbw > 1u && (int64_t)wbw * wb_warp_bytes(Wwb, L.capB) > (int64_t)BC_SMEM_MAX) wbw--;
-      if ((int64_t)wb_warp_bytes(Wwb, L.capB) > (int64_t)BC_SMEM_MAX)
-        L.capB = (uint32_t)((((int64_t)BC_SMEM_MAX - (int64_t)(Wwb + 48u) * 8 - 16) / 2) & ~127ll);
-      L.SA = wbw;   // (warp-per-block levels have no ring A: the field carries the warps per CTA)
-      L.smem = (size_t)wbw * wb_warp_bytes(Wwb, L.capB);
+      uint32_t wbw = 1u, nbuf = 1u;
+      if ((int64_t)wb_warp_bytes(Wwb, L.capB, 1u) > (int64_t)BC_SMEM_MAX)
+        L.capB = (uint32_t)((((int64_t)BC_SMEM_MAX - (int64_t)(Wwb + 48u) * 8 - 16)) & ~127ll);
+      {
+        const uint32_t want = (uint32_t)std::min<int64_t>(WB_WARPS, std::max<int64_t>(1, (G.count + h->sm_count - 1) / h->sm_count));
+        const uint32_t fit1 = (uint32_t)((int64_t)BC_SMEM_MAX / wb_warp_bytes(Wwb, L.capB, 1u));
+        const uint32_t fit2 = (uint32_t)((int64_t)BC_SMEM_MAX / wb_warp_bytes(Wwb, L.capB, 2u));
+        if (fit2 >= want || fit2 >= fit1) { nbuf = 2u; wbw = std::max(1u, std::min(want, fit2)); }
+        else { nbuf = 1u; wbw = std::max(1u, std::min(want, fit1)); }
+      }
+      L.SA = wbw;   // (warp-per-block levels have no rings: the fields carry the warps per CTA and the buffers per warp)
+      L.SB = nbuf;
+      L.smem = (size_t)wbw * wb_warp_bytes(Wwb, L.capB, nbuf);
       L.groups = (uint32_t)((G.count + wbw - 1) / wbw);
       B.levels.push_back(L);
       continue;

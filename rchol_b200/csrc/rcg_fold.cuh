@@ -2,7 +2,8 @@
 // folded into dense panels at set-up, so that the chain's hop is ONE panel apply by ONE warp:
 //
 //     x_k = u_k - M_k x_rec          M_k = Winv_k L_rec   (32 x ncol, columns = the distinct recent columns, set-up)
-//     u_k = Winv_k t'_k              t'_k = start_k - early - late entries                     (near helper, off the chain)
+//     u_k = Winv_k t'_k              (the chain warp that owns chunk k, ahead of its turn: off the critical path)
+//     t'_k = start_k - early - late entries                                                    (near helper)
 //
 // The old chain did  t = t' - L_rec x_rec (sparse gather, shuffle reduction)  THEN  x = Winv t (dense mat-vec, four warps,
 // one named barrier): two dependent stages, ~790 cycles per 32 rows.  Here the only dependent work per hop is: 16 shared-
@@ -226,13 +227,38 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mt[4 * q_]), "=d"(mt[4 * q_ + 1]) : "r"((AS_) + 80u + lane16 + 1024u * q_) : "memory"); \
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mt[4 * q_ + 2]), "=d"(mt[4 * q_ + 3]) : "r"((AS_) + 592u + lane16 + 1024u * q_) : "memory"); \
       }
+      // u = Winv t' of chunk KK_ (staged at AS_): waits for the near helper's t', then a 32 x 32 mat-vec with t' broadcast
+      // straight from the ring (lane = row of the result).  Runs behind the warp's own hop, ahead of its next turn.
+#define FC_MATVEC(KK_, AS_)                                                                                               \
+      do {                                                                                                                \
+        const uint32_t ts_ = (KK_) & (BC_TR - 1u);                                                                        \
+        if (__builtin_expect(lds_volatile_u32(trdy_s + 4u * ts_) != (KK_) + 1u, 0)) {                                     \
+          long long c3_ = 0;                                                                                              \
+          if (prof) c3_ = clock64();                                                                                      \
+          FC_SPIN(ld_acquire_cta_s(trdy_s + 4u * ts_) == (KK_) + 1u, 0x300u);                                             \
+          if (prof) { pc[3] += 1; pc[0] += clock64() - c3_; }                                                             \
+        }                                                                                                                 \
+        const uint32_t tr_ = u_s + (ts_ << 8), wr_ = (AS_) + FC_WOFF + lane16;                                            \
+        double u0_ = 0.0, u1_ = 0.0, u2_ = 0.0, u3_ = 0.0;                                                                \
+        _Pragma("unroll") for (uint32_t pp_ = 0; pp_ < 16u; pp_ += 2u) {                                                  \
+          double ta_, tb_, tc_, td_, wa_, wb_, wc_, wd_;                                                                  \
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ta_), "=d"(tb_) : "r"(tr_ + 16u * pp_) : "memory");      \
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc_), "=d"(td_) : "r"(tr_ + 16u * pp_ + 16u) : "memory"); \
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(wa_), "=d"(wb_) : "r"(wr_ + 512u * pp_) : "memory");     \
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(wc_), "=d"(wd_) : "r"(wr_ + 512u * pp_ + 512u) : "memory"); \
+          u0_ = fma(wa_, ta_, u0_);                                                                                       \
+          u1_ = fma(wb_, tb_, u1_);                                                                                       \
+          u2_ = fma(wc_, tc_, u2_);                                                                                       \
+          u3_ = fma(wd_, td_, u3_);                                                                                       \
+        }                                                                                                                 \
+        un = (u0_ + u1_) + (u2_ + u3_);                                                                                   \
+      } while (0)
       if (cw < nch) {
         FC_SPIN(mbar_try_s(fullA_s + 8u * slot0, par0) != 0u, 0x200u);
         FC_LOAD_OFFS(as_c);
         FC_LOAD_VALS(as_c);
         ncb = lds_u32(as_c);
-        tpf = lds_volatile_u32(trdy_s + 4u * cw);
-        un = lds_f64(ul_s + (cw << 8));
+        FC_MATVEC(cw, as_c);
         if (cw + FC_NC < nch && P.SA >= FC_NC + 1u + cw) ok1 = mbar_test_s(bar1, par1);
       }
 #pragma unroll 1
@@ -245,12 +271,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         // (only when the slot's previous tenant, chunk k + 6 - SA, is a finished chunk: with fewer than 7 slots the parity
         //  of an older phase would answer for it)
         const uint32_t ok2 = look2 ? mbar_test_s(bar2, par2) : 0u;
-        if (__builtin_expect(tpf != k + 1u, 0)) {
-          FC_SPIN((tpf = ld_acquire_cta_s(trdy_s + 4u * (k & (BC_TR - 1u)))) == k + 1u, 0x300u);
-          un = lds_f64(ul_s + ((k & (BC_TR - 1u)) << 8));
-          if (prof) { pc[3] += 1; pc[0] += clock64() - c0; }
-        }
-        double a0 = un, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double a0 = un, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // un = u_k, computed behind this warp's previous hop
         // this warp's turn: the chain has to have solved chunk k-1 (everything above was bookkeeping ahead of it)
         if (k > 0u) {
           long long c2 = 0;
@@ -297,10 +318,6 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
           }
           FC_LOAD_OFFS(as_n);
           ncb = lds_u32(as_n);
-          // flag of u_{k+1}, then the value: shared-memory loads of one warp complete in order, so a value read behind a
-          // set flag is the published one; a clear flag is polled at the top of the next chunk
-          tpf = lds_volatile_u32(trdy_s + 4u * ((k + FC_NC) & (BC_TR - 1u)));
-          un = lds_f64(ul_s + (((k + FC_NC) & (BC_TR - 1u)) << 8));
         }
 #pragma unroll
         for (uint32_t i = 0; i < 16u; i += 4u) {
@@ -316,9 +333,11 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         // progress word: a volatile store behind the window store, by ALL lanes (same word, same value: no divergent
         // branch).  It also frees the staging slot: the producer of ring A polls it.
         sts_volatile_u32(prog_s, k + 1u);
+        if (more) FC_MATVEC(k + FC_NC, as_n);   // u of this warp's next chunk: off the chain
         as_c = as_n; as_n = as_2; bar1 = bar2; par1 = par2; ok1 = ok2;
         if (prof) pc[2] += 1;
       }
+#undef FC_MATVEC
 #undef FC_LOAD_VALS
 #undef FC_LOAD_OFFS
 #undef FC_SPIN
@@ -455,7 +474,6 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         const uint16_t *ec = reinterpret_cast<const uint16_t *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot));
         const double *lv = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot));
         const uint16_t *lc = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(lv) + 256u * nl);
-        const unsigned char *wq = reinterpret_cast<const unsigned char *>(lv) + 320u * nl;   // packed Winv
         // early entries: columns in chunks <= k-E-1 (jagged diagonals, four per trip)
         const uint32_t need1 = k > P.E ? k - P.E : 0u;
         long long h2 = 0;
@@ -493,16 +511,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
           lvr[u] = 0.0;
           if (u < nl) { lcr[u] = lc[u * 32u + lane]; lvr[u] = lv[u * 32u + lane]; }
         }
-        double wv[32];
-#pragma unroll
-        for (uint32_t pp = 0; pp < 16u; pp++) {
-          const uint32_t rr = lane >= 2u * pp ? lane - 2u * pp : 0u;   // rows above the diagonal pair: clamped, then zeroed
-          const double2 w2 = *reinterpret_cast<const double2 *>(wq + 16u * (pp * (33u - pp) + rr));
-          wv[2 * pp] = lane >= 2u * pp ? w2.x : 0.0;
-          wv[2 * pp + 1] = lane >= 2u * pp ? w2.y : 0.0;
-        }
         const bool slot_done = nl <= LB;
-        if (slot_done && lane == 0) mbar_arrive_after3(emptyB + slot, lcr[LB - 1u], lvr[LB - 1u], wv[0] + wv[31]);
+        if (slot_done && lane == 0) mbar_arrive_after(emptyB + slot, lcr[LB - 1u], lvr[LB - 1u]);
         if (kn < nch) {
           if (fln == 0u) BC_WAIT(ld_acquire_gpu(P.tileflag + b.tile0 + tilen) != 0u, 0x400u, 100);
           tiles_known = tilen + 1u;
@@ -559,23 +569,9 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
           }
           t = (t + q1) + (q2 + q3);
         }
-        // u = Winv t : t broadcast through the helper's scratch row, lane = row of the result
-        sts_f64(hs_s + 8u * lane, t);
-        __syncwarp();
-        double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
-#pragma unroll
-        for (uint32_t pp = 0; pp < 16u; pp += 2u) {
-          double ta, tb, tc, td;
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ta), "=d"(tb) : "r"(hs_s + 16u * pp) : "memory");
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc), "=d"(td) : "r"(hs_s + 16u * pp + 16u) : "memory");
-          u0 = fma(wv[2 * pp], ta, u0);
-          u1 = fma(wv[2 * pp + 1], tb, u1);
-          u2 = fma(wv[2 * pp + 2], tc, u2);
-          u3 = fma(wv[2 * pp + 3], td, u3);
-        }
-        const double uk = (u0 + u1) + (u2 + u3);
+        // t' into the ring: the chain warp that owns the chunk multiplies it with Winv
         const uint32_t tsl = k & (BC_TR - 1u);
-        sts_f64(u_s + 8u * (tsl * 32u + lane), uk);
+        sts_f64(u_s + 8u * (tsl * 32u + lane), t);
         __syncwarp();
         if (lane == 0) {
           st_release_cta_s(trdy_s + 4u * tsl, k + 1u);
@@ -610,7 +606,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
 //   k_wb_solve : per chunk: start - far entries of the own block (>= window back, read back through L2) - in-window
 //                entries (blob B: jagged diagonals + ELL) -> mat-vec with the packed inverse -> window, out[], fused dot
 // ---------------------------------------------------------------------------------------------------------
-constexpr int WB_WARPS = 4;
+constexpr int WB_WARPS = 8;   // at most; the level's plan picks the warps per CTA and one or two staging buffers per warp
 
 __global__ void __launch_bounds__(256) k_wb_pre(const BcArgs P) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -649,17 +645,22 @@ __global__ void __launch_bounds__(256) k_wb_pre(const BcArgs P) {
   }
 }
 
-// Per-warp shared memory: window (W + 16 doubles) | t vector (32 doubles) | two staging buffers of capB bytes | two mbarriers.
-__host__ __device__ __forceinline__ uint32_t wb_warp_bytes(uint32_t W, uint32_t capB) { return (W + 48u) * 8u + 2u * capB + 16u; }
+// Per-warp shared memory: window (W + 16 doubles) | t vector (32 doubles) | nbuf staging buffers of capB bytes | two mbarriers.
+__host__ __device__ __forceinline__ uint32_t wb_warp_bytes(uint32_t W, uint32_t capB, uint32_t nbuf) {
+  return (W + 48u) * 8u + nbuf * capB + 16u;
+}
 
+// P.SB = staging buffers per warp: 2 = the next chunk's blob is copied while this one is processed; 1 = the copy starts when
+// this chunk's blob has been read (more warps fit an SM, and their turns hide the copy).
 __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char *mine = smem + (size_t)warp * wb_warp_bytes(P.W, P.capB);
+  const uint32_t nbuf = P.SB;
+  unsigned char *mine = smem + (size_t)warp * wb_warp_bytes(P.W, P.capB, nbuf);
   double *win = reinterpret_cast<double *>(mine);
   double *scr = win + P.W + 16u;
   unsigned char *buf = reinterpret_cast<unsigned char *>(scr + 32u);
-  uint64_t *full = reinterpret_cast<uint64_t *>(buf + 2u * (size_t)P.capB);
+  uint64_t *full = reinterpret_cast<uint64_t *>(buf + (size_t)nbuf * P.capB);
   const uint32_t wmask = P.W - 1u;
   const uint32_t scr_s = smem_u32(scr), full_s = smem_u32(full);
   if (lane < 16u) win[P.W + lane] = 0.0;
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
       const uint32_t j = b.lo + 32u * k + lane;
       const bool valid = j < b.hi;
       const uint32_t i = P.reversed ? P.N - 1u - j : j;
-      const uint32_t cur = k & 1u;
+      const uint32_t cur = nbuf == 2u ? (k & 1u) : 0u, nxt = nbuf == 2u ? (cur ^ 1u) : 0u;
       const int64_t c0 = o0, c1 = o1;
       // next chunk's blob into the other buffer (every lane has finished reading it: __syncwarp at the end of chunk k-1)
       if ((k & 31u) == 0u && k > 0u) {   // next group of 32 offsets
@@ -718,9 +719,9 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
         o1 = WB_OFF(k + 2u);
         const int64_t q0 = WB_OFF(min(k + 3u, nch)), q1 = WB_OFF(min(k + 4u, nch));
         if (lane == 0u) {
-          if (o1 - o0 <= (int64_t)P.capB) {
-            mbar_expect_tx(full + (cur ^ 1u), (uint32_t)(o1 - o0));
-            bulk_g2s(buf + (size_t)(cur ^ 1u) * P.capB, P.blobB + o0, (uint32_t)(o1 - o0), full + (cur ^ 1u));
+          if (nbuf == 2u && o1 - o0 <= (int64_t)P.capB) {
+            mbar_expect_tx(full + nxt, (uint32_t)(o1 - o0));
+            bulk_g2s(buf + (size_t)nxt * P.capB, P.blobB + o0, (uint32_t)(o1 - o0), full + nxt);
           }
           if (q1 > q0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.blobB + q0), "r"((uint32_t)(q1 - q0)) : "memory");   // chunk k+3 towards L2
         }
@@ -837,6 +838,13 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
         if (lane >= 2u * pp + 2u) { u2 = fma(wb.x, tc, u2); u3 = fma(wb.y, td, u3); }
       }
       const double x = (u0 + u1) + (u2 + u3);
+      if (nbuf == 1u && k + 1u < nch) {   // one buffer: every lane has read this chunk's blob; copy the next one
+        __syncwarp();
+        if (lane == 0u && o1 - o0 <= (int64_t)P.capB) {
+          mbar_expect_tx(full, (uint32_t)(o1 - o0));
+          bulk_g2s(buf, P.blobB + o0, (uint32_t)(o1 - o0), full);
+        }
+      }
       win[(32u * k + lane) & wmask] = x;
       if (valid) {
         __stcg(P.out + i, x);

@@ -38,7 +38,7 @@ def oracle():
                                                   ("lap3d", 33, 2, dict(chain_window=1024, early=6)),
                                                   ("lap3d", 40, 8, dict(sep_tile=4, early_sep=12, recent=2)),
                                                   ("lap3d", 14, 4, dict(wb_min=2)), ("lap3d", 40, 8, dict(wb_min=4, recent=2)),
-                                                  ("aniso2d", 64, 8, dict(wb_min=1, chain_window=1024)), ("lap3d", 14, 4, dict(wb_min=2, wb_jagged=True)),
+                                                  ("aniso2d", 64, 8, dict(wb_min=1, chain_window=1024)), ("lap3d", 14, 4, dict(wb_min=2, wb_ell=True)),
                                                   ("lap3d", 33, 2, dict(chain_window=1024, early=255)), ("lap3d", 40, 8, dict(sep_window=2048, wb_min=4))])
 def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
@@ -49,7 +49,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
         lay_f, lay_b = s.blocked_layout(capi.TRSV_FORWARD), s.blocked_layout(capi.TRSV_BACKWARD)
         assert lay_f["active"] and lay_b["active"] and lay_f["fold"] == 1 and lay_b["fold"] == 1
         kw = dict(Kr=lay_f["Kr"], E=lay_f["E"], Dfar=lay_f["Dfar"], Dfar_sep=lay_f["Dfar_sep"], tile_sep=lay_f["tile_sep"],
-                  E_sep=lay_f["E_sep"], fold=True, wb_min=lay_f["wb_min"], Dfar_wb=lay_f["Dfar_wb"], wb_jagged=opts.get("wb_jagged", False))
+                  E_sep=lay_f["E_sep"], fold=True, wb_min=lay_f["wb_min"], Dfar_wb=lay_f["Dfar_wb"], wb_jagged=not opts.get("wb_ell", False))
         L, bounds, depth = direction_matrix(G, part, False)
         compare_layouts(lay_f, build_layout(L, bounds, depth, False, **kw))
         L, bounds, depth = direction_matrix(G, part, True)
@@ -69,7 +69,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
                                   dict(early=6), dict(early=4, recent=3), dict(capb_quarters=4), dict(slots_a=2), dict(slots_a=8, capb_quarters=5),
                                   dict(sep_tile=8, far_lanes2=32), dict(early_sep=16), dict(early_sep=4, early=5), dict(sep_tile=4, chain_window=1024),
                                   dict(wb_min=1), dict(wb_min=2), dict(wb_min=4, recent=2), dict(wb_min=-1), dict(wb_min=2, use_graph=False),
-                                  dict(wb_min=2, wb_jagged=True), dict(early=255), dict(early=255, early_sep=255, recent=2),
+                                  dict(wb_min=2, wb_ell=True), dict(early=255), dict(early=255, early_sep=255, recent=2),
                                   dict(sep_window=2048), dict(slots_a=5)])
 @pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 33, 2), ("aniso2d", 160, 4), ("lap3d", 40, 0)])
 def test_folded_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
