@@ -48,9 +48,12 @@ typedef struct rcg_options {
   int use_graph;           /* 1 = replay one CUDA graph per PCG iteration (default), 0 = plain launches   */
   int spmv_lanes;          /* lanes per row of the CSR SpMV (0 = choose from the row-length histogram)     */
   int chain_generic;       /* 1 = force the non-pipelined fallback kernel of the triangular solve (testing)  */
-  int chain_mode;          /* 0/3 = blocked-inverse chain (default), 4 = the same with the leaf level on the cluster chain (128-row chunks, 4 CTAs
-                              per leaf, DSMEM exchange), 1 = level-space sync-free polling kernel,
-                              2 = level-space role-specialised kernel (experimental)                                 */
+  int chain_mode;          /* 0 (= 5, default): folded chain -- recent entries folded into dense panels at set-up, three chain warps
+                              taking turns -- for tree levels with few blocks, one warp per block for levels with many blocks
+                              (rcg_fold.cuh); 6 = the round-1 blocked-inverse chain (four critical warps, one named barrier per
+                              chunk), 3 = the same with one critical warp, 4 = the same with the leaf level on the cluster chain
+                              (128-row chunks, 4 CTAs per leaf, DSMEM exchange), 1 / 2 = level-space sync-free kernels
+                              (rcg_trisolve.cu).  Modes other than 0 are kept for A/B measurements.                            */
   int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2),
                               [3] blocked solve: recent chunk distance Kr (default 2), [4] window rows of the separator blocks
                               (default 1024), [5] blocked solve: distance E (chunks) that separates the "early" from the "late" entries:
@@ -187,6 +190,12 @@ int rcg_debug_trace(rcg_handle *h, int which, const double *rhs_host, double *ou
  * one device array to the host: 0 offA, 1 offB, 2 blobA, 3 blobB, 4 far rowptr, 5 far col, 6 far val, 7 tile_need,
  * 8 blocks (8 x uint32 each: lo, hi, chunk0, tile0, gidx, pad), 9 per-level plan (10 x uint64 each). */
 int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16);
+/* Blocks that rcg_set_factor derives from G when no `part` is given (the stock signature of the reference's pcg,
+   /root/reference/c++/util/pcg.hpp:13-16, carries none).  Host-only, no device needed: bounds_out gets *nblocks + 1
+   boundaries, depth_out *nblocks tree depths; returns RCG_ERR_INVALID when more than `cap` blocks would be written and
+   *nblocks = 0 when the factor is solved as one block. */
+int rcg_detect_blocks(uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, uint64_t *bounds_out, int32_t *depth_out,
+                      uint64_t cap, uint64_t *nblocks);
 int rcg_debug_counters(rcg_handle *h, uint64_t *out16);   /* raw cycle counters of the last chain kernel (rcg_options.reserved[1] bit 0) */
 int rcg_debug_blocked_copy(rcg_handle *h, int direction, int what, void *dst, uint64_t bytes);
 

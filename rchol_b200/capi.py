@@ -28,7 +28,7 @@ EXPORTED = [
     "rcg_set_factor_blocks", "rcg_nccl_unique_id", "rcg_dist_init", "rcg_dist_finalize",
     "rcg_debug_blocked_info", "rcg_debug_blocked_copy", "rcg_debug_counters",
     "rcg_set_matrix_permuted", "rcg_set_permutation", "rcg_permute_vector", "rcg_unpermute_vector",
-    "rcg_pcg_original", "rcg_get_matrix",
+    "rcg_pcg_original", "rcg_get_matrix", "rcg_detect_blocks",
 ]
 
 TRSV_FORWARD, TRSV_BACKWARD = 0, 1
@@ -116,6 +116,8 @@ def load():
     L.rcg_unpermute_vector.argtypes = [H, _f64p, _f64p]
     L.rcg_pcg_original.argtypes = [H, _f64p, C.c_double, C.c_int, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.rcg_get_matrix.argtypes = [H, _u64p, _u64p, _f64p]
+    L.rcg_detect_blocks.argtypes = [C.c_uint64, _u64p, _u64p, _u64p, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"),
+                                    C.c_uint64, C.POINTER(C.c_uint64)]
     for name in EXPORTED:
         fn = getattr(L, name)
         if name not in ("rcg_last_error", "rcg_version"):
@@ -360,6 +362,23 @@ class Solver:
         ms = C.c_double(0)
         self._check(self._L.rcg_time_phase(self._h, int(phase), int(reps), C.byref(ms)))
         return ms.value
+
+
+def detect_blocks(rowPtr, colIdx, cap: int = 1 << 16):
+    """Blocks (bounds, depth) that set_factor derives from G when no `part` is given; (None, None) = one block.
+    Host-only (no GPU needed)."""
+    L = load()
+    rp = _u64(rowPtr)
+    N = rp.shape[0] - 1
+    bounds = np.zeros(cap + 1, np.uint64)
+    depth = np.zeros(cap, np.int32)
+    nb = C.c_uint64(0)
+    rc = L.rcg_detect_blocks(N, rp, _u64(colIdx), bounds, depth, cap, C.byref(nb))
+    if rc != 0:
+        raise RcgError(rc, "rcg_detect_blocks: more blocks than the caller's capacity")
+    if nb.value == 0:
+        return None, None
+    return bounds[: nb.value + 1].copy(), depth[: nb.value].copy()
 
 
 def nccl_unique_id() -> bytes:

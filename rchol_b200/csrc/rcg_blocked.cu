@@ -1300,7 +1300,8 @@ uint32_t floor_pow2_u32(uint32_t v) {
 }  // namespace
 
 bool rcg_use_blocked(const rcg_handle *h) {
-  return !h->opt.chain_generic && (h->opt.chain_mode == 0 || h->opt.chain_mode == 3 || h->opt.chain_mode == 4 || h->opt.chain_mode == 5);
+  const int m = h->opt.chain_mode;
+  return !h->opt.chain_generic && (m == 0 || m == 3 || m == 4 || m == 5 || m == 6);
 }
 
 void rcg_free_blocked(BlockedDev &b) {
@@ -1320,7 +1321,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   const int nb = (int)bounds.size() - 1;
   // ---- thresholds ------------------------------------------------------------------------------------
   // (the split chain keeps the solution of two chunks in its partial-sum buffers: recent distance at most 2)
-  B.fold = h->opt.chain_mode == 5;
+  B.fold = h->opt.chain_mode == 0 || h->opt.chain_mode == 5;   // default: folded chain + warp-per-block levels
   B.Kr = h->opt.reserved[3] > 0 ? (uint32_t)std::min(h->opt.reserved[3], h->opt.chain_mode == 3 ? 4 : 2) : 2u;
   // folded chain: Kr is the fold depth (chunks whose entries become dense panel columns); it is also the slack, in hops,
   // that the near helper has to deliver u_k after the chain solved chunk k-Kr-1

@@ -12,12 +12,14 @@
 // the far tiles / start vector / progress words).
 //
 // CTA = 12 warps (384 threads, 168 registers each):
-//   warps 0,4,8   chain warps, the only warps of scheduler 0.  Chunk k belongs to chain warp k % 3.  A lone warp needs
-//                 ~700 cycles for the ~110 instructions of a chunk (measured), but only the x loads, 4 dependent DFMA, 2
-//                 DADD and two stores depend on the previous chunk: with three warps taking turns, the bookkeeping of
-//                 chunk k (staging barrier, next tail into registers, flag of u) overlaps the critical section of k+1, k+2.
-//   warp 1        publisher: window -> out[], fused dot product, progress published with release semantics
-//   warp 2 / 3    TMA producers of ring A (panels) / ring B (early + late entries + packed Winv)
+//   warps 0,1,2   chain warps, one per scheduler 0..2.  Chunk k belongs to chain warp k % 3.  A lone warp needs ~700 cycles
+//                 for the ~110 instructions of a chunk (measured), but only the x loads, 4 dependent DFMA, 2 DADD and two
+//                 stores depend on the previous chunk: with three warps taking turns, the bookkeeping of chunk k (staging
+//                 barrier, next tail into registers, Winv t') overlaps the critical sections of k+1, k+2.  They sit on
+//                 DIFFERENT schedulers: a warp that spins for its turn on the scheduler of the warp in its critical
+//                 section takes every other issue slot from it (measured: 1095 cycles per hop with all three on scheduler 0).
+//   warp 3        publisher: window -> out[], fused dot product, progress published with release semantics
+//   warp 4 / 8    TMA producers of ring A (panels + Winv) / ring B (early + late entries); they sleep in mbarrier waits
 //   warps 5,6,7,9,10,11   near helpers: chunk k -> helper k % 6, running up to 6 chunks ahead
 constexpr int FC_THREADS = 384;
 constexpr uint32_t FC_NC = 3;
@@ -178,9 +180,9 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
     if (threadIdx.x == 0) { ctl[0] = 0u; ctl[1] = 0u; }
     __syncthreads();
 
-    if ((warp & 3u) == 0u) {
-      // ------------------------------ chain warps (0, 4, 8) ----------------------------------------------
-      const uint32_t cw = warp >> 2;   // this warp's turn: chunks cw, cw + 3, ...
+    if (warp < FC_NC) {
+      // ------------------------------ chain warps (0, 1, 2) ----------------------------------------------
+      const uint32_t cw = warp;   // this warp's turn: chunks cw, cw + 3, ...
       // A lone warp is bound by the number of instructions between two hops (measured: 4-8 cycles per dependent
       // instruction, 150 for a synchronous mbarrier test, 160-410 for a divergent branch, a MEMBAR for st.release), so:
       // 32-bit shared addresses only, no divergent branch (lane 0's stores are predicated), the progress word is a
@@ -276,7 +278,11 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
         if (k > 0u) {
           long long c2 = 0;
           if (prof) c2 = clock64();
-          FC_SPIN(lds_volatile_u32(prog_s) >= k, 0xD00u);
+          uint32_t pnow;
+          while ((pnow = lds_volatile_u32(prog_s)) < k) {   // two or more hops away: sleep; the last hop: spin
+            if (k - pnow > 1u) __nanosleep(64);
+            if (++spins > (1u << 24)) { atomicCAS(P.abort_g, 0u, 0xD00u); sts_volatile_u32(G.abort_s, 1u); break; }
+          }
           if (prof) pc[1] += clock64() - c2;
         }
         // body: the older batches of a wide panel, two per trip (eight independent gathers in flight)
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
 #undef FC_LOAD_VALS
 #undef FC_LOAD_OFFS
 #undef FC_SPIN
-    } else if (warp == 2u) {
+    } else if (warp == 4u) {
       // ------------------------------ TMA producer, ring A -----------------------------------------------
       int64_t O0n = 0, O1n = 0;
       if (nch > 0) {
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
           __syncwarp();
         }
       }
-    } else if (warp == 3u) {
+    } else if (warp == 8u) {
       // ------------------------------ TMA producer, ring B -----------------------------------------------
       int64_t O0n = 0, O1n = 0;
       if (nch > 0) {
@@ -403,7 +409,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
           __syncwarp();
         }
       }
-    } else if (warp == 1u) {
+    } else if (warp == 3u) {
       // ------------------------------ publisher ----------------------------------------------------------
       uint32_t done = 0;
       double dot = 0.0;

@@ -1305,11 +1305,176 @@ int rcg_download_matrix(rcg_handle *h, uint64_t *rowPtr, uint64_t *colIdx, doubl
 static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                              const std::vector<uint32_t> &bounds, const TreeInfo &tree, bool strict_tree);
 
+// ---------------------------------------------------------------------------------------------------------
+// Blocks of a factor that arrives WITHOUT `part` -- the reference's stock signature pcg(A, b, tol, maxit, G, x, relres, itr)
+// (/root/reference/c++/util/pcg.hpp:13-16, called like that in ex_laplace_parallel.cpp:46) carries no partition.
+// The nested-dissection structure is recovered from G itself.  With jmin(i) = smallest row j < i that has an entry in
+// column i of U (the oldest unknown row i of L = U^T depends on), one sweep over i with a stack of open index ranges:
+//   no jmin            -> i opens a new range (a new independent chain starts);
+//   jmin in the top range -> the top range grows by i;
+//   jmin further down  -> every range from the one that holds jmin to the top closes and becomes a child of a new range
+//                         whose own rows start at i (a separator: it depends on all of them).
+// Ranges of one tree depth never reference each other (a row only reaches into its own range or, through its jmin
+// chain, into descendants), which is the block rule of rcg_setup_factor_blocks -- checked on the device afterwards
+// (k_validate_depths), so a structure the sweep gets wrong is an error, never a wrong result.  Small ranges (artifacts:
+// a row whose lower neighbours all lie outside its leaf) are absorbed by their parent.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct DetNode { uint32_t lo, own_lo, hi; int kid0, nkids; };
+
+bool detect_blocks(uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, std::vector<uint32_t> &bounds, std::vector<int> &depth) {
+  const uint32_t NONE = 0xFFFFFFFFu;
+  std::vector<uint32_t> jmin(N, NONE);
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int64_t j = 0; j < (int64_t)N; j++)
+    for (uint64_t p = rowPtr[j]; p < rowPtr[j + 1]; p++) {
+      const uint64_t c = colIdx[p];
+      if (c <= (uint64_t)j || c >= N) continue;
+      uint32_t old = __atomic_load_n(&jmin[c], __ATOMIC_RELAXED);
+      while ((uint32_t)j < old && !__atomic_compare_exchange_n(&jmin[c], &old, (uint32_t)j, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    }
+  std::vector<DetNode> nodes;
+  std::vector<int> kids, stack, tmp;
+  for (uint32_t i = 0; i < (uint32_t)N; i++) {
+    const uint32_t jm = jmin[i];
+    if (jm == NONE || stack.empty()) {
+      nodes.push_back({i, i, i + 1u, 0, 0});
+      stack.push_back((int)nodes.size() - 1);
+      continue;
+    }
+    DetNode &t = nodes[stack.back()];
+    if (jm >= t.lo) { t.hi = i + 1u; continue; }
+    tmp.clear();
+    uint32_t lo = i;
+    while (!stack.empty()) {
+      const int c = stack.back();
+      stack.pop_back();
+      tmp.push_back(c);
+      lo = nodes[c].lo;
+      if (nodes[c].lo <= jm) break;
+    }
+    DetNode s{lo, i, i + 1u, (int)kids.size(), (int)tmp.size()};
+    for (int q = (int)tmp.size() - 1; q >= 0; q--) kids.push_back(tmp[q]);   // ascending index order
+    nodes.push_back(s);
+    stack.push_back((int)nodes.size() - 1);
+    if (nodes.size() > (size_t)1 << 22) return false;   // not a nested-dissection factor: too fragmented
+  }
+  // bottom-up (children precede their parents in `nodes`): absorb small trailing children, single-child chains and small
+  // subtrees
+  const uint32_t thr = (uint32_t)std::min<uint64_t>(2048, std::max<uint64_t>(8, N / 256));
+  std::vector<char> gone(nodes.size(), 0);
+  for (size_t n = 0; n < nodes.size(); n++) {
+    DetNode &d = nodes[n];
+    auto absorb_all = [&](auto &&self, int c) -> void {
+      DetNode &k = nodes[c];
+      for (int q = 0; q < k.nkids; q++) self(self, kids[k.kid0 + q]);
+      gone[c] = 1;
+    };
+    if (d.hi - d.lo < thr) {   // small subtree: one block
+      for (int q = 0; q < d.nkids; q++) absorb_all(absorb_all, kids[d.kid0 + q]);
+      d.nkids = 0;
+      d.own_lo = d.lo;
+      continue;
+    }
+    {   // a small leaf between two siblings joins the last block of the sibling before it (nothing there references it)
+      int kept = 0;
+      for (int q = 0; q < d.nkids; q++) {
+        const int c = kids[d.kid0 + q];
+        const DetNode &k = nodes[c];
+        if (kept > 0 && k.nkids == 0 && k.hi - k.lo < thr) {
+          nodes[kids[d.kid0 + kept - 1]].hi = k.hi;
+          gone[c] = 1;
+        } else {
+          kids[d.kid0 + kept++] = c;
+        }
+      }
+      d.nkids = kept;
+    }
+    while (d.nkids > 0) {
+      const int c = kids[d.kid0 + d.nkids - 1];
+      const DetNode &k = nodes[c];
+      if (k.nkids == 0 && k.hi - k.lo < thr) { d.own_lo = k.lo; gone[c] = 1; d.nkids--; }
+      else break;
+    }
+    if (d.nkids == 1) {   // chain: merge with the only child (adopt its children)
+      const int c = kids[d.kid0];
+      const DetNode k = nodes[c];
+      d.own_lo = k.own_lo;
+      d.kid0 = k.kid0;
+      d.nkids = k.nkids;
+      gone[c] = 1;
+    }
+  }
+  // depths, top-down (parents follow their children in `nodes`)
+  std::vector<int> dep(nodes.size(), 0);
+  int max_depth = 0;
+  for (size_t n = nodes.size(); n-- > 0;) {
+    if (gone[n]) continue;
+    const DetNode &d = nodes[n];
+    for (int q = 0; q < d.nkids; q++) {
+      dep[kids[d.kid0 + q]] = dep[n] + 1;
+      max_depth = std::max(max_depth, dep[n] + 1);
+    }
+  }
+  if (max_depth > 60) return false;
+  std::vector<std::pair<uint32_t, size_t>> order;
+  for (size_t n = 0; n < nodes.size(); n++)
+    if (!gone[n]) order.push_back({nodes[n].own_lo, n});
+  std::sort(order.begin(), order.end());
+  bounds.clear();
+  depth.clear();
+  uint32_t expect = 0;
+  for (const auto &o : order) {
+    const DetNode &d = nodes[o.second];
+    if (d.own_lo != expect) return false;   // (cannot happen: the blocks tile [0, N))
+    bounds.push_back(d.own_lo);
+    depth.push_back(dep[o.second]);
+    expect = d.hi;
+  }
+  if (expect != (uint32_t)N) return false;
+  bounds.push_back((uint32_t)N);
+  return true;
+}
+}  // namespace
+
+static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
+                             const std::vector<uint32_t> &bounds, const TreeInfo &tree, bool strict_tree);
+
+extern "C" int rcg_detect_blocks(uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, uint64_t *bounds_out,
+                                 int32_t *depth_out, uint64_t cap, uint64_t *nblocks) {
+  if (!rowPtr || !colIdx || !nblocks) return RCG_ERR_INVALID;
+  *nblocks = 0;
+  std::vector<uint32_t> db;
+  std::vector<int> dd;
+  if (N < 64 || N >= 0xFFFFFFFFull || !detect_blocks(N, rowPtr, colIdx, db, dd) || db.size() <= 2) return RCG_OK;
+  if (dd.size() > cap || !bounds_out || !depth_out) return RCG_ERR_INVALID;
+  for (size_t i = 0; i < db.size(); i++) bounds_out[i] = db[i];
+  for (size_t i = 0; i < dd.size(); i++) depth_out[i] = dd[i];
+  *nblocks = dd.size();
+  return RCG_OK;
+}
+
 int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                      const uint64_t *part, uint64_t npart) {
   if (h->haveA && N != h->N) {
     h->err = "factor dimension differs from the matrix's";
     return RCG_ERR_INVALID;
+  }
+  if (!(part && npart >= 2) && N >= 64 && N < 0xFFFFFFFFull && rowPtr && colIdx && !h->opt.chain_generic) {
+    // stock signature: recover the blocks from G (a factor that is one chain comes back as one block)
+    std::vector<uint32_t> db;
+    std::vector<int> dd;
+    const double t0 = wall_ms();
+    if (detect_blocks(N, rowPtr, colIdx, db, dd) && db.size() > 2) {
+      TreeInfo tree;
+      tree.depth = dd;
+      tree.sub_lo.assign(dd.size(), 0);
+      for (int v : dd) tree.max_depth = std::max(tree.max_depth, v);
+      h->stats.reserved[7] = wall_ms() - t0;   // host time of the block detection (ms)
+      const int rc = setup_factor_impl(h, N, rowPtr, colIdx, val, db, tree, false);
+      if (rc != RCG_ERR_STRUCTURE) return rc;
+      h->err.clear();   // the detected structure did not validate: solve as one block
+    }
   }
   // ---- partition -> block boundaries ---------------------------------------------------------------
   std::vector<uint32_t> bounds;

@@ -40,10 +40,10 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
     zo = oracle.trsv_backward(*G, yo)
-    with capi.Solver(0, **opts) as s:
+    with capi.Solver(0, chain_mode=6, **opts) as s:   # the round-1 blocked chain (the default is the folded chain: test_gpu_fold.py)
         s.set_factor(*G, part)
         lay_f, lay_b = s.blocked_layout(capi.TRSV_FORWARD), s.blocked_layout(capi.TRSV_BACKWARD)
-        assert lay_f["active"] and lay_b["active"]
+        assert lay_f["active"] and lay_b["active"] and lay_f["fold"] == 0
         kw = dict(Kr=lay_f["Kr"], E=lay_f["E"], Dfar=lay_f["Dfar"], Dfar_sep=lay_f["Dfar_sep"], tile_sep=lay_f["tile_sep"], E_sep=lay_f["E_sep"])
         L, bounds, depth = direction_matrix(G, part, False)
         compare_layouts(lay_f, build_layout(L, bounds, depth, False, **kw))
@@ -58,18 +58,15 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
 
 
 @needs_producer
-@pytest.mark.parametrize("opts", [dict(), dict(recent=1), dict(recent=3), dict(chain_window=1024), dict(chain_window=2048, recent=1),
-                                  dict(chain_window=8192), dict(plain_launch=True), dict(use_graph=False, chain_window=1024),
-                                  dict(chain_mode=1), dict(chain_mode=3), dict(sep_window=4096), dict(chain_window=2048, sep_window=2048),
-                                  dict(early=6), dict(early=3, recent=2), dict(early=8, chain_mode=3),
-                                  dict(capb_quarters=4), dict(slots_a=2), dict(sep_tile=1), dict(sep_tile=8, far_lanes2=32), dict(early_sep=16), dict(early_sep=3, early=5), dict(sep_tile=4, chain_window=1024), dict(capb_quarters=5, slots_a=6, chain_window=2048),
-                                  dict(chain_mode=4), dict(chain_mode=4, chain_window=1024), dict(chain_mode=4, use_graph=False, chain_window=2048)])
+@pytest.mark.parametrize("opts", [dict(), dict(recent=1), dict(chain_window=1024), dict(chain_window=8192), dict(plain_launch=True),
+                                  dict(use_graph=False, chain_window=1024), dict(chain_mode=1), dict(chain_mode=3), dict(early=3, recent=2),
+                                  dict(sep_tile=8, far_lanes2=32), dict(chain_mode=4), dict(chain_mode=4, use_graph=False, chain_window=2048)])
 @pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 33, 2), ("aniso2d", 160, 4), ("lap3d", 40, 0)])
 def test_blocked_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
     zo = oracle.trsv_backward(*G, yo)
-    with capi.Solver(0, **opts) as s:
+    with capi.Solver(0, **dict(dict(chain_mode=6), **opts)) as s:   # round-1 chains, kept selectable
         s.set_matrix(*A)
         s.set_factor(*G, part)
         for _ in range(2):   # twice: flags and progress counters are reset per solve
@@ -88,7 +85,7 @@ def test_many_leaves_more_blocks_than_chain_ctas(capi, oracle):
     A, b, G, part, f = make_problem("lap3d", 48, 256)
     yo = oracle.trsv_forward(*G, b)
     zo = oracle.trsv_backward(*G, yo)
-    with capi.Solver(0) as s:
+    with capi.Solver(0, chain_mode=6) as s:
         s.set_factor(*G, part)
         assert relerr(s.trsv(capi.TRSV_FORWARD, b), yo) <= TRSV_TOL
         assert relerr(s.precond(b), zo) <= TRSV_TOL

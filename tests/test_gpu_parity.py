@@ -251,6 +251,27 @@ def test_factor_refresh_on_one_handle_and_many_right_hand_sides(capi, oracle):
 
 
 @needs_producer
+@pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 48, 256), ("aniso2d", 160, 4)])
+def test_stock_signature_without_part(capi, oracle, kind, n, threads):
+    """pcg(A, b, tol, maxit, G, x, relres, itr) as the reference declares it (pcg.hpp:13-16) carries no partition: the
+    blocks are recovered from G (rcg_detect_blocks) -- same results as with `part`, and not one N-row chain."""
+    A, b, G, part, f = make_problem(kind, n, threads)
+    yo = oracle.trsv_forward(*G, b)
+    zo = oracle.trsv_backward(*G, yo)
+    with capi.Solver(0) as s:
+        s.set_matrix(*A)
+        s.set_factor(*G, None)
+        assert s.stats()["n_blocks"] > 1
+        assert relerr(s.trsv(capi.TRSV_FORWARD, b), yo) <= TRSV_TOL
+        assert relerr(s.trsv(capi.TRSV_BACKWARD, yo), zo) <= TRSV_TOL
+        x, relres, itr = s.pcg(b, 1e-8, 500)
+    o = oracle.pcg(A, b, 1e-8, 500, G)
+    assert abs(itr - o["itr"]) <= 1 and relres <= 2e-8
+    x1, relres1, itr1, st = capi.pcg(A, b, 1e-8, 500, G, None)      # one-shot entry point, stock call shape
+    assert itr1 == itr and np.array_equal(x1, x)
+
+
+@needs_producer
 def test_matrix_replaced_after_a_solve_same_size(capi, oracle):
     """set_matrix(A1); pcg; set_matrix(A2: same N, different nnz and values); pcg -- the captured iteration (CUDA graph)
     held A1's device pointers and SpMV template; it has to be rebuilt (advisor finding, round 1)."""

@@ -296,3 +296,50 @@ def test_bench_reference_arm_prints_the_contract_line(tmp_path):
     assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"] == dict(value=j["value"], unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert j["config"]["workload"] == "lap3d_20^3_rchol_T4_pcg_tol1e-8"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# stock signature pcg(A, b, tol, maxit, G, x, relres, itr) (/root/reference/c++/util/pcg.hpp:13-16): no `part`
+# ---------------------------------------------------------------------------------------------------------------------
+def _check_block_rule(G, bounds, depth):
+    """An entry (i, c) of U with block(c) != block(i) needs depth(block(c)) < depth(block(i)) -- the rule of
+    rcg_set_factor_blocks (k_validate_depths on the device)."""
+    rp, ci = np.asarray(G[0], np.int64), np.asarray(G[1], np.int64)
+    rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    bi = np.searchsorted(bounds, rows, side="right") - 1
+    bc = np.searchsorted(bounds, ci, side="right") - 1
+    off = bi != bc
+    assert np.all(depth[bc[off]] < depth[bi[off]])
+
+
+@pytest.mark.parametrize("name", ["lap3d_12_t4", "lap3d_10_t8_tol6", "aniso2d_24_t4"])
+def test_blocks_detected_from_the_factor_equal_the_reference_partition(name):
+    """Without `part` the nested-dissection blocks are recovered from G itself (rcg_detect_blocks, host only): on the
+    reference-generated goldens they equal result_idx (rchol_parallel.cpp:64-70) and the tree depths of
+    rchol_lap.cpp:254-261."""
+    from rchol_b200 import capi
+    from blocked_reference import tree_depths
+    g = load_golden(name)
+    bounds, depth = capi.detect_blocks(g["G"][0], g["G"][1])
+    assert bounds is not None
+    assert np.array_equal(bounds, g["part"])
+    assert np.array_equal(depth, tree_depths(len(depth)))
+    _check_block_rule(g["G"], bounds.astype(np.int64), depth)
+
+
+def test_a_factor_that_is_one_chain_stays_one_block():
+    from rchol_b200 import capi
+    g = load_golden("lap3d_8_seq")
+    assert capi.detect_blocks(g["G"][0], g["G"][1]) == (None, None)
+
+
+@needs_producer
+@pytest.mark.parametrize("kind,n,threads", [("lap3d", 40, 8), ("lap3d", 48, 16), ("lap3d", 48, 256), ("aniso2d", 160, 4)])
+def test_detected_blocks_obey_the_block_rule(kind, n, threads):
+    from rchol_b200 import capi
+    A, b, G, part, f = make_problem(kind, n, threads)
+    bounds, depth = capi.detect_blocks(G[0], G[1])
+    assert bounds is not None and bounds[0] == 0 and bounds[-1] == f.N and np.all(np.diff(bounds.astype(np.int64)) > 0)
+    _check_block_rule(G, bounds.astype(np.int64), depth)
+    if threads == 8 or kind == "aniso2d":
+        assert np.array_equal(bounds, part)          # the reference's own partition, exactly
