@@ -1549,12 +1549,14 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       L.Dfar = B.blocks_host[G.first].pad[0];
       const uint32_t Wwb = 32u * L.Dfar;
       // warps per CTA and staging buffers per warp: as many warps as possible (their turns hide each other's latencies;
-      // measured at 256^3 / T=4096: one warp per scheduler needs ~5400 cycles per chunk), then two buffers if they fit;
-      // blobs larger than 48 KB are read from HBM (slow path)
-      L.capB = (uint32_t)std::min<int64_t>((maxB + 127) & ~127ll, 49152);
+      // measured at 256^3 / T=4096: one warp per scheduler needs ~5400 cycles per chunk), then two buffers if they fit
+      L.capB = (uint32_t)((maxB + 127) & ~127ll);   // every blob of the level is staged
       uint32_t wbw = 1u, nbuf = 1u;
-      if ((int64_t)wb_warp_bytes(Wwb, L.capB, 1u) > (int64_t)BC_SMEM_MAX)
-        L.capB = (uint32_t)((((int64_t)BC_SMEM_MAX - (int64_t)(Wwb + 48u) * 8 - 16)) & ~127ll);
+      if ((int64_t)wb_warp_bytes(Wwb, L.capB, 1u) > (int64_t)BC_SMEM_MAX) {
+        cudaFree(dgeom);
+        h->err = "blocked solve: a chunk of a warp-per-block level does not fit shared memory (raise wb_min: rcg_options.reserved[9])";
+        return RCG_ERR_INVALID;
+      }
       {
         const uint32_t want = (uint32_t)std::min<int64_t>(WB_WARPS, std::max<int64_t>(1, (G.count + h->sm_count - 1) / h->sm_count));
         const uint32_t fit1 = (uint32_t)((int64_t)BC_SMEM_MAX / wb_warp_bytes(Wwb, L.capB, 1u));

@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
   unsigned char *buf = reinterpret_cast<unsigned char *>(scr + 32u);
   uint64_t *full = reinterpret_cast<uint64_t *>(buf + (size_t)nbuf * P.capB);
   const uint32_t wmask = P.W - 1u;
-  const uint32_t scr_s = smem_u32(scr), full_s = smem_u32(full);
+  const uint32_t scr_s = smem_u32(scr), full_s = smem_u32(full), buf_s = smem_u32(buf), win_s = smem_u32(win);
   if (lane < 16u) win[P.W + lane] = 0.0;
   if (lane < 2u) mbar_init(full + lane, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -713,7 +713,6 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
       const bool valid = j < b.hi;
       const uint32_t i = P.reversed ? P.N - 1u - j : j;
       const uint32_t cur = nbuf == 2u ? (k & 1u) : 0u, nxt = nbuf == 2u ? (cur ^ 1u) : 0u;
-      const int64_t c0 = o0, c1 = o1;
       // next chunk's blob into the other buffer (every lane has finished reading it: __syncwarp at the end of chunk k-1)
       if ((k & 31u) == 0u && k > 0u) {   // next group of 32 offsets
         ogbase = k;
@@ -765,59 +764,69 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
         }
         t0 = (t0 + t1) + (t2 + t3);
       }
-      const unsigned char *bp;
-      if (c1 - c0 <= (int64_t)P.capB) {
+      // the chunk's blob: always staged (the level's plan sizes the buffers for its largest blob); every access below is a
+      // shared-space load through a 32-bit address -- generic loads cost an address conversion each and twice the latency
+      {
         uint32_t spins = 0;
         while (!mbar_try_s(full_s + 8u * cur, (phase >> cur) & 1u)) {
           if (++spins > (1u << 22)) { atomicCAS(P.abort_g, 0u, 0xC00u); break; }
         }
         phase ^= 1u << cur;
-        bp = buf + (size_t)cur * P.capB;
-      } else {
-        bp = P.blobB + c0;
       }
-      const uint32_t *hd = reinterpret_cast<const uint32_t *>(bp);
-      const uint32_t ne_max = hd[0], ne_tot = hd[1], nl = hd[2];
-      const uint32_t perm = bp[16u + lane], rank = bp[48u + lane];
-      const unsigned char *cnt = bp + BC_BHDR;
-      const double *ev = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max));
-      const uint16_t *ec = reinterpret_cast<const uint16_t *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot));
-      const double *lv = reinterpret_cast<const double *>(bp + BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot));
-      const uint16_t *lc = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(lv) + 256u * nl);
-      const unsigned char *wq = reinterpret_cast<const unsigned char *>(lv) + 320u * nl;   // packed Winv
-      // in-window entries, jagged diagonals (rows sorted by length), four per trip
+      const uint32_t bp_s = buf_s + cur * P.capB;
+      uint32_t ne_max, ne_tot, nl, hd3;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ne_max), "=r"(ne_tot), "=r"(nl), "=r"(hd3) : "r"(bp_s) : "memory");
+      uint32_t perm, rank;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(perm) : "r"(bp_s + 16u + lane) : "memory");
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(rank) : "r"(bp_s + 48u + lane) : "memory");
+      const uint32_t cnt_s = bp_s + BC_BHDR;
+      const uint32_t ev_s = cnt_s + r16(ne_max), ec_s = ev_s + r16(8u * ne_tot);
+      const uint32_t lv_s = ec_s + r16(2u * ne_tot), lc_s = lv_s + 256u * nl, wq_s = lv_s + 320u * nl;
+      // in-window entries, jagged diagonals (rows sorted by length), four per trip; lanes beyond a diagonal's length are
+      // predicated off (no branch)
       double ts = __shfl_sync(0xffffffffu, t0, (int)perm), ts1 = 0.0;
       uint32_t base = 0;
       for (uint32_t s = 0; s < ne_max; s += 4u) {
-        const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cnt + s);
+        const uint32_t c4 = lds_u32(cnt_s + s);
         const uint32_t n0 = c4 & 255u, n1 = (c4 >> 8) & 255u, n2 = (c4 >> 16) & 255u, n3 = c4 >> 24;
-        const uint32_t b1 = base + n0, b2 = b1 + n1, b3 = b2 + n2;
+        const uint32_t b0 = base + lane, b1 = b0 + n0, b2 = b1 + n1, b3 = b2 + n2;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-        if (lane < n0) { v0 = ev[base + lane]; x0 = win[ec[base + lane]]; }
-        if (lane < n1) { v1 = ev[b1 + lane]; x1 = win[ec[b1 + lane]]; }
-        if (lane < n2) { v2 = ev[b2 + lane]; x2 = win[ec[b2 + lane]]; }
-        if (lane < n3) { v3 = ev[b3 + lane]; x3 = win[ec[b3 + lane]]; }
+        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        lds_u16_if(e0, ec_s + 2u * b0, lane < n0);
+        lds_u16_if(e1, ec_s + 2u * b1, lane < n1);
+        lds_u16_if(e2, ec_s + 2u * b2, lane < n2);
+        lds_u16_if(e3, ec_s + 2u * b3, lane < n3);
+        lds_f64_if(v0, ev_s + 8u * b0, lane < n0);
+        lds_f64_if(v1, ev_s + 8u * b1, lane < n1);
+        lds_f64_if(v2, ev_s + 8u * b2, lane < n2);
+        lds_f64_if(v3, ev_s + 8u * b3, lane < n3);
+        lds_f64_if(x0, win_s + 8u * e0, lane < n0);
+        lds_f64_if(x1, win_s + 8u * e1, lane < n1);
+        lds_f64_if(x2, win_s + 8u * e2, lane < n2);
+        lds_f64_if(x3, win_s + 8u * e3, lane < n3);
         ts = fma(-v0, x0, ts);
         ts1 = fma(-v1, x1, ts1);
         ts = fma(-v2, x2, ts);
         ts1 = fma(-v3, x3, ts1);
-        base = b3 + n3;
+        base += n0 + n1 + n2 + n3;
       }
       ts += ts1;
       double t = __shfl_sync(0xffffffffu, ts, (int)rank);
-      {   // ELL class (lane = row; padding slots point at the zero slot): eight independent gathers per trip
+      if (nl) {   // ELL class (lane = row; padding slots point at the zero slot): eight independent gathers per trip
         double q1 = 0.0, q2 = 0.0, q3 = 0.0;
         for (uint32_t s0 = 0; s0 < nl; s0 += 8u) {
           uint32_t cc[8];
           double vv[8], xx[8];
 #pragma unroll
           for (uint32_t u = 0; u < 8u; u++) {
-            const bool have = s0 + u < nl;
-            cc[u] = have ? lc[(s0 + u) * 32u + lane] : P.W;
-            vv[u] = have ? lv[(s0 + u) * 32u + lane] : 0.0;
+            uint32_t cu = 0;
+            vv[u] = 0.0;
+            lds_u16_if(cu, lc_s + 64u * (s0 + u) + 2u * lane, s0 + u < nl);
+            lds_f64_if(vv[u], lv_s + 256u * (s0 + u) + 8u * lane, s0 + u < nl);
+            cc[u] = s0 + u < nl ? cu : P.W;   // slots beyond the chunk's count: the zero slot behind the window
           }
 #pragma unroll
-          for (uint32_t u = 0; u < 8u; u++) xx[u] = win[cc[u]];
+          for (uint32_t u = 0; u < 8u; u++) xx[u] = lds_f64(win_s + 8u * cc[u]);
 #pragma unroll
           for (uint32_t u = 0; u < 8u; u += 4u) {
             t = fma(-vv[u], xx[u], t);
@@ -828,21 +837,26 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
         }
         t = (t + q1) + (q2 + q3);
       }
-      // x = Winv t : t broadcast through the warp's scratch row, lane = row of the result
+      // x = Winv t : t broadcast through the warp's scratch row, lane = row of the result; the packed triangle is read
+      // with a clamped row (lanes above the diagonal pair get a zero factor)
       sts_f64(scr_s + 8u * lane, t);
       __syncwarp();
       double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
 #pragma unroll
       for (uint32_t pp = 0; pp < 16u; pp += 2u) {
-        double ta, tb, tc, td;
+        double ta, tb, tc, td, wa, wb, wc, wd;
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ta), "=d"(tb) : "r"(scr_s + 16u * pp) : "memory");
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc), "=d"(td) : "r"(scr_s + 16u * pp + 16u) : "memory");
         const uint32_t r0 = lane >= 2u * pp ? lane - 2u * pp : 0u, r1 = lane >= 2u * pp + 2u ? lane - 2u * pp - 2u : 0u;
-        const double2 wa = *reinterpret_cast<const double2 *>(wq + 16u * (pp * (33u - pp) + r0));
-        const double2 wb = *reinterpret_cast<const double2 *>(wq + 16u * ((pp + 1u) * (32u - pp) + r1));
-        if (lane >= 2u * pp) { u0 = fma(wa.x, ta, u0); u1 = fma(wa.y, tb, u1); }
-        if (lane >= 2u * pp + 2u) { u2 = fma(wb.x, tc, u2); u3 = fma(wb.y, td, u3); }
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(wa), "=d"(wb) : "r"(wq_s + 16u * (pp * (33u - pp) + r0)) : "memory");
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(wc), "=d"(wd) : "r"(wq_s + 16u * ((pp + 1u) * (32u - pp) + r1)) : "memory");
+        const double f0 = lane >= 2u * pp ? 1.0 : 0.0, f1 = lane >= 2u * pp + 2u ? 1.0 : 0.0;
+        u0 = fma(wa * f0, ta, u0);
+        u1 = fma(wb * f0, tb, u1);
+        u2 = fma(wc * f1, tc, u2);
+        u3 = fma(wd * f1, td, u3);
       }
+      (void)hd3;
       const double x = (u0 + u1) + (u2 + u3);
       if (nbuf == 1u && k + 1u < nch) {   // one buffer: every lane has read this chunk's blob; copy the next one
         __syncwarp();
@@ -851,7 +865,7 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
           bulk_g2s(buf, P.blobB + o0, (uint32_t)(o1 - o0), full);
         }
       }
-      win[(32u * k + lane) & wmask] = x;
+      sts_f64(win_s + 8u * ((32u * k + lane) & wmask), x);
       if (valid) {
         __stcg(P.out + i, x);
         if (P.dotvec && i < P.dot_limit) dot = fma(x, P.dotvec[i], dot);
