@@ -57,22 +57,19 @@ __host__ __device__ __forceinline__ uint32_t rec_batches(uint32_t nslots) { retu
 //     x_k = Winv_k (t'_k - L_rec x_rec) = u_k - M_k x_rec ,   u_k = Winv_k t'_k ,   M_k = Winv_k L_rec  (32 x ncol, dense)
 // so the chain's hop is ONE dense panel apply by one warp; the mat-vec with Winv_k moves off the chain to the near helper.
 // Blob A: 16 B header {batches, rows, columns, 0} | TAIL = the 4 batches of the newest 16 columns: 4 x 4 window byte
-// offsets (u32), 4 x 1024 B of panel values, batch-wise [column pair q][row] double2 | Winv_k, full 32 x 32, [column pair]
-// [row] double2 (the chain warp that owns the chunk applies it to t'_k ahead of its turn) | BODY = the older batches (an
-// even number): offsets, then values.  Column order is ascending over body-then-tail; padding columns come FIRST (value
-// 0, offset of the zero slot behind the window), so the tail always holds the newest columns at fixed offsets.
-// Blob B: the near helper's entries (early jagged diagonals + late ELL) as before.  Warp-per-block levels: blob A is a
-// bare header and blob B ends with Winv_k as a packed lower triangle.
+// offsets (u32), 4 x 1024 B of panel values, batch-wise [column pair q][row] double2 | BODY = the older batches (an even
+// number): offsets, then values.  Column order is ascending over body-then-tail; padding columns come FIRST (value 0,
+// offset of the zero slot behind the window), so the tail always holds the newest columns at fixed offsets.
+// Blob B: as before, then Winv_k as a packed lower triangle.
 constexpr uint32_t FC_MINB = 4;              // tail batches (register-resident in the chain warp)
-constexpr uint32_t FC_WOFF = 16u + 1040u * FC_MINB;    // header + tail: byte offset of Winv
-constexpr uint32_t FC_TAILB = FC_WOFF + BC_WBYTES;     // byte offset of the body
+constexpr uint32_t FC_TAILB = 16u + 1040u * FC_MINB;   // header + tail: byte offset of the body
 constexpr uint32_t FC_KRMAX = 8;             // fold depth limit (bitmap of 32*Kr candidate columns)
 constexpr uint32_t FC_COLCAP = 32;           // panel columns per chunk beyond the previous chunk's (chunk_fold_depth)
 constexpr uint32_t FC_WPACK = 4352;          // packed Winv: pair p holds rows 2p..31 -> 16 * sum(32 - 2p) bytes
 __host__ __device__ __forceinline__ uint32_t fold_batches(uint32_t ncol) {   // tail + an even number of body batches
   return ncol <= 4u * FC_MINB ? FC_MINB : FC_MINB + 2u * ((ncol - 4u * FC_MINB + 7u) / 8u);
 }
-__host__ __device__ __forceinline__ uint32_t fold_bytesA(uint32_t ncb) { return 16u + 1040u * ncb + BC_WBYTES; }
+__host__ __device__ __forceinline__ uint32_t fold_bytesA(uint32_t ncb) { return 16u + 1040u * ncb; }
 // byte offset of the double2 {Winv[row][2p], Winv[row][2p+1]} (row >= 2p) inside the packed triangle
 __host__ __device__ __forceinline__ uint32_t wp_pair_off(uint32_t p, uint32_t row) { return 16u * (p * (33u - p) + row - 2u * p); }
 
@@ -301,7 +298,7 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     if (lane == 0) {
       const uint32_t bbytes = BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot) + 320u * nl;
       sizeA[gc] = g.wb[b] ? 16 : g.fold ? (int64_t)fold_bytesA(fold_batches(ncol)) : (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
-      sizeB[gc] = (int64_t)(bbytes + (g.wb[b] ? FC_WPACK : 0u));
+      sizeB[gc] = (int64_t)(bbytes + (g.fold ? FC_WPACK : 0u));
       if (need) atomicMax(&tile_need[g.tile0[b] + k / g.tile[b]], need);
     }
   }
@@ -424,11 +421,6 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
         unsigned char *v = bt < nbody ? A + FC_TAILB + 16u * nbody + 1024u * bt : A + 16u + 16u * FC_MINB + 1024u * (bt - nbody);
         return reinterpret_cast<double *>(v + 512u * ((ci_ >> 1) & 1u) + 16u * row_) + (ci_ & 1u);
       };
-      for (uint32_t pp = 0; pp < 16u; pp++) {   // Winv for the chain warp that owns the chunk
-        double *dst = reinterpret_cast<double *>(A + FC_WOFF + w_pair_off(pp, lane));
-        dst[0] = Wm[lane][2u * pp];
-        dst[1] = Wm[lane][2u * pp + 1u];
-      }
       if (lane == 0) {
         uint32_t *hd = reinterpret_cast<uint32_t *>(A);
         hd[0] = ncb; hd[1] = nr; hd[2] = ncol; hd[3] = 0;
@@ -491,7 +483,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
         lv[s * 32u + lane] = have ? val[r.p_early + s] : 0.0;
         lc[s * 32u + lane] = have ? (uint16_t)((col[r.p_early + s] - blo) & wmask) : (uint16_t)(wmask + 1u);
       }
-      if (g.wb[b]) {   // warp-per-block levels: Winv, packed lower triangle, behind the late entries
+      if (g.fold) {   // Winv, packed lower triangle, behind the late entries
         unsigned char *Wq = reinterpret_cast<unsigned char *>(lv) + 320u * nl;
         for (uint32_t pp = 0; pp < 16u; pp++)
           if (lane >= 2u * pp) {

@@ -11,8 +11,7 @@ FC_MINB, FC_WPACK = 4, 4352          # folded layout (chain_mode 5, rcg_fold.cuh
 FC_COLCAP = 32                       # panel columns per chunk beyond the previous chunk's (chunk_fold_depth)
 
 
-FC_WOFF = 16 + 1040 * FC_MINB        # header + tail (the newest 16 columns): byte offset of Winv (full, [pair][row] double2)
-FC_TAILB = FC_WOFF + WBYTES          # byte offset of the body
+FC_TAILB = 16 + 1040 * FC_MINB       # header + tail (the newest 16 columns): byte offset of the body
 
 
 def fold_batches(ncol):
@@ -21,7 +20,7 @@ def fold_batches(ncol):
 
 
 def fold_bytesA(ncb):
-    return 16 + 1040 * ncb + WBYTES
+    return 16 + 1040 * ncb
 
 
 def wp_pair_off(p, row):
@@ -40,19 +39,19 @@ def unpack_winv_packed(raw_bytes):
 
 
 def unpack_panel(a):
-    """Folded blob A -> (ncb, nr, ncol, window slots [4*ncb], panel values [32, 4*ncb], Winv or None)."""
+    """Folded blob A -> (ncb, nr, ncol, window slots [4*ncb], panel values [32, 4*ncb])."""
     ncb, nr, ncol = (int(v) for v in a[:12].view(np.uint32))
-    if ncb == 0:                      # block of a warp-per-block level: bare header, nothing folded, Winv in blob B
+    if ncb == 0:                      # block of a warp-per-block level: bare header, nothing folded
         assert len(a) == 16 and ncol == 0
-        return 0, nr, 0, np.zeros(0, np.int64), np.zeros((32, 0)), None
+        return 0, nr, 0, np.zeros(0, np.int64), np.zeros((32, 0))
     assert len(a) == fold_bytesA(ncb) and ncb == fold_batches(ncol)
     nbody = ncb - FC_MINB
     # column order: body batches first (oldest, padding in front), then the tail; the tail sits first in the blob
     offs = np.concatenate([a[FC_TAILB:FC_TAILB + 16 * nbody], a[16:16 + 16 * FC_MINB]]).view(np.uint32).astype(np.int64)
     assert np.all(offs % 8 == 0)
-    vals = np.concatenate([a[FC_TAILB + 16 * nbody:], a[16 + 16 * FC_MINB:FC_WOFF]]).view(np.float64).reshape(ncb, 2, 32, 2)
+    vals = np.concatenate([a[FC_TAILB + 16 * nbody:], a[16 + 16 * FC_MINB:FC_TAILB]]).view(np.float64).reshape(ncb, 2, 32, 2)
     M = vals.transpose(2, 0, 1, 3).reshape(32, 4 * ncb)                    # [batch][pair][row][2] -> [row][column]
-    return ncb, nr, ncol, offs // 8, M, unpack_winv(a[FC_WOFF:FC_TAILB].view(np.float64))
+    return ncb, nr, ncol, offs // 8, M
 
 
 def r16(v):
@@ -125,7 +124,7 @@ def solve_from_layout(lay, rhs, reversed_):
             o += r16(2 * ne_tot)
             lv = b[o: o + 256 * nl].view(np.float64).reshape(nl, 32)
             lc = b[o + 256 * nl: o + 320 * nl].view(np.uint16).astype(np.int64).reshape(nl, 32)
-            assert len(b) - (o + 320 * nl) in ((0, FC_WPACK) if fold else (0,)) and cnt.sum() == ne_tot
+            assert o + 320 * nl + (FC_WPACK if fold else 0) == len(b) and cnt.sum() == ne_tot
             ts = t0[perm]
             base = 0
             for s in range(ne_max):
@@ -138,11 +137,8 @@ def solve_from_layout(lay, rhs, reversed_):
             a = A[lay["offA"][g]: lay["offA"][g + 1]]
             if fold:
                 # ---- helper: u = Winv t ; chain: x = u - M x_rec (dense panel, blob A) ---------------------
-                ncb, nr, ncol, slots, M, W = unpack_panel(a)
-                if W is None:
-                    W = unpack_winv_packed(b[o + 320 * nl:])     # warp-per-block level
-                else:
-                    assert o + 320 * nl == len(b)
+                W = unpack_winv_packed(b[o + 320 * nl:])
+                ncb, nr, ncol, slots, M = unpack_panel(a)
                 assert nr == int(valid.sum())
                 npad = 4 * ncb - ncol
                 assert np.all(slots[:npad] == wrows) and not M[:, :npad].any(), "padding columns come first"

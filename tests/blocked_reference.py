@@ -4,7 +4,7 @@ tests/blocked_emulator.py, to exercise the algorithm on the CPU (-m "not gpu")."
 import numpy as np
 import scipy.sparse as sp
 
-from blocked_emulator import AHDR, BHDR, WBYTES, RBATCH, FC_WPACK, FC_MINB, FC_TAILB, FC_WOFF, FC_COLCAP, r16, w_pair_off, rec_batches, fold_batches, fold_bytesA, wp_pair_off
+from blocked_emulator import AHDR, BHDR, WBYTES, RBATCH, FC_WPACK, FC_MINB, FC_TAILB, FC_COLCAP, r16, w_pair_off, rec_batches, fold_batches, fold_bytesA, wp_pair_off
 
 
 def tree_depths(nb):
@@ -174,12 +174,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
                     vals[ci >> 2, (ci >> 1) & 1, :, ci & 1] = M[:, i]
                 # blob: header | tail offsets | tail values | body offsets | body values
                 a[16:16 + 16 * FC_MINB] = offs[4 * nbody:].view(np.uint8)
-                a[16 + 16 * FC_MINB:FC_WOFF] = vals[nbody:].reshape(-1).view(np.uint8)
-                wp = a[FC_WOFF:FC_TAILB].view(np.float64)                   # Winv for the chain warp that owns the chunk
-                for pp in range(16):
-                    for row in range(32):
-                        o_ = w_pair_off(pp, row) // 8
-                        wp[o_], wp[o_ + 1] = W[row, 2 * pp], W[row, 2 * pp + 1]
+                a[16 + 16 * FC_MINB:FC_TAILB] = vals[nbody:].reshape(-1).view(np.uint8)
                 a[FC_TAILB:FC_TAILB + 16 * nbody] = offs[:4 * nbody].view(np.uint8)
                 a[FC_TAILB + 16 * nbody:] = vals[:nbody].reshape(-1).view(np.uint8)
                 blobsA[g] = a
@@ -209,7 +204,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             order = sorted(range(32), key=lambda l: (-n_early[l], l))
             rank = np.zeros(32, np.int64)
             rank[order] = np.arange(32)
-            bb = np.zeros(BHDR + r16(ne_max) + r16(8 * ne_tot) + r16(2 * ne_tot) + 320 * nl + (FC_WPACK if wb_of[b] else 0), np.uint8)
+            bb = np.zeros(BHDR + r16(ne_max) + r16(8 * ne_tot) + r16(2 * ne_tot) + 320 * nl + (FC_WPACK if fold else 0), np.uint8)
             bb[:16].view(np.uint32)[:] = [ne_max, ne_tot, nl, Dk]
             bb[16:48] = order
             bb[48:80] = rank
@@ -220,7 +215,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             o += r16(2 * ne_tot)
             lv = bb[o: o + 256 * nl].view(np.float64).reshape(nl, 32)
             lc = bb[o + 256 * nl: o + 320 * nl].view(np.uint16).reshape(nl, 32)
-            if wb_of[b]:
+            if fold:
                 wq = bb[o + 320 * nl:].view(np.float64)
                 for pp in range(16):
                     for row in range(2 * pp, 32):
@@ -278,7 +273,7 @@ def compare_layouts(dev, ref, val_tol=1e-12):
             nbody = ncb - FC_MINB
             for lo_, hi_ in ((16, 16 + 16 * FC_MINB), (FC_TAILB, FC_TAILB + 16 * nbody)):
                 assert np.array_equal(a[lo_:hi_], r[lo_:hi_]), ("panel columns", g)
-            for lo_, hi_ in ((16 + 16 * FC_MINB, FC_WOFF), (FC_WOFF, FC_TAILB), (FC_TAILB + 16 * nbody, len(r))):
+            for lo_, hi_ in ((16 + 16 * FC_MINB, FC_TAILB), (FC_TAILB + 16 * nbody, len(r))):
                 md, mr = a[lo_:hi_].view(np.float64), r[lo_:hi_].view(np.float64)
                 if len(mr):
                     assert np.abs(md - mr).max() <= val_tol * max(1.0, np.abs(mr).max()), ("panel", g)
@@ -297,7 +292,7 @@ def compare_layouts(dev, ref, val_tol=1e-12):
         assert np.array_equal(b[o:o + 2 * ne_tot], rb[o:o + 2 * ne_tot]), ("early col", g)
         o += r16(2 * ne_tot)
         assert np.array_equal(b[o:o + 320 * nl], rb[o:o + 320 * nl]), ("late", g)
-        if ref.get("fold") and len(rb) > o + 320 * nl:
+        if ref.get("fold"):
             wd, wr = b[o + 320 * nl:].view(np.float64), rb[o + 320 * nl:].view(np.float64)
             assert len(wd) == len(wr) == FC_WPACK // 8
             assert np.abs(wd - wr).max() <= val_tol * max(1.0, np.abs(wr).max()), ("Winv packed", g)
