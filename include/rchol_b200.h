@@ -48,12 +48,14 @@ typedef struct rcg_options {
   int use_graph;           /* 1 = replay one CUDA graph per PCG iteration (default), 0 = plain launches   */
   int spmv_lanes;          /* lanes per row of the CSR SpMV (0 = choose from the row-length histogram)     */
   int chain_generic;       /* 1 = force the non-pipelined fallback kernel of the triangular solve (testing)  */
-  int chain_mode;          /* 0 (= 5, default): folded chain -- recent entries folded into dense panels at set-up, three chain warps
-                              taking turns -- for tree levels with few blocks, one warp per block for levels with many blocks
-                              (rcg_fold.cuh); 6 = the round-1 blocked-inverse chain (four critical warps, one named barrier per
-                              chunk), 3 = the same with one critical warp, 4 = the same with the leaf level on the cluster chain
-                              (128-row chunks, 4 CTAs per leaf, DSMEM exchange), 1 / 2 = level-space sync-free kernels
-                              (rcg_trisolve.cu).  Modes other than 0 are kept for A/B measurements.                            */
+  int chain_mode;          /* 0 (default): tree levels with few blocks on the blocked-inverse chain (k_bc_solve: four critical warps, one
+                              named barrier per 32-row chunk), tree levels with many blocks (>= 64, reserved[9]) one warp per block
+                              (k_wb_pre + k_wb_solve, rcg_fold.cuh); 5 = the same with the few-block levels on the folded chain
+                              (k_fc_solve: recent entries folded into dense panels at set-up, three chain warps taking turns);
+                              6 = the blocked-inverse chain for every level (round 1), 3 = the same with one critical warp, 4 = the
+                              same with the leaf level on the cluster chain (128-row chunks, 4 CTAs per leaf, DSMEM exchange),
+                              1 / 2 = level-space sync-free kernels (rcg_trisolve.cu).  Modes other than 0 are kept for A/B
+                              measurements.                                                                                     */
   int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2),
                               [3] blocked solve: recent chunk distance Kr (default 2), [4] window rows of the separator blocks
                               (default 1024), [5] blocked solve: distance E (chunks) that separates the "early" from the "late" entries:

@@ -464,7 +464,17 @@ int rcg_get_stats(rcg_handle *h, rcg_stats *out) {
   out->tree_levels = (uint64_t)h->tree_levels;
   size_t dev = 0;
   if (h->haveA) dev += sizeof(int64_t) * (h->N + 1) + (size_t)h->A.nnz * 12;
-  if (h->haveG) dev += 2 * (sizeof(int64_t) * (2 * h->N + 1) + (size_t)h->nnzG * 12);
+  if (h->haveG)
+    for (const DirectionDev *d : {&h->fwd, &h->bwd}) {
+      const BlockedDev &B = d->bc;
+      if (B.on) {   // blocked layouts: chain blobs, far entries, start vector, flags, block table
+        dev += (size_t)B.bytesA + (size_t)B.bytesB + 512 + 2 * sizeof(int64_t) * ((size_t)B.nchunks + 1);
+        dev += sizeof(int64_t) * (h->N + 1) + (size_t)B.far.nnz * 12 + sizeof(uint32_t) * (h->N + 1);
+        dev += sizeof(double) * (h->N + 4) + sizeof(uint32_t) * ((size_t)B.ntiles * 2 + B.nblocks + 4) + sizeof(BcBlock) * B.nblocks;
+      } else {      // level-space layout
+        dev += sizeof(int64_t) * (2 * h->N + 1) + (size_t)h->nnzG * 12;
+      }
+    }
   if (h->b) dev += sizeof(double) * h->N * 8;
   out->device_bytes = dev;
   if (h->clk_probe) {
@@ -474,7 +484,6 @@ int rcg_get_stats(rcg_handle *h, rcg_stats *out) {
     out->reserved[1] = (double)ck[2];                              // 1 + row of a dependency-wait time-out (0 = none)
     for (int i = 0; i < 4; i++) out->reserved[4 + i] = (double)ck[3 + i];   // diagnostics of the critical warp (cycles)
     h->dbg_nbatch = (double)ck[7];
-    out->kernel_launches = out->kernel_launches;
   }
   return RCG_OK;
 }

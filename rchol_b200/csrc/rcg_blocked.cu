@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     if (lane == 0) {
       const uint32_t bbytes = BC_BHDR + r16(ne_max) + r16(8u * ne_tot) + r16(2u * ne_tot) + 320u * nl;
       sizeA[gc] = g.wb[b] ? 16 : g.fold ? (int64_t)fold_bytesA(fold_batches(ncol)) : (int64_t)(BC_AHDR + BC_WBYTES + BC_RBATCH * rec_batches(nslots));
-      sizeB[gc] = (int64_t)(bbytes + (g.fold ? FC_WPACK : 0u));
+      sizeB[gc] = (int64_t)(bbytes + ((g.fold || g.wb[b]) ? FC_WPACK : 0u));
       if (need) atomicMax(&tile_need[g.tile0[b] + k / g.tile[b]], need);
     }
   }
@@ -364,7 +364,13 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
       Wm[i][lane] = s;
       __syncwarp();
     }
-    if (!g.fold) {
+    if (g.wb[b]) {
+      // ---- warp-per-block level: no chain, no panel; the warp that owns the block applies everything ---------------
+      if (lane == 0) {
+        uint32_t *hd = reinterpret_cast<uint32_t *>(A);
+        hd[0] = 0; hd[1] = nr; hd[2] = 0; hd[3] = 0;
+      }
+    } else if (!g.fold) {
       unsigned char *Wp = A + BC_AHDR;
       for (uint32_t pp = 0; pp < 16u; pp++) {
         double *dst = reinterpret_cast<double *>(Wp + w_pair_off(pp, lane));
@@ -388,12 +394,6 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
           reinterpret_cast<uint32_t *>(R + 2048u + 32u * lane + 16u * (u >> 2))[u & 3u] =
               8u * (have ? ((col[r.p_late + sidx] - blo) & wmask) : (wmask + 1u));
         }
-      }
-    } else if (g.wb[b]) {
-      // ---- warp-per-block level: no chain, no panel; the warp that owns the block applies everything ---------------
-      if (lane == 0) {
-        uint32_t *hd = reinterpret_cast<uint32_t *>(A);
-        hd[0] = 0; hd[1] = nr; hd[2] = 0; hd[3] = 0;
       }
     } else {
       // ---- folded panel M = Winv * L_rec, one dense column per distinct recent column (ascending) ----------
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
         lv[s * 32u + lane] = have ? val[r.p_early + s] : 0.0;
         lc[s * 32u + lane] = have ? (uint16_t)((col[r.p_early + s] - blo) & wmask) : (uint16_t)(wmask + 1u);
       }
-      if (g.fold) {   // Winv, packed lower triangle, behind the late entries
+      if (g.fold || g.wb[b]) {   // Winv, packed lower triangle, behind the late entries (near helper / the block's warp)
         unsigned char *Wq = reinterpret_cast<unsigned char *>(lv) + 320u * nl;
         for (uint32_t pp = 0; pp < 16u; pp++)
           if (lane >= 2u * pp) {
@@ -1313,7 +1313,11 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   const int nb = (int)bounds.size() - 1;
   // ---- thresholds ------------------------------------------------------------------------------------
   // (the split chain keeps the solution of two chunks in its partial-sum buffers: recent distance at most 2)
-  B.fold = h->opt.chain_mode == 0 || h->opt.chain_mode == 5;   // default: folded chain + warp-per-block levels
+  // chain_mode 0 (default): round-1 blocked chain (four critical warps) for the tree levels with few blocks -- measured 15 %
+  // faster per chunk than the folded chain -- and warp-per-block launches for the levels with many blocks; 5: folded chain
+  // + warp-per-block levels; 6: round-1 chain for every level
+  B.fold = h->opt.chain_mode == 5;
+  const bool wb_allowed = h->opt.chain_mode == 0 || h->opt.chain_mode == 5;
   B.Kr = h->opt.reserved[3] > 0 ? (uint32_t)std::min(h->opt.reserved[3], h->opt.chain_mode == 3 ? 4 : 2) : 2u;
   // folded chain: Kr is the fold depth (chunks whose entries become dense panel columns); it is also the slack, in hops,
   // that the near helper has to deliver u_k after the chain solved chunk k-Kr-1
@@ -1354,7 +1358,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   std::vector<uint32_t> krblk(nb + 1, B.Kr), wbblk(nb + 1, 0);
   {
     const int wb_opt = (h->opt.reserved[9] >> 16) & 0xFFFF;   // reserved[9] bits 16-31: blocks per level from which the
-    B.wb_min = !B.fold || wb_opt == 0xFFFF ? 0u : wb_opt > 0 ? (uint32_t)wb_opt : 64u;   // level is warp-per-block (0xFFFF: never)
+    B.wb_min = !wb_allowed || wb_opt == 0xFFFF ? 0u : wb_opt > 0 ? (uint32_t)wb_opt : 64u;   // level is warp-per-block (0xFFFF: never)
     // window of a warp-per-block level: 2048 rows.  Older entries of the own block are gathered from HBM/L2 by the block's
     // warp, one dependent round trip after the other (measured at 256^3 / T=512 with a 1024-row window: the plane
     // neighbours of a 32^3 leaf sit ~1024 rows back, 40 % of the factor was "far" and a chunk took 9600 cycles)

@@ -71,6 +71,12 @@ int rcg_nccl_unique_id(void *out128) {
 
 int rcg_dist_init(rcg_handle *h, int nranks, int rank, const void *unique_id128, uint64_t n_sub, int top_depth) {
   if (!h || nranks < 1 || rank < 0 || rank >= nranks || !unique_id128) return RCG_ERR_INVALID;
+  if (n_sub >= 0xFFFFFFFFull) { h->err = "rcg_dist_init: n_sub does not fit 32 bits"; return RCG_ERR_INVALID; }
+  // call order: before the matrices / vectors exist (their sizes depend on the layout) and only once per handle
+  if (h->dist.comm || h->haveA || h->haveG || h->b) {
+    h->err = "rcg_dist_init must be the first call on a handle (before rcg_set_matrix / rcg_set_factor), once";
+    return RCG_ERR_STATE;
+  }
   if (!load_nccl(h->err)) return RCG_ERR_CUDA;
   RCG_CUDA(h, cudaSetDevice(h->device));
   nccl_unique_id id;

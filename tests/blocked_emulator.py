@@ -124,7 +124,9 @@ def solve_from_layout(lay, rhs, reversed_):
             o += r16(2 * ne_tot)
             lv = b[o: o + 256 * nl].view(np.float64).reshape(nl, 32)
             lc = b[o + 256 * nl: o + 320 * nl].view(np.uint16).astype(np.int64).reshape(nl, 32)
-            assert o + 320 * nl + (FC_WPACK if fold else 0) == len(b) and cnt.sum() == ne_tot
+            a = A[lay["offA"][g]: lay["offA"][g + 1]]
+            wb_chunk = len(a) == 16           # block of a warp-per-block level: bare header in blob A, Winv packed in blob B
+            assert o + 320 * nl + (FC_WPACK if (fold or wb_chunk) else 0) == len(b) and cnt.sum() == ne_tot
             ts = t0[perm]
             base = 0
             for s in range(ne_max):
@@ -134,8 +136,7 @@ def solve_from_layout(lay, rhs, reversed_):
             t = ts[rank]
             for s in range(nl):
                 t -= lv[s] * win[lc[s]]
-            a = A[lay["offA"][g]: lay["offA"][g + 1]]
-            if fold:
+            if fold or wb_chunk:
                 # ---- helper: u = Winv t ; chain: x = u - M x_rec (dense panel, blob A) ---------------------
                 W = unpack_winv_packed(b[o + 320 * nl:])
                 ncb, nr, ncol, slots, M = unpack_panel(a)

@@ -59,7 +59,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
     for b in range(nb):
         if bounds[b + 1] > bounds[b]:
             per_depth[int(depth[b])] = per_depth.get(int(depth[b]), 0) + 1
-    wb_of = [1 if fold and wb_min > 0 and per_depth.get(int(depth[b]), 0) >= wb_min else 0 for b in range(nb)]
+    wb_of = [1 if wb_min > 0 and per_depth.get(int(depth[b]), 0) >= wb_min else 0 for b in range(nb)]
     nch_depth = {}
     for b in range(nb):
         if bounds[b + 1] > bounds[b]:
@@ -204,7 +204,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             order = sorted(range(32), key=lambda l: (-n_early[l], l))
             rank = np.zeros(32, np.int64)
             rank[order] = np.arange(32)
-            bb = np.zeros(BHDR + r16(ne_max) + r16(8 * ne_tot) + r16(2 * ne_tot) + 320 * nl + (FC_WPACK if fold else 0), np.uint8)
+            bb = np.zeros(BHDR + r16(ne_max) + r16(8 * ne_tot) + r16(2 * ne_tot) + 320 * nl + (FC_WPACK if (fold or wb_of[b]) else 0), np.uint8)
             bb[:16].view(np.uint32)[:] = [ne_max, ne_tot, nl, Dk]
             bb[16:48] = order
             bb[48:80] = rank
@@ -215,7 +215,7 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
             o += r16(2 * ne_tot)
             lv = bb[o: o + 256 * nl].view(np.float64).reshape(nl, 32)
             lc = bb[o + 256 * nl: o + 320 * nl].view(np.uint16).reshape(nl, 32)
-            if fold:
+            if fold or wb_of[b]:
                 wq = bb[o + 320 * nl:].view(np.float64)
                 for pp in range(16):
                     for row in range(2 * pp, 32):
@@ -266,7 +266,7 @@ def compare_layouts(dev, ref, val_tol=1e-12):
     for g in range(ref["nchunks"]):
         a, r = dev["blobA"][ref["offA"][g]: ref["offA"][g + 1]], ref["blobA"][ref["offA"][g]: ref["offA"][g + 1]]
         assert np.array_equal(a[:12], r[:12]), ("A header", g)
-        if ref.get("fold") and len(r) == 16:
+        if len(r) == 16:
             assert len(a) == 16
         elif ref.get("fold"):
             ncb = int(r[:12].view(np.uint32)[0])
@@ -292,7 +292,7 @@ def compare_layouts(dev, ref, val_tol=1e-12):
         assert np.array_equal(b[o:o + 2 * ne_tot], rb[o:o + 2 * ne_tot]), ("early col", g)
         o += r16(2 * ne_tot)
         assert np.array_equal(b[o:o + 320 * nl], rb[o:o + 320 * nl]), ("late", g)
-        if ref.get("fold"):
+        if len(rb) > o + 320 * nl:
             wd, wr = b[o + 320 * nl:].view(np.float64), rb[o + 320 * nl:].view(np.float64)
             assert len(wd) == len(wr) == FC_WPACK // 8
             assert np.abs(wd - wr).max() <= val_tol * max(1.0, np.abs(wr).max()), ("Winv packed", g)

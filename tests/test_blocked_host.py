@@ -29,7 +29,7 @@ def test_tree_depths_follow_the_reference_post_order():
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 @pytest.mark.parametrize("kw", [dict(), dict(Kr=1, Dfar=32), dict(fold=True, Kr=3), dict(fold=True, Kr=1, Dfar=32),
-                                dict(fold=True, Kr=8, E=10), dict(fold=True, Kr=3, wb_min=2), dict(fold=True, Kr=2, wb_min=1, Dfar_wb=64)])
+                                dict(fold=True, Kr=8, E=10), dict(fold=True, Kr=3, wb_min=2), dict(fold=True, Kr=2, wb_min=1, Dfar_wb=64), dict(wb_min=2), dict(Kr=1, Dfar=32, wb_min=1)])
 def test_blocked_algorithm_on_goldens(name, kw):
     g = load_golden(name)
     part = g["part"] if len(g["part"]) > 2 else None

@@ -40,7 +40,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
     zo = oracle.trsv_backward(*G, yo)
-    with capi.Solver(0, chain_mode=6, **opts) as s:   # the round-1 blocked chain (the default is the folded chain: test_gpu_fold.py)
+    with capi.Solver(0, chain_mode=6, **opts) as s:   # the round-1 blocked chain (the default adds warp-per-block levels: test_gpu_fold.py)
         s.set_factor(*G, part)
         lay_f, lay_b = s.blocked_layout(capi.TRSV_FORWARD), s.blocked_layout(capi.TRSV_BACKWARD)
         assert lay_f["active"] and lay_b["active"] and lay_f["fold"] == 0

@@ -1,4 +1,6 @@
-"""GPU tests of the folded chain (chain_mode 5, rchol_b200/csrc/rcg_fold.cuh), through the C ABI.
+"""GPU tests of the folded chain and of the warp-per-block levels (rchol_b200/csrc/rcg_fold.cuh), through the C ABI.
+(chain_mode 5 = folded chain + warp-per-block levels; the default, chain_mode 0, pairs the round-1 chain with the
+warp-per-block levels: test_default_mode_* below.)
 
 The recent entries of every 32-row chunk are folded with the inverse of the chunk's diagonal block into a dense panel at
 set-up; the chain's hop is one panel apply by one warp, the mat-vec with the inverse moves to the near helpers.
@@ -130,3 +132,51 @@ def test_folded_chain_on_the_reference_goldens(capi, name):
         assert abs(itr - int(g["ref_itr"])) <= 1 and relres <= 2 * float(g["tol"])
         if itr == int(g["ref_itr"]):
             assert relerr(x, g["ref_x"]) <= 1e-9
+
+
+@needs_producer
+@pytest.mark.parametrize("kind,n,threads,opts", [("lap3d", 14, 4, dict(wb_min=2)), ("lap3d", 40, 8, dict(wb_min=4)),
+                                                 ("aniso2d", 64, 8, dict(wb_min=1, chain_window=1024)), ("lap3d", 33, 2, dict(wb_min=2, wb_ell=True))])
+def test_default_mode_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
+    """chain_mode 0: round-1 chain layout for the levels with few blocks, warp-per-block layout for the others."""
+    A, b, G, part, f = make_problem(kind, n, threads)
+    yo = oracle.trsv_forward(*G, b)
+    zo = oracle.trsv_backward(*G, yo)
+    with capi.Solver(0, **opts) as s:
+        s.set_factor(*G, part)
+        lay_f, lay_b = s.blocked_layout(capi.TRSV_FORWARD), s.blocked_layout(capi.TRSV_BACKWARD)
+        assert lay_f["active"] and lay_f["fold"] == 0 and lay_f["wb_min"] == opts["wb_min"]
+        kw = dict(Kr=lay_f["Kr"], E=lay_f["E"], Dfar=lay_f["Dfar"], Dfar_sep=lay_f["Dfar_sep"], tile_sep=lay_f["tile_sep"],
+                  E_sep=lay_f["E_sep"], fold=False, wb_min=lay_f["wb_min"], Dfar_wb=lay_f["Dfar_wb"], wb_jagged=not opts.get("wb_ell", False))
+        L, bounds, depth = direction_matrix(G, part, False)
+        compare_layouts(lay_f, build_layout(L, bounds, depth, False, **kw))
+        L, bounds, depth = direction_matrix(G, part, True)
+        compare_layouts(lay_b, build_layout(L, bounds, depth, True, reversed_=True, **kw))
+        ye, _ = solve_from_layout(lay_f, b, False)
+        assert relerr(ye, yo) <= TRSV_TOL
+        ze, _ = solve_from_layout(lay_b, yo, True)
+        assert relerr(ze, zo) <= TRSV_TOL
+        assert relerr(s.trsv(capi.TRSV_FORWARD, b), yo) <= TRSV_TOL
+        assert relerr(s.trsv(capi.TRSV_BACKWARD, yo), zo) <= TRSV_TOL
+
+
+@needs_producer
+@pytest.mark.parametrize("kind,n,threads,opts", [("lap3d", 48, 256, dict()), ("lap3d", 64, 8, dict(wb_min=8)), ("lap3d", 40, 8, dict(wb_min=2)),
+                                                 ("aniso2d", 256, 64, dict()), ("lap3d", 64, 0, dict(wb_min=1)), ("lap3d", 40, 8, dict(wb_min=1, use_graph=False))])
+def test_default_mode_vs_oracle_and_repeatability(capi, oracle, kind, n, threads, opts):
+    A, b, G, part, f = make_problem(kind, n, threads)
+    yo = oracle.trsv_forward(*G, b)
+    zo = oracle.trsv_backward(*G, yo)
+    with capi.Solver(0, **opts) as s:
+        s.set_matrix(*A)
+        s.set_factor(*G, part)
+        assert relerr(s.trsv(capi.TRSV_FORWARD, b), yo) <= TRSV_TOL
+        assert relerr(s.trsv(capi.TRSV_BACKWARD, yo), zo) <= TRSV_TOL
+        z1 = s.precond(b)
+        z2 = s.precond(b)
+        assert relerr(z1, zo) <= TRSV_TOL and np.array_equal(z1, z2)
+        x, relres, itr = s.pcg(b, 1e-8, 500)
+        x2, relres2, itr2 = s.pcg(b, 1e-8, 500)
+        o = oracle.pcg(A, b, 1e-8, 500, G)
+        assert abs(itr - o["itr"]) <= 1 and relres <= 2e-8
+        assert itr2 == itr and np.array_equal(x, x2)
