@@ -3,9 +3,13 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-Workload (BASELINE.json configs[1]): 3D 7-point Laplacian 256^3, reference `rchol(A, G, P, threads=8)` factorization
-(computed by the UNMODIFIED reference code on the host with a fixed seed -- an input, not timed), PCG to a relative
-residual of 1e-8.  A "step" is one full PCG solve.  The metric is the algorithmic memory traffic of the PCG iterations
+Workload: 3D 7-point Laplacian 256^3, reference `rchol(A, G, P, threads=T)` factorization with T = 4096 nested-dissection
+leaves (computed by the UNMODIFIED reference code on the host with a fixed seed -- an input, not timed), PCG to a relative
+residual of 1e-8.  This is BASELINE.json configs[2] ("2^k ND partition") at the largest grid whose reference factorization
+fits the GPU box: 512^3 needs ~280 GB of host memory (35 GB measured at 256^3, x8) and the box has 206 GB (DESIGN.md
+"Workload"); T is the best of the measured leaves sweep (profiles/r02_leaves_sweep_256.jsonl).  BASELINE.json configs[1]
+(the same grid with the reference example's 8-way partition) is measured beside it in the same line (`configs1`).
+A "step" is one full PCG solve.  The metric is the algorithmic memory traffic of the PCG iterations
 divided by the time they take: bytes per iteration (SURVEY.md 8d / BASELINE.md section 3)
     B_iter = 12 nnz(A) + 4 (N+1) + 2 [12 nnz(G) + 4 (N+1)] + 136 N
 times the iterations done, over the device time of the solve -- "GB/s per iteration vs the HBM roofline".
@@ -277,7 +281,9 @@ def run_reference_arm(args, d, B_iter, rank, world):
 def workload_config(args, d, N):
     return dict(workload=f"lap3d_{args.n}^3_rchol_T{args.threads}_pcg_tol1e-8", n=args.n, N=int(N),
                 nnzA=int(d["A_rp"][-1]), nnzG=int(d["G_rp"][-1]), nd_leaves=args.threads, tol=TOL, maxit=MAXIT,
-                factor_seed=SEED, l2_policy="inputs_exceed_l2 (A+G streamed per iteration >> 126 MB)")
+                factor_seed=SEED, l2_policy="inputs_exceed_l2 (A+G streamed per iteration >> 126 MB)",
+                baseline_config="configs[2] (2^k ND partition) at 256^3: the reference factorization of 512^3 needs ~280 GB of host "
+                                "memory, the GPU box has 206 GB; k = 12 from the measured leaves sweep; configs[1] (T=8) in `configs1`")
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -505,7 +511,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("RCHOL_B200_BENCH_N", 256)))
-    ap.add_argument("--threads", type=int, default=8, help="leaves of the reference's nested-dissection partition")
+    ap.add_argument("--threads", type=int, default=int(os.environ.get("RCHOL_B200_BENCH_T", 4096)),
+                    help="leaves of the reference's nested-dissection partition (2^k)")
     ap.add_argument("--sample-iters", type=int, default=4, help="PCG iterations per CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -532,6 +532,7 @@ struct BcArgs {
   uint32_t col_min;            // multi-GPU top separators: far columns below col_min are left out ...
   const double *corr;          // ... their sum over all ranks arrives here (indexed by vector index - col_min)
   unsigned int *abort_g;
+  uint32_t *ticket;            // warp-per-block levels: next block of the level (zeroed with the flags before the launch)
   unsigned long long *clk;     // nullable diagnostics
   uint32_t dbg;                // bit 0: cycle profile of the critical warp and of near helper 0 (CTA 0) into clk[3..12]
 };
@@ -1486,7 +1487,25 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       G.max_rows = std::max(G.max_rows, bd.hi - bd.lo);
       G.rows += bd.hi - bd.lo;
     }
-    if (G.count > 0) d.groups.push_back(G);
+    if (G.count > 0) {
+      if ((B.blocks_host[G.first].pad[2] >> 16) & 1u) {   // warp-per-block level: longest block first (dynamic hand-out)
+        std::vector<size_t> ord(G.count);
+        for (int q = 0; q < G.count; q++) ord[q] = q;
+        std::stable_sort(ord.begin(), ord.end(), [&](size_t x, size_t y) {
+          const BcBlock &bx = B.blocks_host[G.first + x], &by = B.blocks_host[G.first + y];
+          return bx.hi - bx.lo > by.hi - by.lo;
+        });
+        std::vector<BcBlock> tmpb(G.count);
+        std::vector<int> tmps(G.count);
+        for (int q = 0; q < G.count; q++) { tmpb[q] = B.blocks_host[G.first + ord[q]]; tmps[q] = src_block[G.first + ord[q]]; }
+        for (int q = 0; q < G.count; q++) {
+          tmpb[q].gidx = (uint32_t)(G.first + q);
+          B.blocks_host[G.first + q] = tmpb[q];
+          src_block[G.first + q] = tmps[q];
+        }
+      }
+      d.groups.push_back(G);
+    }
   }
   B.nblocks = (uint32_t)B.blocks_host.size();
   RCG_CUDA(h, cudaMalloc(&B.blocks, sizeof(BcBlock) * std::max<size_t>(1, B.blocks_host.size())));
@@ -1563,6 +1582,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       L.SA = wbw;   // (warp-per-block levels have no rings: the fields carry the warps per CTA and the buffers per warp)
       L.SB = nbuf;
       L.smem = (size_t)wbw * wb_warp_bytes(Wwb, L.capB, nbuf);
+      L.wbocc = std::max<uint32_t>(1u, (uint32_t)((int64_t)BC_SMEM_MAX / (int64_t)(L.smem + 1024)));   // resident CTAs per SM
       L.groups = (uint32_t)((G.count + wbw - 1) / wbw);
       B.levels.push_back(L);
       continue;
@@ -1694,8 +1714,10 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     a.dbg = (uint32_t)h->opt.reserved[1];
     if (L.wb) {   // warp-per-block level: fully parallel pre-pass over the entries of other blocks, then one warp per block
       const uint32_t pre_grid = std::min<uint32_t>((uint32_t)G.count, (uint32_t)h->sm_count * 8u);
+      a.ticket = B.flags + B.ntiles + B.nblocks + gi % 4;   // (four spare words behind the flags: consecutive levels never share one)
+      RCG_CUDA(h, cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), h->stream));
       k_wb_pre<<<pre_grid, 256, 0, h->stream>>>(a);
-      k_wb_solve<<<L.groups, L.SA * 32, L.smem, h->stream>>>(a);
+      k_wb_solve<<<std::min<uint32_t>(L.groups, (uint32_t)h->sm_count * L.wbocc), L.SA * 32, L.smem, h->stream>>>(a);
       RCG_CUDA(h, cudaGetLastError());
       h->stats.kernel_launches += 2;
       continue;

@@ -83,6 +83,7 @@ struct BcLevel {               // per tree level: shared-memory plan of the laun
   uint32_t helpers = 0;        // far CTAs per chain CTA
   uint32_t Dfar = 0;           // window of the level's blocks in chunks
   bool wb = false;             // warp-per-block level: k_wb_pre + k_wb_solve instead of the chain kernel
+  uint32_t wbocc = 1;          // ... resident CTAs per SM (persistent grid: the warps take blocks from a ticket counter)
   size_t smem = 0;
 };
 

@@ -678,8 +678,14 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 1) k_wb_solve(const BcArgs P) {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
   uint32_t phase = 0u;   // bit q: parity of the next phase of staging barrier q
-  const uint32_t wpc = blockDim.x >> 5, nwarps = gridDim.x * wpc;
-  for (uint32_t bi = blockIdx.x * wpc + warp; bi < P.nblocks; bi += nwarps) {
+  // Blocks are handed out dynamically, longest first (the level's blocks are sorted by length at set-up; P.gprog[-1] ... the
+  // word behind the tile flags ... is the level's ticket counter, zeroed with the flags before every launch): leaves of a
+  // METIS partition differ 2x in length, and with a static assignment the longest block of a CTA set the pace.
+  for (;;) {
+    uint32_t bi = 0;
+    if (lane == 0u) bi = atomicAdd(P.ticket, 1u);
+    bi = __shfl_sync(0xffffffffu, bi, 0);
+    if (bi >= P.nblocks) break;
     const BcBlock b = P.blocks[bi];
     const uint32_t nch = (b.hi - b.lo + 31u) >> 5;
     double dot = 0.0;

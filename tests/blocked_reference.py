@@ -241,10 +241,12 @@ def build_layout(L, bounds, depth, root_first, Kr=2, E=16, Dfar=128, Dfar_sep=32
     blocks = []
     for gl in range(max_depth + 1):
         want = gl if root_first else max_depth - gl
-        for b in range(nb):
-            if depth[b] == want and bounds[b + 1] > bounds[b]:
-                blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], tile_of[b],
-                               e_of[b] | (kr_of[b] << 8) | (wb_of[b] << 16)])
+        level = [b for b in range(nb) if depth[b] == want and bounds[b + 1] > bounds[b]]
+        if level and wb_of[level[0]]:     # warp-per-block level: longest block first (dynamic hand-out), stable
+            level.sort(key=lambda b: -(int(bounds[b + 1]) - int(bounds[b])))
+        for b in level:
+            blocks.append([bounds[b], bounds[b + 1], chunk0[b], tile0[b], len(blocks), dfar_of[b], tile_of[b],
+                           e_of[b] | (kr_of[b] << 8) | (wb_of[b] << 16)])
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if len(xs) else np.zeros(0, dt)
     return dict(fold=int(fold), active=1, nchunks=nchunks, ntiles=ntiles, nblocks=len(blocks), N=N, Kr=Kr, E=E, Dfar=Dfar_leaf, Dfar_sep=Dfar_sep,
                 offA=offA, offB=offB, blobA=cat(blobsA, np.uint8), blobB=cat(blobsB, np.uint8), far_rp=far_rp,
