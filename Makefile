@@ -10,7 +10,7 @@ LIB      := rchol_b200/lib/librchol_b200.so
 
 all: $(LIB) cxx
 
-%.o: %.cu rchol_b200/csrc/rcg_common.cuh rchol_b200/csrc/rcg_device.cuh rchol_b200/csrc/rcg_cluster.cuh rchol_b200/csrc/rcg_fold.cuh include/rchol_b200.h
+%.o: %.cu rchol_b200/csrc/rcg_common.cuh rchol_b200/csrc/rcg_device.cuh rchol_b200/csrc/rcg_cluster.cuh rchol_b200/csrc/rcg_fold.cuh rchol_b200/csrc/rcg_dense.cuh include/rchol_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJ)

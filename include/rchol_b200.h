@@ -198,6 +198,7 @@ int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16);
    *nblocks = 0 when the factor is solved as one block. */
 int rcg_detect_blocks(uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, uint64_t *bounds_out, int32_t *depth_out,
                       uint64_t cap, uint64_t *nblocks);
+int rcg_debug_dp_trace(rcg_handle *h, uint64_t *out, uint64_t nwords);   /* per-warp time marks of one hop of the last dense-panel launch (reserved[1] bit 1): [CTA][32 warps][16] */
 int rcg_debug_counters(rcg_handle *h, uint64_t *out16);   /* raw cycle counters of the last chain kernel (rcg_options.reserved[1] bit 0) */
 int rcg_debug_blocked_copy(rcg_handle *h, int direction, int what, void *dst, uint64_t bytes);
 

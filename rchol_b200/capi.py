@@ -26,7 +26,7 @@ EXPORTED = [
     "rcg_get_stats", "rcg_profile_iteration", "rcg_time_phase", "rcg_debug_trace",
     "rcg_get_group_count", "rcg_get_group_info", "rcg_time_group",
     "rcg_set_factor_blocks", "rcg_nccl_unique_id", "rcg_dist_init", "rcg_dist_finalize",
-    "rcg_debug_blocked_info", "rcg_debug_blocked_copy", "rcg_debug_counters",
+    "rcg_debug_blocked_info", "rcg_debug_blocked_copy", "rcg_debug_counters", "rcg_debug_dp_trace",
     "rcg_set_matrix_permuted", "rcg_set_permutation", "rcg_permute_vector", "rcg_unpermute_vector",
     "rcg_pcg_original", "rcg_get_matrix", "rcg_detect_blocks",
 ]
@@ -110,6 +110,7 @@ def load():
     L.rcg_debug_blocked_info.argtypes = [H, C.c_int, C.POINTER(C.c_uint64)]
     L.rcg_debug_blocked_copy.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
     L.rcg_debug_counters.argtypes = [H, C.POINTER(C.c_uint64)]
+    L.rcg_debug_dp_trace.argtypes = [H, C.c_void_p, C.c_uint64]
     L.rcg_set_matrix_permuted.argtypes = [H, C.c_uint64, _u64p, _u64p, _f64p, _u64p]
     L.rcg_set_permutation.argtypes = [H, C.c_uint64, _u64p]
     L.rcg_permute_vector.argtypes = [H, _f64p, _f64p]
@@ -140,7 +141,7 @@ class Solver:
     def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
                  spmv_lanes: int = 0, chain_generic: bool = False, chain_mode: int = 0, backoff_ns: int = 0, dbg: int = 0, producers: int = 0,
                  recent: int = 0, plain_launch: bool = False, sep_window: int = 0, early: int = 0, capb_quarters: int = 0, slots_a: int = 0, far_lanes2: int = 0, sep_tile: int = 0, early_sep: int = 0,
-                 wb_min: int = 0, wb_ell: bool = False):
+                 wb_min: int = 0, wb_ell: bool = False, dp_min_rows: int = 0, dp_panel: int = 0, dp_leaf: bool = False):
         self._L = load()
         self._h = C.c_void_p()
         opt = Options()
@@ -158,7 +159,11 @@ class Solver:
         opt.reserved[8] = int(slots_a)
         # wb_min: tree levels with at least this many blocks are solved warp-per-block (0 = default 64, -1 = never)
         opt.reserved[9] = int(far_lanes2) | (int(sep_tile) << 8) | ((0xFFFF if wb_min < 0 else int(wb_min)) << 16)
-        opt.reserved[6] = int(bool(plain_launch))
+        # dense-panel levels: dp_min_rows = rows of a separator level's longest block from which the level is solved through
+        # inverted panels (0 = default 128, -1 = never; multiples of 32); dp_panel = panel rows (0 = from the level's shape);
+        # dp_leaf = the leaf level too
+        opt.reserved[6] = (int(bool(plain_launch)) | (2 if dp_leaf else 0) | ((255 if dp_min_rows < 0 else min(254, int(dp_min_rows) // 32)) << 8)
+                           | (int(dp_panel) << 16))
         rc = self._L.rcg_create_with_options(C.byref(self._h), int(device), C.byref(opt))
         if rc != 0:
             raise RcgError(rc, (self._L.rcg_last_error(None) or b"").decode())
@@ -321,6 +326,12 @@ class Solver:
         out = (C.c_uint64 * 16)()
         self._check(self._L.rcg_debug_counters(self._h, out))
         return [int(v) for v in out]
+
+    def dp_trace(self):
+        """[CTA][warp][16] clock64 marks of one hop of the last traced dense-panel launch (dbg bit 1)."""
+        a = np.zeros(160 * 32 * 16, dtype=np.uint64)
+        self._check(self._L.rcg_debug_dp_trace(self._h, a.ctypes.data_as(C.c_void_p), a.size))
+        return a.reshape(160, 32, 16)
 
     def cluster_levels(self, direction: int) -> int:
         """Tree levels of one direction that are launched on the cluster chain (chain_mode 4); 0 = 32-row chain everywhere."""

@@ -40,8 +40,9 @@ int ensure_vectors(rcg_handle *h) {
   RCG_CUDA(h, cudaMemsetAsync(h->partials, 0, sizeof(double) * (2 * (size_t)h->partial_cap + (size_t)h->rz_slots + 8), h->stream));
   RCG_CUDA(h, cudaMalloc(&h->counters, sizeof(unsigned int) * 8));
   RCG_CUDA(h, cudaMemsetAsync(h->counters, 0, sizeof(unsigned int) * 8, h->stream));
-  RCG_CUDA(h, cudaMalloc(&h->clk_probe, sizeof(unsigned long long) * 16));
-  RCG_CUDA(h, cudaMemsetAsync(h->clk_probe, 0, sizeof(unsigned long long) * 16, h->stream));
+  // 16 counters + the per-warp time marks of one hop of k_dp_solve (RCG_DP_TRACE_WORDS, rcg_debug_dp_trace)
+  RCG_CUDA(h, cudaMalloc(&h->clk_probe, sizeof(unsigned long long) * (16 + RCG_DP_TRACE_WORDS)));
+  RCG_CUDA(h, cudaMemsetAsync(h->clk_probe, 0, sizeof(unsigned long long) * (16 + RCG_DP_TRACE_WORDS), h->stream));
   if (!h->abort_flag) {
     RCG_CUDA(h, cudaMalloc(&h->abort_flag, sizeof(unsigned int) * 4));
     RCG_CUDA(h, cudaMemsetAsync(h->abort_flag, 0, sizeof(unsigned int) * 4, h->stream));
@@ -471,6 +472,9 @@ int rcg_get_stats(rcg_handle *h, rcg_stats *out) {
         dev += (size_t)B.bytesA + (size_t)B.bytesB + 512 + 2 * sizeof(int64_t) * ((size_t)B.nchunks + 1);
         dev += sizeof(int64_t) * (h->N + 1) + (size_t)B.far.nnz * 12 + sizeof(uint32_t) * (h->N + 1);
         dev += sizeof(double) * (h->N + 4) + sizeof(uint32_t) * ((size_t)B.ntiles * 2 + B.nblocks + 4) + sizeof(BcBlock) * B.nblocks;
+        if (B.dp.on)   // dense-panel levels: packed inverses, near rows, panel table
+          dev += sizeof(double) * (size_t)B.dp.inv_doubles + (size_t)B.dp.near.nnz * 12 + sizeof(int64_t) * ((size_t)B.dp.nrows + 4) +
+                 sizeof(DpPanel) * B.dp.npanels;
       } else {      // level-space layout
         dev += sizeof(int64_t) * (2 * h->N + 1) + (size_t)h->nnzG * 12;
       }
@@ -558,6 +562,16 @@ int rcg_debug_counters(rcg_handle *h, uint64_t *out16) {
   RCG_CUDA(h, cudaSetDevice(h->device));
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   RCG_CUDA(h, cudaMemcpy(out16, h->clk_probe, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
+  return RCG_OK;
+}
+
+// Time marks of the last traced k_dp_solve launch (rcg_options.reserved[1] bit 1): [CTA][warp][16] clock64 values.
+int rcg_debug_dp_trace(rcg_handle *h, uint64_t *out, uint64_t nwords) {
+  if (!h || !out) return RCG_ERR_INVALID;
+  if (!h->clk_probe) { memset(out, 0, sizeof(uint64_t) * nwords); return RCG_OK; }
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  RCG_CUDA(h, cudaMemcpy(out, h->clk_probe + 16, sizeof(uint64_t) * std::min<uint64_t>(nwords, RCG_DP_TRACE_WORDS), cudaMemcpyDeviceToHost));
   return RCG_OK;
 }
 

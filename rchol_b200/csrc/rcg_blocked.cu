@@ -191,6 +191,9 @@ struct BcGeom {               // blocks in ascending solve order (device arrays 
   const uint32_t *eblk;                             // early/late distance E, per block
   const uint32_t *krblk;                            // recent / fold depth Kr, per block (0 for warp-per-block levels)
   const uint32_t *wb;                               // 1: block of a warp-per-block level (k_wb_solve): blob A is a bare header
+  const uint32_t *dpc;                              // > 0: block of a dense-panel level (rcg_dense.cuh), panel rows C: no blobs, the
+                                                    // far row holds the entries of other blocks, the NEAR row (DenseDev::near, compact
+  const uint32_t *dpq0;                             // row index dpq0[b] + row - lo) the own-block entries left of the row's panel
   int nb;
   uint32_t Kr, E;
   uint32_t fold;                                    // 1: folded layout (panels in blob A, Winv in blob B)
@@ -265,10 +268,20 @@ __device__ __forceinline__ uint32_t chunk_fold_depth(const int64_t *__restrict__
   return D;
 }
 
+// first position p in [s, e) with col[p] >= c (rows are sorted by column)
+__device__ __forceinline__ int64_t lower_bound_col(const uint32_t *__restrict__ col, int64_t s, int64_t e, uint32_t c) {
+  while (s < e) {
+    const int64_t mid = (s + e) >> 1;
+    if (col[mid] < c) s = mid + 1; else e = mid;
+  }
+  return s;
+}
+
 // warp per chunk: blob sizes, far row lengths, far-tile requirements
 __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp, const uint32_t *__restrict__ col, BcGeom g,
                                                   uint32_t nchunks, int64_t *__restrict__ sizeA, int64_t *__restrict__ sizeB,
-                                                  int64_t *__restrict__ far_cnt, uint32_t *__restrict__ tile_need, int *err) {
+                                                  int64_t *__restrict__ far_cnt, uint32_t *__restrict__ tile_need, int *err,
+                                                  int64_t *__restrict__ near_cnt) {
   __shared__ uint32_t bm_all[8][FC_KRMAX];
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t wpc = blockDim.x >> 5;
@@ -279,6 +292,19 @@ __global__ void __launch_bounds__(256) k_bc_count(const int64_t *__restrict__ rp
     const uint32_t j = blo + 32u * k + lane;
     uint32_t n_rec = 0, n_late = 0, n_early = 0, need = 0;
     uint32_t ncol = 0, Dk = g.krblk[b];
+    if (g.dpc[b]) {   // dense-panel block: other blocks -> far row, own block left of the panel -> near row, the rest is inverted
+      if (j < bhi) {
+        const int64_t s = rp[j], pd = rp[j + 1] - 1;
+        if (pd < s || col[pd] != j) atomicExch(err, 1);
+        else {
+          const int64_t a = lower_bound_col(col, s, pd, blo);
+          far_cnt[j] = a - s;
+          near_cnt[g.dpq0[b] + (j - blo)] = lower_bound_col(col, a, pd, blo + ((j - blo) / g.dpc[b]) * g.dpc[b]) - a;
+        }
+      }
+      if (lane == 0) { sizeA[gc] = 0; sizeB[gc] = 0; }
+      continue;
+    }
     if (g.fold && !g.wb[b]) Dk = chunk_fold_depth(rp, col, j, j < bhi, blo, k, g.krblk[b], g.dfar[b], g.eblk[b], bm, lane, ncol);
     if (j < bhi) {
       const RowSplit r = split_row(rp, col, j, blo, k, Dk, g.dfar[b], g.eblk[b]);
@@ -310,7 +336,9 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
                                                  int reversed, const int64_t *__restrict__ offA, const int64_t *__restrict__ offB,
                                                  unsigned char *__restrict__ blobA, unsigned char *__restrict__ blobB,
                                                  const int64_t *__restrict__ far_rp, uint32_t *__restrict__ far_col,
-                                                 double *__restrict__ far_val, uint32_t *__restrict__ far_split) {
+                                                 double *__restrict__ far_val, uint32_t *__restrict__ far_split,
+                                                 const int64_t *__restrict__ near_rp, uint32_t *__restrict__ near_col,
+                                                 double *__restrict__ near_val) {
   __shared__ double Wm_all[4][32][33];
   __shared__ uint32_t bm_all[4][FC_KRMAX];
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -321,6 +349,24 @@ __global__ void __launch_bounds__(128) k_bc_fill(const int64_t *__restrict__ rp,
     const uint32_t k = gc - g.chunk0[b], blo = g.bounds[b], bhi = g.bounds[b + 1];
     const uint32_t j = blo + 32u * k + lane;
     const bool valid = j < bhi;
+    if (g.dpc[b]) {   // dense-panel block: the far and near rows only (their lengths were counted by k_bc_count)
+      if (valid) {
+        int64_t o = far_rp[j], p = rp[j];
+        const int64_t n = far_rp[j + 1] - o;
+        for (const int64_t pe = p + n; p < pe; p++, o++) {
+          far_col[o] = reversed ? N - 1u - col[p] : col[p];
+          far_val[o] = val[p];
+        }
+        far_split[j] = (uint32_t)n;
+        const uint32_t q = g.dpq0[b] + (j - blo);
+        o = near_rp[q];
+        for (const int64_t pe = p + (near_rp[q + 1] - o); p < pe; p++, o++) {
+          near_col[o] = reversed ? N - 1u - col[p] : col[p];
+          near_val[o] = val[p];
+        }
+      }
+      continue;
+    }
     const uint32_t nr = min(32u, bhi - (blo + 32u * k));
     RowSplit r;
     r.s = r.p_far = r.p_early = r.p_late = r.p_rec = r.p_diag = 0;
@@ -1289,6 +1335,7 @@ uint32_t floor_pow2_u32(uint32_t v) {
 
 #include "rcg_cluster.cuh"
 #include "rcg_fold.cuh"
+#include "rcg_dense.cuh"
 
 }  // namespace
 
@@ -1301,6 +1348,8 @@ void rcg_free_blocked(BlockedDev &b) {
   cudaFree(b.offA); cudaFree(b.offB); cudaFree(b.blobA); cudaFree(b.blobB);
   rcg_free_csr(b.far);
   cudaFree(b.tile_need); cudaFree(b.flags); cudaFree(b.w); cudaFree(b.blocks); cudaFree(b.far_split);
+  cudaFree(b.dp.panels); cudaFree(b.dp.hop_ptr); cudaFree(b.dp.inv); cudaFree(b.dp.bar);
+  rcg_free_csr(b.dp.near);
   cudaFree(b.cl.wslab); cudaFree(b.cl.blobN); cudaFree(b.cl.offN); cudaFree(b.cl.c0); cudaFree(b.cl.prog4);
   b = BlockedDev();
 }
@@ -1389,6 +1438,31 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
         wbblk[b] = 1; krblk[b] = 0; eblk[b] = h->opt.reserved[2] == 1 ? dw : 0u; dfar[b] = dw; tilesz[b] = B.tile_sep;
       }
   }
+  // Dense-panel levels (k_dp_solve, rcg_dense.cuh): every separator level whose longest block has at least dp_min rows is
+  // solved in lock step on the whole GPU through explicitly inverted C x C diagonal panels (C per level).
+  // reserved[6] bits 8-15: 0 = default (128 rows), 255 = never, else rows / 32; bits 16-31: panel rows (0 = from the level's
+  // shape, dp_choose_panel); bit 1: the leaf level too.
+  std::vector<uint32_t> dpcblk(nb + 1, 0), dpq0(nb + 1, 0);
+  int64_t dp_rows_total = 0;
+  {
+    const int dp_opt = (h->opt.reserved[6] >> 8) & 0xFF, dp_c = (h->opt.reserved[6] >> 16) & 0xFFFF;
+    const bool dp_leaf = (h->opt.reserved[6] & 2) != 0;
+    const uint32_t dp_min = !wb_allowed || dp_opt == 255 ? 0xFFFFFFFFu : dp_opt > 0 ? 32u * (uint32_t)dp_opt : 128u;
+    std::vector<uint32_t> mx(max_depth + 2, 0);
+    std::vector<int64_t> sum(max_depth + 2, 0);
+    for (int b = 0; b < nb; b++) {
+      mx[depth[b]] = std::max(mx[depth[b]], bounds[b + 1] - bounds[b]);
+      sum[depth[b]] += bounds[b + 1] - bounds[b];
+    }
+    for (int b = 0; b < nb; b++) {
+      const int dd = depth[b];
+      if ((dd == max_depth && !dp_leaf) || mx[dd] < dp_min || bounds[b + 1] == bounds[b]) continue;
+      dpcblk[b] = dp_choose_panel(mx[dd], sum[dd], dp_c);
+      dpq0[b] = (uint32_t)dp_rows_total;
+      dp_rows_total += bounds[b + 1] - bounds[b];
+      wbblk[b] = 0; krblk[b] = 0; dfar[b] = dpcblk[b]; tilesz[b] = B.tile_sep;
+    }
+  }
   for (int b = 0; b < nb; b++) {
     const uint32_t nch = (bounds[b + 1] - bounds[b] + 31u) / 32u;
     chunk0[b + 1] = chunk0[b] + nch;
@@ -1396,8 +1470,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   }
   B.nchunks = chunk0[nb];
   B.ntiles = tile0[nb];
-  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0 | dfar | tile size | E | Kr | warp-per-block flag
-  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 8 * (nb + 1)));
+  uint32_t *dgeom = nullptr;   // bounds | chunk0 | tile0 | dfar | tile size | E | Kr | warp-per-block flag | panel rows | first compact row
+  RCG_CUDA(h, cudaMalloc(&dgeom, sizeof(uint32_t) * 10 * (nb + 1)));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom + 9 * (nb + 1), dpq0.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
+  RCG_CUDA(h, cudaMemcpyAsync(dgeom + 8 * (nb + 1), dpcblk.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 7 * (nb + 1), wbblk.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 6 * (nb + 1), krblk.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(dgeom + 5 * (nb + 1), eblk.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, h->stream));
@@ -1413,6 +1489,8 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   g.eblk = dgeom + 5 * (nb + 1);
   g.krblk = dgeom + 6 * (nb + 1);
   g.wb = dgeom + 7 * (nb + 1);
+  g.dpc = dgeom + 8 * (nb + 1);
+  g.dpq0 = dgeom + 9 * (nb + 1);
   g.nb = nb; g.Kr = B.Kr; g.E = B.E;
   g.fold = B.fold ? 1u : 0u;
 
@@ -1428,9 +1506,12 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   RCG_CUDA(h, cudaMemsetAsync(B.offB, 0, sizeof(int64_t) * ((size_t)B.nchunks + 1), h->stream));
   RCG_CUDA(h, cudaMemsetAsync(B.far.rowptr, 0, sizeof(int64_t) * ((size_t)N + 1), h->stream));
   RCG_CUDA(h, cudaMemsetAsync(B.tile_need, 0, sizeof(uint32_t) * std::max(1u, B.ntiles), h->stream));
+  B.dp.nrows = dp_rows_total;
+  RCG_CUDA(h, cudaMalloc(&B.dp.near.rowptr, sizeof(int64_t) * ((size_t)dp_rows_total + 4)));
+  RCG_CUDA(h, cudaMemsetAsync(B.dp.near.rowptr, 0, sizeof(int64_t) * ((size_t)dp_rows_total + 4), h->stream));
   const int cgrid = (int)std::min<int64_t>(((int64_t)B.nchunks + 7) / 8, (int64_t)h->sm_count * 16);
   k_bc_count<<<std::max(1, cgrid), 256, 0, h->stream>>>(comb.rowptr, comb.col, g, B.nchunks, B.offA, B.offB, B.far.rowptr,
-                                                       B.tile_need, derr);
+                                                       B.tile_need, derr, B.dp.near.rowptr);
   h->stats.kernel_launches += 1;
   int herr = 0;
   RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1444,6 +1525,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   RCG_TRY(rcg_exclusive_scan(h, B.offA, (int64_t)B.nchunks + 1));
   RCG_TRY(rcg_exclusive_scan(h, B.offB, (int64_t)B.nchunks + 1));
   RCG_TRY(rcg_exclusive_scan(h, B.far.rowptr, (int64_t)N + 1));
+  RCG_TRY(rcg_exclusive_scan(h, B.dp.near.rowptr, dp_rows_total + 1));
+  RCG_CUDA(h, cudaMemcpy(&B.dp.near.nnz, B.dp.near.rowptr + dp_rows_total, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  RCG_CUDA(h, cudaMalloc(&B.dp.near.col, sizeof(uint32_t) * (size_t)(B.dp.near.nnz + 32)));
+  RCG_CUDA(h, cudaMalloc(&B.dp.near.val, sizeof(double) * (size_t)(B.dp.near.nnz + 16)));
   int64_t far_total = 0;
   RCG_CUDA(h, cudaMemcpy(&B.bytesA, B.offA + B.nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost));
   RCG_CUDA(h, cudaMemcpy(&B.bytesB, B.offB + B.nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -1459,7 +1544,8 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   RCG_CUDA(h, cudaMalloc(&B.far.val, sizeof(double) * (size_t)(far_total + 8)));
   const int fgrid = (int)std::min<int64_t>(((int64_t)B.nchunks + 3) / 4, (int64_t)h->sm_count * 16);
   k_bc_fill<<<std::max(1, fgrid), 128, 0, h->stream>>>(comb.rowptr, comb.col, comb.val, g, B.nchunks, N, d.reversed ? 1 : 0,
-                                                      B.offA, B.offB, B.blobA, B.blobB, B.far.rowptr, B.far.col, B.far.val, B.far_split);
+                                                      B.offA, B.offB, B.blobA, B.blobB, B.far.rowptr, B.far.col, B.far.val, B.far_split,
+                                                      B.dp.near.rowptr, B.dp.near.col, B.dp.near.val);
   h->stats.kernel_launches += 1;
   RCG_CUDA(h, cudaGetLastError());
 
@@ -1480,7 +1566,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
       bd.gidx = (uint32_t)B.blocks_host.size();
       bd.pad[0] = dfar[b];
       bd.pad[1] = tilesz[b];
-      bd.pad[2] = eblk[b] | (krblk[b] << 8) | (wbblk[b] << 16);   // E | Kr << 8 | warp-per-block << 16
+      bd.pad[2] = eblk[b] | (krblk[b] << 8) | (wbblk[b] << 16) | ((dpcblk[b] ? 1u : 0u) << 17);   // E | Kr << 8 | warp-per-block << 16 | dense-panel << 17 (pad[0] = panel rows)
       B.blocks_host.push_back(bd);
       src_block.push_back(b);
       G.count++;
@@ -1508,6 +1594,8 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     }
   }
   B.nblocks = (uint32_t)B.blocks_host.size();
+  B.dp.q0_of_block.assign(B.blocks_host.size(), 0);
+  for (size_t q = 0; q < B.blocks_host.size(); q++) B.dp.q0_of_block[q] = dpq0[src_block[q]];
   RCG_CUDA(h, cudaMalloc(&B.blocks, sizeof(BcBlock) * std::max<size_t>(1, B.blocks_host.size())));
   RCG_CUDA(h, cudaMemcpyAsync(B.blocks, B.blocks_host.data(), sizeof(BcBlock) * B.blocks_host.size(), cudaMemcpyHostToDevice,
                               h->stream));
@@ -1559,6 +1647,13 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     }
     G.max_stage = (uint32_t)maxA;
     BcLevel L;
+    if ((B.blocks_host[G.first].pad[2] >> 17) & 1u) {   // dense-panel level: no blobs, no rings (dp_build below)
+      L.dp = true;
+      L.Dfar = B.blocks_host[G.first].pad[0];
+      L.groups = (uint32_t)G.count;
+      B.levels.push_back(L);
+      continue;
+    }
     if ((B.blocks_host[G.first].pad[2] >> 16) & 1u) {   // warp-per-block level: per-warp window + scratch, no rings
       L.wb = true;
       L.Dfar = B.blocks_host[G.first].pad[0];
@@ -1628,6 +1723,10 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     const int rc = cl_build(h, d, comb, max_depth);
     if (rc != RCG_OK) { rcg_free_csr(comb); return rc; }
   }
+  {
+    const int rc = dp_build(h, d, comb);
+    if (rc != RCG_OK) { rcg_free_csr(comb); return rc; }
+  }
   rcg_free_csr(comb);
   if (!h->abort_flag) {
     RCG_CUDA(h, cudaMalloc(&h->abort_flag, sizeof(unsigned int) * 4));
@@ -1668,6 +1767,7 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
   if (only_kernel > 0) return RCG_OK;   // the level kernel is the only kernel of a group
   RCG_CUDA(h, cudaMemsetAsync(B.flags, 0, sizeof(uint32_t) * ((size_t)B.ntiles + B.nblocks), h->stream));
   if (B.cl.on) RCG_CUDA(h, cudaMemsetAsync(B.cl.prog4, 0, sizeof(uint32_t) * 4 * (size_t)B.nblocks, h->stream));
+  if (B.dp.on) RCG_CUDA(h, cudaMemsetAsync(B.dp.bar, 0, sizeof(uint32_t) * d.groups.size() * (size_t)B.dp.max_ctas, h->stream));
   double *rz_part = h->partials + 2 * (size_t)h->partial_cap;
   const bool dist_fwd = h->dist.on && !d.reversed && h->N > h->dist.n_sub;
   const uint32_t dot_limit = h->dist.on ? h->dist.dot_limit : 0xFFFFFFFFu;
@@ -1712,6 +1812,10 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     a.abort_g = h->abort_flag;
     a.clk = h->clk_probe;
     a.dbg = (uint32_t)h->opt.reserved[1];
+    if (L.dp) {   // dense-panel level: one launch (start vector of all rows, then the lock-step hops)
+      RCG_TRY(dp_launch(h, B, a, gi));
+      continue;
+    }
     if (L.wb) {   // warp-per-block level: fully parallel pre-pass over the entries of other blocks, then one warp per block
       const uint32_t pre_grid = std::min<uint32_t>((uint32_t)G.count, (uint32_t)h->sm_count * 8u);
       a.ticket = B.flags + B.ntiles + B.nblocks + gi % 4;   // (four spare words behind the flags: consecutive levels never share one)
@@ -1735,7 +1839,7 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at;
-    cfg.numAttrs = h->opt.reserved[6] ? 0 : 1;   // reserved[6] = 1: plain launch (the grid never exceeds the SM count)
+    cfg.numAttrs = (h->opt.reserved[6] & 1) ? 0 : 1;   // reserved[6] = 1: plain launch (the grid never exceeds the SM count)
     const bool split = h->opt.chain_mode != 3;   // default: four critical warps
     void (*kern)(const BcArgs) = (a.dbg & 1u) ? (split ? k_bc_solve<4, true> : k_bc_solve<1, true>)
                                               : (split ? k_bc_solve<4, false> : k_bc_solve<1, false>);

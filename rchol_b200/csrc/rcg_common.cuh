@@ -8,6 +8,7 @@
 #include "../../include/rchol_b200.h"
 
 #define RCG_SM_COUNT_FALLBACK 148
+#define RCG_DP_TRACE_WORDS (160 * 32 * 16)   // diagnostics: [CTA][warp][mark] of one hop of k_dp_solve
 
 // ---------------------------------------------------------------------------------------------------------
 // Device data layout (all arrays live in HBM for the life of the handle)
@@ -83,6 +84,7 @@ struct BcLevel {               // per tree level: shared-memory plan of the laun
   uint32_t helpers = 0;        // far CTAs per chain CTA
   uint32_t Dfar = 0;           // window of the level's blocks in chunks
   bool wb = false;             // warp-per-block level: k_wb_pre + k_wb_solve instead of the chain kernel
+  bool dp = false;             // dense-panel level: k_wb_pre + k_dp_solve (rcg_dense.cuh); see DenseDev
   uint32_t wbocc = 1;          // ... resident CTAs per SM (persistent grid: the warps take blocks from a ticket counter)
   size_t smem = 0;
 };
@@ -106,8 +108,51 @@ struct ClusterDev {
   int max_clusters = 0;                  // co-resident clusters of 4 CTAs (cudaOccupancyMaxActiveClusters)
 };
 
+// Dense-panel levels (rcg_dense.cuh): the rows of every block of the level are cut into PANELS of C rows (C per level, a
+// multiple of 32, up to 1024); the inverse of each panel's C x C lower-triangular diagonal block is computed at set-up and
+// stored as a packed lower triangle.  All blocks of the level advance in lock step, one panel per HOP:
+//     t_k = start_k - (entries of the own block left of the panel) x        sparse, all SMs       | grid barrier
+//     x_k = Inv_k t_k                                                       dense mat-vec, all SMs | grid barrier
+// so the dependency chain of a 65 536-row separator is 64 hops of the whole GPU instead of 2048 hops of one CTA.
+struct DpPanel {               // one panel (device); the level's panels are ordered hop-major
+  uint32_t row0, m;            // rows [row0, row0 + m) in the direction's solve index space, m <= C
+  uint32_t slice0;             // set-up: global index of the panel's first 32-column slice (inversion tasks)
+  uint32_t slot;               // dot-partial slot of the panel
+  int64_t inv_off;             // offset (doubles) of the packed inverse in DenseDev::inv
+  uint32_t q0;                 // compact index of the panel's first row in DenseDev::near
+  uint32_t pad;
+  int64_t e0, e1;              // near entries of the panel's rows: [e0, e1) (contiguous: bulk L2 prefetch a hop ahead)
+};
+
+struct DpLevel {               // host: one entry per tree level of the direction (parallel to DirectionDev::groups)
+  bool on = false;
+  uint32_t C = 0;              // panel rows of the level
+  uint32_t nhops = 0;          // panels of the level's longest block
+  uint32_t panel0 = 0;         // first panel of the level in DenseDev::panels
+  uint32_t hop0 = 0;           // first entry of the level in DenseDev::hop_ptr (nhops + 1 entries, relative to panel0)
+  uint32_t npanels = 0;
+  int64_t inv_bytes = 0;
+};
+
+struct DenseDev {
+  bool on = false;
+  DpPanel *panels = nullptr;
+  uint32_t *hop_ptr = nullptr;
+  double *inv = nullptr;
+  CsrDev near;                           // own-block entries left of the row's panel; rows = compact index of the dense-panel rows
+                                         // (level by level, block by block), columns in vector space, raw values
+  std::vector<uint32_t> q0_of_block;     // set-up: compact index of the first row of every block (by gidx), 0 if not dense-panel
+  int64_t nrows = 0;                     // rows of all dense-panel levels
+  uint32_t *bar = nullptr;               // one grid-barrier counter per tree level, zeroed at the start of every solve
+  int64_t inv_doubles = 0;
+  uint32_t npanels = 0;
+  int max_ctas = 0;                      // co-resident CTAs of k_dp_solve (occupancy x SMs)
+  std::vector<DpLevel> levels;
+};
+
 struct BlockedDev {
   ClusterDev cl;
+  DenseDev dp;
   bool on = false;
   bool fold = false;                     // folded layout (chain_mode 5, rcg_fold.cuh): dense panels in blob A, packed Winv in blob B
   uint32_t Kr = 2, E = 16, Dfar = 128;   // chunk-distance thresholds (see above); window = 32*Dfar rows (leaf blocks)

@@ -887,7 +887,8 @@ uint32_t aux_grid_x(const rcg_handle *h, const GroupHost &g, uint32_t rows_per_c
 
 // number of dot-partial slots a direction's post kernels write (one per CTA), and each group's first slot
 int rcg_post_slots(const rcg_handle *h, const DirectionDev &d, std::vector<int> *first_slot) {
-  if (d.bc.on) return (int)d.bc.nblocks;   // blocked solve: one partial per block, written by the block's publisher warp
+  // blocked solve: one partial per block, written by the block's publisher warp; dense-panel levels: one per panel
+  if (d.bc.on) return (int)(d.bc.nblocks + d.bc.dp.npanels);
   int total = 0;
   if (first_slot) first_slot->clear();
   for (const GroupHost &g : d.groups) {

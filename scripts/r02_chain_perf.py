@@ -50,6 +50,8 @@ for spec in sys.argv[3:]:
                         mhz = s.stats()["chain_sm_mhz"] or 1965.0
                         e["cta0"] = dict(total_cyc=c[0], waitA=c[3], waitU=c[4], chunks=c[6], late_u=c[15],
                                          cyc_per_chunk=c[0] / max(c[6], 1), helper0=c[8:13])
+                        # dense-panel levels (k_dp_solve, CTA 0): total, barrier waits, phase 0, phase 1, phase 2, hops, CTAs
+                        e["dp"] = dict(total=c[3], sync=c[4], p0=c[5], p1=c[6], p2=c[7], hops=c[8], ctas=c[9])
                     lv[f"{dname}{gi}"] = e
             out["levels"] = lv
     except Exception as e:  # keep going: the other variants still tell something

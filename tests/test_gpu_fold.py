@@ -46,7 +46,7 @@ def test_device_layout_replayed_on_host(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
     zo = oracle.trsv_backward(*G, yo)
-    with capi.Solver(0, chain_mode=5, **opts) as s:
+    with capi.Solver(0, chain_mode=5, dp_min_rows=-1, **opts) as s:   # (separator levels on the chain: the dense-panel levels have no blobs)
         s.set_factor(*G, part)
         lay_f, lay_b = s.blocked_layout(capi.TRSV_FORWARD), s.blocked_layout(capi.TRSV_BACKWARD)
         assert lay_f["active"] and lay_b["active"] and lay_f["fold"] == 1 and lay_b["fold"] == 1
@@ -78,7 +78,7 @@ def test_folded_solve_vs_oracle(capi, oracle, kind, n, threads, opts):
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
     zo = oracle.trsv_backward(*G, yo)
-    with capi.Solver(0, chain_mode=5, **opts) as s:
+    with capi.Solver(0, chain_mode=5, dp_min_rows=-1, **opts) as s:   # (with the dense-panel levels: tests/test_gpu_dense.py)
         s.set_matrix(*A)
         s.set_factor(*G, part)
         for _ in range(2):   # twice: flags and progress counters are reset per solve
@@ -142,7 +142,7 @@ def test_default_mode_layout_replayed_on_host(capi, oracle, kind, n, threads, op
     A, b, G, part, f = make_problem(kind, n, threads)
     yo = oracle.trsv_forward(*G, b)
     zo = oracle.trsv_backward(*G, yo)
-    with capi.Solver(0, **opts) as s:
+    with capi.Solver(0, dp_min_rows=-1, **opts) as s:
         s.set_factor(*G, part)
         lay_f, lay_b = s.blocked_layout(capi.TRSV_FORWARD), s.blocked_layout(capi.TRSV_BACKWARD)
         assert lay_f["active"] and lay_f["fold"] == 0 and lay_f["wb_min"] == opts["wb_min"]
