@@ -141,7 +141,7 @@ class Solver:
     def __init__(self, device: int = 0, chain_threads: int = 0, chain_window: int = 0, use_graph: bool = True,
                  spmv_lanes: int = 0, chain_generic: bool = False, chain_mode: int = 0, backoff_ns: int = 0, dbg: int = 0, producers: int = 0,
                  recent: int = 0, plain_launch: bool = False, sep_window: int = 0, early: int = 0, capb_quarters: int = 0, slots_a: int = 0, far_lanes2: int = 0, sep_tile: int = 0, early_sep: int = 0,
-                 wb_min: int = 0, wb_ell: bool = False, dp_min_rows: int = 0, dp_panel: int = 0, dp_leaf: bool = False):
+                 wb_min: int = 0, wb_ell: bool = False, dp_min_rows: int = 0, dp_panel: int = 0, dp_leaf: bool = False, dp_max_blocks: int = 0):
         self._L = load()
         self._h = C.c_void_p()
         opt = Options()
@@ -162,7 +162,9 @@ class Solver:
         # dense-panel levels: dp_min_rows = rows of a separator level's longest block from which the level is solved through
         # inverted panels (0 = default 128, -1 = never; multiples of 32); dp_panel = panel rows (0 = from the level's shape);
         # dp_leaf = the leaf level too
-        opt.reserved[6] = (int(bool(plain_launch)) | (2 if dp_leaf else 0) | ((255 if dp_min_rows < 0 else min(254, int(dp_min_rows) // 32)) << 8)
+        # dp_max_blocks: levels with more blocks are not dense-panel levels (0 = default, -1 = no limit, else a power of two)
+        mb = 0 if dp_max_blocks == 0 else 63 if dp_max_blocks < 0 else min(31, int(dp_max_blocks).bit_length())
+        opt.reserved[6] = (int(bool(plain_launch)) | (2 if dp_leaf else 0) | (mb << 2) | ((255 if dp_min_rows < 0 else min(254, int(dp_min_rows) // 32)) << 8)
                            | (int(dp_panel) << 16))
         rc = self._L.rcg_create_with_options(C.byref(self._h), int(device), C.byref(opt))
         if rc != 0:

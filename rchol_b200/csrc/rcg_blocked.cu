@@ -1333,6 +1333,9 @@ uint32_t floor_pow2_u32(uint32_t v) {
   return p;
 }
 
+// dense-panel levels: tree levels with at most this many blocks (measured at 256^3 / T = 4096, profiles/r02_levels_256.md:
+// faster than the chains up to 64 blocks per level, slower than the warp-per-block kernels from 128 on)
+constexpr uint32_t DP_MAX_BLOCKS_DEFAULT = 64u;
 #include "rcg_cluster.cuh"
 #include "rcg_fold.cuh"
 #include "rcg_dense.cuh"
@@ -1348,7 +1351,7 @@ void rcg_free_blocked(BlockedDev &b) {
   cudaFree(b.offA); cudaFree(b.offB); cudaFree(b.blobA); cudaFree(b.blobB);
   rcg_free_csr(b.far);
   cudaFree(b.tile_need); cudaFree(b.flags); cudaFree(b.w); cudaFree(b.blocks); cudaFree(b.far_split);
-  cudaFree(b.dp.panels); cudaFree(b.dp.hop_ptr); cudaFree(b.dp.inv); cudaFree(b.dp.bar);
+  cudaFree(b.dp.panels); cudaFree(b.dp.hop_ptr); cudaFree(b.dp.inv); cudaFree(b.dp.t0); cudaFree(b.dp.t1);
   rcg_free_csr(b.dp.near);
   cudaFree(b.cl.wslab); cudaFree(b.cl.blobN); cudaFree(b.cl.offN); cudaFree(b.cl.c0); cudaFree(b.cl.prog4);
   b = BlockedDev();
@@ -1447,6 +1450,13 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   {
     const int dp_opt = (h->opt.reserved[6] >> 8) & 0xFF, dp_c = (h->opt.reserved[6] >> 16) & 0xFFFF;
     const bool dp_leaf = (h->opt.reserved[6] & 2) != 0;
+    // bits 2-7: levels with more than 2^(v-1) blocks stay on the chain / warp-per-block kernels (0 = default, 63 = no limit):
+    // the lock-step hops pay off where a level has FEW long blocks; many short blocks are throughput work (k_wb_solve)
+    const int dp_mb = (h->opt.reserved[6] >> 2) & 0x3F;
+    uint32_t dp_max_blocks = dp_mb == 0 ? DP_MAX_BLOCKS_DEFAULT : dp_mb >= 32 ? 0xFFFFFFFFu : (1u << (dp_mb - 1));
+    if (const char *e = getenv("RCG_DP_MAX_BLOCKS")) if (atoi(e) > 0) dp_max_blocks = (uint32_t)atoi(e);   // tuning experiments
+    std::vector<uint32_t> cnt(max_depth + 2, 0);
+    for (int b = 0; b < nb; b++) if (bounds[b + 1] > bounds[b]) cnt[depth[b]]++;
     const uint32_t dp_min = !wb_allowed || dp_opt == 255 ? 0xFFFFFFFFu : dp_opt > 0 ? 32u * (uint32_t)dp_opt : 128u;
     std::vector<uint32_t> mx(max_depth + 2, 0);
     std::vector<int64_t> sum(max_depth + 2, 0);
@@ -1456,8 +1466,8 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     }
     for (int b = 0; b < nb; b++) {
       const int dd = depth[b];
-      if ((dd == max_depth && !dp_leaf) || mx[dd] < dp_min || bounds[b + 1] == bounds[b]) continue;
-      dpcblk[b] = dp_choose_panel(mx[dd], sum[dd], dp_c);
+      if ((dd == max_depth && !dp_leaf) || mx[dd] < dp_min || bounds[b + 1] == bounds[b] || cnt[dd] > dp_max_blocks) continue;
+      dpcblk[b] = dp_choose_panel(mx[dd], sum[dd], dp_c, cnt[dd]);
       dpq0[b] = (uint32_t)dp_rows_total;
       dp_rows_total += bounds[b + 1] - bounds[b];
       wbblk[b] = 0; krblk[b] = 0; dfar[b] = dpcblk[b]; tilesz[b] = B.tile_sep;
@@ -1767,7 +1777,6 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
   if (only_kernel > 0) return RCG_OK;   // the level kernel is the only kernel of a group
   RCG_CUDA(h, cudaMemsetAsync(B.flags, 0, sizeof(uint32_t) * ((size_t)B.ntiles + B.nblocks), h->stream));
   if (B.cl.on) RCG_CUDA(h, cudaMemsetAsync(B.cl.prog4, 0, sizeof(uint32_t) * 4 * (size_t)B.nblocks, h->stream));
-  if (B.dp.on) RCG_CUDA(h, cudaMemsetAsync(B.dp.bar, 0, sizeof(uint32_t) * d.groups.size() * (size_t)B.dp.max_ctas, h->stream));
   double *rz_part = h->partials + 2 * (size_t)h->partial_cap;
   const bool dist_fwd = h->dist.on && !d.reversed && h->N > h->dist.n_sub;
   const uint32_t dot_limit = h->dist.on ? h->dist.dot_limit : 0xFFFFFFFFu;

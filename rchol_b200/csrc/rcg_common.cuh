@@ -143,7 +143,7 @@ struct DenseDev {
                                          // (level by level, block by block), columns in vector space, raw values
   std::vector<uint32_t> q0_of_block;     // set-up: compact index of the first row of every block (by gidx), 0 if not dense-panel
   int64_t nrows = 0;                     // rows of all dense-panel levels
-  uint32_t *bar = nullptr;               // one grid-barrier counter per tree level, zeroed at the start of every solve
+  double *t0 = nullptr, *t1 = nullptr;   // per compact row: start vector after the entries of other blocks / after the near entries
   int64_t inv_doubles = 0;
   uint32_t npanels = 0;
   int max_ctas = 0;                      // co-resident CTAs of k_dp_solve (occupancy x SMs)

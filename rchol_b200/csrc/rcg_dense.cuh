@@ -18,7 +18,7 @@
 // the diagonal inside the diagonal 32 x 32 tile), so a warp reads a row as (g + 1) coalesced 256-byte segments.
 #pragma once
 
-constexpr int DP_THREADS = 1024;             // one CTA per SM (two at most): few participants keep the grid barrier cheap
+constexpr int DP_THREADS = 512;              // one CTA per SM, 128 registers per thread: the static loads of the next step stay in flight
 constexpr uint32_t DP_WARPS = DP_THREADS / 32;
 constexpr uint32_t DP_CMAX = 1024;           // largest panel
 constexpr uint32_t DP_SMEM = 0;
@@ -81,11 +81,21 @@ __global__ void k_dp_spans(DpPanel *panels, uint32_t npanels, const int64_t *__r
 // ---------------------------------------------------------------------------------------------------------
 // solve
 // ---------------------------------------------------------------------------------------------------------
+// No grid barriers (measured: 3 000 cycles each for the fences and the polling alone, two per hop).  Every value that
+// crosses CTAs carries its own readiness: the three vectors below are filled with a sentinel (a NaN payload no
+// computation produces) before the launch, producers store the value with one 8-byte store, consumers re-load a word
+// until it is not the sentinel.  No fences are needed because no consumer infers anything about OTHER words.
+//   t0[q]  start vector of row q after phase 0 (rows of hop 0: written straight to t1)
+//   t1[q]  final right-hand side of the row's panel solve (t0 minus the near entries)
+//   out[]  the solution (vector space), rows of this level
+// Every warp works through its rows / its CTA's tasks in hop order; all CTAs are co-resident (cooperative launch), so
+// every wait is on work that an earlier step of some resident CTA produces: no cycles.  Waits are bounded like all
+// waits of the blocked solve (time-out -> device-wide abort word -> RCG_ERR_CUDA).
 struct DpArgs {
   const DpPanel *panels;       // the level's panels, hop-major
   const uint32_t *hop_ptr;     // nhops + 1 offsets into panels
   uint32_t nhops, C;
-  uint32_t wpr;                // warps per row of the dense phase: 4 (C >= 512), 2 (C >= 256) or 1
+  uint32_t wpr;                // warps per row of the dense phase: 2 (C >= 512) or 1
   const double *inv;
   const int64_t *near_rp;      // own-block entries left of the row's panel (compact rows, DpPanel::q0)
   const uint32_t *near_col;
@@ -96,69 +106,90 @@ struct DpArgs {
   const double *rhs;           // right-hand side (vector space)
   uint32_t col_min;            // multi-GPU top separators: far columns below col_min are left out ...
   const double *corr;          // ... their sum over all ranks arrives here (indexed by vector index - col_min)
-  double *w;                   // start vector (solve space)
-  double *out;                 // solution (vector space)
+  double *t0, *t1;             // compact rows (DpPanel::q0 + i), sentinel-filled before the launch
+  double *out;                 // solution (vector space); this level's rows sentinel-filled before the launch
   const double *dotvec;        // nullable
   double *dot_partials;        // one slot per panel (DpPanel::slot)
   uint32_t dot_limit;
   uint32_t N;
   int reversed;
-  uint32_t *bar;               // grid-barrier slots of this level, one per CTA (zero at launch)
   unsigned int *abort_g;
   unsigned long long *clk;     // nullable diagnostics (rcg_options.reserved[1] bit 0): cycle profile of CTA 0 into clk[3..9]
-  unsigned long long *trace;   // nullable diagnostics (reserved[1] bit 1): [CTA][warp][16] clock64 marks of hop nhops / 2
+  unsigned long long *trace;   // nullable diagnostics (reserved[1] bit 1): [CTA][warp][16] globaltimer marks of hop nhops / 2
 };
+
+constexpr unsigned long long DP_SENT = 0xFFF8DEADBEEF0001ull;
+__device__ __forceinline__ unsigned long long dp_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool dp_is_sent(double v) { return (unsigned long long)__double_as_longlong(v) == DP_SENT; }
+__device__ __forceinline__ double dp_ld(const double *p) {   // L2-coherent load (never a stale L1 line)
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// Publishing store.  An atomic exchange is performed at L2 at once; a plain store may sit in the SM's write buffer until
+// something flushes it, and every consumer's wait would include that time.
+__device__ __forceinline__ void dp_st(double *p, double v) {
+  unsigned long long old;
+  asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(__double_as_longlong(v)) : "memory");
+}
+
+__global__ void k_dp_fill(const DpPanel *__restrict__ panels, uint32_t npanels, uint32_t C, double *__restrict__ t0,
+                          double *__restrict__ t1, double *__restrict__ out, uint32_t N, int reversed) {
+  const double sent = __longlong_as_double((long long)DP_SENT);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < npanels * C; t += gridDim.x * blockDim.x) {
+    const uint32_t pi = t / C, i = t - pi * C;
+    if (i < panels[pi].m) {
+      const uint32_t j = panels[pi].row0 + i, q = panels[pi].q0 + i;
+      t0[q] = sent;
+      t1[q] = sent;
+      out[reversed ? N - 1u - j : j] = sent;
+    }
+  }
+}
+
+// Bounded waiting: called after a poll that found the sentinel; true = give up (results are garbage, the host reports it).
+struct DpSpin {
+  uint32_t n = 0;
+  long long t0 = 0;
+  bool dead = false;
+};
+__device__ __forceinline__ bool dp_spin_fail(const DpArgs &P, DpSpin &s) {
+  if (s.dead) return true;
+  if ((++s.n & 255u) == 0u) {
+    if (__ldcg(P.abort_g) != 0u) { s.dead = true; return true; }
+    const long long now = clock64();
+    if (s.n == 256u) s.t0 = now;
+    else if (now - s.t0 > BC_TIMEOUT_CYCLES) {
+      atomicCAS(P.abort_g, 0u, 0xD000u);
+      s.dead = true;
+      return true;
+    }
+  }
+  return false;
+}
+__device__ __forceinline__ double dp_wait(const DpArgs &P, const double *p, DpSpin &s) {   // re-load until the value is there
+  double v = dp_ld(p);
+  while (dp_is_sent(v)) {
+    if (dp_spin_fail(P, s)) break;
+    v = dp_ld(p);
+  }
+  s.n = 0;
+  return v;
+}
 
 __device__ __forceinline__ void dp_prefetch_bulk(const void *p, uint32_t bytes) {   // p 16-byte aligned, bytes a multiple of 16
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void dp_prefetch_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Grid barrier without atomics: CTA c publishes the barrier's generation in slot c, warp 0 of every CTA polls all slots
-// (lanes over slots).  Nothing is serialised at one L2 address: measured with one atomic counter, 12 ns per arriving CTA.
-// Returns false when the wait was abandoned (time-out or another CTA's abort): the kernel then returns, results are
-// garbage and the host reports RCG_ERR_CUDA.
-__device__ __forceinline__ bool dp_grid_sync(const DpArgs &P, uint32_t gen, volatile uint32_t *dead_s, unsigned long long *tr = nullptr) {
-  __syncthreads();
-  if (tr && threadIdx.x == 0u) tr[0] = clock64();
-  if (threadIdx.x < 32u) {
-    if (threadIdx.x == 0u) st_release_gpu(P.bar + blockIdx.x, gen);
-    if (tr && threadIdx.x == 0u) tr[1] = clock64();
-    uint32_t n = 0;
-    long long t0 = 0;
-    for (;;) {
-      bool ok = true;
-      for (uint32_t c = threadIdx.x; c < gridDim.x; c += 32u) {
-        uint32_t v;
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.bar + c) : "memory");
-        ok = ok && v >= gen;
-      }
-      if (__all_sync(0xffffffffu, ok)) break;
-      if ((++n & 63u) == 0u) {
-        bool dead = false;
-        if (threadIdx.x == 0u) {
-          if (__ldcg(P.abort_g) != 0u) dead = true;
-          const long long now = clock64();
-          if (n == 64u) t0 = now;
-          else if (now - t0 > BC_TIMEOUT_CYCLES) { atomicCAS(P.abort_g, 0u, 0xD000u); dead = true; }
-          if (dead) *dead_s = 1u;
-        }
-        if (__any_sync(0xffffffffu, dead)) break;
-      }
-    }
-    if (tr && threadIdx.x == 0u) tr[2] = clock64();
-    __threadfence();   // (relaxed polls + fence = acquire)
-    if (tr && threadIdx.x == 0u) tr[3] = clock64();
-  }
-  __syncthreads();
-  return *dead_s == 0u;
-}
 
 // L2 prefetch of everything hop `hop` will read: the packed inverses and the near rows (pointers, columns, values) of
-// its panels, all contiguous per panel.  Bulk prefetches of up to 32 KiB, ONE per warp at a time (the instruction is
-// warp-uniform: lanes with different addresses are serialised, measured ~40 cycles each), spread over `nwarps`
-// participating warps (this warp = widx).
-constexpr uint32_t DP_PF = 32768;
+// its panels, all contiguous per panel.  Bulk prefetches of up to 8 KiB, at most ONE per warp and call site iteration
+// (the instruction is warp-uniform: lanes with different addresses are serialised), spread evenly over all warps of the
+// grid -- an SM that issues hundreds of KiB of prefetches stalls its own memory pipe for thousands of cycles (measured).
+constexpr uint32_t DP_PF = 8192;
 __device__ __forceinline__ void dp_prefetch_span(const char *lo, const char *hi, uint32_t piece) {
   lo = reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(lo) & ~(uintptr_t)15);
   hi = reinterpret_cast<const char *>((reinterpret_cast<uintptr_t>(hi) + 15) & ~(uintptr_t)15);
@@ -177,8 +208,8 @@ __device__ __forceinline__ void dp_prefetch_hop(const DpArgs &P, uint32_t hop, u
     dp_prefetch_span(b, b + dp_inv_doubles(pan->m) * 8, pc);
   }
   if (!with_rows) return;
-  for (uint32_t t = widx; t < np * 32u; t += nwarps) {   // 32 slots per panel; slot k takes pieces k, k + 32, ... of the spans
-    const uint32_t pi = t >> 5;
+  for (uint32_t t = nwarps - 1u - widx; t < np * 256u; t += nwarps) {   // 256 slots per panel; slot k: pieces k, k + 256, ...
+    const uint32_t pi = t >> 8;
     const DpPanel *pan = P.panels + p0 + pi;
     const int64_t e0 = pan->e0, e1 = pan->e1;
     const uint32_t q0 = pan->q0, m = pan->m;
@@ -187,7 +218,7 @@ __device__ __forceinline__ void dp_prefetch_hop(const DpArgs &P, uint32_t hop, u
     const char *v0 = reinterpret_cast<const char *>(P.near_val + e0), *v1 = reinterpret_cast<const char *>(P.near_val + e1);
     const uint32_t nr = (uint32_t)((r1 - r0 + DP_PF - 1 + 32) / DP_PF), nc = (uint32_t)((c1 - c0 + DP_PF - 1 + 32) / DP_PF);
     const uint32_t nv = (uint32_t)((v1 - v0 + DP_PF - 1 + 32) / DP_PF);
-    for (uint32_t k = t & 31u; k < nr + nc + nv; k += 32u) {
+    for (uint32_t k = t & 255u; k < nr + nc + nv; k += 256u) {
       if (k < nr) dp_prefetch_span(r0, r1, k);
       else if (k < nr + nc) dp_prefetch_span(c0, c1, k - nr);
       else dp_prefetch_span(v0, v1, k - nr - nc);
@@ -198,87 +229,38 @@ __device__ __forceinline__ void dp_prefetch_hop(const DpArgs &P, uint32_t hop, u
 // ---- sparse phases ---------------------------------------------------------------------------------------------------
 // Rows are numbered flat, panel * C + i.  LPR lanes per row, 32 / LPR rows per warp at a time ("batch"); the warp's first
 // batch is base = gw * RPW, the next ones follow at a stride of nw * RPW.
-// Everything a sparse row needs except x is static: the row pointers, columns and values of a warp's FIRST batch are
-// loaded BEFORE the grid barrier in front of the phase (SpPre); behind the barrier only the gather of x, the reduction and
-// the update of the start vector remain on the critical path.
-struct SpPre {
-  int64_t e, e1;               // next entry of this lane, end of the row
-  uint32_t j;                  // row (solve space)
-  uint32_t c0, c1, c2, c3;     // first four columns of this lane (where the row is shorter: c0 again, with value 0.0)
-  double v0, v1, v2, v3;
-  double wv;                   // start vector entry
-  bool valid;                  // the lane has a row with at least one entry for this lane (else nothing is gathered)
-  bool row;                    // the lane has a row
-};
 
-// stage A (issued a phase early, 5 registers): the row and its pointers
-struct SpRow {
-  int64_t e, e1;
-  uint32_t j;
-  bool row;
-};
-template <uint32_t LPR>
-__device__ __forceinline__ SpRow dp_near_row(const DpArgs &P, const DpPanel *__restrict__ pans, uint32_t total, uint32_t base,
-                                             uint32_t lane) {
-  SpRow r;
-  const uint32_t sub = lane & (LPR - 1u), t = base + lane / LPR;
-  const uint32_t pi = t / P.C, i = t - pi * P.C;
-  r.row = t < total;
-  r.j = 0; r.e = r.e1 = 0;
-  if (r.row) {
-    const DpPanel *pan = pans + pi;
-    r.row = i < pan->m;
-    if (r.row) {
-      r.j = pan->row0 + i;
-      const uint32_t q = pan->q0 + i;
-      r.e = P.near_rp[q] + sub;
-      r.e1 = P.near_rp[q + 1];
-    }
-  }
-  return r;
-}
-// stage B (in front of the barrier): the first entries of this lane and the start vector entry
-template <uint32_t LPR>
-__device__ __forceinline__ SpPre dp_near_pre(const DpArgs &P, const SpRow &r) {
-  SpPre s;
-  s.row = r.row;
-  s.valid = false;
-  s.j = r.j; s.e = r.e; s.e1 = r.e1;
-  s.c0 = s.c1 = s.c2 = s.c3 = 0u;
-  s.v0 = s.v1 = s.v2 = s.v3 = 0.0;
-  s.wv = 0.0;
-  if (s.row) {
-    const int64_t e = r.e, e1 = r.e1;
-    if (e < e1) {   // (padding entries gather x[c0] too -- a solved column, finite -- and multiply it by 0.0)
-      s.valid = true;
-      s.c0 = P.near_col[e]; s.v0 = P.near_val[e];
-      s.c1 = s.c2 = s.c3 = s.c0;
-      if (e + LPR < e1) { s.c1 = P.near_col[e + LPR]; s.v1 = P.near_val[e + LPR]; }
-      if (e + 2 * LPR < e1) { s.c2 = P.near_col[e + 2 * LPR]; s.v2 = P.near_val[e + 2 * LPR]; }
-      if (e + 3 * LPR < e1) { s.c3 = P.near_col[e + 3 * LPR]; s.v3 = P.near_val[e + 3 * LPR]; }
-    }
-    s.e = e + 4 * LPR;
-    s.wv = __ldcg(P.w + s.j);   // (written in phase 0, barriers ago)
-  }
-  return s;
-}
-
-// the rest of a row from entry e on (entries e, e + LPR, ...), 4 at a time
-template <uint32_t LPR, bool FAR>
+// the rest of a row from entry e on (entries e, e + LPR, ...), 4 at a time.  WAIT: the columns may still be unsolved.
+template <uint32_t LPR, bool FAR, bool WAIT>
 __device__ __forceinline__ double dp_row_tail(const DpArgs &P, const uint32_t *__restrict__ col, const double *__restrict__ val,
-                                              int64_t e, int64_t e1, double acc) {
+                                              int64_t e, int64_t e1, double acc, DpSpin &sp) {
   double a0 = acc, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   for (; e + 3 * LPR < e1; e += 4 * LPR) {
     const uint32_t c0 = col[e], c1 = col[e + LPR], c2 = col[e + 2 * LPR], c3 = col[e + 3 * LPR];
     const double v0 = val[e], v1 = val[e + LPR], v2 = val[e + 2 * LPR], v3 = val[e + 3 * LPR];
-    if (!FAR || c0 >= P.col_min) a0 = fma(v0, __ldcg(P.out + c0), a0);
-    if (!FAR || c1 >= P.col_min) a1 = fma(v1, __ldcg(P.out + c1), a1);
-    if (!FAR || c2 >= P.col_min) a2 = fma(v2, __ldcg(P.out + c2), a2);
-    if (!FAR || c3 >= P.col_min) a3 = fma(v3, __ldcg(P.out + c3), a3);
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+    if (!FAR || c0 >= P.col_min) x0 = dp_ld(P.out + c0);
+    if (!FAR || c1 >= P.col_min) x1 = dp_ld(P.out + c1);
+    if (!FAR || c2 >= P.col_min) x2 = dp_ld(P.out + c2);
+    if (!FAR || c3 >= P.col_min) x3 = dp_ld(P.out + c3);
+    if (WAIT) {
+      if (dp_is_sent(x0)) x0 = dp_wait(P, P.out + c0, sp);
+      if (dp_is_sent(x1)) x1 = dp_wait(P, P.out + c1, sp);
+      if (dp_is_sent(x2)) x2 = dp_wait(P, P.out + c2, sp);
+      if (dp_is_sent(x3)) x3 = dp_wait(P, P.out + c3, sp);
+    }
+    a0 = fma(v0, x0, a0);
+    a1 = fma(v1, x1, a1);
+    a2 = fma(v2, x2, a2);
+    a3 = fma(v3, x3, a3);
   }
   for (; e < e1; e += LPR) {
     const uint32_t c0 = col[e];
-    if (!FAR || c0 >= P.col_min) a0 = fma(val[e], __ldcg(P.out + c0), a0);
+    if (!FAR || c0 >= P.col_min) {
+      double x0 = dp_ld(P.out + c0);
+      if (WAIT && dp_is_sent(x0)) x0 = dp_wait(P, P.out + c0, sp);
+      a0 = fma(val[e], x0, a0);
+    }
   }
   return (a0 + a1) + (a2 + a3);
 }
@@ -290,156 +272,259 @@ __device__ __forceinline__ double dp_lanes_sum(double acc) {
   return acc;
 }
 
-// phase 1 of one hop: start -= near entries * x.  `pre` = the warp's first batch, loaded before the barrier.
+// phase 1 of one hop: t1 = t0 - near entries * x, for this warp's rows of the hop.  Everything but x is static (t0 was
+// produced long ago), so the loads of a warp's FIRST batch are issued early, in two stages, and overlap the waits of the
+// steps in between:  NearA (row pointers; issued a hop ahead)  ->  NearB (first four entries per lane, t0; issued
+// before the gathers can succeed).
+struct NearA {
+  int64_t e, e1;
+  uint32_t q;
+  bool row;
+};
+constexpr uint32_t DP_NPRE = 8;   // entries per lane that are preloaded (256 per row with a warp per row)
+struct NearB {
+  int64_t e, e1;
+  uint32_t q;
+  uint32_t c[DP_NPRE];         // first n (1..DP_NPRE) columns of this lane
+  uint32_t n;
+  double v[DP_NPRE];
+  double t0v;                  // start vector entry (may still be the sentinel)
+  uint32_t c_last;             // the row's last (newest) column: the word the row's first lane polls before anyone gathers
+  bool row, any;               // the lane has a row / at least one entry of it
+  bool row_any;                // the row has entries at all
+};
+template <uint32_t LPR>
+__device__ __forceinline__ NearA dp_near_a(const DpArgs &P, const DpPanel *__restrict__ pans, uint32_t total, uint32_t base,
+                                           uint32_t lane) {
+  NearA r;
+  const uint32_t sub = lane & (LPR - 1u), t = base + lane / LPR;
+  const uint32_t pi = t / P.C, i = t - pi * P.C;
+  r.row = t < total;
+  r.q = 0; r.e = r.e1 = 0;
+  if (r.row) {
+    const DpPanel *pan = pans + pi;
+    r.row = i < pan->m;
+    if (r.row) {
+      r.q = pan->q0 + i;
+      r.e = P.near_rp[r.q] + sub;
+      r.e1 = P.near_rp[r.q + 1];
+    }
+  }
+  return r;
+}
+template <uint32_t LPR>
+__device__ __forceinline__ NearB dp_near_b(const DpArgs &P, const NearA &r, uint32_t lane) {
+  NearB s;
+  s.row = r.row; s.any = false; s.row_any = false;
+  s.c_last = 0u; s.n = 0u;
+  s.q = r.q; s.e = r.e; s.e1 = r.e1;
+#pragma unroll
+  for (uint32_t u = 0; u < DP_NPRE; u++) { s.c[u] = 0u; s.v[u] = 0.0; }
+  s.t0v = 0.0;
+  if (s.row) {
+    const int64_t e = r.e, e1 = r.e1;
+    s.any = e < e1;
+#pragma unroll
+    for (uint32_t u = 0; u < DP_NPRE; u++)   // (no use of a loaded value in here: the loads only issue)
+      if (e + (int64_t)(u * LPR) < e1) { s.c[u] = P.near_col[e + u * LPR]; s.v[u] = P.near_val[e + u * LPR]; s.n = u + 1u; }
+    s.e = e + DP_NPRE * LPR;
+    s.row_any = e1 > e - (int64_t)(lane & (LPR - 1u));   // (e - sub = the row's first entry)
+    if (s.row_any) s.c_last = P.near_col[e1 - 1];
+    s.t0v = dp_ld(P.t0 + s.q);
+  }
+  return s;
+}
 template <uint32_t LPR>
 __device__ __forceinline__ void dp_near_rows(const DpArgs &P, const DpPanel *__restrict__ pans, uint32_t total, uint32_t gw,
-                                             uint32_t nw, uint32_t lane, const SpPre &pre) {
+                                             uint32_t nw, uint32_t lane, const NearB &nb, DpSpin &sp, unsigned long long *tr) {
   constexpr uint32_t RPW = 32u / LPR;
   const uint32_t sub = lane & (LPR - 1u);
-  if (gw * RPW < total) {   // first batch (warp-uniform)
+  if (gw * RPW < total) {   // first batch (warp-uniform), from the preloaded entries
+    // The row's first lane polls ONE word -- the row's newest column -- before anyone gathers: scattered gathers are one
+    // L2 request per lane, and thousands of warps re-polling all of theirs saturate the L2 request queues.
+    if (nb.row_any && sub == 0u) dp_wait(P, P.out + nb.c_last, sp);
+    __syncwarp();
     double acc = 0.0;
-    if (pre.valid) {
-      const double x0 = __ldcg(P.out + pre.c0), x1 = __ldcg(P.out + pre.c1), x2 = __ldcg(P.out + pre.c2), x3 = __ldcg(P.out + pre.c3);
-      acc = fma(pre.v0, x0, fma(pre.v1, x1, 0.0)) + fma(pre.v2, x2, fma(pre.v3, x3, 0.0));
-      if (pre.e < pre.e1) acc = dp_row_tail<LPR, false>(P, P.near_col, P.near_val, pre.e, pre.e1, acc);
+    if (tr && lane == 0u) tr[0] = dp_gtime();
+    if (nb.any) {
+      // (entries the lane does not have gather x[c[0]] again -- it is waited for anyway -- and carry the value 0.0)
+      uint32_t cc[DP_NPRE];
+      double x[DP_NPRE];
+#pragma unroll
+      for (uint32_t u = 0; u < DP_NPRE; u++) cc[u] = u < nb.n ? nb.c[u] : nb.c[0];
+#pragma unroll
+      for (uint32_t u = 0; u < DP_NPRE; u++) x[u] = dp_ld(P.out + cc[u]);
+      for (;;) {   // (all pending words per round trip)
+        bool pend = false;
+#pragma unroll
+        for (uint32_t u = 0; u < DP_NPRE; u++) pend = pend || dp_is_sent(x[u]);
+        if (!pend || dp_spin_fail(P, sp)) break;
+#pragma unroll
+        for (uint32_t u = 0; u < DP_NPRE; u++)
+          if (dp_is_sent(x[u])) x[u] = dp_ld(P.out + cc[u]);
+      }
+      sp.n = 0;
+      if (tr && lane == 0u) tr[1] = dp_gtime();
+      double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+      for (uint32_t u = 0; u < DP_NPRE; u += 2u) {
+        b0 = fma(nb.v[u], x[u], b0);
+        b1 = fma(nb.v[u + 1u], x[u + 1u], b1);
+      }
+      acc = b0 + b1;
+      if (nb.e < nb.e1) acc = dp_row_tail<LPR, false, true>(P, P.near_col, P.near_val, nb.e, nb.e1, acc, sp);
     }
+    if (tr && lane == 0u) tr[2] = dp_gtime();
     acc = dp_lanes_sum<LPR>(acc);
-    if (pre.row && sub == 0u) __stcg(P.w + pre.j, pre.wv - acc);
+    if (nb.row && sub == 0u) {
+      double t0v = nb.t0v;
+      if (dp_is_sent(t0v)) t0v = dp_wait(P, P.t0 + nb.q, sp);
+      dp_st(P.t1 + nb.q, t0v - acc);
+    }
+    if (tr && lane == 0u) tr[3] = dp_gtime();
   }
   for (uint32_t base = gw * RPW + nw * RPW; base < total; base += nw * RPW) {
-    const uint32_t t = base + lane / LPR;
-    const uint32_t pi = t / P.C, i = t - pi * P.C;
-    bool valid = t < total;
-    uint32_t j = 0, q = 0;
-    if (valid) {
-      const DpPanel *pan = pans + pi;
-      valid = i < pan->m;
-      j = pan->row0 + i;
-      q = pan->q0 + i;
-    }
+    const NearA r = dp_near_a<LPR>(P, pans, total, base, lane);
+    if (r.row && sub == 0u && r.e1 > r.e) dp_wait(P, P.out + P.near_col[r.e1 - 1], sp);
+    __syncwarp();
     double acc = 0.0;
-    if (valid) acc = dp_row_tail<LPR, false>(P, P.near_col, P.near_val, P.near_rp[q] + sub, P.near_rp[q + 1], 0.0);
+    if (r.row && r.e < r.e1) acc = dp_row_tail<LPR, false, true>(P, P.near_col, P.near_val, r.e, r.e1, 0.0, sp);
     acc = dp_lanes_sum<LPR>(acc);
-    if (valid && sub == 0u) __stcg(P.w + j, __ldcg(P.w + j) - acc);
+    if (r.row && sub == 0u) dp_st(P.t1 + r.q, dp_wait(P, P.t0 + r.q, sp) - acc);
   }
 }
 
-// phase 0: start[j] = rhs[j] - entries of other (already solved) blocks, all rows of the level, 8 lanes per row
-__device__ __forceinline__ void dp_far_rows(const DpArgs &P, uint32_t total, uint32_t gw, uint32_t nw, uint32_t lane) {
+// phase 0: t0[q] (t1[q] for the rows of hop 0) = rhs[j] - entries of other (already solved) blocks, all rows of the
+// level, 8 lanes per row
+__device__ __forceinline__ void dp_far_rows(const DpArgs &P, uint32_t total, uint32_t hop0_panels, uint32_t gw, uint32_t nw,
+                                            uint32_t lane, DpSpin &sp) {
   const uint32_t sub = lane & 7u;
   for (uint32_t base = gw * 4u; base < total; base += nw * 4u) {
     const uint32_t t = base + (lane >> 3);
     const uint32_t pi = t / P.C, i = t - pi * P.C;
     bool valid = t < total;
-    uint32_t j = 0;
+    uint32_t j = 0, q = 0;
     if (valid) {
       const DpPanel *pan = P.panels + pi;
       valid = i < pan->m;
       j = pan->row0 + i;
+      q = pan->q0 + i;
     }
     double acc = 0.0;
-    if (valid) acc = dp_row_tail<8, true>(P, P.far_col, P.far_val, P.far_rp[j] + sub, P.far_rp[j + 1], 0.0);
+    if (valid) acc = dp_row_tail<8, true, false>(P, P.far_col, P.far_val, P.far_rp[j] + sub, P.far_rp[j + 1], 0.0, sp);
     acc = dp_lanes_sum<8>(acc);
     if (valid && sub == 0u) {
       const uint32_t v = P.reversed ? P.N - 1u - j : j;
       double s0 = P.rhs[v];
       if (P.corr) s0 -= P.corr[v - P.col_min];
-      __stcg(P.w + j, s0 - acc);
+      dp_st((pi < hop0_panels ? P.t1 : P.t0) + q, s0 - acc);
     }
   }
 }
 
 // ---- dense phase -----------------------------------------------------------------------------------------------------
-// A CTA takes R = 32 / WPR consecutive rows of one panel at a time, WPR warps per row (warp w: row w / WPR, segments
-// k, k + WPR, ... of the row with k = w % WPR; a segment = 32 consecutive columns).  The packed inverse is static: the
-// (up to 8) segments of the CTA's FIRST task are loaded before the barrier (DnPre); behind it: t -> shared memory, FMAs,
-// warp reduction, WPR partial sums per row added in a fixed order.
-struct DnPre {
-  double v[8];
-  uint32_t row0, m, i;         // panel rows [row0, row0 + m), this warp's row i (panel-local)
-  uint32_t nload;              // t entries the task's rows read
-  bool have;                   // the CTA has a task in this hop
+// A CTA (16 warps) takes R = 16 / WPR consecutive rows of one panel at a time, WPR warps per row (warp w: row w / WPR,
+// segments k, k + WPR, ... of the row with k = w % WPR; a segment = 32 consecutive columns; at most 16 segments per warp:
+// WPR = 2 for C >= 512).  The packed inverse is static: the segments of a task are loaded while the PREVIOUS task (or the
+// previous step of the hop) still waits and computes (DenseB); then: wait for t1 -> shared memory, FMAs, warp reduction,
+// WPR partial sums per row added in a fixed order.
+constexpr uint32_t DP_SEG = 16;
+struct DenseB {
+  double v[DP_SEG];
+  uint32_t row0, m, q0;        // panel rows [row0, row0 + m), compact index of its first row
+  uint32_t ck;                 // the task's chunk of R rows inside the panel
+  bool have;                   // there is such a task
 };
-
 template <uint32_t WPR>
-__device__ __forceinline__ DnPre dp_dense_pre(const DpArgs &P, const DpPanel *__restrict__ pans, uint32_t ntasks, uint32_t task,
-                                              uint32_t warp, uint32_t lane) {
-  constexpr uint32_t R = 32u / WPR;
-  DnPre d;
+__device__ __forceinline__ DenseB dp_dense_b(const DpArgs &P, const DpPanel *__restrict__ pans, uint32_t ntasks, uint32_t task,
+                                             uint32_t warp, uint32_t lane) {
+  constexpr uint32_t R = DP_WARPS / WPR;
+  DenseB d;
 #pragma unroll
-  for (int u = 0; u < 8; u++) d.v[u] = 0.0;
-  d.row0 = d.m = d.i = d.nload = 0u;
+  for (int u = 0; u < (int)DP_SEG; u++) d.v[u] = 0.0;
+  d.row0 = d.m = d.q0 = d.ck = 0u;
   d.have = task < ntasks;
   if (d.have) {
     const uint32_t tpp = P.C / R;
-    const uint32_t pi = task / tpp, ck = task - pi * tpp;
+    const uint32_t pi = task / tpp;
+    d.ck = task - pi * tpp;
     const DpPanel *pan = pans + pi;
-    d.row0 = pan->row0; d.m = pan->m;
-    d.i = ck * R + warp / WPR;
-    d.nload = ((ck * R + R - 1u) | 31u) + 1u;
-    if (d.i < d.m) {
-      const uint32_t g = d.i >> 5, k = warp % WPR;
-      const double *ip = P.inv + pan->inv_off + dp_row_off(d.i) + lane;
+    d.row0 = pan->row0; d.m = pan->m; d.q0 = pan->q0;
+    const uint32_t i = d.ck * R + warp / WPR;
+    if (i < d.m) {
+      const uint32_t g = i >> 5, k = warp % WPR;
+      const double *ip = P.inv + pan->inv_off + dp_row_off(i) + lane;
 #pragma unroll
-      for (uint32_t u = 0; u < 8u; u++)
+      for (uint32_t u = 0; u < DP_SEG; u++)
         if (k + WPR * u <= g) d.v[u] = __ldcs(ip + 32u * (k + WPR * u));
     }
   }
   return d;
 }
-
 template <uint32_t WPR>
 __device__ __forceinline__ void dp_dense_tasks(const DpArgs &P, const DpPanel *__restrict__ pans, uint32_t ntasks, double *tsm,
-                                               double *part, uint32_t warp, uint32_t lane, DnPre d) {
-  constexpr uint32_t R = 32u / WPR;
+                                               double *part, uint32_t warp, uint32_t lane, DenseB d, DpSpin &sp,
+                                               unsigned long long *tr) {
+  constexpr uint32_t R = DP_WARPS / WPR;
   for (uint32_t task = blockIdx.x; task < ntasks; task += gridDim.x) {
-    if (task != blockIdx.x) d = dp_dense_pre<WPR>(P, pans, ntasks, task, warp, lane);
-    if (threadIdx.x < d.nload) tsm[threadIdx.x] = threadIdx.x < d.m ? __ldcg(P.w + d.row0 + threadIdx.x) : 0.0;
-    __syncthreads();
-    double acc = 0.0;
-    if (d.i < d.m) {
-      const uint32_t g = d.i >> 5, k = warp % WPR;
-      const double *tp = tsm + lane;
-      double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-      for (uint32_t u = 0; u < 8u; u += 2u) {
-        if (k + WPR * u <= g) a0 = fma(d.v[u], tp[32u * (k + WPR * u)], a0);
-        if (k + WPR * (u + 1u) <= g) a1 = fma(d.v[u + 1u], tp[32u * (k + WPR * (u + 1u))], a1);
+    // the CTA's next task of this hop: its loads are in flight while this one waits and computes
+    const DenseB nx = dp_dense_b<WPR>(P, pans, ntasks, task + gridDim.x, warp, lane);
+    if (d.ck * R < d.m) {   // (CTA-uniform; a panel shorter than C has empty chunks)
+      const uint32_t i = d.ck * R + warp / WPR, k = warp % WPR, g = i >> 5;
+      const uint32_t nload = ((d.ck * R + R - 1u) | 31u) + 1u;   // t entries the task's rows read
+      if (tr && lane == 0u) tr[4] = dp_gtime();
+      {   // (nload <= 1024: at most two words per thread, both loads in flight before either is waited for)
+        const uint32_t qa = threadIdx.x, qb = threadIdx.x + DP_THREADS;
+        double ta = 0.0, tb = 0.0;
+        if (qa < d.m && qa < nload) ta = dp_ld(P.t1 + d.q0 + qa);
+        if (qb < d.m && qb < nload) tb = dp_ld(P.t1 + d.q0 + qb);
+        if (dp_is_sent(ta)) ta = dp_wait(P, P.t1 + d.q0 + qa, sp);
+        if (dp_is_sent(tb)) tb = dp_wait(P, P.t1 + d.q0 + qb, sp);
+        if (qa < nload) tsm[qa] = ta;
+        if (qb < nload) tsm[qb] = tb;
       }
-      acc = a0 + a1;
-      if (g >= 8u * WPR) {   // (panels of up to 1024 rows have at most 32 segments: never taken with WPR = 4)
-        const DpPanel *pan = pans + task / (P.C / R);
-        const double *ip = P.inv + pan->inv_off + dp_row_off(d.i) + lane;
-        for (uint32_t sgm = k + 8u * WPR; sgm <= g; sgm += WPR) acc = fma(__ldcs(ip + 32u * sgm), tp[32u * sgm], acc);
-      }
-    }
-    acc = warp_sum(acc);
-    if (lane == 0u) part[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x < R) {
-      const uint32_t i = (d.i - warp / WPR) + threadIdx.x;   // (d.i - warp / WPR = first row of the task)
+      if (tr && lane == 0u) tr[5] = dp_gtime();
+      __syncthreads();
+      if (tr && lane == 0u) tr[6] = dp_gtime();
+      double acc = 0.0;
       if (i < d.m) {
-        double x = part[threadIdx.x * WPR];
+        const double *tp = tsm + lane;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (uint32_t k = 1; k < WPR; k++) x += part[threadIdx.x * WPR + k];
-        const uint32_t j = d.row0 + i;
-        __stcg(P.out + (P.reversed ? P.N - 1u - j : j), x);
+        for (uint32_t u = 0; u < DP_SEG; u += 2u) {
+          if (k + WPR * u <= g) a0 = fma(d.v[u], tp[32u * (k + WPR * u)], a0);
+          if (k + WPR * (u + 1u) <= g) a1 = fma(d.v[u + 1u], tp[32u * (k + WPR * (u + 1u))], a1);
+        }
+        acc = a0 + a1;
       }
+      acc = warp_sum(acc);
+      if (lane == 0u) part[warp] = acc;
+      __syncthreads();
+      if (threadIdx.x < R) {
+        const uint32_t ii = d.ck * R + threadIdx.x;
+        if (ii < d.m) {
+          double x = part[threadIdx.x * WPR];
+#pragma unroll
+          for (uint32_t kk = 1; kk < WPR; kk++) x += part[threadIdx.x * WPR + kk];
+          const uint32_t j = d.row0 + ii;
+          dp_st(P.out + (P.reversed ? P.N - 1u - j : j), x);
+        }
+      }
+      if (tr && lane == 0u) tr[7] = dp_gtime();
     }
+    d = nx;
   }
 }
 
 __global__ void __launch_bounds__(DP_THREADS, 1) k_dp_solve(const DpArgs P) {
   __shared__ __align__(16) double tsm[DP_CMAX];
   __shared__ double part[DP_WARPS];
-  __shared__ uint32_t dead_s;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   // consecutive work items go to different SMs: warp w of CTA c is global warp w * gridDim + c
   const uint32_t gw = warp * gridDim.x + blockIdx.x, nw = gridDim.x * DP_WARPS;
-  if (threadIdx.x == 0) dead_s = 0u;
-  uint32_t gen = 0;
+  DpSpin sp;
   const bool prof = P.clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-  long long c_sync = 0, c_p1 = 0, c_p2 = 0, c_p0 = 0, c_t = 0, c_start = 0;
+  long long c_p1 = 0, c_p2 = 0, c_p0 = 0, c_pf = 0, c_t = 0, c_start = 0;
   if (prof) c_start = c_t = clock64();
   auto lap = [&](long long &acc) {
     if (prof) {
@@ -448,102 +533,83 @@ __global__ void __launch_bounds__(DP_THREADS, 1) k_dp_solve(const DpArgs P) {
       c_t = now;
     }
   };
-  const uint32_t R = 32u / P.wpr, tpp = P.C / R;   // rows per dense task, dense tasks per panel
-  auto dense_pre = [&](uint32_t hop) -> DnPre {
+  const uint32_t R = DP_WARPS / P.wpr, tpp = P.C / R;   // rows per dense task, dense tasks per panel
+  // the near phase of hop h takes a whole warp per row when there are warps to spare, else 8 lanes per row
+  auto rows_of = [&](uint32_t hop) { return (P.hop_ptr[hop + 1] - P.hop_ptr[hop]) * P.C; };
+  auto near_a = [&](uint32_t hop) -> NearA {
+    if (hop >= P.nhops) return NearA{0, 0, 0u, false};
+    const uint32_t total = rows_of(hop);
+    return total <= nw ? dp_near_a<32>(P, P.panels + P.hop_ptr[hop], total, gw, lane)
+                       : dp_near_a<8>(P, P.panels + P.hop_ptr[hop], total, gw * 4u, lane);
+  };
+  auto dense_b = [&](uint32_t hop) -> DenseB {
     const uint32_t p0 = P.hop_ptr[hop], ntasks = (P.hop_ptr[hop + 1] - p0) * tpp;
-    return P.wpr == 4u   ? dp_dense_pre<4>(P, P.panels + p0, ntasks, blockIdx.x, warp, lane)
-           : P.wpr == 2u ? dp_dense_pre<2>(P, P.panels + p0, ntasks, blockIdx.x, warp, lane)
-                         : dp_dense_pre<1>(P, P.panels + p0, ntasks, blockIdx.x, warp, lane);
+    return P.wpr == 2u ? dp_dense_b<2>(P, P.panels + p0, ntasks, blockIdx.x, warp, lane)
+                       : dp_dense_b<1>(P, P.panels + p0, ntasks, blockIdx.x, warp, lane);
   };
-  // L2 prefetch of a later hop: by the CTAs that have no dense task in this hop when there are such, else by all
-  auto prefetch = [&](uint32_t hop, uint32_t busy_ctas, bool with_rows) {
-    if (busy_ctas + 4u <= gridDim.x) {   // at least four idle CTAs
-      if (blockIdx.x >= busy_ctas)
-        dp_prefetch_hop(P, hop, warp * (gridDim.x - busy_ctas) + (blockIdx.x - busy_ctas), (gridDim.x - busy_ctas) * DP_WARPS, lane, with_rows);
-    } else {
-      dp_prefetch_hop(P, hop, gw, nw, lane, with_rows);
-    }
-  };
-  prefetch(0, 0, false);
-  if (P.nhops > 1u) prefetch(1, 0, true);
-  __syncthreads();
-
-  // sum over a panel's rows of out * dotvec (fused r.z of the backward solve), one warp per panel, fixed order
-  auto panel_dot = [&](const DpPanel *pan) {
-    double d0 = 0.0, d1 = 0.0;
-    uint32_t i = lane;
-    for (; i + 32u < pan->m; i += 64u) {
-      const uint32_t j0 = pan->row0 + i, j1 = j0 + 32u;
-      const uint32_t v0 = P.reversed ? P.N - 1u - j0 : j0, v1 = P.reversed ? P.N - 1u - j1 : j1;
-      if (v0 < P.dot_limit) d0 = fma(__ldcg(P.out + v0), P.dotvec[v0], d0);
-      if (v1 < P.dot_limit) d1 = fma(__ldcg(P.out + v1), P.dotvec[v1], d1);
-    }
-    if (i < pan->m) {
-      const uint32_t j0 = pan->row0 + i;
-      const uint32_t v0 = P.reversed ? P.N - 1u - j0 : j0;
-      if (v0 < P.dot_limit) d0 = fma(__ldcg(P.out + v0), P.dotvec[v0], d0);
-    }
-    d0 = warp_sum(d0 + d1);
-    if (lane == 0u) P.dot_partials[pan->slot] = d0;
-  };
+  for (uint32_t hh = 0; hh < 3u && hh < P.nhops; hh++) dp_prefetch_hop(P, hh, gw, nw, lane, hh > 0u);
+  lap(c_pf);
+  NearA na = near_a(1);
+  DenseB db = dense_b(0);
 
   // ---- phase 0: start vector of all rows of the level ----------------------------------------------------------------
-  dp_far_rows(P, P.hop_ptr[P.nhops] * P.C, gw, nw, lane);
-  DnPre dn = dense_pre(0);
+  dp_far_rows(P, P.hop_ptr[P.nhops] * P.C, P.hop_ptr[1], gw, nw, lane, sp);
   lap(c_p0);
-  if (!dp_grid_sync(P, ++gen, &dead_s)) return;
-  lap(c_sync);
   for (uint32_t hop = 0; hop < P.nhops; hop++) {
     const uint32_t p0 = P.hop_ptr[hop], np = P.hop_ptr[hop + 1] - p0;
-    unsigned long long *tr = (P.trace && hop == P.nhops / 2u) ? P.trace + ((size_t)blockIdx.x * 32u + warp) * 16u : nullptr;
-    auto mark = [&](int k) {
-      if (tr && lane == 0u) tr[k] = clock64();
-    };
-    mark(0);
-    // (phase 1 of the next hop: own-block entries left of its panels; a whole warp per row when there are warps to
-    //  spare.  Its static loads are issued early: row pointers before the dense tasks, first entries after them.)
-    const uint32_t p1 = hop + 1u < P.nhops ? P.hop_ptr[hop + 1] : 0u;
-    const uint32_t total = hop + 1u < P.nhops ? (P.hop_ptr[hop + 2] - p1) * P.C : 0u;
-    const bool wide = total <= nw;
-    const SpRow sr = wide ? dp_near_row<32>(P, P.panels + p1, total, gw, lane) : dp_near_row<8>(P, P.panels + p1, total, gw * 4u, lane);
-    mark(1);
-    // ---- phase 2: x = Inv t ------------------------------------------------------------------------------------
-    if (P.wpr == 4u) dp_dense_tasks<4>(P, P.panels + p0, np * tpp, tsm, part, warp, lane, dn);
-    else if (P.wpr == 2u) dp_dense_tasks<2>(P, P.panels + p0, np * tpp, tsm, part, warp, lane, dn);
-    else dp_dense_tasks<1>(P, P.panels + p0, np * tpp, tsm, part, warp, lane, dn);
-    mark(2);
-    if (hop + 1u == P.nhops) {
-      lap(c_p2);
-      break;
-    }
-    const SpPre sp = wide ? dp_near_pre<32>(P, sr) : dp_near_pre<8>(P, sr);
-    mark(3);
-    if (hop + 2u < P.nhops) prefetch(hop + 2u, min(np * tpp, gridDim.x), true);
-    mark(4);
+    unsigned long long *tr = (P.trace && hop == P.nhops / 2u) ? P.trace + ((size_t)blockIdx.x * 32u + warp) * 16u : nullptr;   // ([CTA][32][16]: 16 of the 32 warp slots used)
+    unsigned long long *tr2 = (P.trace && hop == P.nhops / 2u + 1u) ? P.trace + ((size_t)blockIdx.x * 32u + warp) * 16u + 8u : nullptr;
+    if (tr2) tr = tr2;   // (the hop after the traced one: its dense marks go to the second half)
+    // ---- phase 2 of this hop: x = Inv t -----------------------------------------------------------------------------
+    if (P.wpr == 2u) dp_dense_tasks<2>(P, P.panels + p0, np * tpp, tsm, part, warp, lane, db, sp, tr);
+    else dp_dense_tasks<1>(P, P.panels + p0, np * tpp, tsm, part, warp, lane, db, sp, tr);
+    if (tr2) tr = nullptr;
     lap(c_p2);
-    if (!dp_grid_sync(P, ++gen, &dead_s, tr ? tr + 8 : nullptr)) return;
-    mark(5);
-    lap(c_sync);
-    if (wide) dp_near_rows<32>(P, P.panels + p1, total, gw, nw, lane, sp);
-    else dp_near_rows<8>(P, P.panels + p1, total, gw, nw, lane, sp);
-    mark(6);
-    // fused dot of this hop's panels (their rows are final), warps taken from the far end of the grid
-    if (P.dot_partials)
-      for (uint32_t d = nw - 1u - gw; d < np; d += nw) panel_dot(P.panels + p0 + d);
-    dn = dense_pre(hop + 1u);
-    mark(7);
+    if (hop + 1u == P.nhops) break;
+    // ---- static loads of the next hop (near entries, inverse), then its phase 1 ------------------------------------------
+    const uint32_t p1 = P.hop_ptr[hop + 1], total = rows_of(hop + 1u);
+    const bool wide = total <= nw;
+    const NearB nb = wide ? dp_near_b<32>(P, na, lane) : dp_near_b<8>(P, na, lane);
+    db = dense_b(hop + 1u);
+    // L2 prefetch three hops ahead by ONE warp per CTA, paced by the solve: not before the first row of this hop is
+    // solved (a CTA without work would otherwise run ahead and push the inverses of all hops through L2 at once; one
+    // polling warp per CTA: thousands of warps polling one word queue up at its L2 slice, measured 17k cycles per hop)
+    if (hop + 3u < P.nhops && warp == DP_WARPS - 1u) {
+      if (lane == 0u) {
+        const uint32_t j = P.panels[p0].row0;
+        dp_wait(P, P.out + (P.reversed ? P.N - 1u - j : j), sp);
+      }
+      dp_prefetch_hop(P, hop + 3u, blockIdx.x, gridDim.x, lane, true);
+    }
+    lap(c_pf);
+    if (wide) dp_near_rows<32>(P, P.panels + p1, total, gw, nw, lane, nb, sp, tr);
+    else dp_near_rows<8>(P, P.panels + p1, total, gw, nw, lane, nb, sp, tr);
+    na = near_a(hop + 2u);
     lap(c_p1);
-    if (!dp_grid_sync(P, ++gen, &dead_s, tr ? tr + 12 : nullptr)) return;
-    lap(c_sync);
   }
-  if (P.dot_partials) {   // the last hop's panels
-    if (!dp_grid_sync(P, ++gen, &dead_s)) return;
-    const uint32_t q0 = P.hop_ptr[P.nhops - 1u], nq = P.hop_ptr[P.nhops] - q0;
-    for (uint32_t d = gw; d < nq; d += nw) panel_dot(P.panels + q0 + d);
+  // ---- fused r.z of the backward solve: sum over a panel's rows of out * dotvec, one warp per panel, fixed order --------
+  if (P.dot_partials) {
+    const uint32_t npan = P.hop_ptr[P.nhops];
+    for (uint32_t d = gw; d < npan; d += nw) {
+      const DpPanel *pan = P.panels + d;
+      double d0 = 0.0, d1 = 0.0;
+      for (uint32_t i = lane; i < pan->m; i += 64u) {
+        const uint32_t j0 = pan->row0 + i, j1 = j0 + 32u;
+        const uint32_t v0 = P.reversed ? P.N - 1u - j0 : j0, v1 = P.reversed ? P.N - 1u - j1 : j1;
+        const bool h1 = i + 32u < pan->m;
+        double x0 = dp_ld(P.out + v0), x1 = h1 ? dp_ld(P.out + v1) : 0.0;
+        if (dp_is_sent(x0)) x0 = dp_wait(P, P.out + v0, sp);
+        if (h1 && dp_is_sent(x1)) x1 = dp_wait(P, P.out + v1, sp);
+        if (v0 < P.dot_limit) d0 = fma(x0, P.dotvec[v0], d0);
+        if (h1 && v1 < P.dot_limit) d1 = fma(x1, P.dotvec[v1], d1);
+      }
+      d0 = warp_sum(d0 + d1);
+      if (lane == 0u) P.dot_partials[pan->slot] = d0;
+    }
   }
   if (prof) {
     P.clk[3] = (unsigned long long)(clock64() - c_start);
-    P.clk[4] = (unsigned long long)c_sync;
+    P.clk[4] = (unsigned long long)c_pf;
     P.clk[5] = (unsigned long long)c_p0;
     P.clk[6] = (unsigned long long)c_p1;
     P.clk[7] = (unsigned long long)c_p2;
@@ -557,10 +623,15 @@ __global__ void __launch_bounds__(DP_THREADS, 1) k_dp_solve(const DpArgs P) {
 // ---------------------------------------------------------------------------------------------------------
 // Panel rows of a level from its shape: time ~ hops * t_hop + bytes / bandwidth with hops = max_rows / C and
 // bytes = 4 C per row, minimal at C = sqrt(t_hop * bandwidth * max_rows / (4 * rows)); t_hop * bandwidth ~ 2 us * 5 TB/s.
-inline uint32_t dp_choose_panel(uint32_t max_rows, int64_t rows, int forced) {
+inline uint32_t dp_choose_panel(uint32_t max_rows, int64_t rows, int forced, uint32_t blocks) {
   uint32_t C;
   if (forced > 0) C = (uint32_t)forced;
-  else C = (uint32_t)std::lround(std::sqrt(1.0e7 * (double)max_rows / (4.0 * (double)std::max<int64_t>(1, rows))) / 32.0) * 32u;
+  else {
+    C = (uint32_t)std::lround(std::sqrt(1.0e7 * (double)max_rows / (4.0 * (double)std::max<int64_t>(1, rows))) / 32.0) * 32u;
+    // with several panels per hop the dense phase runs best with one warp per row (rows of at most 16 segments, 16 rows
+    // per CTA task): measured at 256^3, 8 blocks of 15 691 rows, C = 576 (two warps per row, 576 tasks per hop): 15.7 us per hop
+    if (blocks >= 8u && C >= 512u) C = 480u;
+  }
   C = std::min(C, ((max_rows + 31u) / 32u) * 32u);
   return std::max(32u, std::min(DP_CMAX, (C / 32u) * 32u));
 }
@@ -616,11 +687,11 @@ int dp_build(rcg_handle *h, DirectionDev &d, const CsrDev &comb) {
   int per_sm = 0;
   RCG_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_solve, DP_THREADS, DP_SMEM));
   D.max_ctas = std::max(1, per_sm) * h->sm_count;
-  RCG_CUDA(h, cudaMalloc(&D.bar, sizeof(uint32_t) * d.groups.size() * (size_t)D.max_ctas));
+  RCG_CUDA(h, cudaMalloc(&D.t0, sizeof(double) * ((size_t)D.nrows + 4)));
+  RCG_CUDA(h, cudaMalloc(&D.t1, sizeof(double) * ((size_t)D.nrows + 4)));
   RCG_CUDA(h, cudaMemcpyAsync(D.panels, panels.data(), sizeof(DpPanel) * panels.size(), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemcpyAsync(D.hop_ptr, hop_ptr.data(), sizeof(uint32_t) * hop_ptr.size(), cudaMemcpyHostToDevice, h->stream));
   RCG_CUDA(h, cudaMemsetAsync(D.inv, 0, sizeof(double) * (size_t)inv_doubles + 256, h->stream));
-  RCG_CUDA(h, cudaMemsetAsync(D.bar, 0, sizeof(uint32_t) * d.groups.size() * (size_t)D.max_ctas, h->stream));
   k_dp_spans<<<(D.npanels + 255) / 256, 256, 0, h->stream>>>(D.panels, D.npanels, D.near.rowptr);
   const int igrid = (int)std::min<int64_t>(((int64_t)slices + 7) / 8, (int64_t)h->sm_count * 8);
   k_dp_invert<<<std::max(1, igrid), 256, 0, h->stream>>>(comb.rowptr, comb.col, comb.val, B.far.rowptr, D.near.rowptr, D.panels,
@@ -640,20 +711,23 @@ int dp_launch(rcg_handle *h, BlockedDev &B, const BcArgs &a, size_t gi) {
   p.panels = D.panels + L.panel0;
   p.hop_ptr = D.hop_ptr + L.hop0;
   p.nhops = L.nhops; p.C = L.C;
-  p.wpr = L.C >= 512u ? 4u : L.C >= 256u ? 2u : 1u;
+  p.wpr = L.C >= 512u ? 2u : 1u;
   p.inv = D.inv;
   p.near_rp = D.near.rowptr; p.near_col = D.near.col; p.near_val = D.near.val;
   p.far_rp = a.far_rp; p.far_col = a.far_col; p.far_val = a.far_val;
   p.rhs = a.rhs; p.col_min = a.col_min; p.corr = a.corr;
-  p.w = a.w; p.out = a.out;
+  p.t0 = D.t0; p.t1 = D.t1; p.out = a.out;
   p.dotvec = a.dotvec; p.dot_partials = a.dot_partials; p.dot_limit = a.dot_limit;
   p.N = a.N; p.reversed = a.reversed;
-  p.bar = D.bar + gi * (size_t)D.max_ctas;
   p.abort_g = a.abort_g;
   p.clk = (a.dbg & 1u) ? a.clk : nullptr;
   p.trace = (a.dbg & 2u) && h->clk_probe ? h->clk_probe + 16 : nullptr;
-  // grid: every CTA takes part in every barrier: one CTA per SM, and no more CTAs than phase 0 (4 rows per warp at a
-  // time) can use
+  if (p.trace) RCG_CUDA(h, cudaMemsetAsync(p.trace, 0, sizeof(unsigned long long) * RCG_DP_TRACE_WORDS, h->stream));   // (the last launch's marks remain)
+  // sentinels into this level's rows of t0 / t1 / out
+  k_dp_fill<<<std::max<uint32_t>(1u, std::min<uint32_t>((L.npanels * L.C + 255u) / 256u, (uint32_t)h->sm_count * 8u)), 256, 0, h->stream>>>(
+      p.panels, L.npanels, L.C, p.t0, p.t1, p.out, p.N, p.reversed);
+  h->stats.kernel_launches += 1;
+  // grid: one CTA per SM, and no more CTAs than phase 0 (4 rows per warp at a time) can use
   const int64_t tasks = ((int64_t)L.npanels * L.C + 4 * DP_WARPS - 1) / (4 * DP_WARPS);
   int64_t cap = std::min<int64_t>(D.max_ctas, h->sm_count);
   if (const char *e = getenv("RCG_DP_CTAS_PER_SM"))   // tuning experiments: resident CTAs per SM that take part

@@ -1,4 +1,5 @@
-"""Per-warp time marks of one hop of a dense-panel level (development tool).  Usage: python scripts/r02_dp_trace.py n T dir level"""
+"""Time marks (globaltimer, ns) of one hop of a dense-panel level (development tool).
+Usage: python scripts/r02_dp_trace.py n T dir level"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -17,27 +18,29 @@ with capi.Solver(0, dbg=2) as s:
     ms = s.time_group(direction, gi, 0, 2)
     tr = s.dp_trace().astype(np.int64)
 print("level ms", ms)
-ctas = [c for c in range(160) if tr[c, 0, 0] != 0]
-print("CTAs traced", len(ctas))
-names = ["m0 hop start", "m1 rowptr issued", "m2 dense done", "m3 near-pre issued", "m4 prefetch done", "m5 barrier A passed", "m6 near rows done",
-         "m7 dense-pre issued"]
-for c in (ctas[0], ctas[len(ctas) // 2], ctas[-1]):
-    base = tr[c, :, 0].min()
-    print(f"CTA {c}: marks relative to the CTA's first warp entering the hop (min / median / max over warps)")
-    for k in range(8):
-        v = tr[c, :, k] - base
-        print(f"   {names[k]:22s} {v.min():7d} {int(np.median(v)):7d} {v.max():7d}   slowest warp {int(v.argmax())}")
-    b = tr[c, 0, 8:16] - base
-    print("   barrier A (thread 0): cta-synced, released, polled, fenced:", b[:4].tolist(), " barrier B:", b[4:8].tolist())
-# across CTAs: duration of the pieces for warp 0 / max over warps
-def span(a, b):
-    return np.array([(tr[c, :, b] - tr[c, :, a]).max() for c in ctas])
-for a, b, nm in ((0, 2, "dense (m0->m2)"), (2, 4, "pre+prefetch (m2->m4)"), (5, 6, "near rows (m5->m6)"), (6, 7, "dot+dense-pre (m6->m7)")):
-    v = span(a, b)
-    print(f"{nm:26s} max over warps, per CTA: min {v.min()} median {int(np.median(v))} max {v.max()} (CTA {ctas[int(v.argmax())]})")
-wa = np.array([tr[c, 0, 10] - tr[c, 0, 8] for c in ctas])
-wb = np.array([tr[c, 0, 14] - tr[c, 0, 12] for c in ctas])
-print("barrier A wait (cta-synced -> polled): min", wa.min(), "median", int(np.median(wa)), "max", wa.max())
-print("barrier B wait (cta-synced -> polled): min", wb.min(), "median", int(np.median(wb)), "max", wb.max())
-hop = np.array([tr[c, 0, 15] - tr[c, 0, 0] for c in ctas])
-print("whole hop (m0 -> barrier B fenced), warp 0: min", hop.min(), "median", int(np.median(hop)), "max", hop.max())
+def stats(name, v):
+    v = np.asarray(v)
+    if v.size == 0:
+        print(f"{name:40s} (none)"); return
+    print(f"{name:40s} n={v.size:5d} min {v.min():7d} p10 {int(np.percentile(v, 10)):7d} med {int(np.median(v)):7d} p90 {int(np.percentile(v, 90)):7d} max {v.max():7d}")
+dn = tr[:, :, 4]
+ctas = [c for c in range(160) if dn[c, 0] != 0]
+T0 = min(dn[c, 0] for c in ctas)
+print("CTAs with a dense task in the traced hop:", len(ctas), " all times in ns after the first of them started waiting for t1")
+stats("dense(H)  start waiting (warp 0)", [tr[c, 0, 4] - T0 for c in ctas])
+stats("dense(H)  t1 there (slowest warp of CTA)", [tr[c, :, 5].max() - T0 for c in ctas])
+stats("dense(H)  synced (warp 0)", [tr[c, 0, 6] - T0 for c in ctas])
+stats("dense(H)  x stored (warp 0)", [tr[c, 0, 7] - T0 for c in ctas])
+order = np.argsort([tr[c, 0, 7] for c in ctas])
+print("   x stored, by CTA (= task) index, every 16th:", [(ctas[k], int(tr[ctas[k], 0, 7] - T0)) for k in range(0, len(ctas), 16)])
+nr = [(c, w) for c in range(160) for w in range(32) if tr[c, w, 3] != 0]
+stats("near(H+1) indicator word there", [tr[c, w, 0] - T0 for c, w in nr])
+stats("near(H+1) first gathers there", [tr[c, w, 1] - T0 for c, w in nr if tr[c, w, 1]])
+stats("near(H+1) row tail done", [tr[c, w, 2] - T0 for c, w in nr])
+stats("near(H+1) t1 stored", [tr[c, w, 3] - T0 for c, w in nr])
+stats("near(H+1) tail time", [tr[c, w, 2] - max(tr[c, w, 1], tr[c, w, 0]) for c, w in nr])
+c2 = [c for c in range(160) if tr[c, 0, 12] != 0]
+stats("dense(H+1) start waiting (warp 0)", [tr[c, 0, 12] - T0 for c in c2])
+stats("dense(H+1) t1 there (slowest warp)", [tr[c, :, 13].max() - T0 for c in c2])
+stats("dense(H+1) x stored (warp 0)", [tr[c, 0, 15] - T0 for c in c2])
+print("   x stored, by CTA (= task) index, every 16th:", [(c2[k], int(tr[c2[k], 0, 15] - T0)) for k in range(0, len(c2), 16)])
