@@ -10,9 +10,10 @@
 // At solve time all blocks of the level advance in lock step, one panel per HOP, on the whole GPU:
 //     phase 1:  t_k = start_k - sum over own-block entries left of the panel  L[j,c] x_c     (8 lanes per row)
 //     phase 2:  x_k = Inv_k t_k                                                              (one warp per row)
-// with one grid barrier behind each phase.  The start vector (right-hand side minus the entries of other, already
-// solved blocks) is formed for all rows of the level before the hops start (phase 0, HBM-bound, all rows in parallel).
-// The next hop's inverses and sparse rows are prefetched into L2 a hop ahead, so every load behind a barrier is an L2 hit.
+// The start vector (right-hand side minus the entries of other, already solved blocks) is formed for all rows of the
+// level before the hops start (k_dp_pre: HBM-bound, all rows in parallel).  There are no grid barriers: every value
+// that crosses CTAs carries its own readiness (see "solve" below).  The inverses and sparse rows of the next hops are
+// prefetched into L2 three hops ahead, so the loads on the dependency chain are L2 hits.
 //
 // Packed inverse of one panel: row-major, rows grouped by 32; every row of group g holds 32 (g + 1) doubles (zeros above
 // the diagonal inside the diagonal 32 x 32 tile), so a warp reads a row as (g + 1) coalesced 256-byte segments.
@@ -135,20 +136,6 @@ __device__ __forceinline__ double dp_ld(const double *p) {   // L2-coherent load
 __device__ __forceinline__ void dp_st(double *p, double v) {
   unsigned long long old;
   asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(__double_as_longlong(v)) : "memory");
-}
-
-__global__ void k_dp_fill(const DpPanel *__restrict__ panels, uint32_t npanels, uint32_t C, double *__restrict__ t0,
-                          double *__restrict__ t1, double *__restrict__ out, uint32_t N, int reversed) {
-  const double sent = __longlong_as_double((long long)DP_SENT);
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < npanels * C; t += gridDim.x * blockDim.x) {
-    const uint32_t pi = t / C, i = t - pi * C;
-    if (i < panels[pi].m) {
-      const uint32_t j = panels[pi].row0 + i, q = panels[pi].q0 + i;
-      t0[q] = sent;
-      t1[q] = sent;
-      out[reversed ? N - 1u - j : j] = sent;
-    }
-  }
 }
 
 // Bounded waiting: called after a poll that found the sentinel; true = give up (results are garbage, the host reports it).
@@ -417,9 +404,20 @@ __device__ __forceinline__ void dp_far_rows(const DpArgs &P, uint32_t total, uin
       const uint32_t v = P.reversed ? P.N - 1u - j : j;
       double s0 = P.rhs[v];
       if (P.corr) s0 -= P.corr[v - P.col_min];
-      dp_st((pi < hop0_panels ? P.t1 : P.t0) + q, s0 - acc);
+      const double sent = __longlong_as_double((long long)DP_SENT);
+      P.out[v] = sent;   // (plain stores: the kernel ends before k_dp_solve starts)
+      if (pi < hop0_panels) P.t1[q] = s0 - acc;
+      else { P.t0[q] = s0 - acc; P.t1[q] = sent; }
     }
   }
+}
+
+// Start vector of all rows of the level (HBM-bound, all rows in parallel, 64 warps per SM), and the sentinels of the
+// words k_dp_solve waits for.
+__global__ void __launch_bounds__(256) k_dp_pre(const DpArgs P) {
+  const uint32_t lane = threadIdx.x & 31u;
+  DpSpin sp;
+  dp_far_rows(P, P.hop_ptr[P.nhops] * P.C, P.hop_ptr[1], blockIdx.x * 8u + (threadIdx.x >> 5), gridDim.x * 8u, lane, sp);
 }
 
 // ---- dense phase -----------------------------------------------------------------------------------------------------
@@ -552,9 +550,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) k_dp_solve(const DpArgs P) {
   NearA na = near_a(1);
   DenseB db = dense_b(0);
 
-  // ---- phase 0: start vector of all rows of the level ----------------------------------------------------------------
-  dp_far_rows(P, P.hop_ptr[P.nhops] * P.C, P.hop_ptr[1], gw, nw, lane, sp);
-  lap(c_p0);
+  lap(c_p0);   // (phase 0, the start vector of all rows of the level: k_dp_pre)
   for (uint32_t hop = 0; hop < P.nhops; hop++) {
     const uint32_t p0 = P.hop_ptr[hop], np = P.hop_ptr[hop + 1] - p0;
     unsigned long long *tr = (P.trace && hop == P.nhops / 2u) ? P.trace + ((size_t)blockIdx.x * 32u + warp) * 16u : nullptr;   // ([CTA][32][16]: 16 of the 32 warp slots used)
@@ -723,12 +719,14 @@ int dp_launch(rcg_handle *h, BlockedDev &B, const BcArgs &a, size_t gi) {
   p.clk = (a.dbg & 1u) ? a.clk : nullptr;
   p.trace = (a.dbg & 2u) && h->clk_probe ? h->clk_probe + 16 : nullptr;
   if (p.trace) RCG_CUDA(h, cudaMemsetAsync(p.trace, 0, sizeof(unsigned long long) * RCG_DP_TRACE_WORDS, h->stream));   // (the last launch's marks remain)
-  // sentinels into this level's rows of t0 / t1 / out
-  k_dp_fill<<<std::max<uint32_t>(1u, std::min<uint32_t>((L.npanels * L.C + 255u) / 256u, (uint32_t)h->sm_count * 8u)), 256, 0, h->stream>>>(
-      p.panels, L.npanels, L.C, p.t0, p.t1, p.out, p.N, p.reversed);
-  h->stats.kernel_launches += 1;
-  // grid: one CTA per SM, and no more CTAs than phase 0 (4 rows per warp at a time) can use
-  const int64_t tasks = ((int64_t)L.npanels * L.C + 4 * DP_WARPS - 1) / (4 * DP_WARPS);
+  // start vector (right-hand side minus the entries of other blocks) and sentinels of this level's rows
+  {
+    const int64_t batches = ((int64_t)L.npanels * L.C + 31) / 32;   // 32 rows per CTA at a time
+    k_dp_pre<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(batches, (int64_t)h->sm_count * 8)), 256, 0, h->stream>>>(p);
+    h->stats.kernel_launches += 1;
+  }
+  // grid: one CTA per SM, and no more CTAs than the first hop's near phase (4 rows per warp at a time) can use
+  const int64_t tasks = std::max<int64_t>(((int64_t)a.nblocks * L.C + 4 * DP_WARPS - 1) / (4 * DP_WARPS), ((int64_t)a.nblocks * L.C + 7) / 8);
   int64_t cap = std::min<int64_t>(D.max_ctas, h->sm_count);
   if (const char *e = getenv("RCG_DP_CTAS_PER_SM"))   // tuning experiments: resident CTAs per SM that take part
     if (atoi(e) > 0) cap = std::min<int64_t>(D.max_ctas, (int64_t)atoi(e) * h->sm_count);
