@@ -4,7 +4,7 @@ NVCC     ?= /usr/local/cuda/bin/nvcc
 HOSTCXX  ?= /usr/bin/g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-fopenmp
-SRC      := rchol_b200/csrc/rcg_api.cu rchol_b200/csrc/rcg_setup.cu rchol_b200/csrc/rcg_kernels.cu rchol_b200/csrc/rcg_trisolve.cu rchol_b200/csrc/rcg_blocked.cu rchol_b200/csrc/rcg_dist.cu
+SRC      := rchol_b200/csrc/rcg_api.cu rchol_b200/csrc/rcg_setup.cu rchol_b200/csrc/rcg_kernels.cu rchol_b200/csrc/rcg_trisolve.cu rchol_b200/csrc/rcg_blocked.cu rchol_b200/csrc/rcg_dist.cu rchol_b200/csrc/rcg_pool.cu
 OBJ      := $(SRC:.cu=.o)
 LIB      := rchol_b200/lib/librchol_b200.so
 

@@ -350,7 +350,7 @@ def measure_resident(d, threads, steps, warmup, peak, levels=True):
         spmv_ms = prof["spmv_ms"]
         ach = tot_bytes / tot_ms / 1e6
         out["roofline"] = dict(
-            bound="hbm", kernel="triangular-solve level launches (k_fc_solve / k_wb_solve): all launches of one forward + one backward solve",
+            bound="hbm", kernel="triangular-solve level launches (k_wb_pre + k_wb_solve / k_dp_pre + k_dp_solve / k_bc_solve): all launches of one forward + one backward solve",
             achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, launches_per_solve_pair=nl, bytes_per_launch=tot_bytes / nl,
             ms_per_launch=tot_ms / nl, trsv_kernel_ms_per_iteration=tot_ms,
             largest_launch=dict(kernel=dom[0], ms=dom[1], gbs=dom[2] / dom[1] / 1e6),

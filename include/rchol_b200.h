@@ -48,8 +48,11 @@ typedef struct rcg_options {
   int use_graph;           /* 1 = replay one CUDA graph per PCG iteration (default), 0 = plain launches   */
   int spmv_lanes;          /* lanes per row of the CSR SpMV (0 = choose from the row-length histogram)     */
   int chain_generic;       /* 1 = force the non-pipelined fallback kernel of the triangular solve (testing)  */
-  int chain_mode;          /* 0 (default): tree levels with few blocks on the blocked-inverse chain (k_bc_solve: four critical warps, one
-                              named barrier per 32-row chunk), tree levels with many blocks (>= 64, reserved[9]) one warp per block
+  int chain_mode;          /* 0 (default): separator levels with at most 64 blocks as dense-panel levels (k_dp_pre + k_dp_solve,
+                              rcg_dense.cuh: explicitly inverted C x C diagonal panels, all blocks of the level in lock step on the
+                              whole GPU; reserved[6]), other tree levels with few blocks on the blocked-inverse chain (k_bc_solve:
+                              four critical warps, one named barrier per 32-row chunk), tree levels with many blocks (>= 64,
+                              reserved[9]) one warp per block
                               (k_wb_pre + k_wb_solve, rcg_fold.cuh); 5 = the same with the few-block levels on the folded chain
                               (k_fc_solve: recent entries folded into dense panels at set-up, three chain warps taking turns);
                               6 = the blocked-inverse chain for every level (round 1), 3 = the same with one critical warp, 4 = the
@@ -59,7 +62,10 @@ typedef struct rcg_options {
   int reserved[10];        /* [0] helper back-off ns, [1] timing-experiment bits, [2] TMA producer warps (default 2),
                               [3] blocked solve: recent chunk distance Kr (default 2), [4] window rows of the separator blocks
                               (default 1024), [5] blocked solve: distance E (chunks) that separates the "early" from the "late" entries:
-                              bits 0-7 leaf blocks (default 16), bits 8-15 separator blocks (default 6), [6] 1 = plain (non-cooperative) launch, [7] staging slot of the helpers' ring in quarters of
+                              bits 0-7 leaf blocks (default 16), bits 8-15 separator blocks (default 6), [6] bit 0: plain (non-cooperative) launch; dense-panel levels: bit 1 = the leaf
+                              level too, bits 2-7 = levels with more than 2^(v-1) blocks are not dense-panel levels (0 = default 64 blocks,
+                              >= 32 = no limit), bits 8-15 = rows / 32 of a level's longest block from which the level is a dense-panel
+                              level (0 = default 128 rows, 255 = never), bits 16-31 = panel rows C (0 = from the level's shape), [7] staging slot of the helpers' ring in quarters of
                               the mean blob (default 12), [8] staging slots of the chain's ring (0 = automatic), [9] bits 0-7: lanes per row of the
                               far CTAs' in-block pass (8 default, 32); bits 8-15: chunks per far tile of the separator blocks
                               (default 1; leaves use 8) */

@@ -23,6 +23,7 @@
 // Every spin wait is bounded (clock64 time-out -> abort flag, all waits of all CTAs then fall through): corrupt input
 // or a scheduling accident cannot hang the GPU; the host turns the flag into an error.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -1519,6 +1520,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   B.dp.nrows = dp_rows_total;
   RCG_CUDA(h, cudaMalloc(&B.dp.near.rowptr, sizeof(int64_t) * ((size_t)dp_rows_total + 4)));
   RCG_CUDA(h, cudaMemsetAsync(B.dp.near.rowptr, 0, sizeof(int64_t) * ((size_t)dp_rows_total + 4), h->stream));
+  const auto t_count = std::chrono::steady_clock::now();
   const int cgrid = (int)std::min<int64_t>(((int64_t)B.nchunks + 7) / 8, (int64_t)h->sm_count * 16);
   k_bc_count<<<std::max(1, cgrid), 256, 0, h->stream>>>(comb.rowptr, comb.col, g, B.nchunks, B.offA, B.offB, B.far.rowptr,
                                                        B.tile_need, derr, B.dp.near.rowptr);
@@ -1527,6 +1529,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));
   RCG_CUDA(h, cudaFree(derr));
+  if (getenv("RCG_TIMING")) fprintf(stderr, "[rcg] k_bc_count: %.1f ms\n", 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_count).count());
   if (herr) {
     cudaFree(dgeom);
     h->err = "factor row without a trailing diagonal after transposition (G is not triangular)";
@@ -1558,6 +1561,11 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
                                                       B.dp.near.rowptr, B.dp.near.col, B.dp.near.val);
   h->stats.kernel_launches += 1;
   RCG_CUDA(h, cudaGetLastError());
+  if (getenv("RCG_TIMING")) {
+    const auto t_fill = std::chrono::steady_clock::now();
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    fprintf(stderr, "[rcg] k_bc_fill (+ blob memsets): %.1f ms after the launch\n", 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fill).count());
+  }
 
   // ---- levels (dependency groups) and their blocks -----------------------------------------------------------
   d.groups.clear();
@@ -1826,10 +1834,14 @@ int rcg_launch_blocked(rcg_handle *h, DirectionDev &d, const double *rhs, double
       continue;
     }
     if (L.wb) {   // warp-per-block level: fully parallel pre-pass over the entries of other blocks, then one warp per block
-      const uint32_t pre_grid = std::min<uint32_t>((uint32_t)G.count, (uint32_t)h->sm_count * 8u);
+      // pre-pass grid: (CTAs per block, blocks) -- about 16 CTAs per SM in total, a CTA takes 128 rows at a time
+      const uint32_t pre_y = std::min<uint32_t>((uint32_t)G.count, 32768u);
+      const uint32_t pre_x = std::max(1u, std::min<uint32_t>((G.max_rows + 127u) / 128u, ((uint32_t)h->sm_count * 16u + pre_y - 1u) / pre_y));
       a.ticket = B.flags + B.ntiles + B.nblocks + gi % 4;   // (four spare words behind the flags: consecutive levels never share one)
       RCG_CUDA(h, cudaMemsetAsync(a.ticket, 0, sizeof(uint32_t), h->stream));
-      k_wb_pre<<<pre_grid, 256, 0, h->stream>>>(a);
+      BcArgs ap = a;
+      if (gi == 0 && !h->dist.on) ap.far_lpr2 = 0xFFFFFFFFu;   // no block is solved before the direction's first level: start = rhs
+      k_wb_pre<<<dim3(pre_x, pre_y), 256, 0, h->stream>>>(ap);
       k_wb_solve<<<std::min<uint32_t>(L.groups, (uint32_t)h->sm_count * L.wbocc), L.SA * 32, L.smem, h->stream>>>(a);
       RCG_CUDA(h, cudaGetLastError());
       h->stats.kernel_launches += 2;

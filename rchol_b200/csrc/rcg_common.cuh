@@ -257,6 +257,22 @@ struct rcg_handle {
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// device memory
+// ---------------------------------------------------------------------------------------------------------
+// The set-up allocates and frees tens of GB in a dozen pieces per call (CSR copies of G, its transpose, the blocked
+// layouts); cudaMalloc / cudaFree of GB-sized pieces map and unmap physical memory and took 25 ... 3000 ms of a 30 ms
+// analysis from one call to the next (measured, 128^3).  All device allocations of the library therefore go through the
+// device's stream-ordered memory pool with an unlimited release threshold: freed memory stays mapped in the pool and the
+// next handle -- the reference's one-shot `pcg(...)` constructor creates and destroys one per solve -- reuses it.
+// RCG_POOL=0 in the environment restores plain cudaMalloc / cudaFree.
+cudaError_t rcg_pool_malloc(void **p, size_t bytes);
+cudaError_t rcg_pool_free(void *p);
+#ifndef RCG_POOL_IMPL
+#define cudaMalloc(p, s) rcg_pool_malloc((void **)(p), (s))
+#define cudaFree(p) rcg_pool_free((void *)(p))
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------------------------------------
 #define RCG_CUDA(h, expr)                                                                         \

@@ -56,16 +56,34 @@ __global__ void __launch_bounds__(256) k_dp_invert(const int64_t *__restrict__ r
     const DpPanel pan = panels[lo];
     const uint32_t c0 = 32u * (task - pan.slice0), c = c0 + lane;
     double *X = inv + pan.inv_off;
+    // (the row's bounds are loaded one row ahead; the entries of a row eight at a time, all loads of a batch in flight
+    //  together: a thread has no other memory-level parallelism here.  The order of the additions is the row's order.)
+    auto bounds = [&](uint32_t i, int64_t &p0, int64_t &pd) {
+      const uint32_t j = pan.row0 + i, q = pan.q0 + i;
+      pd = rp[j + 1] - 1;
+      p0 = rp[j] + (far_rp[j + 1] - far_rp[j]) + (near_rp[q + 1] - near_rp[q]);
+    };
+    int64_t p0 = 0, pd = 0, np0 = 0, npd = 0;
+    if (c0 < pan.m) bounds(c0, p0, pd);
     for (uint32_t i = c0; i < pan.m; i++) {
-      const uint32_t j = pan.row0 + i;
-      const int64_t pd = rp[j + 1] - 1;
+      if (i + 1u < pan.m) bounds(i + 1u, np0, npd);
       double acc = i == c ? 1.0 : 0.0;
-      const uint32_t q = pan.q0 + i;
-      for (int64_t p = rp[j] + (far_rp[j + 1] - far_rp[j]) + (near_rp[q + 1] - near_rp[q]); p < pd; p++) {
-        const uint32_t cc = col[p] - pan.row0;
-        if (cc >= c0) acc = fma(-val[p], X[dp_row_off(cc) + c], acc);
+      for (int64_t p = p0; p < pd; p += 8) {
+        uint32_t cc[8];
+        double vv[8], xx[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          cc[u] = 0u; vv[u] = 0.0;
+          if (p + u < pd) { cc[u] = col[p + u] - pan.row0; vv[u] = val[p + u]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) xx[u] = (p + u < pd && cc[u] >= c0) ? X[dp_row_off(cc[u]) + c] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (p + u < pd && cc[u] >= c0) acc = fma(-vv[u], xx[u], acc);
       }
       X[dp_row_off(i) + c] = acc / val[pd];
+      p0 = np0; pd = npd;
     }
   }
 }
@@ -677,6 +695,8 @@ int dp_build(rcg_handle *h, DirectionDev &d, const CsrDev &comb) {
   D.npanels = (uint32_t)panels.size();
   D.inv_doubles = inv_doubles;
   if (panels.empty()) return RCG_OK;
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  const auto t_start = std::chrono::steady_clock::now();
   RCG_CUDA(h, cudaMalloc(&D.panels, sizeof(DpPanel) * panels.size()));
   RCG_CUDA(h, cudaMalloc(&D.hop_ptr, sizeof(uint32_t) * hop_ptr.size()));
   RCG_CUDA(h, cudaMalloc(&D.inv, sizeof(double) * (size_t)inv_doubles + 256));
@@ -695,6 +715,9 @@ int dp_build(rcg_handle *h, DirectionDev &d, const CsrDev &comb) {
   h->stats.kernel_launches += 2;
   RCG_CUDA(h, cudaGetLastError());
   RCG_CUDA(h, cudaStreamSynchronize(h->stream));   // (panels / hop_ptr are host vectors of this scope)
+  if (getenv("RCG_TIMING")) fprintf(stderr, "[rcg] dp_build: %u panels, %lld rows, %.1f MB of inverses, %.1f ms (allocations, k_dp_invert)\n",
+                                    D.npanels, (long long)D.nrows, (double)inv_doubles * 8e-6,
+                                    1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
   D.on = true;
   return RCG_OK;
 }

@@ -618,39 +618,63 @@ __global__ void __launch_bounds__(FC_THREADS, 1) k_fc_solve(const BcArgs P) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WB_WARPS = 4;
 
+// grid (x, blocks): the CTAs of one block share its rows in units of 128 (8 warps x 4 rows x 4 row batches per trip).
+// A row is a dependent chain of loads (far row pointer / split -> columns, values -> x), so a thread keeps the chains of
+// FOUR rows in flight (measured with one: 1.18 ms for the 1.3 GB of the backward leaf level at 256^3 / T = 4096, 1.1 TB/s;
+// ncu launch list, profiles/r02_launches_T4096.csv).  P.far_lpr2 == 0xFFFFFFFF: no block is solved before this level
+// (forward leaves, backward root): the start vector is the right-hand side.
 __global__ void __launch_bounds__(256) k_wb_pre(const BcArgs P) {
+  constexpr int U = 4;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t sub = lane & 7u;   // 8 lanes per row, 4 rows per warp, 32 rows per CTA pass
-  for (uint32_t bi = blockIdx.x; bi < P.nblocks; bi += gridDim.x) {
+  const uint32_t sub = lane & 7u;   // 8 lanes per row, 4 rows per warp, 32 rows per CTA and batch
+  const bool no_far = P.far_lpr2 == 0xFFFFFFFFu && P.corr == nullptr;
+  for (uint32_t bi = blockIdx.y; bi < P.nblocks; bi += gridDim.y) {
     const BcBlock b = P.blocks[bi];
-    for (uint32_t base = b.lo + 4u * warp; base < b.hi; base += 32u) {
-      const uint32_t j = base + (lane >> 3);
-      const bool valid = j < b.hi;
-      double acc = 0.0;
-      if (valid) {
-        const int64_t e0 = P.far_rp[j], e1 = e0 + P.far_split[j];   // [e0, e1): entries of other blocks
-        double acc1 = 0.0;
-        int64_t e = e0 + sub;
-        for (; e + 8 < e1; e += 16) {
-          const uint32_t c = P.far_col[e], c2 = P.far_col[e + 8];
-          if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
-          if (c2 >= P.col_min) acc1 = fma(P.far_val[e + 8], __ldcg(P.out + c2), acc1);
+    for (uint32_t base = b.lo + blockIdx.x * (32u * U); base < b.hi; base += gridDim.x * (32u * U)) {
+      uint32_t j[U];
+      int64_t e[U], e1[U];
+      double acc[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        j[u] = base + 32u * (uint32_t)u + 4u * warp + (lane >> 3);
+        e[u] = e1[u] = 0;
+        acc[u] = 0.0;
+        if (j[u] < b.hi && !no_far) {
+          e[u] = P.far_rp[j[u]];
+          e1[u] = e[u] + P.far_split[j[u]];   // [e, e1): entries of other blocks
+          e[u] += sub;
         }
-        if (e < e1) {
-          const uint32_t c = P.far_col[e];
-          if (c >= P.col_min) acc = fma(P.far_val[e], __ldcg(P.out + c), acc);
+      }
+      bool more = true;
+      while (more) {
+        uint32_t c[U];
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (e[u] < e1[u]) { c[u] = P.far_col[e[u]]; v[u] = P.far_val[e[u]]; }
+        more = false;
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (e[u] < e1[u]) {
+            if (c[u] >= P.col_min) acc[u] = fma(v[u], __ldcg(P.out + c[u]), acc[u]);
+            e[u] += 8;
+            more = more || e[u] < e1[u];
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 4);
+        acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 2);
+        acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 1);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (j[u] < b.hi && sub == 0u) {
+          const uint32_t i = P.reversed ? P.N - 1u - j[u] : j[u];
+          double s = P.rhs[i];
+          if (P.corr) s -= P.corr[i - P.col_min];
+          __stcg(P.w + j[u], s - acc[u]);
         }
-        acc += acc1;
-      }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (valid && sub == 0u) {
-        const uint32_t i = P.reversed ? P.N - 1u - j : j;
-        double s = P.rhs[i];
-        if (P.corr) s -= P.corr[i - P.col_min];
-        __stcg(P.w + j, s - acc);
-      }
     }
   }
 }

@@ -26,23 +26,58 @@ __global__ void __launch_bounds__(256) k_spmv(const int64_t *__restrict__ rowptr
   const int sub = threadIdx.x % LPR;
   const uint32_t rows_per_cta = blockDim.x / LPR;
   double pq = 0.0, pr = 0.0;
-  for (uint32_t base = blockIdx.x * rows_per_cta; base < N; base += gridDim.x * rows_per_cta) {
-    const uint32_t row = base + threadIdx.x / LPR;
-    double s = 0.0;
-    if (row < N) {
-      const int64_t e = rowptr[row + 1];
-      for (int64_t k = rowptr[row] + sub; k < e; k += LPR) s = fma(val[k], __ldg(&x[col[k]]), s);
-    }
+  // U row batches per trip: the loads of a row are a dependent chain (row pointers -> columns / values -> x), so a warp
+  // with one batch in flight moves 4 rows per three memory round trips (measured 2.1 TB/s); U independent chains overlap.
+  // The order in which a thread adds up its rows is unchanged (bit-identical p.q / p.r).
+  constexpr int U = 4;
+  const uint32_t stride = gridDim.x * rows_per_cta;
+  for (uint32_t base = blockIdx.x * rows_per_cta; base < N; base += U * stride) {
+    uint32_t row[U];
+    int64_t k[U], e[U];
+    double s[U];
 #pragma unroll
-    for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (row < N && sub == 0) {
-      y[row] = s;
-      if (DOTS) {
-        const double xr = x[row];
-        pq = fma(xr, s, pq);
-        pr = fma(xr, r[row], pr);
+    for (int u = 0; u < U; u++) {
+      const uint64_t r64 = (uint64_t)base + (uint64_t)u * stride + threadIdx.x / LPR;
+      const bool in = r64 < N;
+      row[u] = in ? (uint32_t)r64 : 0xFFFFFFFFu;
+      k[u] = e[u] = 0;
+      s[u] = 0.0;
+      if (in) {
+        k[u] = rowptr[row[u]] + sub;
+        e[u] = rowptr[row[u] + 1];
       }
     }
+    bool more = true;
+    while (more) {
+      uint32_t c[U];
+      double a[U];
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (k[u] < e[u]) { c[u] = col[k[u]]; a[u] = val[k[u]]; }
+      more = false;
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (k[u] < e[u]) {
+          s[u] = fma(a[u], __ldg(&x[c[u]]), s[u]);
+          k[u] += LPR;
+          more = more || k[u] < e[u];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int o = LPR >> 1; o > 0; o >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (row[u] != 0xFFFFFFFFu && sub == 0) {
+        y[row[u]] = s[u];
+        if (DOTS) {
+          const double xr = x[row[u]];
+          pq = fma(xr, s[u], pq);
+          pr = fma(xr, r[row[u]], pr);
+        }
+      }
   }
   if (DOTS) {
     double v[2] = {pq, pr};

@@ -17,7 +17,7 @@ for r in rows[1:]:
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1)
     launches.setdefault(lid, dict(name=name))[metric] = val * scale
 seq = [launches[k] for k in sorted(launches)]
-solve = [l for l in seq if any(t in l["name"] for t in ("k_wb_solve", "k_wb_pre", "k_bc_solve", "k_fc_solve"))]
+solve = [l for l in seq if any(t in l["name"] for t in ("k_wb_solve", "k_wb_pre", "k_bc_solve", "k_fc_solve", "k_dp_solve", "k_dp_pre"))]
 half = len(solve) // 2                       # the target applies the preconditioner twice: keep the second application
 solve = solve[half:]
 by = {}
