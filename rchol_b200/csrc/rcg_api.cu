@@ -222,7 +222,7 @@ int rcg_destroy(rcg_handle *h) {
   if (h->haveG) { rcg_free_direction(h->fwd); rcg_free_direction(h->bwd); }
   cudaFree(h->perm);
   for (int i = 0; i < 2; i++) {
-    if (h->stage_buf[i]) cudaFreeHost(h->stage_buf[i]);
+    rcg_release_stage_buffer(h->stage_buf[i]);
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
   }
   cudaEventDestroy(h->ev0);
@@ -443,15 +443,22 @@ int rcg_pcg_oneshot(int device, uint64_t N, const uint64_t *ArowPtr, const uint6
   double t0 = wall_ms();
   int rc = rcg_create(&h, device);
   if (rc != RCG_OK) return rc;
+  const double t1 = wall_ms();
   rc = rcg_set_matrix(h, N, ArowPtr, AcolIdx, Aval);
+  const double t2 = wall_ms();
   if (rc == RCG_OK) rc = rcg_set_factor(h, N, GrowPtr, GcolIdx, Gval, part, npart);
+  const double t3 = wall_ms();
   if (rc == RCG_OK) rc = rcg_pcg(h, b, tol, maxit, x, relres, itr);
+  const double t4 = wall_ms();
   if (rc != RCG_OK) g_create_error = h->err;
   if (stats_or_null) {
     rcg_get_stats(h, stats_or_null);
     stats_or_null->total_ms = wall_ms() - t0;
   }
   rcg_destroy(h);
+  if (getenv("RCG_TIMING"))
+    fprintf(stderr, "[rcg] one-shot: create %.1f ms, set_matrix %.1f, set_factor %.1f, pcg %.1f, destroy %.1f\n", t1 - t0, t2 - t1, t3 - t2,
+            t4 - t3, wall_ms() - t4);
   return rc;
 }
 

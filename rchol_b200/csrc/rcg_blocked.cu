@@ -1365,6 +1365,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   BlockedDev &B = d.bc;
   const uint32_t N = (uint32_t)h->N;
   const int nb = (int)bounds.size() - 1;
+  RcgPhases ph;
   // ---- thresholds ------------------------------------------------------------------------------------
   // (the split chain keeps the solution of two chunks in its partial-sum buffers: recent distance at most 2)
   // chain_mode 0 (default): round-1 blocked chain (four critical warps) for the tree levels with few blocks -- measured 15 %
@@ -1535,6 +1536,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     h->err = "factor row without a trailing diagonal after transposition (G is not triangular)";
     return RCG_ERR_STRUCTURE;
   }
+  ph.mark(h->stream, "  layout: geometry, k_bc_count");
   RCG_TRY(rcg_exclusive_scan(h, B.offA, (int64_t)B.nchunks + 1));
   RCG_TRY(rcg_exclusive_scan(h, B.offB, (int64_t)B.nchunks + 1));
   RCG_TRY(rcg_exclusive_scan(h, B.far.rowptr, (int64_t)N + 1));
@@ -1555,6 +1557,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
   RCG_CUDA(h, cudaMemsetAsync(B.far_split, 0, sizeof(uint32_t) * ((size_t)N + 1), h->stream));
   RCG_CUDA(h, cudaMalloc(&B.far.col, sizeof(uint32_t) * (size_t)(far_total + 8)));
   RCG_CUDA(h, cudaMalloc(&B.far.val, sizeof(double) * (size_t)(far_total + 8)));
+  ph.mark(h->stream, "  layout: scans, allocations, memsets");
   const int fgrid = (int)std::min<int64_t>(((int64_t)B.nchunks + 3) / 4, (int64_t)h->sm_count * 16);
   k_bc_fill<<<std::max(1, fgrid), 128, 0, h->stream>>>(comb.rowptr, comb.col, comb.val, g, B.nchunks, N, d.reversed ? 1 : 0,
                                                       B.offA, B.offB, B.blobA, B.blobB, B.far.rowptr, B.far.col, B.far.val, B.far_split,
@@ -1567,6 +1570,7 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     fprintf(stderr, "[rcg] k_bc_fill (+ blob memsets): %.1f ms after the launch\n", 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fill).count());
   }
 
+  ph.mark(h->stream, "  layout: k_bc_fill");
   // ---- levels (dependency groups) and their blocks -----------------------------------------------------------
   d.groups.clear();
   B.blocks_host.clear();
@@ -1741,11 +1745,14 @@ int rcg_build_blocked(rcg_handle *h, DirectionDev &d, CsrDev &comb, const std::v
     const int rc = cl_build(h, d, comb, max_depth);
     if (rc != RCG_OK) { rcg_free_csr(comb); return rc; }
   }
+  ph.mark(h->stream, "  layout: levels, staging plan");
   {
     const int rc = dp_build(h, d, comb);
     if (rc != RCG_OK) { rcg_free_csr(comb); return rc; }
   }
+  ph.mark(h->stream, "  layout: dp_build");
   rcg_free_csr(comb);
+  ph.mark(h->stream, "  layout: free of the direction's CSR");
   if (!h->abort_flag) {
     RCG_CUDA(h, cudaMalloc(&h->abort_flag, sizeof(unsigned int) * 4));
     RCG_CUDA(h, cudaMemset(h->abort_flag, 0, sizeof(unsigned int) * 4));

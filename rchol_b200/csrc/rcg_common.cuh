@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <string>
 #include <vector>
 
@@ -261,9 +264,10 @@ struct rcg_handle {
 // ---------------------------------------------------------------------------------------------------------
 // The set-up allocates and frees tens of GB in a dozen pieces per call (CSR copies of G, its transpose, the blocked
 // layouts); cudaMalloc / cudaFree of GB-sized pieces map and unmap physical memory and took 25 ... 3000 ms of a 30 ms
-// analysis from one call to the next (measured, 128^3).  All device allocations of the library therefore go through the
-// device's stream-ordered memory pool with an unlimited release threshold: freed memory stays mapped in the pool and the
-// next handle -- the reference's one-shot `pcg(...)` constructor creates and destroys one per solve -- reuses it.
+// analysis from one call to the next (measured at 128^3; at 256^3 1400 ms of the second one-shot solve, also with
+// cudaMallocAsync and an unlimited release threshold).  All device allocations of the library therefore go through a
+// small caching allocator (rcg_pool.cu): freed blocks are kept and handed to the next request of the same size -- the
+// reference's one-shot `pcg(...)` constructor creates and destroys a handle per solve and repeats the same sizes.
 // RCG_POOL=0 in the environment restores plain cudaMalloc / cudaFree.
 cudaError_t rcg_pool_malloc(void **p, size_t bytes);
 cudaError_t rcg_pool_free(void *p);
@@ -271,6 +275,25 @@ cudaError_t rcg_pool_free(void *p);
 #define cudaMalloc(p, s) rcg_pool_malloc((void **)(p), (s))
 #define cudaFree(p) rcg_pool_free((void *)(p))
 #endif
+
+// Phase times of the set-up on stderr when RCG_TIMING is set in the environment (development aid; syncs the stream).
+struct RcgPhases {
+  bool on;
+  double t;
+  explicit RcgPhases() : on(getenv("RCG_TIMING") != nullptr), t(now()) {}
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+  }
+  void mark(cudaStream_t s, const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    const double n = now();
+    fprintf(stderr, "[rcg]   %-44s %8.1f ms\n", what, n - t);
+    t = n;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------------------
 // error plumbing
@@ -305,6 +328,7 @@ int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const ui
                      const uint64_t *part, uint64_t npart);
 int rcg_setup_factor_blocks(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                             const uint64_t *bounds, const int32_t *depth, uint64_t nblocks);
+void rcg_release_stage_buffer(void *pinned);
 void rcg_free_direction(DirectionDev &d);
 void rcg_free_csr(CsrDev &a);
 

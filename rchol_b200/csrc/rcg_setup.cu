@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "rcg_common.cuh"
 
@@ -123,11 +124,30 @@ int exclusive_scan_inplace(rcg_handle *h, int64_t *data, int64_t n) {
 // staging buffers (narrowing the 64-bit column indices to 32 bits and range-checking them on the way, so only 12 B
 // per entry cross PCIe instead of 16) while the copy engine drains the other buffer.
 constexpr size_t STAGE_BYTES = (size_t)64 << 20;
+}  // namespace
+
+// Pinning 2 x 64 MiB costs tens of milliseconds per handle, and the reference's one-shot `pcg(...)` creates a handle per
+// solve: released staging buffers are kept (at most four per process) and handed to the next handle.
+static std::mutex g_stage_mu;
+static std::vector<void *> g_stage_free;
+
+void rcg_release_stage_buffer(void *p) {   // rcg_destroy
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_stage_mu);
+  if (g_stage_free.size() < 4) g_stage_free.push_back(p);
+  else cudaFreeHost(p);
+}
+
+namespace {
 
 int stage_init(rcg_handle *h) {
   if (h->stage_buf[0]) return RCG_OK;
   for (int i = 0; i < 2; i++) {
-    RCG_CUDA(h, cudaHostAlloc(&h->stage_buf[i], STAGE_BYTES, cudaHostAllocDefault));
+    {
+      std::lock_guard<std::mutex> lock(g_stage_mu);
+      if (!g_stage_free.empty()) { h->stage_buf[i] = g_stage_free.back(); g_stage_free.pop_back(); }
+    }
+    if (!h->stage_buf[i]) RCG_CUDA(h, cudaHostAlloc(&h->stage_buf[i], STAGE_BYTES, cudaHostAllocPortable));
     RCG_CUDA(h, cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
   }
   return RCG_OK;
@@ -1532,7 +1552,9 @@ static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, 
   if (h->haveG) { rcg_free_direction(h->fwd); rcg_free_direction(h->bwd); h->haveG = false; }
   const int nb = (int)bounds.size() - 1;
   CsrDev U;
+  RcgPhases ph;
   RCG_TRY(upload_csr(h, N, rowPtr, colIdx, val, U));
+  ph.mark(h->stream, "set_factor: upload of G");
   h->N = N;
   const int64_t nnz = U.nnz;
   const uint32_t n32 = (uint32_t)N;
@@ -1574,6 +1596,7 @@ static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, 
     }
   }
   RCG_CUDA(h, cudaFree(derr));
+  ph.mark(h->stream, "set_factor: validation");
 
   // ---- forward direction: L = U^T ---------------------------------------------------------------------
   CsrDev L;
@@ -1596,6 +1619,7 @@ static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, 
     RCG_CUDA(h, cudaFree(cursor));
   }
 
+  ph.mark(h->stream, "set_factor: transpose + row sort (L)");
   // ---- backward direction: reversed U ------------------------------------------------------------------
   CsrDev R;
   R.nnz = nnz;
@@ -1611,13 +1635,16 @@ static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, 
   h->bwd.reversed = true;
   h->fwd.reversed = false;
 
+  ph.mark(h->stream, "set_factor: reversed copy (R), free U");
   // ---- schedules ---------------------------------------------------------------------------------------
   RCG_TRY(finish_direction(h, h->fwd, L, bounds, tree.depth, tree.max_depth, /*root_first=*/false));
+  ph.mark(h->stream, "set_factor: forward layout");
   std::vector<uint32_t> rbounds(nb + 1);
   std::vector<int> rdepth(nb);
   for (int i = 0; i <= nb; i++) rbounds[i] = n32 - bounds[nb - i];
   for (int b = 0; b < nb; b++) rdepth[b] = tree.depth[nb - 1 - b];
   RCG_TRY(finish_direction(h, h->bwd, R, rbounds, rdepth, tree.max_depth, /*root_first=*/true));
+  ph.mark(h->stream, "set_factor: backward layout");
 
   h->stats.analysis_ms += wall_ms() - t0;
   h->haveG = true;
