@@ -57,11 +57,12 @@ def log(*a):
 # ------------------------------------------------------------------------------------------------------------
 # problem construction (inputs of the hot path; cached on local disk so that the two arms share the factor)
 # ------------------------------------------------------------------------------------------------------------
-def build_problem(n: int, threads: int):
-    """A, G, part, b, P of the workload.  Generated once per box (reference factorization on the host, fixed seed) and
+def build_problem(n: int, threads: int, kind: str = "lap3d"):
+    """A, G, part, b, P of the workload (`kind`: "lap3d" = 7-point Laplacian on n^3, "aniso2d" = the anisotropic
+    random-weight 5-point SDDM on n^2).  Generated once per box (reference factorization on the host, fixed seed) and
     cached on local disk; under torchrun only local rank 0 generates, the other ranks wait for the cache and map it."""
     cache_root = os.environ.get("RCHOL_B200_CACHE", "/tmp/rchol_b200_cache")
-    tag = os.path.join(cache_root, f"lap3d_{n}_T{threads}_s{SEED}")
+    tag = os.path.join(cache_root, f"{kind}_{n}_T{threads}_s{SEED}")
     names = ["A_rp", "A_ci", "A_v", "G_rp", "G_ci", "G_v", "part", "b", "P"]
     ready = f"{tag}.ready"
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -83,7 +84,7 @@ def build_problem(n: int, threads: int):
             time.sleep(1.0)
         return load()
     t0 = time.time()
-    A = problems.laplace_3d(n)
+    A = problems.laplace_3d(n) if kind == "lap3d" else problems.aniso_2d(n)
     t1 = time.time()
     f = producer.factor(*A, threads=threads, seed=SEED)
     t2 = time.time()
@@ -95,7 +96,7 @@ def build_problem(n: int, threads: int):
         Ap, bp = A, b
     t3 = time.time()
     d = dict(A_rp=Ap[0], A_ci=Ap[1], A_v=Ap[2], G_rp=f.rowPtr, G_ci=f.colIdx, G_v=f.val, part=f.part, b=bp, P=f.P)
-    log(f"[bench] generated lap3d {n}^3: gen {t1 - t0:.1f}s, reference factorization (T={threads}) {t2 - t1:.1f}s, "
+    log(f"[bench] generated {kind} {n}^{3 if kind == 'lap3d' else 2}: gen {t1 - t0:.1f}s, reference factorization (T={threads}) {t2 - t1:.1f}s, "
         f"reorder {t3 - t2:.1f}s, nnzG={f.nnz}")
     try:
         os.makedirs(cache_root, exist_ok=True)
@@ -401,6 +402,61 @@ def parity_at_bench_config(s, d, tag):
     return out
 
 
+# ------------------------------------------------------------------------------------------------------------
+# secondary workloads measured beside the headline, each in its OWN process (a failure or time-out of a leg never
+# costs the headline line): BASELINE.json configs[3] -- 2-D anisotropic random-weight SDDM (pure-chain separators)
+# ------------------------------------------------------------------------------------------------------------
+def run_leg(args):
+    """Child process of the N = 1 arm: one secondary workload measured like the headline -- A, G, b resident, `steps`
+    timed PCG solves after `warmup`, the per-level split of the triangular solves, parity against the oracle at this size
+    (both triangular solves; iteration count of one converged CPU solve) -- printed as one JSON object."""
+    d, info = build_problem(args.n, args.threads, args.leg)
+    peak, _ = measured_peak_gbs()
+    m, s = measure_resident(d, args.threads, args.steps, args.warmup, peak)
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_at_bench_config(s, d, info.get("tag"))
+            parity["itr"] = m["iters_total"] // args.steps
+        except Exception as e:  # pragma: no cover
+            parity = dict(error=repr(e)[:300])
+    s.close()
+    r = m["roofline"]
+    dims = 3 if args.leg == "lap3d" else 2
+    out = dict(workload=f"{args.leg}_{args.n}^{dims}_rchol_T{args.threads}_pcg_tol1e-8", N=int(m["N"]), nnzA=m["nnzA"], nnzG=m["nnzG"],
+               nd_leaves=args.threads, iterations=m["iters_total"] // args.steps, relres=m["relres"],
+               ms_per_iter=m["dev_ms"] / max(m["iters_total"], 1), ms_per_solve=m["dev_ms"] / args.steps, value=m["value"], unit="GB/s",
+               frac_of_peak=m["value"] / peak, bytes_per_iteration=m["B_iter"],
+               trsv=dict(frac_of_peak=r["frac"], gbs=r["achieved"], ms_per_iteration=r["trsv_kernel_ms_per_iteration"],
+                         launches_per_solve_pair=r["launches_per_solve_pair"], largest_launch=r["largest_launch"]),
+               spmv_ms=r["iteration"]["spmv_ms"], spmv_gbs=r["iteration"]["spmv_gbs"], blas1_ms=r["iteration"]["blas1_ms"],
+               tree_levels={k: dict(rows=v["rows"], max_rows=v["max_rows"], ms=v["ms"], gbs=v["gbs"]) for k, v in r["tree_levels"].items()},
+               parity=parity, setup=m["setup"], gpu_launches=m["launches"], clocks=m["clocks"],
+               factor_s=info.get("factor_s"), steps=args.steps, warmup=args.warmup)
+    if parity and parity.get("cpu_solve_s") and parity.get("itr_ref"):
+        out["cpu_port_ms_per_iter"] = 1e3 * parity["cpu_solve_s"] / parity["itr_ref"]
+        out["cpu_port_threads"] = parity.get("threads")
+    print(json.dumps(out), flush=True)
+
+
+def leg_in_subprocess(kind: str, n: int, threads: int, steps: int, warmup: int, timeout_s: float):
+    """Runs `bench.py --leg ...` as a child with a time limit; returns its JSON object, or {"error": ...}."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--leg", kind, "--n", str(n), "--threads", str(threads),
+           "--steps", str(steps), "--warmup", str(warmup)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE")}
+    t0 = time.time()
+    try:
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=None, text=True, timeout=timeout_s, env=env, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return dict(error=f"leg exceeded its {timeout_s:.0f} s limit (reference factorization on the host + solves)")
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    if p.returncode != 0 or not lines:
+        return dict(error=f"leg ended with status {p.returncode}", stdout_tail=p.stdout[-300:])
+    out = json.loads(lines[-1])
+    out["leg_wall_s"] = time.time() - t0
+    return out
+
+
 def run_ours_single(args, d, B_iter, gen_info=None):
     gen_info = gen_info or {}
     from rchol_b200 import capi
@@ -490,6 +546,13 @@ def run_ours_single(args, d, B_iter, gen_info=None):
         except Exception as e:  # pragma: no cover - informational leg
             configs1 = dict(error=repr(e)[:300])
 
+    # ---- BASELINE.json configs[3] beside the headline: 2-D anisotropic random-weight SDDM, in its own process ----------
+    configs3 = None
+    if args.configs3:
+        configs3 = leg_in_subprocess("aniso2d", args.aniso_n, args.aniso_threads, 2, 2, args.leg_timeout)
+        configs3["baseline_config"] = (f"configs[3] (2-D anisotropic random-weight SDDM) at {args.aniso_n}^2 instead of 8192^2: the reference "
+                                       "factorization of 8192^2 takes ~15 min of host time per run (measured: 57 s at 2048^2 on 8 cores, linear in N)")
+
     line = dict(metric="pcg_gbps_per_iter", value=value, unit="GB/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
                 ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                 dtype="f64", data="synthetic", config=workload_config(args, d, N),
@@ -499,7 +562,7 @@ def run_ours_single(args, d, B_iter, gen_info=None):
                 roofline=roofline, cpu_baseline=cpu, parity=parity,
                 e2e=dict(value=e2e_value, unit="GB/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                          steps=e2e_steps, ms_per_step=e2e_ms / e2e_steps, host_memory="pageable (caller's SparseCSR arrays)"),
-                gpu_launches=m["launches"], clocks=m["clocks"], device_reorder=reorder_info, configs1=configs1,
+                gpu_launches=m["launches"], clocks=m["clocks"], device_reorder=reorder_info, configs1=configs1, configs3=configs3,
                 setup=m["setup"])
     print(json.dumps(line), flush=True)
 
@@ -519,8 +582,18 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison at the bench configuration")
     ap.add_argument("--no-configs1", dest="configs1", action="store_false",
                     help="skip the BASELINE.json configs[1] leg (same grid, the reference's 8-way partition)")
+    ap.add_argument("--no-configs3", dest="configs3", action="store_false",
+                    help="skip the BASELINE.json configs[3] leg (2-D anisotropic SDDM, run in a child process)")
+    ap.add_argument("--aniso-n", type=int, default=int(os.environ.get("RCHOL_B200_BENCH_ANISO_N", 4096)))
+    ap.add_argument("--aniso-threads", type=int, default=int(os.environ.get("RCHOL_B200_BENCH_ANISO_T", 4096)))
+    ap.add_argument("--leg-timeout", type=float, default=900.0, help="time limit of a secondary-workload child, seconds")
+    ap.add_argument("--leg", default=None, choices=["lap3d", "aniso2d"],
+                    help="(internal) measure one secondary workload given by --n/--threads and print its JSON object")
     args = ap.parse_args()
 
+    if args.leg:
+        run_leg(args)
+        return 0
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
 

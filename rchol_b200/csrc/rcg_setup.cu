@@ -260,36 +260,42 @@ int upload_csr(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t
     h->err = "empty matrix";
     return RCG_ERR_INVALID;
   }
-  double t0 = wall_ms();
-  out.nnz = nnz;
-  RCG_CUDA(h, cudaMalloc(&out.rowptr, sizeof(int64_t) * (N + 1)));
-  RCG_CUDA(h, cudaMalloc(&out.col, sizeof(uint32_t) * (size_t)nnz));
-  RCG_CUDA(h, cudaMalloc(&out.val, sizeof(double) * (size_t)nnz));
   int *derr = nullptr;
-  RCG_CUDA(h, cudaMalloc(&derr, sizeof(int)));
-  RCG_CUDA(h, cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
-  bool bad_col = false;
-  RCG_TRY(staged_copy(h, out.rowptr, rowPtr, sizeof(int64_t) * (N + 1)));
-  RCG_TRY(staged_narrow(h, out.col, colIdx, (size_t)nnz, N, &bad_col));
-  RCG_TRY(staged_copy(h, out.val, val, sizeof(double) * (size_t)nnz));
-  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->stats.upload_ms += wall_ms() - t0;
-  h->stats.h2d_bytes += sizeof(int64_t) * (N + 1) + (size_t)nnz * 12;
+  // the copies and the row-pointer check; on any failure the caller's `out` is left empty (nothing stays allocated)
+  auto body = [&]() -> int {
+    double t0 = wall_ms();
+    out.nnz = nnz;
+    RCG_CUDA(h, cudaMalloc(&out.rowptr, sizeof(int64_t) * (N + 1)));
+    RCG_CUDA(h, cudaMalloc(&out.col, sizeof(uint32_t) * (size_t)nnz));
+    RCG_CUDA(h, cudaMalloc(&out.val, sizeof(double) * (size_t)nnz));
+    RCG_CUDA(h, cudaMalloc(&derr, sizeof(int)));
+    RCG_CUDA(h, cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+    bool bad_col = false;
+    RCG_TRY(staged_copy(h, out.rowptr, rowPtr, sizeof(int64_t) * (N + 1)));
+    RCG_TRY(staged_narrow(h, out.col, colIdx, (size_t)nnz, N, &bad_col));
+    RCG_TRY(staged_copy(h, out.val, val, sizeof(double) * (size_t)nnz));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->stats.upload_ms += wall_ms() - t0;
+    h->stats.h2d_bytes += sizeof(int64_t) * (N + 1) + (size_t)nnz * 12;
 
-  double t1 = wall_ms();
-  k_check_rowptr<<<grid_for(h, (int64_t)N, 256), 256, 0, h->stream>>>(out.rowptr, (int64_t)N, nnz, derr);
-  h->stats.kernel_launches += 1;
-  int herr = 0;
-  RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
-  RCG_CUDA(h, cudaFree(derr));
-  h->stats.analysis_ms += wall_ms() - t1;
-  if (bad_col) herr = 1;
-  if (herr) {
-    h->err = "malformed CSR: column index out of range or row pointers not monotone";
-    return RCG_ERR_INVALID;
-  }
-  return RCG_OK;
+    double t1 = wall_ms();
+    k_check_rowptr<<<grid_for(h, (int64_t)N, 256), 256, 0, h->stream>>>(out.rowptr, (int64_t)N, nnz, derr);
+    h->stats.kernel_launches += 1;
+    int herr = 0;
+    RCG_CUDA(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->stats.analysis_ms += wall_ms() - t1;
+    if (bad_col) herr = 1;
+    if (herr) {
+      h->err = "malformed CSR: column index out of range or row pointers not monotone";
+      return RCG_ERR_INVALID;
+    }
+    return RCG_OK;
+  };
+  const int rc = body();
+  cudaFree(derr);
+  if (rc != RCG_OK) rcg_free_csr(out);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -500,18 +506,27 @@ int sort_segments(rcg_handle *h, const int64_t *rp, uint32_t *key, double *val, 
     int64_t gstride = 0;
     uint32_t *gkeys = nullptr;
     double *gvals = nullptr;
+    unsigned int batch = hn_long;
     if (maxlen > smem_cap) {
       gstride = 1;
       while (gstride < maxlen) gstride <<= 1;
-      // process the long segments in batches so that the padded scratch area stays bounded (<= 1 GiB)
-      RCG_CUDA(h, cudaMalloc(&gkeys, sizeof(uint32_t) * (size_t)gstride * hn_long));
-      RCG_CUDA(h, cudaMalloc(&gvals, sizeof(double) * (size_t)gstride * hn_long));
+      // the long segments are processed in batches so that the padded scratch area (gstride entries per CTA of a
+      // launch, 12 B each) stays at or below 1 GiB
+      const int64_t fit = ((int64_t)1 << 30) / (12 * gstride);
+      batch = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(fit, (int64_t)hn_long));
+      RCG_CUDA(h, cudaMalloc(&gkeys, sizeof(uint32_t) * (size_t)gstride * batch));
+      RCG_CUDA(h, cudaMalloc(&gvals, sizeof(double) * (size_t)gstride * batch));
     }
-    k_sort_rows_bitonic<<<hn_long, 512, smem_bytes, h->stream>>>(rp, key, val, long_rows, smem_cap, gkeys, gvals, gstride);
-    h->stats.kernel_launches += 1;
-    RCG_CUDA(h, cudaGetLastError());
-    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (unsigned int first = 0; first < hn_long; first += batch) {
+      const unsigned int cnt = std::min(batch, hn_long - first);
+      k_sort_rows_bitonic<<<cnt, 512, smem_bytes, h->stream>>>(rp, key, val, long_rows + first, smem_cap, gkeys, gvals, gstride);
+      h->stats.kernel_launches += 1;
+    }
+    cudaError_t se = cudaGetLastError();
+    if (se == cudaSuccess) se = cudaStreamSynchronize(h->stream);
     cudaFree(gkeys); cudaFree(gvals);
+    if (se != cudaSuccess) { cudaFree(long_rows); cudaFree(n_long); }
+    RCG_CUDA(h, se);
   }
   RCG_CUDA(h, cudaFree(long_rows));
   RCG_CUDA(h, cudaFree(n_long));
@@ -1116,11 +1131,11 @@ void rcg_free_direction(DirectionDev &d) {
 }
 
 int rcg_setup_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val) {
-  if (h->haveA) { rcg_free_csr(h->A); h->haveA = false; }
-  if (h->haveG && N != h->N) {
+  if (h->haveG && N != h->N) {   // (checked first: a rejected call leaves the handle's matrix in place)
     h->err = "matrix dimension differs from the factor's";
     return RCG_ERR_INVALID;
   }
+  if (h->haveA) { rcg_free_csr(h->A); h->haveA = false; }
   RCG_TRY(upload_csr(h, N, rowPtr, colIdx, val, h->A));
   h->N = N;
   h->haveA = true;
@@ -1551,7 +1566,10 @@ static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, 
                              const std::vector<uint32_t> &bounds, const TreeInfo &tree, bool strict_tree) {
   if (h->haveG) { rcg_free_direction(h->fwd); rcg_free_direction(h->bwd); h->haveG = false; }
   const int nb = (int)bounds.size() - 1;
-  CsrDev U;
+  CsrDev U, L, R;
+  // whatever of U, L, R is still allocated when the function returns (an error path) is released; the success path has
+  // handed L and R to the layouts and freed U (rcg_free_csr leaves null pointers behind, so this is a no-op then)
+  struct Scope { CsrDev *m[3]; ~Scope() { for (CsrDev *c : m) rcg_free_csr(*c); } } scope{{&U, &L, &R}};
   RcgPhases ph;
   RCG_TRY(upload_csr(h, N, rowPtr, colIdx, val, U));
   ph.mark(h->stream, "set_factor: upload of G");
@@ -1599,7 +1617,6 @@ static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, 
   ph.mark(h->stream, "set_factor: validation");
 
   // ---- forward direction: L = U^T ---------------------------------------------------------------------
-  CsrDev L;
   L.nnz = nnz;
   RCG_CUDA(h, cudaMalloc(&L.rowptr, sizeof(int64_t) * (N + 4)));   // padded: staged in 16-byte aligned slices
   RCG_CUDA(h, cudaMalloc(&L.col, sizeof(uint32_t) * (size_t)nnz));
@@ -1621,7 +1638,6 @@ static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, 
 
   ph.mark(h->stream, "set_factor: transpose + row sort (L)");
   // ---- backward direction: reversed U ------------------------------------------------------------------
-  CsrDev R;
   R.nnz = nnz;
   RCG_CUDA(h, cudaMalloc(&R.rowptr, sizeof(int64_t) * (N + 4)));
   RCG_CUDA(h, cudaMalloc(&R.col, sizeof(uint32_t) * (size_t)nnz));
