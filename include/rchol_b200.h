@@ -98,11 +98,18 @@ const char *rcg_version(void);
 /* ---- inputs (replaces pcg::create_sparse, pcg.cpp:31-54) ----------------------------------------------- */
 /* A: the (permuted) system matrix, general CSR. */
 int rcg_set_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val);
+/* Value-only refresh of A: a new matrix with the SAME sparsity pattern as the one set by rcg_set_matrix (the reference's
+ * reuse flow -- python/rchol/rchol.py:25-40 keeps perm / part for "a new matrix with the same sparsity",
+ * python/ex_reuse_partition.py).  val = nnz values in the order of the colIdx given to rcg_set_matrix.  The structure on
+ * the device and the captured iteration stay; 8 B per entry are uploaded.  RCG_ERR_STATE after rcg_set_matrix_permuted
+ * (the device re-sorted the rows), RCG_ERR_INVALID when nnz differs. */
+int rcg_update_matrix_values(rcg_handle *h, uint64_t nnz, const double *val);
 /* G: CSR of the upper-triangular factor U as returned by rchol(...) (rchol_lap.cpp:146-149): every row sorted,
  * diagonal first and positive.  `part` (may be NULL, npart = 0) = block boundaries of the reference's
  * nested-dissection layout in permuted index space (rchol_parallel.cpp:64-70 `result_idx`, ground vertex
  * dropped): npart = 2T entries, part[0] = 0, part[npart-1] = N, blocks in post-order
- * [left subtree..., right subtree..., separator].  Without it the factor is solved as one block. */
+ * [left subtree..., right subtree..., separator].  Without it (the reference's stock pcg signature, pcg.hpp:13-16) the
+ * blocks are recovered from G itself (rcg_detect_blocks below); a factor without that structure is solved as one block. */
 int rcg_set_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                    const uint64_t *part, uint64_t npart);
 

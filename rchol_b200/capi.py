@@ -28,7 +28,7 @@ EXPORTED = [
     "rcg_set_factor_blocks", "rcg_nccl_unique_id", "rcg_dist_init", "rcg_dist_finalize",
     "rcg_debug_blocked_info", "rcg_debug_blocked_copy", "rcg_debug_counters", "rcg_debug_dp_trace",
     "rcg_set_matrix_permuted", "rcg_set_permutation", "rcg_permute_vector", "rcg_unpermute_vector",
-    "rcg_pcg_original", "rcg_get_matrix", "rcg_detect_blocks",
+    "rcg_pcg_original", "rcg_get_matrix", "rcg_detect_blocks", "rcg_update_matrix_values",
 ]
 
 TRSV_FORWARD, TRSV_BACKWARD = 0, 1
@@ -117,6 +117,7 @@ def load():
     L.rcg_unpermute_vector.argtypes = [H, _f64p, _f64p]
     L.rcg_pcg_original.argtypes = [H, _f64p, C.c_double, C.c_int, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.rcg_get_matrix.argtypes = [H, _u64p, _u64p, _f64p]
+    L.rcg_update_matrix_values.argtypes = [H, C.c_uint64, _f64p]
     L.rcg_detect_blocks.argtypes = [C.c_uint64, _u64p, _u64p, _u64p, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"),
                                     C.c_uint64, C.POINTER(C.c_uint64)]
     for name in EXPORTED:
@@ -196,6 +197,11 @@ class Solver:
         rp = _u64(rowPtr)
         self.N = rp.shape[0] - 1
         self._check(self._L.rcg_set_matrix(self._h, self.N, rp, _u64(colIdx), _f64(val)))
+
+    def update_matrix_values(self, val):
+        """New values on the SAME sparsity pattern as the last set_matrix (the reference's reuse flow): 8 B per entry."""
+        v = _f64(val)
+        self._check(self._L.rcg_update_matrix_values(self._h, v.shape[0], v))
 
     # ---- permutation steps either side of the path, on the device (reference: util.cpp:16-57, util.hpp:147-155) ----
     def set_matrix_permuted(self, rowPtr, colIdx, val, P):

@@ -250,6 +250,12 @@ int rcg_set_matrix_permuted(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, c
   return rcg_setup_matrix_permuted(h, N, rowPtr, colIdx, val, P);
 }
 
+int rcg_update_matrix_values(rcg_handle *h, uint64_t nnz, const double *val) {
+  if (!h) return RCG_ERR_INVALID;
+  RCG_CUDA(h, cudaSetDevice(h->device));
+  return rcg_refresh_matrix_values(h, nnz, val);   // same device arrays: the captured iteration stays valid
+}
+
 int rcg_set_permutation(rcg_handle *h, uint64_t N, const uint64_t *P) {
   if (!h) return RCG_ERR_INVALID;
   RCG_CUDA(h, cudaSetDevice(h->device));

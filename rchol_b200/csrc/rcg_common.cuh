@@ -253,6 +253,8 @@ struct rcg_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   uint32_t *perm = nullptr;   // device copy of the caller's permutation P (rcg_set_permutation / rcg_set_matrix_permuted)
+  bool a_resorted = false;    // A was built on the device from the ORIGINAL ordering (rcg_set_matrix_permuted): its entries are
+                              // not in the caller's order, so a value-only refresh does not apply
 
   // two pinned staging buffers of the host->device upload (rcg_setup.cu), allocated at the first upload
   void *stage_buf[2] = {nullptr, nullptr};
@@ -323,6 +325,7 @@ int rcg_setup_permutation(rcg_handle *h, uint64_t N, const uint64_t *P);
 int rcg_setup_matrix_permuted(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                               const uint64_t *P);
 int rcg_download_matrix(rcg_handle *h, uint64_t *rowPtr, uint64_t *colIdx, double *val);
+int rcg_refresh_matrix_values(rcg_handle *h, uint64_t nnz, const double *val);
 int rcg_apply_permutation(rcg_handle *h, const double *src, double *dst, bool inverse);   // device vectors
 int rcg_setup_factor(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                      const uint64_t *part, uint64_t npart);

@@ -1139,6 +1139,7 @@ int rcg_setup_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const ui
   RCG_TRY(upload_csr(h, N, rowPtr, colIdx, val, h->A));
   h->N = N;
   h->haveA = true;
+  h->a_resorted = false;
   h->stats.N = N;
   h->stats.nnzA = (uint64_t)h->A.nnz;
   // lanes per row of the SpMV from the mean row length ("chosen per row-length histogram")
@@ -1299,6 +1300,7 @@ int rcg_setup_matrix_permuted(rcg_handle *h, uint64_t N, const uint64_t *rowPtr,
   h->A = B;
   h->N = N;
   h->haveA = true;
+  h->a_resorted = true;
   h->stats.N = N;
   h->stats.nnzA = (uint64_t)B.nnz;
   if (h->opt.spmv_lanes > 0) {
@@ -1319,6 +1321,25 @@ int rcg_apply_permutation(rcg_handle *h, const double *src, double *dst, bool in
   else k_vec_gather<<<grid_for(h, n32, 256), 256, 0, h->stream>>>(src, h->perm, n32, dst);
   h->stats.kernel_launches += 1;
   RCG_CUDA(h, cudaGetLastError());
+  return RCG_OK;
+}
+
+// SURVEY.md 8f row 1 (the reference's reuse flow, python/rchol/rchol.py:25-40, python/ex_reuse_partition.py: a new matrix
+// with the SAME sparsity pattern keeps perm / part): only the values of A cross PCIe (8 B per entry instead of 12 B plus the
+// row pointers), the structure on the device, the SpMV's lane choice and the captured iteration graph stay as they are.
+int rcg_refresh_matrix_values(rcg_handle *h, uint64_t nnz, const double *val) {
+  if (!h->haveA) { h->err = "rcg_update_matrix_values: no matrix set"; return RCG_ERR_STATE; }
+  if (h->a_resorted) {
+    h->err = "rcg_update_matrix_values: the matrix was permuted and re-sorted on the device (rcg_set_matrix_permuted); its "
+             "entries are not in the caller's order -- call rcg_set_matrix_permuted again";
+    return RCG_ERR_STATE;
+  }
+  if (!val || nnz != (uint64_t)h->A.nnz) { h->err = "rcg_update_matrix_values: nnz differs from the matrix on the device"; return RCG_ERR_INVALID; }
+  const double t0 = wall_ms();
+  RCG_TRY(staged_copy(h, h->A.val, val, sizeof(double) * (size_t)nnz));
+  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->stats.upload_ms += wall_ms() - t0;
+  h->stats.h2d_bytes += sizeof(double) * (size_t)nnz;
   return RCG_OK;
 }
 

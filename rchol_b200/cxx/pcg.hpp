@@ -21,7 +21,7 @@ public:
 
   // Additive overload: `part` = the nested-dissection block boundaries (2T entries, part[0]=0, part.back()=N) that
   // the reference computes in rchol(A,G,P,threads) (rchol_parallel.cpp:64-70) but does not return from its C++ API
-  // (its Python/MATLAB bindings do).  With it the triangular solves run block-parallel; without it G is one block.
+  // (its Python/MATLAB bindings do).  With it the block structure is taken as given; without it (the stock signature above) it is recovered from G.
   pcg(const SparseCSR &A, const std::vector<double> &b, double tol, int maxit, const SparseCSR &G,
       const std::vector<size_t> &part, std::vector<double> &x, double &relres, int &itr);
 

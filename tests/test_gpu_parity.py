@@ -297,6 +297,48 @@ def test_matrix_replaced_after_a_solve_same_size(capi, oracle):
 
 
 @needs_producer
+def test_value_only_refresh_of_the_matrix(capi, oracle):
+    """SURVEY 8f row 1 (the reference's reuse flow, python/rchol/rchol.py:25-40: a new matrix with the same sparsity keeps
+    perm / part): rcg_update_matrix_values replaces the values of A in place -- structure, lane choice and the captured
+    iteration stay -- and the next solve is the solve of the NEW matrix (checked against the oracle on it)."""
+    A, b, G, part, f = make_problem("lap3d", 20, 4)
+    rng = np.random.default_rng(7)
+    import scipy.sparse as sp
+    N = f.N
+    M = sp.csr_matrix((A[2], A[1].astype(np.int64), A[0].astype(np.int64)), shape=(N, N))
+    d = 1.0 + 0.2 * rng.random(N)                       # D A D with a mild diagonal scaling: same pattern, still SPD
+    M2 = (sp.diags(d) @ M @ sp.diags(d)).tocsr()
+    M2.sort_indices()
+    assert np.array_equal(M2.indptr, M.indptr) and np.array_equal(M2.indices, M.indices)
+    A2 = (A[0], A[1], np.ascontiguousarray(M2.data, dtype=np.float64))
+    with capi.Solver(0) as s:
+        s.set_matrix(*A); s.set_factor(*G, part)
+        x1, r1, i1 = s.pcg(b, 1e-8, 500)                # (captures the iteration graph on A's arrays)
+        h2d0 = s.stats()["h2d_bytes"]
+        s.update_matrix_values(A2[2])
+        assert s.stats()["h2d_bytes"] - h2d0 == 8 * A2[2].shape[0]
+        assert relerr(s.spmv(b), oracle.spmv(*A2, b)) < 1e-14
+        x2, r2, i2 = s.pcg(b, 1e-8, 500)
+        o2 = oracle.pcg(A2, b, 1e-8, 500, G)
+        assert abs(i2 - o2["itr"]) <= 1 and r2 <= 2e-8 and relerr(x2, o2["x"]) <= 1e-6
+        s.update_matrix_values(A[2])                    # and back: bit-identical to the first solve
+        x3, r3, i3 = s.pcg(b, 1e-8, 500)
+        assert i3 == i1 and np.array_equal(x3, x1)
+        with pytest.raises(capi.RcgError) as e:
+            s.update_matrix_values(A[2][:-1])
+        assert e.value.code == capi.RCG_ERR_INVALID
+    with capi.Solver(0) as s:
+        with pytest.raises(capi.RcgError) as e:
+            s.update_matrix_values(A[2])
+        assert e.value.code == capi.RCG_ERR_STATE       # no matrix yet
+        A0 = __import__("rchol_b200.problems", fromlist=["x"]).laplace_3d(20)
+        s.set_matrix_permuted(*A0, f.P)
+        with pytest.raises(capi.RcgError) as e:
+            s.update_matrix_values(A0[2])
+        assert e.value.code == capi.RCG_ERR_STATE       # rows were re-sorted on the device
+
+
+@needs_producer
 def test_resident_solve_and_repeatability(capi):
     A, b, G, part, f = make_problem("lap3d", 32, 4)
     with capi.Solver(0) as s:
