@@ -853,10 +853,9 @@ static int cl_build(rcg_handle *h, DirectionDev &d, const CsrDev &comb, int max_
 
 static int cl_launch(rcg_handle *h, BlockedDev &B, BcArgs a, const GroupHost &G, size_t gi) {
   ClusterDev &C = B.cl;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(h->smem_optin_mask & (1u << 9))) {   // per handle = per device
     RCG_CUDA(h, cudaFuncSetAttribute(k_cl_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_MAX));
-    attr_set = true;
+    h->smem_optin_mask |= 1u << 9;
   }
   ClArgs A;
   memset(&A, 0, sizeof(A));

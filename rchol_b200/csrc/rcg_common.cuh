@@ -245,6 +245,7 @@ struct rcg_handle {
   unsigned long long *clk_probe = nullptr;   // device {cycles, ns} written by CTA 0 of the chain kernel
   unsigned int *abort_flag = nullptr;        // device: non-zero when a dependency wait of the blocked solve timed out
   bool smem_optin_blocked = false;           // large dynamic shared memory enabled for this handle's device (rcg_blocked.cu)
+  uint32_t smem_optin_mask = 0;              // same for the opt-in paths: bit MODE = k_tri_chain<MODE>, bit 8 = k_tri_chain_lv, bit 9 = k_cl_solve
   cudaGraphExec_t iter_graph = nullptr;
   std::vector<double> history;
 

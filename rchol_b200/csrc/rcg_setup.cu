@@ -392,17 +392,20 @@ __global__ void k_scatter_transpose(const int64_t *__restrict__ rp, const uint32
 constexpr int SORT_SMALL = 64;
 
 // thread-per-row insertion sort (rows arrive nearly sorted because U rows are scattered in ascending order);
-// longer rows are appended to `long_rows` for the block-wide bitonic sort.
+// longer rows are appended to `long_rows` for the block-wide bitonic sort; n_long[0] = their number, n_long[1] = the
+// length of the longest of them (capped at 2^32 - 1), so that the host needs 8 bytes back and no row pointers.
 __global__ void k_sort_rows_small(const int64_t *__restrict__ rp, uint32_t *__restrict__ col, double *val,
                                   uint32_t N, uint32_t *__restrict__ long_rows, unsigned int *n_long) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t stride = gridDim.x * blockDim.x;
   for (; j < N; j += stride) {
     const int64_t s = rp[j];
-    const int len = (int)(rp[j + 1] - s);
-    if (len > SORT_SMALL) {
+    const int64_t len64 = rp[j + 1] - s;
+    const int len = (int)len64;
+    if (len64 > SORT_SMALL) {
       unsigned int slot = atomicAdd(n_long, 1u);
       long_rows[slot] = j;
+      atomicMax(n_long + 1, (unsigned int)(len64 > 0xFFFFFFFFll ? 0xFFFFFFFFll : len64));
       continue;
     }
     for (int a = 1; a < len; a++) {
@@ -471,38 +474,24 @@ __global__ void k_sort_rows_bitonic(const int64_t *__restrict__ rp, uint32_t *__
 // sort for long ones.  Used for the rows of L = U^T, for the level segments and for the level-space rows.
 int sort_segments(rcg_handle *h, const int64_t *rp, uint32_t *key, double *val, uint32_t nseg) {
   uint32_t *long_rows = nullptr;
-  unsigned int *n_long = nullptr;
+  unsigned int *n_long = nullptr;   // {number of long segments, length of the longest}
   RCG_CUDA(h, cudaMalloc(&long_rows, sizeof(uint32_t) * std::max<uint32_t>(nseg, 1)));
-  RCG_CUDA(h, cudaMalloc(&n_long, sizeof(unsigned int)));
-  RCG_CUDA(h, cudaMemsetAsync(n_long, 0, sizeof(unsigned int), h->stream));
-  k_sort_rows_small<<<grid_for(h, nseg, 128), 128, 0, h->stream>>>(rp, key, val, nseg, long_rows, n_long);
-  h->stats.kernel_launches += 1;
-  unsigned int hn_long = 0;
-  RCG_CUDA(h, cudaMemcpyAsync(&hn_long, n_long, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-  RCG_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (hn_long > 0) {
+  RCG_CUDA(h, cudaMalloc(&n_long, 2 * sizeof(unsigned int)));
+  auto body = [&]() -> int {
+    RCG_CUDA(h, cudaMemsetAsync(n_long, 0, 2 * sizeof(unsigned int), h->stream));
+    k_sort_rows_small<<<grid_for(h, nseg, 128), 128, 0, h->stream>>>(rp, key, val, nseg, long_rows, n_long);
+    h->stats.kernel_launches += 1;
+    unsigned int hl[2] = {0, 0};
+    RCG_CUDA(h, cudaMemcpyAsync(hl, n_long, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    RCG_CUDA(h, cudaStreamSynchronize(h->stream));
+    const unsigned int hn_long = hl[0];
+    const int64_t maxlen = (int64_t)hl[1];
+    if (hn_long == 0) return RCG_OK;
+    // (The order of `long_rows` varies from run to run; every segment is sorted on its own, so the result does not.)
+    if (maxlen >= ((int64_t)1 << 30)) { h->err = "a row with 2^30 or more entries cannot be sorted on the device"; return RCG_ERR_INVALID; }
     const int smem_cap = 8192;                      // entries: 8192 * 12 B = 96 KB of shared memory
     const size_t smem_bytes = (size_t)smem_cap * 12;
     RCG_CUDA(h, cudaFuncSetAttribute(k_sort_rows_bitonic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    std::vector<uint32_t> lr(hn_long);
-    RCG_CUDA(h, cudaMemcpy(lr.data(), long_rows, sizeof(uint32_t) * hn_long, cudaMemcpyDeviceToHost));
-    std::sort(lr.begin(), lr.end());   // deterministic processing order
-    RCG_CUDA(h, cudaMemcpy(long_rows, lr.data(), sizeof(uint32_t) * hn_long, cudaMemcpyHostToDevice));
-    int64_t maxlen = 0;
-    {
-      std::vector<int64_t> all;
-      if (hn_long > 4096) {
-        all.resize((size_t)nseg + 1);
-        RCG_CUDA(h, cudaMemcpy(all.data(), rp, sizeof(int64_t) * ((size_t)nseg + 1), cudaMemcpyDeviceToHost));
-        for (uint32_t r : lr) maxlen = std::max(maxlen, all[r + 1] - all[r]);
-      } else {
-        int64_t rp2[2];
-        for (uint32_t r : lr) {
-          RCG_CUDA(h, cudaMemcpy(rp2, rp + r, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost));
-          maxlen = std::max(maxlen, rp2[1] - rp2[0]);
-        }
-      }
-    }
     int64_t gstride = 0;
     uint32_t *gkeys = nullptr;
     double *gvals = nullptr;
@@ -514,8 +503,10 @@ int sort_segments(rcg_handle *h, const int64_t *rp, uint32_t *key, double *val, 
       // launch, 12 B each) stays at or below 1 GiB
       const int64_t fit = ((int64_t)1 << 30) / (12 * gstride);
       batch = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(fit, (int64_t)hn_long));
-      RCG_CUDA(h, cudaMalloc(&gkeys, sizeof(uint32_t) * (size_t)gstride * batch));
-      RCG_CUDA(h, cudaMalloc(&gvals, sizeof(double) * (size_t)gstride * batch));
+      cudaError_t ae = cudaMalloc(&gkeys, sizeof(uint32_t) * (size_t)gstride * batch);
+      if (ae == cudaSuccess) ae = cudaMalloc(&gvals, sizeof(double) * (size_t)gstride * batch);
+      if (ae != cudaSuccess) { cudaFree(gkeys); cudaFree(gvals); }
+      RCG_CUDA(h, ae);
     }
     for (unsigned int first = 0; first < hn_long; first += batch) {
       const unsigned int cnt = std::min(batch, hn_long - first);
@@ -525,12 +516,13 @@ int sort_segments(rcg_handle *h, const int64_t *rp, uint32_t *key, double *val, 
     cudaError_t se = cudaGetLastError();
     if (se == cudaSuccess) se = cudaStreamSynchronize(h->stream);
     cudaFree(gkeys); cudaFree(gvals);
-    if (se != cudaSuccess) { cudaFree(long_rows); cudaFree(n_long); }
     RCG_CUDA(h, se);
-  }
-  RCG_CUDA(h, cudaFree(long_rows));
-  RCG_CUDA(h, cudaFree(n_long));
-  return RCG_OK;
+    return RCG_OK;
+  };
+  const int rc = body();
+  cudaFree(long_rows);
+  cudaFree(n_long);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------

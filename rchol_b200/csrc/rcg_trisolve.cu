@@ -785,11 +785,10 @@ constexpr int SMEM_MAX = 232448 - 1024;   // 227 KB per CTA minus some slack
 template <int MODE>
 int launch_chain(rcg_handle *h, const CsrDev &loc, const BlockDesc *blocks_dev, const GroupHost &g, double *w,
                  const uint32_t *grp_mask) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(h->smem_optin_mask & (1u << MODE))) {   // per handle = per device: the attribute belongs to the device's instance of the kernel
     RCG_CUDA(h, cudaFuncSetAttribute(k_tri_chain<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     RCG_CUDA(h, cudaFuncSetAttribute(k_tri_chain_fast<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    attr_set = true;
+    h->smem_optin_mask |= 1u << MODE;
   }
   int threads = h->opt.chain_threads > 0 ? h->opt.chain_threads : 512;
   threads = std::min(992, std::max(32, (threads + 31) / 32 * 32));   // + 1 producer warp
@@ -816,10 +815,9 @@ int launch_chain(rcg_handle *h, const CsrDev &loc, const BlockDesc *blocks_dev, 
   // (opt-in: chain_mode == 2.  Measured on B200 it does not yet beat the polling kernel -- its per-group prologue on a
   //  lone warp costs more than the polling trips it saves)
   if (MODE == 0 && !h->opt.chain_generic && grp_mask && h->opt.chain_mode == 2 && need <= 16384) {
-    static bool lv_attr = false;
-    if (!lv_attr) {
+    if (!(h->smem_optin_mask & (1u << 8))) {
       RCG_CUDA(h, cudaFuncSetAttribute(k_tri_chain_lv, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-      lv_attr = true;
+      h->smem_optin_mask |= 1u << 8;
     }
     const size_t slot_bytes = (size_t)cap_need * 12 + (SLOT_RP + SLOT_VEC) * 8;
     const size_t win_bytes = ((size_t)need + 2) * 8 + (size_t)need * 8;
