@@ -405,7 +405,8 @@ __global__ void k_sort_rows_small(const int64_t *__restrict__ rp, uint32_t *__re
     if (len64 > SORT_SMALL) {
       unsigned int slot = atomicAdd(n_long, 1u);
       long_rows[slot] = j;
-      atomicMax(n_long + 1, (unsigned int)(len64 > 0xFFFFFFFFll ? 0xFFFFFFFFll : len64));
+      const unsigned int l32 = (unsigned int)(len64 > 0xFFFFFFFFll ? 0xFFFFFFFFll : len64);
+      if (l32 > *(volatile unsigned int *)(n_long + 1)) atomicMax(n_long + 1, l32);   // (the maximum only grows: most rows skip the atomic)
       continue;
     }
     for (int a = 1; a < len; a++) {
