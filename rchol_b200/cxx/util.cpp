@@ -43,6 +43,15 @@ void reorder(const SparseCSR &A, const std::vector<size_t> &P, SparseCSR &B) {
   B.init(rp, ci, v);
 }
 
+void reorder(const SparseCSR &A, std::vector<size_t> &rowPtr, std::vector<size_t> &colIdx, std::vector<double> &val,
+             const std::vector<size_t> &P) {
+  SparseCSR B;
+  reorder(A, P, B);
+  rowPtr.assign(B.rowPtr, B.rowPtr + B.N + 1);
+  colIdx.assign(B.colIdx, B.colIdx + B.nnz());
+  val.assign(B.val, B.val + B.nnz());
+}
+
 void rand(std::vector<double> &x, uint64_t seed) {
   std::mt19937_64 gen(seed);
   std::uniform_real_distribution<double> dist(0.0, 1.0);

@@ -160,7 +160,19 @@ int main() {
   SparseCSR G(A);
   double tol = 1e-6; int maxit = 200; double relres; int itr; std::vector<double> x;
   if (N < 0) pcg(A, b, tol, maxit, G, x, relres, itr);   // constructor-as-entry-point, like ex_laplace.cpp:42
-  return (A.nnz() == 135 && G.nnz() == 135 && G.ownMemory) ? 0 : 1;
+  // the other helpers of util.hpp:34-46,147-164 with the reference's call shapes (ex_laplace_parallel.cpp:38-39,
+  // rchol_parallel.cpp:71, find_separator.cpp:145)
+  std::vector<size_t> P(N); for (int i = 0; i < N; i++) P[i] = (size_t)((i * 5 + 3) % N);   // 5 and 27 coprime: a permutation
+  SparseCSR Ap; reorder(A, P, Ap);
+  std::vector<size_t> rp, ci; std::vector<double> v; reorder(A, rp, ci, v, P);
+  bool same = rp.size() == (size_t)N + 1 && ci.size() == Ap.nnz();
+  for (size_t k = 0; same && k < ci.size(); k++) same = ci[k] == Ap.colIdx[k] && v[k] == Ap.val[k];
+  std::vector<double> bp; reorder(b, P, bp);
+  std::vector<double> bq = reorder(b, P);
+  std::vector<double> back; unpermute(bp, P, back);
+  same = same && bq == bp && back == b && bp[0] == b[P[0]];
+  print(P, "P");
+  return (same && A.nnz() == 135 && G.nnz() == 135 && G.ownMemory) ? 0 : 1;
 }
 ''')
     exe = tmp_path / "drv"
