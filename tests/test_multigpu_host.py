@@ -1,6 +1,6 @@
 """CPU tests of the multi-GPU host logic (rchol_b200/multigpu.py): the sharding plan along the reference's
 nested-dissection tree and the exchange pattern (two vector all-reduces over the top separators + scalar all-reduces),
-run with world size 2 and 4 over gloo and compared with the oracle's monolithic solve."""
+run with world size 2, 4 and 8 over gloo and compared with the oracle's monolithic solve."""
 import os
 import sys
 
@@ -117,7 +117,7 @@ def _worker(rank, world, name, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("lap3d_12_t4", 2), ("lap3d_12_t4", 4), ("aniso2d_24_t4", 2)])
+@pytest.mark.parametrize("name,world", [("lap3d_12_t4", 2), ("lap3d_12_t4", 4), ("aniso2d_24_t4", 2), ("lap3d_10_t8_tol6", 8)])
 def test_distributed_pcg_over_gloo_matches_the_oracle(tmp_path, name, world):
     import torch.multiprocessing as mp
     from oracle import oracle
