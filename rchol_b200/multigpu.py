@@ -152,10 +152,12 @@ def assemble(pl: Plan, pieces):
 # ---------------------------------------------------------------------------------------------------------------------
 def _roofline(value_gbs, world, B_iter, ms_per_iter):
     """Iteration-level roofline of the sharded solve: aggregate algorithmic GB/s against world x the measured HBM peak
-    (the dominant kernel is k_bc_solve, as on one GPU; its per-launch figures are in the N = 1 line)."""
+    (the dominant kernels are the triangular-solve level launches, as on one GPU; their per-launch figures are in the
+    N = 1 line)."""
     import bench as _bench
     peak, src = _bench.measured_peak_gbs()
-    return dict(bound="hbm", kernel="PCG iteration (k_bc_solve dominates: see the N=1 line)", achieved=value_gbs,
+    return dict(bound="hbm", kernel="PCG iteration, sharded (triangular-solve level launches k_wb_* / k_dp_* dominate: per-launch figures in the N=1 line; "
+                       "the 2^g - 1 top separators are solved on every rank)", achieved=value_gbs,
                 peak=peak * world, unit="GB/s", frac=value_gbs / (peak * world), traffic=None, peak_source=src + f" x {world} GPUs",
                 bytes_per_iteration=B_iter, ms_per_iteration=ms_per_iter)
 
