@@ -8,7 +8,8 @@ leaves (computed by the UNMODIFIED reference code on the host with a fixed seed 
 residual of 1e-8.  This is BASELINE.json configs[2] ("2^k ND partition") at the largest grid whose reference factorization
 fits the GPU box: 512^3 needs ~280 GB of host memory (35 GB measured at 256^3, x8) and the box has 206 GB (DESIGN.md
 "Workload"); T is the best of the measured leaves sweep (profiles/r02_leaves_sweep_256.jsonl).  BASELINE.json configs[1]
-(the same grid with the reference example's 8-way partition) is measured beside it in the same line (`configs1`).
+(the same grid with the reference example's 8-way partition) is measured beside it in the same line (`configs1`), and
+configs[3] (the 2-D anisotropic random-weight SDDM, at 4096^2) in a child process with a time limit (`configs3`).
 A "step" is one full PCG solve.  The metric is the algorithmic memory traffic of the PCG iterations
 divided by the time they take: bytes per iteration (SURVEY.md 8d / BASELINE.md section 3)
     B_iter = 12 nnz(A) + 4 (N+1) + 2 [12 nnz(G) + 4 (N+1)] + 136 N
