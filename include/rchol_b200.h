@@ -205,6 +205,12 @@ int rcg_debug_trace(rcg_handle *h, int which, const double *rhs_host, double *ou
  * one device array to the host: 0 offA, 1 offB, 2 blobA, 3 blobB, 4 far rowptr, 5 far col, 6 far val, 7 tile_need,
  * 8 blocks (8 x uint32 each: lo, hi, chunk0, tile0, gidx, pad), 9 per-level plan (10 x uint64 each). */
 int rcg_debug_blocked_info(rcg_handle *h, int direction, uint64_t *info16);
+/* Host only: the row-length histogram the SpMV plan is chosen from (BASELINE north star: "chosen per row-length histogram";
+ * replaces nothing in the reference, whose mkl_sparse_d_mv at pcg.cpp:137 runs without optimize hints).  entries5[k] = entries in
+ * rows of length <= 2, 3..5, 6..12, 13..24, > 24; *lanes = lanes per row (2 ... 32): the smallest whose bucket edge covers
+ * 90 % of the entries.  rcg_options.spmv_lanes > 0 overrides the choice. */
+int rcg_spmv_row_histogram(uint64_t N, const uint64_t *rowPtr, uint64_t *entries5, int *lanes);
+
 /* Blocks that rcg_set_factor derives from G when no `part` is given (the stock signature of the reference's pcg,
    /root/reference/c++/util/pcg.hpp:13-16, carries none).  Host-only, no device needed: bounds_out gets *nblocks + 1
    boundaries, depth_out *nblocks tree depths; returns RCG_ERR_INVALID when more than `cap` blocks would be written and

@@ -28,7 +28,7 @@ EXPORTED = [
     "rcg_set_factor_blocks", "rcg_nccl_unique_id", "rcg_dist_init", "rcg_dist_finalize",
     "rcg_debug_blocked_info", "rcg_debug_blocked_copy", "rcg_debug_counters", "rcg_debug_dp_trace",
     "rcg_set_matrix_permuted", "rcg_set_permutation", "rcg_permute_vector", "rcg_unpermute_vector",
-    "rcg_pcg_original", "rcg_get_matrix", "rcg_detect_blocks", "rcg_update_matrix_values",
+    "rcg_pcg_original", "rcg_get_matrix", "rcg_detect_blocks", "rcg_update_matrix_values", "rcg_spmv_row_histogram",
 ]
 
 TRSV_FORWARD, TRSV_BACKWARD = 0, 1
@@ -118,6 +118,7 @@ def load():
     L.rcg_pcg_original.argtypes = [H, _f64p, C.c_double, C.c_int, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.rcg_get_matrix.argtypes = [H, _u64p, _u64p, _f64p]
     L.rcg_update_matrix_values.argtypes = [H, C.c_uint64, _f64p]
+    L.rcg_spmv_row_histogram.argtypes = [C.c_uint64, _u64p, _u64p, C.POINTER(C.c_int)]
     L.rcg_detect_blocks.argtypes = [C.c_uint64, _u64p, _u64p, _u64p, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"),
                                     C.c_uint64, C.POINTER(C.c_uint64)]
     for name in EXPORTED:
@@ -381,6 +382,19 @@ class Solver:
         ms = C.c_double(0)
         self._check(self._L.rcg_time_phase(self._h, int(phase), int(reps), C.byref(ms)))
         return ms.value
+
+
+def spmv_row_histogram(rowPtr):
+    """(entries by row-length bucket [<=2, 3..5, 6..12, 13..24, >24], lanes per row) -- the SpMV plan of set_matrix.
+    Host-only (no GPU needed)."""
+    L = load()
+    rp = _u64(rowPtr)
+    hist = np.zeros(5, np.uint64)
+    lanes = C.c_int(0)
+    rc = L.rcg_spmv_row_histogram(rp.shape[0] - 1, rp, hist, C.byref(lanes))
+    if rc != 0:
+        raise RcgError(rc, "rcg_spmv_row_histogram: bad arguments")
+    return hist, lanes.value
 
 
 def detect_blocks(rowPtr, colIdx, cap: int = 1 << 16):

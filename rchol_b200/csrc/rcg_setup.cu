@@ -169,6 +169,35 @@ int host_threads() {
   return t < 1 ? 1 : (t > 16 ? 16 : t);
 }
 
+// Lanes per row of the CSR SpMV from the row-length histogram (north star: "warp-per-row or merge-based, chosen per
+// row-length histogram").  The histogram counts ENTRIES by the length of the row they sit in, with the bucket edges at the
+// lengths up to which 2 / 4 / 8 / 16 lanes per row keep their lanes busy (2, 5, 12, 24); the choice is the smallest lane
+// count whose bucket edge covers at least 90 % of the entries -- a matrix with a few very long rows among many short ones is
+// served by its bulk, a matrix whose entries sit mostly in long rows gets a warp per row.  Integer sums: the result does not
+// depend on the thread count or on the order of the rows (a permuted matrix gets the same plan).
+int spmv_lanes_from_rows(uint64_t N, const uint64_t *rowPtr, uint64_t entries[5]) {
+  unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
+  const int T = host_threads();
+#pragma omp parallel for num_threads(T) schedule(static) reduction(+ : e0, e1, e2, e3, e4)
+  for (long long i = 0; i < (long long)N; i++) {
+    const uint64_t len = rowPtr[i + 1] - rowPtr[i];
+    if (len <= 2) e0 += len;
+    else if (len <= 5) e1 += len;
+    else if (len <= 12) e2 += len;
+    else if (len <= 24) e3 += len;
+    else e4 += len;
+  }
+  const unsigned long long e[5] = {e0, e1, e2, e3, e4};
+  unsigned long long total = 0, cum = 0;
+  for (int k = 0; k < 5; k++) { total += e[k]; if (entries) entries[k] = e[k]; }
+  static const int lanes[5] = {2, 4, 8, 16, 32};
+  for (int k = 0; k < 5; k++) {
+    cum += e[k];
+    if ((long double)cum * 10.0L >= (long double)total * 9.0L) return lanes[k];
+  }
+  return 32;
+}
+
 // fill(dst, first, count) writes elements [first, first + count) of the device array into the pinned buffer `dst`
 template <class Fill>
 int staged_h2d(rcg_handle *h, void *dst, size_t n, size_t elem_bytes, Fill fill) {
@@ -1135,13 +1164,8 @@ int rcg_setup_matrix(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const ui
   h->a_resorted = false;
   h->stats.N = N;
   h->stats.nnzA = (uint64_t)h->A.nnz;
-  // lanes per row of the SpMV from the mean row length ("chosen per row-length histogram")
-  if (h->opt.spmv_lanes > 0) {
-    h->spmv_lanes = h->opt.spmv_lanes;
-  } else {
-    double mean = (double)h->A.nnz / (double)N;
-    h->spmv_lanes = mean <= 2.5 ? 2 : mean <= 5.0 ? 4 : mean <= 12.0 ? 8 : mean <= 24.0 ? 16 : 32;
-  }
+  // lanes per row of the SpMV from the row-length histogram (spmv_lanes_from_rows above)
+  h->spmv_lanes = h->opt.spmv_lanes > 0 ? h->opt.spmv_lanes : spmv_lanes_from_rows(N, rowPtr, nullptr);
   return RCG_OK;
 }
 
@@ -1296,12 +1320,8 @@ int rcg_setup_matrix_permuted(rcg_handle *h, uint64_t N, const uint64_t *rowPtr,
   h->a_resorted = true;
   h->stats.N = N;
   h->stats.nnzA = (uint64_t)B.nnz;
-  if (h->opt.spmv_lanes > 0) {
-    h->spmv_lanes = h->opt.spmv_lanes;
-  } else {
-    double mean = (double)B.nnz / (double)N;
-    h->spmv_lanes = mean <= 2.5 ? 2 : mean <= 5.0 ? 4 : mean <= 12.0 ? 8 : mean <= 24.0 ? 16 : 32;
-  }
+  // (the histogram of row lengths is invariant under the symmetric permutation: the same plan as for the permuted matrix)
+  h->spmv_lanes = h->opt.spmv_lanes > 0 ? h->opt.spmv_lanes : spmv_lanes_from_rows(N, rowPtr, nullptr);
   h->stats.analysis_ms += wall_ms() - t0;
   return RCG_OK;
 }
@@ -1488,6 +1508,14 @@ bool detect_blocks(uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, s
 
 static int setup_factor_impl(rcg_handle *h, uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, const double *val,
                              const std::vector<uint32_t> &bounds, const TreeInfo &tree, bool strict_tree);
+
+// Host only (no GPU needed): the row-length histogram of a CSR matrix as the SpMV plan sees it -- entries5[k] = entries in rows
+// of length <= 2, 3..5, 6..12, 13..24, > 24 -- and the lanes per row chosen from it.
+extern "C" int rcg_spmv_row_histogram(uint64_t N, const uint64_t *rowPtr, uint64_t *entries5, int *lanes) {
+  if (!rowPtr || !lanes || N == 0) return RCG_ERR_INVALID;
+  *lanes = spmv_lanes_from_rows(N, rowPtr, entries5);
+  return RCG_OK;
+}
 
 extern "C" int rcg_detect_blocks(uint64_t N, const uint64_t *rowPtr, const uint64_t *colIdx, uint64_t *bounds_out,
                                  int32_t *depth_out, uint64_t cap, uint64_t *nblocks) {

@@ -122,6 +122,37 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert b"rchol_b200" in lib.rcg_version() and b"sm_100a" in lib.rcg_version()
 
 
+def test_spmv_plan_from_the_row_length_histogram():
+    """rcg_spmv_row_histogram (host only): entries by row-length bucket and the lanes per row chosen from them -- the
+    smallest lane count whose bucket edge covers 90 % of the ENTRIES.  The bench matrices keep the plan they were measured
+    with (7-point Laplacian: 8 lanes, 5-point SDDM: 4); a few very long rows among many short ones do not change the plan
+    of the bulk, a matrix whose entries sit in long rows gets a warp per row; the plan is invariant under permutation."""
+    from rchol_b200 import capi
+    for n in (8, 20, 40):
+        rp = problems.laplace_3d(n)[0]
+        hist, lanes = capi.spmv_row_histogram(rp)
+        lens = np.diff(rp.astype(np.int64))
+        assert int(hist.sum()) == int(rp[-1]) and lanes == 8
+        assert int(hist[1]) == int(lens[(lens > 2) & (lens <= 5)].sum()) and int(hist[2]) == int(lens[(lens > 5) & (lens <= 12)].sum())
+    for n in (24, 96):
+        hist, lanes = capi.spmv_row_histogram(problems.aniso_2d(n)[0])
+        assert lanes == 4 and int(hist[2:].sum()) == 0
+    rng = np.random.default_rng(3)
+    lens = np.full(10000, 3, np.int64)
+    lens[:5] = 2000                                            # 5 rows hold 25 % of the entries: the short rows cover only 75 %,
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    assert capi.spmv_row_histogram(rp)[1] == 32                # less than 90 %, so the plan serves the long rows (a warp per row)
+    lens[:5] = 300                                             # 5 % of the entries in long rows: plan of the bulk
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    assert capi.spmv_row_histogram(rp)[1] == 4
+    perm = rng.permutation(lens.shape[0])
+    rp2 = np.concatenate([[0], np.cumsum(lens[perm])]).astype(np.uint64)
+    h1, l1 = capi.spmv_row_histogram(rp); h2, l2 = capi.spmv_row_histogram(rp2)
+    assert l1 == l2 and np.array_equal(h1, h2)
+    assert capi.spmv_row_histogram(np.array([0, 40, 80, 120], np.uint64))[1] == 32
+    assert capi.spmv_row_histogram(np.array([0, 1, 3, 4], np.uint64))[1] == 2
+
+
 def test_no_cpu_fallback_without_a_gpu():
     """On a box without a B200 creating a solver must fail loudly (RCG_ERR_CUDA), never compute on the CPU."""
     import torch
